@@ -1,0 +1,359 @@
+"""Drop-in surface of the recsys-lite hot path on a B200: same names, arguments and error behaviour as
+/root/reference/src/recsys_lite/algo.py, with the arithmetic done by librecsys_b200.so (sm_100a kernels).
+
+Mirrors (reference file:line):
+  RecommenderSystem.__init__/is_fitted   algo.py:50-79
+  RecommenderSystem.fit                  algo.py:81-118   (als -> _fit_als :300-337, svd -> _fit_svd_dense :210-248)
+  RecommenderSystem.predict              algo.py:120-170  (als :143-147, svd -> _predict_svd :352-375)
+  RecommenderSystem.recommend            algo.py:172-208
+  save / load / get_params / clone / reset   algo.py:377-409
+  svd_reconstruct                        algo.py:412-530
+  top_n                                  algo.py:587-659
+  compute_rmse / compute_mae             algo.py:662-743
+
+Validation, error strings and output post-processing stay in Python; there is no
+NumPy fallback for the device work: without the shared library or a B200 the calls raise RecsysB200Error.
+
+Documented deviations from the reference:
+  * ALS accepts scipy.sparse input (the reference raises IndexError for it) and the extra keyword arguments
+    ``precision`` ("fp32_ir" default | "fp64"), ``ir_steps`` and ``init=(U0, V0)``;
+  * factors are kept in float32 on the device and returned as float64 (reference: float64 throughout):
+    relative factor error ~1e-6 against the reference, inside the stated 1e-4 tolerance;
+  * equal scores are ordered by ascending item index (the reference's tie order is implementation defined);
+  * ``algorithm="knn"`` is accepted by the constructor but ``fit`` raises NotImplementedError (out of scope).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import numpy as np
+from scipy import sparse
+
+from . import _ffi
+from .csr import observed_pattern, transpose_pattern
+
+MAX_FACTORS = 128   # rl_padded_k
+MAX_TOP_N = 128     # on-chip list capacity of the selection kernels
+
+_PRECISIONS = {"fp32_ir": _ffi.RL_PREC_FP32_IR, "fp64": _ffi.RL_PREC_FP64}
+
+
+def _dense(x):
+    return x.toarray() if sparse.issparse(x) else x
+
+
+def _as_float_matrix(x, allow=(np.float32, np.float64), default=np.float64):
+    a = np.asarray(_dense(x))
+    if a.dtype.type not in allow:
+        a = a.astype(default)
+    return np.ascontiguousarray(a)
+
+
+def _rl_dtype(a):
+    return _ffi.RL_F64 if a.dtype == np.float64 else _ffi.RL_F32
+
+
+def _finish_topn(idx, n_valid):
+    """-1 padded (n_users, n) int32 + valid counts -> the reference's trimmed result (algo.py:629-639)."""
+    widest = int(n_valid.max()) if n_valid.size else 0
+    if widest == 0:
+        return np.empty((idx.shape[0], 0), dtype=int)
+    return idx[:, :widest]
+
+
+class RecommenderSystem:
+    """B200 implementation of the reference's ``RecommenderSystem`` for ``algorithm="als" | "svd"``."""
+
+    def __init__(self, algorithm: str = "svd", random_state: Optional[int] = None, use_sparse: bool = True) -> None:
+        self.algorithm = algorithm
+        self.random_state = random_state
+        self.use_sparse = use_sparse
+        self._model: Optional[Dict[str, Any]] = None
+        self._fitted = False
+        if algorithm not in ("svd", "als", "knn"):
+            raise ValueError(f"Unsupported algorithm: '{algorithm}'")
+
+    def is_fitted(self) -> bool:
+        return self._fitted
+
+    # ------------------------------------------------------------------------------------------ fit
+    def fit(self, ratings, k: Optional[int] = None, **kwargs) -> "RecommenderSystem":
+        if self.algorithm == "als":
+            factors = kwargs.get("factors", k or 10)
+            self._model = self._fit_als(
+                ratings, factors, kwargs.get("iterations", 10), kwargs.get("lambda_", 0.01),
+                precision=kwargs.get("precision", "fp32_ir"), ir_steps=kwargs.get("ir_steps", 2),
+                init=kwargs.get("init"),
+            )
+        elif self.algorithm == "svd":
+            self._model = self._fit_svd(ratings, k)
+        elif self.algorithm == "knn":
+            raise NotImplementedError("algorithm='knn' is outside the B200 hot path (SURVEY.md section 2 row 10)")
+        else:
+            raise ValueError(f"Unsupported algorithm: {self.algorithm}")
+        self._fitted = True
+        return self
+
+    def _fit_als(self, ratings, factors: int, iterations: int = 10, lambda_: float = 0.01, *,
+                 precision: str = "fp32_ir", ir_steps: int = 2, init=None) -> Dict[str, Any]:
+        """algo.py:300-337: init from the GLOBAL NumPy RNG (U then V), binarise, `iterations` sweeps."""
+        if ratings.ndim != 2:
+            raise ValueError(f"Input matrix must be 2D (users x items), got {ratings.ndim}D.")
+        n_users, n_items = ratings.shape
+        factors = int(factors)
+        if not 1 <= factors <= MAX_FACTORS:
+            raise NotImplementedError(f"factors={factors}: the device kernels cover 1..{MAX_FACTORS}")
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}, got {precision!r}")
+        if init is None:
+            user_f = np.random.rand(n_users, factors)   # draw order of algo.py:309-310
+            item_f = np.random.rand(n_items, factors)
+        else:
+            user_f = np.array(init[0], dtype=np.float64, order="C", copy=True)
+            item_f = np.array(init[1], dtype=np.float64, order="C", copy=True)
+            if user_f.shape != (n_users, factors) or item_f.shape != (n_items, factors):
+                raise ValueError("init factors must have shapes (n_users, factors) and (n_items, factors)")
+        indptr, indices = observed_pattern(ratings)
+        indptr_t, indices_t = transpose_pattern(indptr, indices, n_items)
+        if n_users and n_items and iterations > 0:
+            h = _ffi.default_handle()
+            h.call("rl_als_fit_host", n_users, n_items, factors, _ffi.ptr(indptr), _ffi.ptr(indices),
+                   _ffi.ptr(indptr_t), _ffi.ptr(indices_t), int(iterations), float(lambda_),
+                   _PRECISIONS[precision], int(ir_steps), _ffi.ptr(user_f), _ffi.ptr(item_f), _ffi.RL_F64)
+        return {"user_factors": user_f, "item_factors": item_f, "factors": factors}
+
+    def _fit_svd(self, ratings, k: Optional[int]) -> Dict[str, Any]:
+        """algo.py:210-248: biases over entries > 0, centre every cell, rank-k SVD of the centred matrix.
+
+        The bias means are plain NumPy reductions on the host (stage N3 of SURVEY 8(f) moves them on device);
+        the factorisation runs on the device.  Model keys as pinned by tests/test_algo.py:659-684.
+        """
+        r = np.asarray(_dense(ratings))
+        n_users, n_items = r.shape
+        if k is None:
+            k = max(1, min(n_users, n_items) // 4)
+        k_eff = max(1, min(int(k), n_users, n_items))  # slicing u[:, :k] tolerates k > rank (algo.py:240-243)
+        pos = r > 0
+        cnt = pos.sum()
+        ftype = np.float32 if r.dtype == np.float32 else np.float64
+        rs = np.where(pos, r, 0).astype(np.float64)
+        gb = ftype(rs.sum() / cnt) if cnt else ftype(np.nan)
+        cu, ci = pos.sum(axis=1), pos.sum(axis=0)
+        ub = np.where(cu > 0, rs.sum(axis=1) / np.maximum(cu, 1) - float(gb), 0.0).astype(ftype)
+        ib = np.where(ci > 0, rs.sum(axis=0) / np.maximum(ci, 1) - float(gb), 0.0).astype(ftype)
+        centred = np.ascontiguousarray((r - gb - ub[:, None] - ib[None, :]).astype(np.float32))
+        s = np.empty(k_eff, dtype=np.float64)
+        left = np.empty((n_users, k_eff), dtype=np.float64)
+        right = np.empty((n_items, k_eff), dtype=np.float64)
+        if np.isfinite(centred).all() and centred.any():
+            h = _ffi.default_handle()
+            h.call("rl_svd_reconstruct_host", _ffi.ptr(centred), n_users, n_items, k_eff, None,
+                   _ffi.ptr(s), _ffi.ptr(left), _ffi.ptr(right))
+        else:
+            s[:], left[:], right[:] = 0.0, 0.0, 0.0
+        safe = np.where(s > 0, s, 1.0)
+        if n_users >= n_items:   # left = U S, right = V
+            u, vt = left / safe, right.T
+        else:                    # left = U, right = V S
+            u, vt = left, (right / safe).T
+        return {
+            "u": u.astype(np.float32), "s": s.astype(np.float32), "vt": np.ascontiguousarray(vt).astype(np.float32),
+            "k": k, "global_bias": gb, "user_bias": ub, "item_bias": ib,
+        }
+
+    # -------------------------------------------------------------------------------------- predict
+    def _need_model(self) -> Dict[str, Any]:
+        if not self._fitted:
+            raise RuntimeError("Model must be fitted before making predictions. Call .fit() first.")
+        if self._model is None:
+            raise RuntimeError("Model not fitted. Call .fit() first.")
+        return self._model
+
+    def _factor_view(self):
+        """(row factors, column factors, global bias, row bias, col bias, output dtype) of the fitted model."""
+        m = self._need_model()
+        if self.algorithm == "als":
+            return m["user_factors"], m["item_factors"], 0.0, None, None, np.float64
+        us = np.ascontiguousarray(m["u"].astype(np.float64) * m["s"].astype(np.float64)[None, :])
+        v = np.ascontiguousarray(m["vt"].T.astype(np.float64))
+        out_t = np.float32 if np.asarray(m["user_bias"]).dtype == np.float32 else np.float64
+        return (us, v, float(m["global_bias"]), np.ascontiguousarray(m["user_bias"], dtype=np.float32),
+                np.ascontiguousarray(m["item_bias"], dtype=np.float32), out_t)
+
+    def predict(self, ratings):
+        """als: U @ V.T float64, argument ignored (algo.py:143-147); svd: u@(s*vt)+biases (algo.py:363-368)."""
+        if self.algorithm == "knn":
+            self._need_model()
+            raise NotImplementedError("algorithm='knn' is outside the B200 hot path")
+        a, b, gb, rb, cb, out_t = self._factor_view()
+        m, n = a.shape[0], b.shape[0]
+        kk = a.shape[1]
+        out = np.empty((m, n), dtype=out_t)
+        if m and n:
+            h = _ffi.default_handle()
+            h.call("rl_predict_host", _ffi.ptr(np.ascontiguousarray(a)), _ffi.ptr(np.ascontiguousarray(b)),
+                   _ffi.RL_F64, m, n, kk, gb, _ffi.ptr(rb), _ffi.ptr(cb), _ffi.ptr(out), _rl_dtype(out))
+        if self.algorithm == "svd" and self.use_sparse:
+            return sparse.csr_matrix(out)
+        return out
+
+    # ------------------------------------------------------------------------------------ recommend
+    def recommend(self, ratings, n: int = 10, exclude_rated: bool = True) -> np.ndarray:
+        """predict + top_n fused on the device: the score matrix is never formed (algo.py:172-208)."""
+        if n <= 0:
+            raise ValueError(f"n must be positive. Got n={n}.")
+        if self.algorithm == "knn":
+            self._need_model()
+            raise NotImplementedError("algorithm='knn' is outside the B200 hot path")
+        a, b, gb, rb, cb, _ = self._factor_view()
+        n_users, n_items = a.shape[0], b.shape[0]
+        if exclude_rated and tuple(ratings.shape) != (n_users, n_items):
+            raise ValueError(
+                "Estimated and known matrices must have the same shape. "
+                f"Got {(n_users, n_items)} and {tuple(ratings.shape)}."
+            )
+        if n_users == 0 or n_items == 0:
+            return np.empty((0, 0), dtype=int)
+        n_dev = min(int(n), n_items)
+        if n_dev > MAX_TOP_N:
+            raise NotImplementedError(f"n={n}: the selection kernels keep at most {MAX_TOP_N} items per user")
+        idx = np.empty((n_users, n_dev), dtype=np.int32)
+        indptr = indices = None
+        if exclude_rated:
+            indptr, indices = observed_pattern(ratings)
+        h = _ffi.default_handle()
+        h.call("rl_recommend_host", _ffi.ptr(np.ascontiguousarray(a)), _ffi.ptr(np.ascontiguousarray(b)), _ffi.RL_F64,
+               n_users, n_items, a.shape[1], _ffi.ptr(indptr), _ffi.ptr(indices), gb, _ffi.ptr(rb), _ffi.ptr(cb),
+               n_dev, _ffi.ptr(idx), None, _ffi.RL_SCORE_AUTO)
+        if not exclude_rated:
+            return idx.astype(np.int64)   # reference: argsort result, int64 (algo.py:207)
+        n_valid = np.minimum(n_dev, n_items - np.diff(indptr)).astype(np.int32)
+        return _finish_topn(idx, n_valid)
+
+    # ---------------------------------------------------------------------------------- persistence
+    def save(self, path: str) -> None:
+        import joblib
+        with open(path, "wb") as f:
+            joblib.dump(self, f)
+
+    @classmethod
+    def load(cls, path: str) -> "RecommenderSystem":
+        import joblib
+        with open(path, "rb") as f:
+            obj = joblib.load(f)
+        if not isinstance(obj, cls):
+            raise ValueError(f"Loaded object is not a {cls.__name__}")
+        return obj
+
+    def get_params(self) -> Dict[str, Any]:
+        return {"algorithm": getattr(self, "algorithm", None), "use_sparse": getattr(self, "use_sparse", False)}
+
+    def clone(self) -> "RecommenderSystem":
+        return RecommenderSystem(algorithm=self.algorithm, random_state=self.random_state, use_sparse=self.use_sparse)
+
+    def reset(self) -> None:
+        self._model = None
+        self._fitted = False
+
+
+def _reconstruct_device(mat32: np.ndarray, k: int) -> np.ndarray:
+    out = np.empty_like(mat32)
+    h = _ffi.default_handle()
+    h.call("rl_svd_reconstruct_host", _ffi.ptr(mat32), mat32.shape[0], mat32.shape[1], int(k), _ffi.ptr(out),
+           None, None, None)
+    return out
+
+
+def svd_reconstruct(mat, *, k: Optional[int] = None, random_state: Optional[int] = None, use_sparse: bool = True,
+                    chunk_size: Optional[int] = None):
+    """Rank-k reconstruction of ``mat`` (algo.py:412-530) with the SVD done on the device.
+
+    ``random_state`` is accepted for signature compatibility; the device factorisation is deterministic.
+    """
+    if mat.ndim != 2:
+        raise ValueError(f"Input matrix must be 2D (users x items), got {mat.ndim}D.")
+    n_users, n_items = mat.shape
+    if n_users == 0 or n_items == 0:
+        raise ValueError("Input matrix cannot have zero dimensions.")
+    k = max(1, min(n_users, n_items) // 4) if k is None else k
+    if not 1 <= k <= min(n_users, n_items):
+        raise ValueError(
+            f"k must be between 1 and min(n_users, n_items)={min(n_users, n_items)}, got k={k}."
+        )
+    dense = np.asarray(_dense(mat))
+    if not dense.any():
+        return np.zeros_like(dense)          # all-zero guard, input dtype (algo.py:489-490)
+    if chunk_size:
+        # per-chunk rank-k estimator of algo.py:491-505 (a different estimator from the unchunked call)
+        out = np.zeros_like(dense)
+        for start in range(0, n_users, chunk_size):
+            chunk = dense[start:start + chunk_size]
+            if not chunk.any():
+                continue
+            kc = min(int(k), min(chunk.shape))
+            out[start:start + chunk.shape[0]] = _reconstruct_device(
+                np.ascontiguousarray(chunk, dtype=np.float32), kc)
+        return out
+    recon = _reconstruct_device(np.ascontiguousarray(dense, dtype=np.float32), int(k))
+    return sparse.csr_matrix(recon) if use_sparse else recon
+
+
+def top_n(est, known, *, n: int = 10) -> np.ndarray:
+    """Top-n unseen items per user from dense/sparse score and known matrices (algo.py:587-659)."""
+    if n <= 0:
+        raise ValueError(f"n must be positive. Got n={n}.")
+    if tuple(est.shape) != tuple(known.shape):
+        raise ValueError(
+            f"Estimated and known matrices must have the same shape. Got {tuple(est.shape)} and {tuple(known.shape)}."
+        )
+    n_users, n_items = est.shape
+    if n_users == 0 or n_items == 0:
+        return np.empty((0, 0), dtype=int)
+    est_d = _as_float_matrix(est)
+    known_d = _as_float_matrix(known, default=np.float32)
+    n_dev = min(int(n), n_items)
+    if n_dev > MAX_TOP_N:
+        raise NotImplementedError(f"n={n}: the selection kernels keep at most {MAX_TOP_N} items per user")
+    idx = np.empty((n_users, n_dev), dtype=np.int32)
+    n_valid = np.empty(n_users, dtype=np.int32)
+    h = _ffi.default_handle()
+    h.call("rl_topn_dense_host", _ffi.ptr(est_d), _rl_dtype(est_d), _ffi.ptr(known_d), _rl_dtype(known_d),
+           n_users, n_items, n_dev, _ffi.ptr(idx), _ffi.ptr(n_valid))
+    return _finish_topn(idx, n_valid)
+
+
+def _metric_inputs(predictions, actual):
+    if predictions.shape != actual.shape:
+        raise ValueError(
+            "Predictions and actual matrices must have the same shape. "
+            f"Got {predictions.shape} and {actual.shape}."
+        )
+    p, a = np.asarray(_dense(predictions)), np.asarray(_dense(actual))
+    if np.any(np.isinf(p)) or np.any(np.isinf(a)):
+        raise ValueError("Input matrices must not contain infinite values.")
+    if np.any(np.isnan(p)) or np.any(np.isnan(a)):
+        raise ValueError("Input matrices must not contain NaN values.")
+    return p, a
+
+
+def compute_rmse(predictions, actual) -> float:
+    """RMSE over cells with ``actual > 0`` (algo.py:662-701).  Host-side reduction, as in the reference; the
+    device version for factor models is ``observed_error`` (no score matrix)."""
+    p, a = _metric_inputs(predictions, actual)
+    m = a > 0
+    if not np.any(m):
+        return 0.0
+    d = p[m] - a[m]
+    return float(np.sqrt(np.mean(d ** 2)))
+
+
+def compute_mae(predictions, actual) -> float:
+    """MAE over cells with ``actual > 0`` (algo.py:704-743)."""
+    p, a = _metric_inputs(predictions, actual)
+    m = a > 0
+    if not np.any(m):
+        return 0.0
+    return float(np.mean(np.abs(p[m] - a[m])))
+
+
+__all__ = ["RecommenderSystem", "svd_reconstruct", "top_n", "compute_rmse", "compute_mae"]

@@ -1,0 +1,451 @@
+// api.cu -- the C ABI of librecsys_b200.so (include/recsys_b200.h): handle, memory helpers, host-buffer wrappers.
+#include <cstdarg>
+#include <vector>
+
+#include "common.cuh"
+
+namespace rl {
+
+thread_local std::string g_last_error;
+
+int fail(rl_context* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  if (h) h->err = buf;
+  return code;
+}
+
+int cuda_fail(rl_context* h, cudaError_t e, const char* what) {
+  const int code = (e == cudaErrorMemoryAllocation) ? RL_ERR_NOMEM : RL_ERR_CUDA;
+  return fail(h, code, "CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+}
+
+int scratch(rl_context* h, size_t bytes, void** out) {
+  if (bytes > h->scratch_bytes) {
+    if (h->scratch) {
+      RL_CUDA(h, cudaStreamSynchronize(h->stream));
+      RL_CUDA(h, cudaFree(h->scratch));
+      h->scratch = nullptr;
+      h->scratch_bytes = 0;
+    }
+    const size_t want = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+    RL_CUDA(h, cudaMalloc(&h->scratch, want));
+    h->scratch_bytes = want;
+  }
+  *out = h->scratch;
+  return RL_OK;
+}
+
+namespace {
+
+// (rows x k, stride src_ld) -> (rows x dst_ld) with zero fill of the padding columns
+template <typename TS, typename TD>
+__global__ void convert_kernel(const TS* __restrict__ src, int64_t rows, int k, int src_ld, TD* __restrict__ dst, int dst_ld) {
+  const int64_t total = rows * dst_ld;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
+       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = p / dst_ld;
+    const int c = static_cast<int>(p - r * dst_ld);
+    dst[p] = (c < k) ? static_cast<TD>(src[r * src_ld + c]) : static_cast<TD>(0);
+  }
+}
+
+struct DevBuf {  // RAII device allocation for the host wrappers
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(rl_context* h, size_t bytes) {
+    RL_CUDA(h, cudaMalloc(&p, bytes ? bytes : 16));
+    return RL_OK;
+  }
+  template <typename T> T* as() { return static_cast<T*>(p); }
+};
+
+#define RL_TRY(expr)            \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != RL_OK) return _rc; \
+  } while (0)
+
+int upload(rl_context* h, DevBuf& b, const void* host, size_t bytes) {
+  RL_TRY(b.alloc(h, bytes));
+  if (bytes) RL_CUDA(h, cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, h->stream));
+  return RL_OK;
+}
+
+}  // namespace
+
+int launch_factors_convert(rl_context* h, const void* src, int src_dtype, int64_t rows, int k, int src_ld,
+                           void* dst, int dst_dtype, int dst_ld) {
+  if (rows == 0) return RL_OK;
+  const int64_t total = rows * dst_ld;
+  int64_t grid = (total + 255) / 256;
+  if (grid > 16 * h->sm_count) grid = 16 * h->sm_count;
+  if (src_dtype == RL_F64 && dst_dtype == RL_F32)
+    convert_kernel<double, float><<<grid, 256, 0, h->stream>>>(static_cast<const double*>(src), rows, k, src_ld, static_cast<float*>(dst), dst_ld);
+  else if (src_dtype == RL_F32 && dst_dtype == RL_F32)
+    convert_kernel<float, float><<<grid, 256, 0, h->stream>>>(static_cast<const float*>(src), rows, k, src_ld, static_cast<float*>(dst), dst_ld);
+  else if (src_dtype == RL_F32 && dst_dtype == RL_F64)
+    convert_kernel<float, double><<<grid, 256, 0, h->stream>>>(static_cast<const float*>(src), rows, k, src_ld, static_cast<double*>(dst), dst_ld);
+  else
+    return fail(h, RL_ERR_INVALID, "factors_convert: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
+  RL_LAUNCH_CHECK(h, "convert_kernel");
+  return RL_OK;
+}
+
+}  // namespace rl
+
+using namespace rl;
+
+#define RL_NEED(h)                                                     \
+  do {                                                                 \
+    if (!(h)) return rl::fail(nullptr, RL_ERR_INVALID, "null handle"); \
+    cudaError_t _e = cudaSetDevice((h)->device);                       \
+    if (_e != cudaSuccess) return rl::cuda_fail((h), _e, "cudaSetDevice"); \
+  } while (0)
+
+extern "C" {
+
+int rl_abi_version(void) { return RL_ABI_VERSION; }
+
+int rl_padded_k(int k) { return rl::padded_k(k); }
+
+const char* rl_last_error(rl_handle h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int rl_create(int device, rl_handle* out) {
+  if (!out) return fail(nullptr, RL_ERR_INVALID, "rl_create: out is null");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(nullptr, RL_ERR_NO_DEVICE, "rl_create: no CUDA device (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (device >= count) return fail(nullptr, RL_ERR_INVALID, "rl_create: device %d out of range (%d devices)", device, count);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return fail(nullptr, RL_ERR_NO_DEVICE, "rl_create: device %d is sm_%d%d; kernels are built for sm_100a only", device,
+                prop.major, prop.minor);
+  rl_context* h = new rl_context();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->cc_major = prop.major;
+  h->cc_minor = prop.minor;
+  h->total_mem = prop.totalGlobalMem;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaSetDevice"); }
+  if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
+  h->stream = h->own_stream;
+  if ((e = cudaMalloc(&h->counter, 64 * sizeof(unsigned int))) != cudaSuccess) {
+    cudaStreamDestroy(h->own_stream);
+    delete h;
+    return cuda_fail(nullptr, e, "cudaMalloc(counter)");
+  }
+  cudaMemset(h->counter, 0, 64 * sizeof(unsigned int));
+  *out = h;
+  return RL_OK;
+}
+
+int rl_destroy(rl_handle h) {
+  if (!h) return RL_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->scratch) cudaFree(h->scratch);
+  if (h->counter) cudaFree(h->counter);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return RL_OK;
+}
+
+int rl_set_stream(rl_handle h, void* cuda_stream) {
+  RL_NEED(h);
+  h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return RL_OK;
+}
+
+int rl_synchronize(rl_handle h) {
+  RL_NEED(h);
+  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RL_OK;
+}
+
+int rl_device_info(rl_handle h, int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem_bytes) {
+  RL_NEED(h);
+  if (sm_count) *sm_count = h->sm_count;
+  if (cc_major) *cc_major = h->cc_major;
+  if (cc_minor) *cc_minor = h->cc_minor;
+  if (total_mem_bytes) *total_mem_bytes = static_cast<int64_t>(h->total_mem);
+  return RL_OK;
+}
+
+int64_t rl_launch_count(rl_handle h) { return h ? h->launches : -1; }
+
+int rl_pinned_alloc(int64_t bytes, void** out) {
+  if (!out || bytes < 0) return fail(nullptr, RL_ERR_INVALID, "rl_pinned_alloc: bad argument");
+  cudaError_t e = cudaMallocHost(out, static_cast<size_t>(bytes ? bytes : 16));
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaMallocHost");
+  return RL_OK;
+}
+
+int rl_pinned_free(void* p) {
+  if (p) cudaFreeHost(p);
+  return RL_OK;
+}
+
+int rl_dev_alloc(rl_handle h, int64_t bytes, void** out) {
+  RL_NEED(h);
+  if (!out || bytes < 0) return fail(h, RL_ERR_INVALID, "rl_dev_alloc: bad argument");
+  RL_CUDA(h, cudaMalloc(out, static_cast<size_t>(bytes ? bytes : 16)));
+  return RL_OK;
+}
+
+int rl_dev_free(rl_handle h, void* p) {
+  RL_NEED(h);
+  if (p) RL_CUDA(h, cudaFree(p));
+  return RL_OK;
+}
+
+int rl_memcpy_h2d(rl_handle h, void* dst_dev, const void* src_host, int64_t bytes) {
+  RL_NEED(h);
+  if (bytes > 0) RL_CUDA(h, cudaMemcpyAsync(dst_dev, src_host, static_cast<size_t>(bytes), cudaMemcpyHostToDevice, h->stream));
+  return RL_OK;
+}
+
+int rl_memcpy_d2h(rl_handle h, void* dst_host, const void* src_dev, int64_t bytes) {
+  RL_NEED(h);
+  if (bytes > 0) {
+    RL_CUDA(h, cudaMemcpyAsync(dst_host, src_dev, static_cast<size_t>(bytes), cudaMemcpyDeviceToHost, h->stream));
+    RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return RL_OK;
+}
+
+int rl_factors_upload(rl_handle h, const void* src_host, int src_dtype, int64_t rows, int k, float* dst_dev) {
+  RL_NEED(h);
+  const int kp = rl::padded_k(k);
+  if (kp == 0) return fail(h, RL_ERR_INVALID, "rl_factors_upload: k=%d outside [1, 128]", k);
+  if (src_dtype != RL_F32 && src_dtype != RL_F64) return fail(h, RL_ERR_INVALID, "rl_factors_upload: bad dtype");
+  if (rows == 0) return RL_OK;
+  const size_t es = src_dtype == RL_F64 ? 8 : 4;
+  const size_t bytes = static_cast<size_t>(rows) * k * es;
+  void* stage = nullptr;
+  RL_TRY(scratch(h, bytes, &stage));
+  RL_CUDA(h, cudaMemcpyAsync(stage, src_host, bytes, cudaMemcpyHostToDevice, h->stream));
+  return launch_factors_convert(h, stage, src_dtype, rows, k, k, dst_dev, RL_F32, kp);
+}
+
+int rl_factors_download(rl_handle h, const float* src_dev, int64_t rows, int k, void* dst_host, int dst_dtype) {
+  RL_NEED(h);
+  const int kp = rl::padded_k(k);
+  if (kp == 0) return fail(h, RL_ERR_INVALID, "rl_factors_download: k=%d outside [1, 128]", k);
+  if (dst_dtype != RL_F32 && dst_dtype != RL_F64) return fail(h, RL_ERR_INVALID, "rl_factors_download: bad dtype");
+  if (rows == 0) return RL_OK;
+  const size_t es = dst_dtype == RL_F64 ? 8 : 4;
+  const size_t bytes = static_cast<size_t>(rows) * k * es;
+  void* stage = nullptr;
+  RL_TRY(scratch(h, bytes, &stage));
+  RL_TRY(launch_factors_convert(h, src_dev, RL_F32, rows, k, kp, stage, dst_dtype, k));
+  RL_CUDA(h, cudaMemcpyAsync(dst_host, stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RL_OK;
+}
+
+int rl_als_half_step_dev(rl_handle h, int64_t n_rows, int64_t n_other, int k, const int64_t* indptr_dev,
+                         const int32_t* indices_dev, const float* conf_dev, const float* pref_dev,
+                         const float* other_dev, float* mine_dev, double lambda, double w0, const double* gram0_dev,
+                         int precision, int ir_steps, const int32_t* row_order_dev) {
+  RL_NEED(h);
+  return launch_als_half_step(h, n_rows, n_other, k, indptr_dev, indices_dev, conf_dev, pref_dev, other_dev, mine_dev,
+                              lambda, w0, gram0_dev, precision, ir_steps, row_order_dev);
+}
+
+int rl_gram_dev(rl_handle h, const float* y_dev, int64_t n, int k, double* gram_dev) {
+  RL_NEED(h);
+  return launch_gram(h, y_dev, n, k, gram_dev);
+}
+
+int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const int64_t* indptr, const int32_t* indices,
+                    const int64_t* indptr_t, const int32_t* indices_t, int iterations, double lambda, int precision,
+                    int ir_steps, void* user_f, void* item_f, int factor_dtype) {
+  RL_NEED(h);
+  const int kp = rl::padded_k(k);
+  if (kp == 0) return fail(h, RL_ERR_INVALID, "rl_als_fit_host: k=%d outside [1, 128]", k);
+  if (n_users < 0 || n_items < 0 || iterations < 0) return fail(h, RL_ERR_INVALID, "rl_als_fit_host: negative size");
+  if (!indptr || !indptr_t || !user_f || !item_f) return fail(h, RL_ERR_INVALID, "rl_als_fit_host: null pointer");
+  const int64_t nnz = indptr[n_users];
+  if (nnz != indptr_t[n_items]) return fail(h, RL_ERR_INVALID, "rl_als_fit_host: CSR and transposed CSR disagree on nnz");
+  DevBuf d_ip, d_ix, d_tp, d_tx, d_u, d_v;
+  RL_TRY(upload(h, d_ip, indptr, sizeof(int64_t) * (n_users + 1)));
+  RL_TRY(upload(h, d_ix, indices, sizeof(int32_t) * nnz));
+  RL_TRY(upload(h, d_tp, indptr_t, sizeof(int64_t) * (n_items + 1)));
+  RL_TRY(upload(h, d_tx, indices_t, sizeof(int32_t) * nnz));
+  RL_TRY(d_u.alloc(h, sizeof(float) * n_users * kp));
+  RL_TRY(d_v.alloc(h, sizeof(float) * n_items * kp));
+  RL_TRY(rl_factors_upload(h, user_f, factor_dtype, n_users, k, d_u.as<float>()));
+  RL_TRY(rl_factors_upload(h, item_f, factor_dtype, n_items, k, d_v.as<float>()));
+  for (int it = 0; it < iterations; ++it) {
+    RL_TRY(launch_als_half_step(h, n_users, n_items, k, d_ip.as<int64_t>(), d_ix.as<int32_t>(), nullptr, nullptr,
+                                d_v.as<float>(), d_u.as<float>(), lambda, 0.0, nullptr, precision, ir_steps, nullptr));
+    RL_TRY(launch_als_half_step(h, n_items, n_users, k, d_tp.as<int64_t>(), d_tx.as<int32_t>(), nullptr, nullptr,
+                                d_u.as<float>(), d_v.as<float>(), lambda, 0.0, nullptr, precision, ir_steps, nullptr));
+  }
+  RL_TRY(rl_factors_download(h, d_u.as<float>(), n_users, k, user_f, factor_dtype));
+  RL_TRY(rl_factors_download(h, d_v.as<float>(), n_items, k, item_f, factor_dtype));
+  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RL_OK;
+}
+
+int rl_score_topn_dev(rl_handle h, const float* user_f_dev, int64_t n_users, const float* item_f_dev, int64_t n_items,
+                      int k, const int64_t* seen_indptr_dev, const int32_t* seen_indices_dev, double global_bias,
+                      const float* user_bias_dev, const float* item_bias_dev, int n, int32_t* idx_out_dev,
+                      double* score_out_dev, int mode) {
+  RL_NEED(h);
+  return launch_score_topn(h, user_f_dev, n_users, item_f_dev, n_items, k, seen_indptr_dev, seen_indices_dev, global_bias,
+                           user_bias_dev, item_bias_dev, n, idx_out_dev, score_out_dev, mode);
+}
+
+int rl_recommend_host(rl_handle h, const void* user_f, const void* item_f, int factor_dtype, int64_t n_users,
+                      int64_t n_items, int k, const int64_t* seen_indptr, const int32_t* seen_indices, double global_bias,
+                      const float* user_bias, const float* item_bias, int n, int32_t* idx_out, double* score_out, int mode) {
+  RL_NEED(h);
+  const int kp = rl::padded_k(k);
+  if (kp == 0) return fail(h, RL_ERR_INVALID, "rl_recommend_host: k=%d outside [1, 128]", k);
+  if (n <= 0) return fail(h, RL_ERR_INVALID, "rl_recommend_host: n must be positive, got %d", n);
+  if (n_users < 0 || n_items < 0) return fail(h, RL_ERR_INVALID, "rl_recommend_host: negative size");
+  if (n_users == 0) return RL_OK;
+  if (!user_f || !item_f || !idx_out) return fail(h, RL_ERR_INVALID, "rl_recommend_host: null pointer");
+  DevBuf d_u, d_v, d_sp, d_sx, d_ub, d_ib, d_idx, d_sc;
+  RL_TRY(d_u.alloc(h, sizeof(float) * n_users * kp));
+  RL_TRY(d_v.alloc(h, sizeof(float) * n_items * kp));
+  RL_TRY(rl_factors_upload(h, user_f, factor_dtype, n_users, k, d_u.as<float>()));
+  RL_TRY(rl_factors_upload(h, item_f, factor_dtype, n_items, k, d_v.as<float>()));
+  if (seen_indptr) {
+    const int64_t nnz = seen_indptr[n_users];
+    RL_TRY(upload(h, d_sp, seen_indptr, sizeof(int64_t) * (n_users + 1)));
+    RL_TRY(upload(h, d_sx, seen_indices, sizeof(int32_t) * nnz));
+  }
+  if (user_bias) RL_TRY(upload(h, d_ub, user_bias, sizeof(float) * n_users));
+  if (item_bias) RL_TRY(upload(h, d_ib, item_bias, sizeof(float) * n_items));
+  RL_TRY(d_idx.alloc(h, sizeof(int32_t) * n_users * n));
+  if (score_out) RL_TRY(d_sc.alloc(h, sizeof(double) * n_users * n));
+  RL_TRY(launch_score_topn(h, d_u.as<float>(), n_users, d_v.as<float>(), n_items, k, seen_indptr ? d_sp.as<int64_t>() : nullptr,
+                           seen_indptr ? d_sx.as<int32_t>() : nullptr, global_bias, user_bias ? d_ub.as<float>() : nullptr,
+                           item_bias ? d_ib.as<float>() : nullptr, n, d_idx.as<int32_t>(), score_out ? d_sc.as<double>() : nullptr, mode));
+  RL_CUDA(h, cudaMemcpyAsync(idx_out, d_idx.p, sizeof(int32_t) * n_users * n, cudaMemcpyDeviceToHost, h->stream));
+  if (score_out) RL_CUDA(h, cudaMemcpyAsync(score_out, d_sc.p, sizeof(double) * n_users * n, cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RL_OK;
+}
+
+int rl_topn_dense_dev(rl_handle h, const void* est_dev, int est_dtype, const void* known_dev, int known_dtype,
+                      int64_t n_users, int64_t n_items, int n, int32_t* idx_out_dev, int32_t* n_valid_out_dev) {
+  RL_NEED(h);
+  return launch_topn_dense(h, est_dev, est_dtype, known_dev, known_dtype, n_users, n_items, n, idx_out_dev, n_valid_out_dev);
+}
+
+int rl_topn_dense_host(rl_handle h, const void* est, int est_dtype, const void* known, int known_dtype, int64_t n_users,
+                       int64_t n_items, int n, int32_t* idx_out, int32_t* n_valid_out) {
+  RL_NEED(h);
+  if (n <= 0) return fail(h, RL_ERR_INVALID, "rl_topn_dense_host: n must be positive, got %d", n);
+  if (n_users < 0 || n_items < 0) return fail(h, RL_ERR_INVALID, "rl_topn_dense_host: negative size");
+  if (n_users == 0 || n_items == 0) return RL_OK;
+  if (!est || !known || !idx_out) return fail(h, RL_ERR_INVALID, "rl_topn_dense_host: null pointer");
+  const size_t cells = static_cast<size_t>(n_users) * n_items;
+  DevBuf d_e, d_k, d_idx, d_nv;
+  RL_TRY(upload(h, d_e, est, cells * (est_dtype == RL_F64 ? 8 : 4)));
+  RL_TRY(upload(h, d_k, known, cells * (known_dtype == RL_F64 ? 8 : 4)));
+  RL_TRY(d_idx.alloc(h, sizeof(int32_t) * n_users * n));
+  RL_TRY(d_nv.alloc(h, sizeof(int32_t) * n_users));
+  RL_TRY(launch_topn_dense(h, d_e.p, est_dtype, d_k.p, known_dtype, n_users, n_items, n, d_idx.as<int32_t>(), d_nv.as<int32_t>()));
+  RL_CUDA(h, cudaMemcpyAsync(idx_out, d_idx.p, sizeof(int32_t) * n_users * n, cudaMemcpyDeviceToHost, h->stream));
+  if (n_valid_out) RL_CUDA(h, cudaMemcpyAsync(n_valid_out, d_nv.p, sizeof(int32_t) * n_users, cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RL_OK;
+}
+
+int rl_svd_topk_dev(rl_handle h, const float* m_dev, int64_t m, int64_t n, int k, double* s_out_dev, double* left_out_dev,
+                    double* right_out_dev) {
+  RL_NEED(h);
+  return launch_svd_topk(h, m_dev, m, n, k, s_out_dev, left_out_dev, right_out_dev);
+}
+
+int rl_lowrank_dev(rl_handle h, const void* a_dev, const void* b_dev, int in_dtype, int64_t m, int64_t n, int k,
+                   double global_bias, const float* row_bias_dev, const float* col_bias_dev, void* out_dev, int out_dtype) {
+  RL_NEED(h);
+  return launch_lowrank(h, a_dev, b_dev, in_dtype, m, n, k, global_bias, row_bias_dev, col_bias_dev, out_dev, out_dtype);
+}
+
+int rl_svd_reconstruct_host(rl_handle h, const float* mat, int64_t m, int64_t n, int k, float* recon, double* s_out,
+                            double* left_out, double* right_out) {
+  RL_NEED(h);
+  if (m <= 0 || n <= 0) return fail(h, RL_ERR_INVALID, "rl_svd_reconstruct_host: zero dimension");
+  if (k < 1 || k > (m < n ? m : n)) return fail(h, RL_ERR_INVALID, "rl_svd_reconstruct_host: k=%d out of range", k);
+  if (!mat) return fail(h, RL_ERR_INVALID, "rl_svd_reconstruct_host: null pointer");
+  DevBuf d_m, d_r, d_s, d_l, d_rt;
+  const size_t cells = static_cast<size_t>(m) * n;
+  RL_TRY(upload(h, d_m, mat, cells * sizeof(float)));
+  RL_TRY(d_s.alloc(h, sizeof(double) * k));
+  RL_TRY(d_l.alloc(h, sizeof(double) * m * k));
+  RL_TRY(d_rt.alloc(h, sizeof(double) * n * k));
+  RL_TRY(launch_svd_topk(h, d_m.as<float>(), m, n, k, d_s.as<double>(), d_l.as<double>(), d_rt.as<double>()));
+  if (recon) {
+    RL_TRY(d_r.alloc(h, cells * sizeof(float)));
+    RL_TRY(launch_lowrank(h, d_l.p, d_rt.p, RL_F64, m, n, k, 0.0, nullptr, nullptr, d_r.p, RL_F32));
+    RL_CUDA(h, cudaMemcpyAsync(recon, d_r.p, cells * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (s_out) RL_CUDA(h, cudaMemcpyAsync(s_out, d_s.p, sizeof(double) * k, cudaMemcpyDeviceToHost, h->stream));
+  if (left_out) RL_CUDA(h, cudaMemcpyAsync(left_out, d_l.p, sizeof(double) * m * k, cudaMemcpyDeviceToHost, h->stream));
+  if (right_out) RL_CUDA(h, cudaMemcpyAsync(right_out, d_rt.p, sizeof(double) * n * k, cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RL_OK;
+}
+
+int rl_predict_host(rl_handle h, const void* user_f, const void* item_f, int factor_dtype, int64_t n_users, int64_t n_items,
+                    int k, double global_bias, const float* user_bias, const float* item_bias, void* out, int out_dtype) {
+  RL_NEED(h);
+  if (k <= 0) return fail(h, RL_ERR_INVALID, "rl_predict_host: k must be positive");
+  if (n_users < 0 || n_items < 0) return fail(h, RL_ERR_INVALID, "rl_predict_host: negative size");
+  if (n_users == 0 || n_items == 0) return RL_OK;
+  if (!user_f || !item_f || !out) return fail(h, RL_ERR_INVALID, "rl_predict_host: null pointer");
+  if (out_dtype != RL_F32 && out_dtype != RL_F64) return fail(h, RL_ERR_INVALID, "rl_predict_host: bad out dtype");
+  if (factor_dtype != RL_F32 && factor_dtype != RL_F64) return fail(h, RL_ERR_INVALID, "rl_predict_host: bad factor dtype");
+  // factors go to the device as dense float64 (n x k): no padding, no k limit, one rounding at the output
+  DevBuf d_u, d_v, d_raw, d_ub, d_ib, d_o;
+  const size_t es = factor_dtype == RL_F64 ? 8 : 4;
+  if (factor_dtype == RL_F64) {
+    RL_TRY(upload(h, d_u, user_f, es * n_users * k));
+    RL_TRY(upload(h, d_v, item_f, es * n_items * k));
+  } else {
+    RL_TRY(d_u.alloc(h, sizeof(double) * n_users * k));
+    RL_TRY(d_v.alloc(h, sizeof(double) * n_items * k));
+    RL_TRY(d_raw.alloc(h, es * (n_users > n_items ? n_users : n_items) * k));
+    RL_CUDA(h, cudaMemcpyAsync(d_raw.p, user_f, es * n_users * k, cudaMemcpyHostToDevice, h->stream));
+    RL_TRY(launch_factors_convert(h, d_raw.p, RL_F32, n_users, k, k, d_u.p, RL_F64, k));
+    RL_CUDA(h, cudaMemcpyAsync(d_raw.p, item_f, es * n_items * k, cudaMemcpyHostToDevice, h->stream));
+    RL_TRY(launch_factors_convert(h, d_raw.p, RL_F32, n_items, k, k, d_v.p, RL_F64, k));
+  }
+  if (user_bias) RL_TRY(upload(h, d_ub, user_bias, sizeof(float) * n_users));
+  if (item_bias) RL_TRY(upload(h, d_ib, item_bias, sizeof(float) * n_items));
+  const size_t bytes = static_cast<size_t>(n_users) * n_items * (out_dtype == RL_F64 ? 8 : 4);
+  RL_TRY(d_o.alloc(h, bytes));
+  RL_TRY(launch_lowrank(h, d_u.p, d_v.p, RL_F64, n_users, n_items, k, global_bias, user_bias ? d_ub.as<float>() : nullptr,
+                        item_bias ? d_ib.as<float>() : nullptr, d_o.p, out_dtype));
+  RL_CUDA(h, cudaMemcpyAsync(out, d_o.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RL_OK;
+}
+
+int rl_observed_error_dev(rl_handle h, const float* user_f_dev, const float* item_f_dev, int k, int64_t n_users,
+                          const int64_t* indptr_dev, const int32_t* indices_dev, const float* values_dev, double* out2_dev) {
+  RL_NEED(h);
+  return launch_observed_error(h, user_f_dev, item_f_dev, k, n_users, indptr_dev, indices_dev, values_dev, out2_dev);
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// common.cuh -- shared declarations of librecsys_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/recsys_b200.h"
+
+struct rl_context {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t total_mem = 0;
+  cudaStream_t stream = nullptr;      // stream kernels are enqueued on
+  cudaStream_t own_stream = nullptr;  // created by rl_create
+  unsigned int* counter = nullptr;    // device work counters (row schedulers), 64 x u32
+  int64_t launches = 0;
+  std::string err;
+  // grow-only device scratch (svd, scoring candidates, ...)
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+};
+
+namespace rl {
+
+extern thread_local std::string g_last_error;
+
+int fail(rl_context* h, int code, const char* fmt, ...);
+int cuda_fail(rl_context* h, cudaError_t e, const char* what);
+// returns a device scratch buffer of at least `bytes` (grow-only, stream-ordered with respect to h->stream)
+int scratch(rl_context* h, size_t bytes, void** out);
+
+#define RL_CUDA(h, expr)                                         \
+  do {                                                           \
+    cudaError_t _e = (expr);                                     \
+    if (_e != cudaSuccess) return rl::cuda_fail((h), _e, #expr); \
+  } while (0)
+
+#define RL_LAUNCH_CHECK(h, name)                                  \
+  do {                                                            \
+    cudaError_t _e = cudaGetLastError();                          \
+    if (_e != cudaSuccess) return rl::cuda_fail((h), _e, (name)); \
+    (h)->launches++;                                              \
+  } while (0)
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+__host__ __device__ constexpr int padded_k(int k) {
+  return k <= 0 ? 0 : k <= 16 ? 16 : k <= 32 ? 32 : k <= 64 ? 64 : k <= 128 ? 128 : 0;
+}
+
+// ---- kernels' host launchers (one per .cu) --------------------------------------------------------------
+int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, const int64_t* indptr,
+                         const int32_t* indices, const float* conf, const float* pref, const float* other,
+                         float* mine, double lambda, double w0, const double* gram0, int precision,
+                         int ir_steps, const int32_t* row_order);
+int launch_gram(rl_context* h, const float* y, int64_t n, int k, double* gram);
+int launch_score_topn(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k,
+                      const int64_t* seen_indptr, const int32_t* seen_indices, double gbias, const float* ubias,
+                      const float* ibias, int n, int32_t* idx_out, double* score_out, int mode);
+int launch_topn_dense(rl_context* h, const void* est, int est_dtype, const void* known, int known_dtype,
+                      int64_t n_users, int64_t n_items, int n, int32_t* idx_out, int32_t* n_valid_out);
+int launch_svd_topk(rl_context* h, const float* m_dev, int64_t m, int64_t n, int k, double* s_out, double* left_out,
+                    double* right_out);
+int launch_lowrank(rl_context* h, const void* a, const void* b, int in_dtype, int64_t m, int64_t n, int k, double gbias,
+                   const float* rbias, const float* cbias, void* out, int out_dtype);
+int launch_observed_error(rl_context* h, const float* uf, const float* vf, int k, int64_t n_users,
+                          const int64_t* indptr, const int32_t* indices, const float* values, double* out2);
+int launch_factors_convert(rl_context* h, const void* src, int src_dtype, int64_t rows, int k, int src_ld,
+                           void* dst, int dst_dtype, int dst_ld);
+
+// ---- small device helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+}  // namespace rl

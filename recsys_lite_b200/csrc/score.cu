@@ -1,0 +1,157 @@
+// score.cu -- scoring + masking + top-n entry points: exact CUDA-core path, dense top_n, observed-entry error.
+#include "score_exact.cuh"
+
+namespace rl {
+
+namespace {
+
+// ---- standalone masked row top-n over dense est / known (reference _top_n_numba, algo.py:533-584) -----------
+// One warp per user row; est and known are streamed once with coalesced loads (HBM-bound), the running top-n
+// lives in registers.  n_valid = min(n, #items with known <= 0) (algo.py:571-575).
+template <typename TE, typename TK, int R>
+__global__ void __launch_bounds__(256) topn_dense_kernel(const TE* __restrict__ est, const TK* __restrict__ known,
+                                                         int64_t n_users, int64_t n_items, int n,
+                                                         int32_t* __restrict__ idx_out, int32_t* __restrict__ n_valid) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_users) return;
+  const TE* e = est + row * n_items;
+  const TK* kn = known + row * n_items;
+  WarpTopK<R> list;
+  list.init();
+  double tv;
+  int tix;
+  list.threshold(n, tv, tix);
+  int unrated = 0;
+  for (int64_t j0 = 0; j0 < n_items; j0 += 32) {
+    const int64_t j = j0 + lane;
+    double sv = -CUDART_INF;
+    bool open = false;
+    if (j < n_items) {
+      open = !(static_cast<double>(kn[j]) > 0.0);
+      if (open) sv = static_cast<double>(e[j]);
+    }
+    unrated += __popc(__ballot_sync(FULL_MASK, open));
+    unsigned m = __ballot_sync(FULL_MASK, open && sv != -CUDART_INF && beats(sv, static_cast<int>(j), tv, tix));
+    while (m) {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      const double cs = __shfl_sync(FULL_MASK, sv, l);
+      const int cj = static_cast<int>(j0) + l;
+      if (beats(cs, cj, tv, tix)) {
+        list.insert(cs, cj, lane);
+        list.threshold(n, tv, tix);
+      }
+    }
+  }
+  list.store(n, lane, idx_out + row * n, nullptr);
+  if (lane == 0 && n_valid) n_valid[row] = min(n, unrated);
+}
+
+template <typename TE, typename TK>
+int launch_topn_dense_t(rl_context* h, const TE* est, const TK* known, int64_t n_users, int64_t n_items, int n,
+                        int32_t* idx_out, int32_t* n_valid) {
+  const unsigned grid = static_cast<unsigned>((n_users + 7) / 8);
+  if (n <= 32) topn_dense_kernel<TE, TK, 1><<<grid, 256, 0, h->stream>>>(est, known, n_users, n_items, n, idx_out, n_valid);
+  else if (n <= 64) topn_dense_kernel<TE, TK, 2><<<grid, 256, 0, h->stream>>>(est, known, n_users, n_items, n, idx_out, n_valid);
+  else if (n <= 128) topn_dense_kernel<TE, TK, 4><<<grid, 256, 0, h->stream>>>(est, known, n_users, n_items, n, idx_out, n_valid);
+  else return fail(h, RL_ERR_INVALID, "topn_dense: n=%d exceeds the on-chip list capacity of 128", n);
+  RL_LAUNCH_CHECK(h, "topn_dense_kernel");
+  return RL_OK;
+}
+
+// ---- sum of squared / absolute errors of U V^T over a CSR pattern (reference compute_rmse/mae, algo.py:662-743)
+template <int KP>
+__global__ void __launch_bounds__(256) observed_error_kernel(const float* __restrict__ uf, const float* __restrict__ vf,
+                                                             int64_t n_users, const int64_t* __restrict__ indptr,
+                                                             const int32_t* __restrict__ indices,
+                                                             const float* __restrict__ values, double* __restrict__ out2) {
+  // one warp per user; lanes split the factor dimension (KP/32 or fewer entries each) -> coalesced row reads
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  constexpr int Q = (KP + 31) / 32;
+  double se = 0.0, ae = 0.0;
+  for (int64_t u = warp_global; u < n_users; u += n_warps) {
+    double ux[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int c = lane + 32 * q;
+      ux[q] = (c < KP) ? static_cast<double>(uf[u * KP + c]) : 0.0;
+    }
+    for (int64_t p = indptr[u]; p < indptr[u + 1]; ++p) {
+      const int64_t it = indices[p];
+      double d = 0.0;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int c = lane + 32 * q;
+        if (c < KP) d = fma(ux[q], static_cast<double>(vf[it * KP + c]), d);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(FULL_MASK, d, o);
+      const double err = d - (values ? static_cast<double>(values[p]) : 1.0);
+      se += err * err;
+      ae += fabs(err);
+    }
+  }
+  if (lane == 0) {  // every lane holds the same sums
+    atomicAdd(out2, se);
+    atomicAdd(out2 + 1, ae);
+  }
+}
+
+}  // namespace
+
+int launch_score_topn(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k,
+                      const int64_t* seen_indptr, const int32_t* seen_indices, double gbias, const float* ubias,
+                      const float* ibias, int n, int32_t* idx_out, double* score_out, int mode) {
+  const int kp = padded_k(k);
+  if (kp == 0) return fail(h, RL_ERR_INVALID, "score_topn: k=%d outside [1, 128]", k);
+  if (n <= 0) return fail(h, RL_ERR_INVALID, "score_topn: n must be positive, got %d", n);
+  if (n_users < 0 || n_items < 0 || n_items > INT_MAX - 64) return fail(h, RL_ERR_INVALID, "score_topn: bad shape");
+  if (n_users == 0) return RL_OK;
+  if (!uf || !vf || !idx_out) return fail(h, RL_ERR_INVALID, "score_topn: null pointer");
+  if ((seen_indptr == nullptr) != (seen_indices == nullptr) && seen_indptr == nullptr)
+    return fail(h, RL_ERR_INVALID, "score_topn: seen_indices without seen_indptr");
+  ScoreArgs a{uf, vf, n_users, n_items, seen_indptr, seen_indices, gbias, ubias, ibias, n, idx_out, score_out, nullptr, 0};
+  if (mode == RL_SCORE_TENSOR) return fail(h, RL_ERR_INVALID, "score_topn: tensor-core candidate pass not built in this version");
+  return launch_score_exact(h, kp, a);
+}
+
+int launch_topn_dense(rl_context* h, const void* est, int est_dtype, const void* known, int known_dtype,
+                      int64_t n_users, int64_t n_items, int n, int32_t* idx_out, int32_t* n_valid_out) {
+  if (n <= 0) return fail(h, RL_ERR_INVALID, "topn_dense: n must be positive, got %d", n);
+  if (n_users < 0 || n_items < 0 || n_items > INT_MAX - 64) return fail(h, RL_ERR_INVALID, "topn_dense: bad shape");
+  if (n_users == 0) return RL_OK;
+  if (!est || !known || !idx_out) return fail(h, RL_ERR_INVALID, "topn_dense: null pointer");
+  if (est_dtype == RL_F32 && known_dtype == RL_F32)
+    return launch_topn_dense_t(h, static_cast<const float*>(est), static_cast<const float*>(known), n_users, n_items, n, idx_out, n_valid_out);
+  if (est_dtype == RL_F32 && known_dtype == RL_F64)
+    return launch_topn_dense_t(h, static_cast<const float*>(est), static_cast<const double*>(known), n_users, n_items, n, idx_out, n_valid_out);
+  if (est_dtype == RL_F64 && known_dtype == RL_F32)
+    return launch_topn_dense_t(h, static_cast<const double*>(est), static_cast<const float*>(known), n_users, n_items, n, idx_out, n_valid_out);
+  if (est_dtype == RL_F64 && known_dtype == RL_F64)
+    return launch_topn_dense_t(h, static_cast<const double*>(est), static_cast<const double*>(known), n_users, n_items, n, idx_out, n_valid_out);
+  return fail(h, RL_ERR_INVALID, "topn_dense: unknown dtype");
+}
+
+int launch_observed_error(rl_context* h, const float* uf, const float* vf, int k, int64_t n_users,
+                          const int64_t* indptr, const int32_t* indices, const float* values, double* out2) {
+  const int kp = padded_k(k);
+  if (kp == 0) return fail(h, RL_ERR_INVALID, "observed_error: k=%d outside [1, 128]", k);
+  if (!uf || !vf || !indptr || !out2) return fail(h, RL_ERR_INVALID, "observed_error: null pointer");
+  RL_CUDA(h, cudaMemsetAsync(out2, 0, 2 * sizeof(double), h->stream));
+  if (n_users == 0) return RL_OK;
+  int64_t grid = (n_users + 7) / 8;
+  if (grid > 8 * h->sm_count) grid = 8 * h->sm_count;
+  switch (kp) {
+    case 16: observed_error_kernel<16><<<grid, 256, 0, h->stream>>>(uf, vf, n_users, indptr, indices, values, out2); break;
+    case 32: observed_error_kernel<32><<<grid, 256, 0, h->stream>>>(uf, vf, n_users, indptr, indices, values, out2); break;
+    case 64: observed_error_kernel<64><<<grid, 256, 0, h->stream>>>(uf, vf, n_users, indptr, indices, values, out2); break;
+    case 128: observed_error_kernel<128><<<grid, 256, 0, h->stream>>>(uf, vf, n_users, indptr, indices, values, out2); break;
+  }
+  RL_LAUNCH_CHECK(h, "observed_error_kernel");
+  return RL_OK;
+}
+
+}  // namespace rl

@@ -1,0 +1,195 @@
+// score_exact.cuh -- CUDA-core float64 scoring fused with seen-item masking and top-n (exact path).
+//
+// Replaces predict (reference algo.py:143-147 `U @ V.T`, or algo.py:363-368 with bias terms) + top_n
+// (algo.py:533-659) as composed in recommend (algo.py:172-201).  Scores are float64 dot products of the
+// float32 factors, so the only difference to the reference's float64 GEMM is summation order (~1e-16 relative).
+// One CTA owns 64 users and sweeps the items in tiles of 64; the 64 x 64 score tile lives in shared memory only.
+// This kernel is the exact fallback of the tensor-core candidate pass and the path for small / odd shapes.
+#pragma once
+
+#include "common.cuh"
+#include "topk.cuh"
+
+namespace rl {
+
+struct ScoreArgs {
+  const float* uf;
+  const float* vf;
+  int64_t n_users, n_items;
+  const int64_t* seen_indptr;
+  const int32_t* seen_indices;
+  double gbias;
+  const float* ubias;
+  const float* ibias;
+  int n;
+  int32_t* idx_out;
+  double* score_out;
+  const int32_t* user_list;  // optional: score only these users (rows of idx_out follow the list order)
+  int64_t n_list;
+};
+
+constexpr int SE_UT = 64, SE_IT = 64, SE_THREADS = 256, SE_UPW = 8;  // users per warp
+
+template <int KP>
+constexpr size_t score_exact_smem() {
+  return sizeof(double) * (static_cast<size_t>(KP) * SE_UT + static_cast<size_t>(KP) * SE_IT + SE_UT * (SE_IT + 1));
+}
+
+template <int KP, int R>
+__global__ void __launch_bounds__(SE_THREADS) score_topn_exact_kernel(const ScoreArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Ut = reinterpret_cast<double*>(smem_raw);  // [KP][UT]
+  double* Vt = Ut + KP * SE_UT;                      // [KP][IT]
+  double* S = Vt + KP * SE_IT;                       // [UT][IT+1]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t total = a.user_list ? a.n_list : a.n_users;
+  const int64_t t0 = static_cast<int64_t>(blockIdx.x) * SE_UT;
+
+  // stage the user tile (transposed, float64)
+  for (int p = tid; p < SE_UT * (KP / 4); p += SE_THREADS) {
+    const int u = p % SE_UT, c4 = p / SE_UT;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t0 + u < total) {
+      const int64_t ur = a.user_list ? a.user_list[t0 + u] : t0 + u;
+      x = *reinterpret_cast<const float4*>(a.uf + ur * KP + 4 * c4);
+    }
+    Ut[(4 * c4 + 0) * SE_UT + u] = x.x;
+    Ut[(4 * c4 + 1) * SE_UT + u] = x.y;
+    Ut[(4 * c4 + 2) * SE_UT + u] = x.z;
+    Ut[(4 * c4 + 3) * SE_UT + u] = x.w;
+  }
+
+  WarpTopK<R> lists[SE_UPW];
+  int64_t cur[SE_UPW], end[SE_UPW];
+  double ub[SE_UPW];
+#pragma unroll
+  for (int uu = 0; uu < SE_UPW; ++uu) {
+    lists[uu].init();
+    const int64_t t = t0 + warp * SE_UPW + uu;
+    cur[uu] = end[uu] = 0;
+    ub[uu] = 0.0;
+    if (t < total) {
+      const int64_t ur = a.user_list ? a.user_list[t] : t;
+      if (a.seen_indptr) { cur[uu] = a.seen_indptr[ur]; end[uu] = a.seen_indptr[ur + 1]; }
+      if (a.ubias) ub[uu] = a.ubias[ur];
+    }
+  }
+  const int tu = tid >> 4, ti = tid & 15;
+
+  for (int64_t j0 = 0; j0 < a.n_items; j0 += SE_IT) {
+    __syncthreads();  // previous tile fully consumed (and Ut visible on the first trip)
+    for (int p = tid; p < SE_IT * (KP / 4); p += SE_THREADS) {
+      const int i = p % SE_IT, c4 = p / SE_IT;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 + i < a.n_items) x = *reinterpret_cast<const float4*>(a.vf + (j0 + i) * KP + 4 * c4);
+      Vt[(4 * c4 + 0) * SE_IT + i] = x.x;
+      Vt[(4 * c4 + 1) * SE_IT + i] = x.y;
+      Vt[(4 * c4 + 2) * SE_IT + i] = x.z;
+      Vt[(4 * c4 + 3) * SE_IT + i] = x.w;
+    }
+    __syncthreads();
+    double acc[4][4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
+#pragma unroll 4
+    for (int c = 0; c < KP; ++c) {
+      const double2 u01 = *reinterpret_cast<const double2*>(Ut + c * SE_UT + 4 * tu);
+      const double2 u23 = *reinterpret_cast<const double2*>(Ut + c * SE_UT + 4 * tu + 2);
+      const double2 v01 = *reinterpret_cast<const double2*>(Vt + c * SE_IT + 4 * ti);
+      const double2 v23 = *reinterpret_cast<const double2*>(Vt + c * SE_IT + 4 * ti + 2);
+      const double ux[4] = {u01.x, u01.y, u23.x, u23.y};
+      const double vx[4] = {v01.x, v01.y, v23.x, v23.y};
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fma(ux[x], vx[y], acc[x][y]);
+    }
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const int64_t j = j0 + 4 * ti + y;
+      const double ibv = (a.ibias && j < a.n_items) ? static_cast<double>(a.ibias[j]) : 0.0;
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+        S[(4 * tu + x) * (SE_IT + 1) + 4 * ti + y] = (j < a.n_items) ? acc[x][y] + ibv + a.gbias : -CUDART_INF;
+    }
+    __syncthreads();
+
+    // per-warp: mask the seen items of its 8 users, then offer the row to the user's list
+#pragma unroll
+    for (int uu = 0; uu < SE_UPW; ++uu) {
+      const int ul = warp * SE_UPW + uu;
+      if (t0 + ul >= total) continue;
+      double* Srow = S + ul * (SE_IT + 1);
+      for (;;) {
+        const int64_t p = cur[uu] + lane;
+        const int idx = (p < end[uu]) ? a.seen_indices[p] : INT_MAX;
+        const bool in = idx < j0 + SE_IT;
+        if (in) Srow[idx - j0] = -CUDART_INF;
+        const unsigned b = __ballot_sync(FULL_MASK, in);
+        cur[uu] += __popc(b);
+        if (b != FULL_MASK) break;
+      }
+      __syncwarp();
+      double tv;
+      int tix;
+      lists[uu].threshold(a.n, tv, tix);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int col = lane + 32 * half;
+        const double sv = Srow[col] + ((Srow[col] == -CUDART_INF) ? 0.0 : ub[uu]);
+        const int jj = static_cast<int>(j0) + col;
+        unsigned m = __ballot_sync(FULL_MASK, sv != -CUDART_INF && beats(sv, jj, tv, tix));
+        while (m) {
+          const int l = __ffs(m) - 1;
+          m &= m - 1;
+          const double cs = __shfl_sync(FULL_MASK, sv, l);
+          const int cj = static_cast<int>(j0) + l + 32 * half;
+          if (beats(cs, cj, tv, tix)) {
+            lists[uu].insert(cs, cj, lane);
+            lists[uu].threshold(a.n, tv, tix);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int uu = 0; uu < SE_UPW; ++uu) {
+    const int64_t t = t0 + warp * SE_UPW + uu;
+    if (t < total) lists[uu].store(a.n, lane, a.idx_out + t * a.n, a.score_out ? a.score_out + t * a.n : nullptr);
+  }
+}
+
+template <int KP, int R>
+int launch_score_exact_kr(rl_context* h, const ScoreArgs& a) {
+  auto kern = score_topn_exact_kernel<KP, R>;
+  constexpr size_t smem = score_exact_smem<KP>();
+  RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int64_t total = a.user_list ? a.n_list : a.n_users;
+  const int64_t grid = (total + SE_UT - 1) / SE_UT;
+  if (grid == 0) return RL_OK;
+  kern<<<static_cast<unsigned>(grid), SE_THREADS, smem, h->stream>>>(a);
+  RL_LAUNCH_CHECK(h, "score_topn_exact_kernel");
+  return RL_OK;
+}
+
+template <int KP>
+int launch_score_exact_k(rl_context* h, const ScoreArgs& a) {
+  if (a.n <= 32) return launch_score_exact_kr<KP, 1>(h, a);
+  if (a.n <= 64) return launch_score_exact_kr<KP, 2>(h, a);
+  if (a.n <= 128) return launch_score_exact_kr<KP, 4>(h, a);
+  return fail(h, RL_ERR_INVALID, "score_topn: n=%d exceeds the on-chip list capacity of 128", a.n);
+}
+
+inline int launch_score_exact(rl_context* h, int kp, const ScoreArgs& a) {
+  switch (kp) {
+    case 16: return launch_score_exact_k<16>(h, a);
+    case 32: return launch_score_exact_k<32>(h, a);
+    case 64: return launch_score_exact_k<64>(h, a);
+    case 128: return launch_score_exact_k<128>(h, a);
+  }
+  return fail(h, RL_ERR_INVALID, "score_topn: unsupported padded k %d", kp);
+}
+
+}  // namespace rl

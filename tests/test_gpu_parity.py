@@ -1,0 +1,346 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI / the drop-in API) against the CPU oracle and the
+committed golden outputs of the reference.  Tolerances are the ones stated in oracle/compare.py."""
+import os
+
+import numpy as np
+import pytest
+from scipy import sparse
+
+from oracle import als as o_als, compare, generators as gen, metrics as o_metrics, svd as o_svd, topn as o_topn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def h():
+    from recsys_lite_b200 import _ffi
+    return _ffi.default_handle()
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def _ratings(g):
+    shape = tuple(int(x) for x in g["shape"])
+    return np.unpackbits(g["ratings"], axis=1)[:, : shape[1]].astype(np.float32)
+
+
+def _f32(x):
+    return np.asarray(x).astype(np.float32).astype(np.float64)
+
+
+# ------------------------------------------------------------------------------------------------ ALS
+@pytest.mark.parametrize("precision", ["fp32_ir", "fp64"])
+@pytest.mark.parametrize("name", ["als_small_k8", "als_small_k64", "als_test_literal", "als_c1"])
+def test_als_fit_matches_reference_golden(golden_dir, name, precision):
+    """RecommenderSystem('als').fit from the shared seed vs the reference's own output (algo.py:300-337)."""
+    from recsys_lite_b200 import RecommenderSystem
+    g = _load(golden_dir, name)
+    r = _ratings(g)
+    np.random.seed(int(g["init_seed"]))
+    model = RecommenderSystem(algorithm="als").fit(r, k=int(g["k"]), iterations=int(g["iterations"]),
+                                                   lambda_=float(g["lam"]), precision=precision)
+    m = model._model
+    assert set(m) == {"user_factors", "item_factors", "factors"} and m["user_factors"].dtype == np.float64
+    for key in ("user_factors", "item_factors"):
+        fro, mx = compare.factor_error(m[key], g[key])
+        assert fro <= compare.FACTOR_RTOL and mx <= compare.FACTOR_RTOL, (key, fro, mx)
+    pred = model.predict(r)
+    assert pred.dtype == np.float64 and pred.shape == r.shape
+    assert abs(o_metrics.rmse(pred, r) - float(g["rmse"])) <= compare.RMSE_ATOL
+    rec = model.recommend(r, n=10)
+    assert rec.shape == g["recommend"].shape and rec.dtype == g["recommend"].dtype
+    uf, vf = _f32(m["user_factors"]), _f32(m["item_factors"])
+    indptr, indices = o_als.pattern_to_csr(r)
+    ours, _ = o_topn.recommend_blocked(uf, vf, indptr, indices, n=rec.shape[1])
+    res = compare.topn_matches(rec, ours, lambda row: uf[row] @ vf.T, lambda row: indices[indptr[row]:indptr[row + 1]])
+    assert not res["bad"], res
+
+
+@pytest.mark.parametrize("k", [3, 16, 40, 64, 100, 128])
+@pytest.mark.parametrize("precision", [0, 1])
+def test_half_step_dev_vs_oracle(h, k, precision):
+    """rl_als_half_step_dev on device pointers vs oracle.half_step_csr (algo.py:314-322), incl. empty rows."""
+    from devbuf import Dev, padded, unpadded
+    n_rows, n_other = 700, 300
+    indptr, indices = gen.synth_pattern(n_rows, n_other, mean_deg=25, seed=k)
+    keep = np.ones(n_rows, bool)
+    keep[[0, 17, n_rows - 1]] = False                    # rows without observations keep their value
+    cnt = np.diff(indptr) * keep
+    sel = np.repeat(keep, np.diff(indptr))
+    indices = indices[sel]
+    indptr = np.concatenate(([0], np.cumsum(cnt))).astype(np.int64)
+    rng = np.random.default_rng(k)
+    other = rng.random((n_other, k))
+    mine0 = rng.random((n_rows, k))
+    ref = o_als.half_step_csr(indptr, indices, _f32(other), _f32(mine0).copy(), 0.01)
+    d_other, d_mine = padded(h, other, k), padded(h, mine0, k)
+    d_ip, d_ix = Dev(h, indptr), Dev(h, indices)
+    h.call("rl_als_half_step_dev", n_rows, n_other, k, d_ip.ptr, d_ix.ptr, None, None, d_other.ptr, d_mine.ptr,
+           0.01, 0.0, None, precision, 2, None)
+    got = unpadded(h, d_mine, k)
+    fro, mx = compare.factor_error(got, ref)
+    assert fro <= 2e-6 and mx <= 2e-5, (fro, mx)        # fp32 storage of the result: ~6e-8 relative per entry
+    assert np.array_equal(got[[0, 17, n_rows - 1]], _f32(mine0)[[0, 17, n_rows - 1]])
+    # padding columns of the device matrix stay zero
+    raw = d_mine.get()
+    assert not raw[:, k:].any()
+
+
+def test_half_step_long_and_skewed_rows(h):
+    """item-side shape: few rows with hundreds..thousands of observations (chunked gather, many chunks)."""
+    from devbuf import Dev, padded, unpadded
+    k, n_rows, n_other = 64, 60, 5000
+    rng = np.random.default_rng(5)
+    degs = np.concatenate(([1, 2, 15, 16, 17, 31, 32, 33, 4000], rng.integers(100, 900, n_rows - 9)))
+    rows = [np.sort(rng.choice(n_other, d, replace=False)) for d in degs]
+    indptr = np.concatenate(([0], np.cumsum(degs))).astype(np.int64)
+    indices = np.concatenate(rows).astype(np.int32)
+    other = rng.random((n_other, k))
+    mine0 = rng.random((n_rows, k))
+    ref = o_als.half_step_csr(indptr, indices, _f32(other), _f32(mine0).copy(), 0.01)
+    order = np.argsort(-degs).astype(np.int32)            # longest first
+    for precision in (0, 1):
+        d_other, d_mine = padded(h, other, k), padded(h, mine0, k)
+        d_ip, d_ix, d_ord = Dev(h, indptr), Dev(h, indices), Dev(h, order)
+        h.call("rl_als_half_step_dev", n_rows, n_other, k, d_ip.ptr, d_ix.ptr, None, None, d_other.ptr, d_mine.ptr,
+               0.01, 0.0, None, precision, 2, d_ord.ptr)
+        fro, mx = compare.factor_error(unpadded(h, d_mine, k), ref)
+        assert fro <= 2e-6 and mx <= 2e-5, (precision, fro, mx)
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_half_step_general_weights_vs_dense_restatement(h, precision):
+    """w0 = 1, c = 1 + alpha*r (Hu-Koren-Volinsky) -- NOT reference parity; checked against oracle.half_step_general."""
+    from devbuf import Dev, padded, unpadded
+    k, n_rows, n_other = 32, 200, 150
+    indptr, indices = gen.synth_pattern(n_rows, n_other, mean_deg=12, seed=4)
+    rng = np.random.default_rng(4)
+    conf = (1.0 + 4.0 * rng.random(len(indices))).astype(np.float32)
+    pref = np.ones(len(indices), np.float32)
+    other = rng.standard_normal((n_other, k)) * 0.3
+    mine0 = rng.random((n_rows, k))
+    ref = o_als.half_step_general(indptr, indices, _f32(other), _f32(mine0).copy(), 0.1, w0=1.0,
+                                  conf=conf.astype(np.float64), pref=pref.astype(np.float64))
+    d_other, d_mine = padded(h, other, k), padded(h, mine0, k)
+    kp = h.lib.rl_padded_k(k)
+    d_g = Dev(h, shape=(kp, kp), dtype=np.float64)
+    h.call("rl_gram_dev", d_other.ptr, n_other, k, d_g.ptr)
+    g = d_g.get()
+    assert np.allclose(g[:k, :k], _f32(other).T @ _f32(other), rtol=1e-12, atol=1e-12)
+    d_ip, d_ix, d_c, d_p = Dev(h, indptr), Dev(h, indices), Dev(h, conf), Dev(h, pref)
+    h.call("rl_als_half_step_dev", n_rows, n_other, k, d_ip.ptr, d_ix.ptr, d_c.ptr, d_p.ptr, d_other.ptr, d_mine.ptr,
+           0.1, 1.0, d_g.ptr, precision, 2, None)
+    fro, mx = compare.factor_error(unpadded(h, d_mine, k), ref)
+    assert fro <= 5e-6 and mx <= 5e-5, (fro, mx)
+
+
+def test_als_medium_config3_shape_vs_oracle():
+    """C3-shaped problem scaled to what the oracle finishes in seconds: 6000 x 1500, ~50 nnz/user, k = 64."""
+    from recsys_lite_b200 import RecommenderSystem
+    n_users, n_items, k = 6000, 1500, 64
+    indptr, indices = gen.synth_pattern(n_users, n_items, mean_deg=50, seed=3)
+    r = sparse.csr_matrix((np.ones(len(indices), np.float32), indices, indptr), shape=(n_users, n_items))
+    u0, v0 = gen.seeded_factors(n_users, n_items, k, 3)
+    ti, tx = o_als.transpose_pattern(indptr, indices, n_items)
+    ref = o_als.fit_csr(indptr, indices, ti, tx, k, iterations=2, lam=0.01, init=(u0, v0))
+    for precision in ("fp32_ir", "fp64"):
+        m = RecommenderSystem("als").fit(r, k=k, iterations=2, lambda_=0.01, init=(u0, v0), precision=precision)._model
+        for key in ("user_factors", "item_factors"):
+            fro, mx = compare.factor_error(m[key], ref[key])
+            assert fro <= compare.FACTOR_RTOL and mx <= compare.FACTOR_RTOL, (precision, key, fro, mx)
+
+
+# -------------------------------------------------------------------------------------- scoring / top-n
+@pytest.mark.parametrize("k,n", [(8, 3), (16, 10), (64, 10), (64, 40), (128, 100)])
+def test_score_topn_dev_vs_oracle(h, k, n):
+    """rl_score_topn_dev (fused U V^T + seen mask + top-n) vs oracle.recommend_blocked (algo.py:172-201)."""
+    from devbuf import Dev, padded
+    n_users, n_items = 333, 1111
+    rng = np.random.default_rng(k + n)
+    uf, vf = _f32(rng.standard_normal((n_users, k))), _f32(rng.standard_normal((n_items, k)))
+    indptr, indices = gen.synth_pattern(n_users, n_items, mean_deg=40, seed=2)
+    ref_idx, ref_val = o_topn.recommend_blocked(uf, vf, indptr, indices, n=n)
+    d_u, d_v = padded(h, uf, k), padded(h, vf, k)
+    d_ip, d_ix = Dev(h, indptr), Dev(h, indices)
+    d_idx = Dev(h, shape=(n_users, n), dtype=np.int32)
+    d_val = Dev(h, shape=(n_users, n), dtype=np.float64)
+    h.call("rl_score_topn_dev", d_u.ptr, n_users, d_v.ptr, n_items, k, d_ip.ptr, d_ix.ptr, 0.0, None, None, n,
+           d_idx.ptr, d_val.ptr, 0)
+    idx, val = d_idx.get(), d_val.get()
+    res = compare.topn_matches(idx, ref_idx, lambda row: uf[row] @ vf.T, lambda row: indices[indptr[row]:indptr[row + 1]])
+    assert not res["bad"], res
+    assert np.allclose(val, ref_val, rtol=1e-12, atol=1e-12)
+    # no masking (exclude_rated=False, algo.py:202-208)
+    h.call("rl_score_topn_dev", d_u.ptr, n_users, d_v.ptr, n_items, k, None, None, 0.0, None, None, n,
+           d_idx.ptr, None, 0)
+    ref2, _ = o_topn.recommend_blocked(uf, vf, indptr, indices, n=n, exclude_rated=False)
+    assert not compare.topn_matches(d_idx.get(), ref2, lambda row: uf[row] @ vf.T)["bad"]
+
+
+def test_score_topn_ragged_ties_and_bias(h):
+    """fewer unseen items than n (-1 padding), exact ties (lower index first), bias terms (algo.py:363-368)."""
+    from devbuf import Dev, padded
+    k, n_users, n_items, n = 16, 70, 90, 12
+    rng = np.random.default_rng(0)
+    uf = _f32(rng.integers(-2, 3, (n_users, k)))          # small integers -> many exactly equal scores
+    vf = _f32(rng.integers(-2, 3, (n_items, k)))
+    dense = (rng.random((n_users, n_items)) < 0.3)
+    dense[3, :] = True                                     # everything seen -> all -1
+    dense[5, :85] = True                                   # 5 unseen < n
+    dense[7, :] = False
+    indptr, indices = o_als.pattern_to_csr(dense.astype(np.float32))
+    ub = rng.standard_normal(n_users).astype(np.float32)
+    ib = rng.integers(-1, 2, n_items).astype(np.float32)
+    bias = (0.5, ub, ib)
+    ref_idx, ref_val = o_topn.recommend_blocked(uf, vf, indptr, indices, n=n, bias=bias)
+    d_u, d_v, d_ip, d_ix = padded(h, uf, k), padded(h, vf, k), Dev(h, indptr), Dev(h, indices)
+    d_ub, d_ib = Dev(h, ub), Dev(h, ib)
+    d_idx, d_val = Dev(h, shape=(n_users, n), dtype=np.int32), Dev(h, shape=(n_users, n), dtype=np.float64)
+    h.call("rl_score_topn_dev", d_u.ptr, n_users, d_v.ptr, n_items, k, d_ip.ptr, d_ix.ptr, 0.5, d_ub.ptr, d_ib.ptr, n,
+           d_idx.ptr, d_val.ptr, 0)
+    idx, val = d_idx.get(), d_val.get()
+    assert (idx[3] == -1).all() and (idx[5, 5:] == -1).all() and (idx[5, :5] >= 85).all()
+    # integer-valued scores are exact in every summation order -> the documented tie rule makes this bit-exact
+    # up to the float32 rounding of the user bias, so compare through the tie-aware comparator and the values
+    res = compare.topn_matches(idx, ref_idx, lambda row: uf[row] @ vf.T + 0.5 + np.float64(ub[row]) + ib.astype(np.float64),
+                               lambda row: indices[indptr[row]:indptr[row + 1]], rtol=1e-12)
+    assert not res["bad"], res
+    assert np.allclose(val[ref_idx >= 0], ref_val[ref_idx >= 0], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("case", ["lit", "order", "ragged", "rand_f64", "rand_f32"])
+def test_top_n_api_matches_reference_golden(golden_dir, case):
+    """top_n(est, known, n) vs the reference's output (algo.py:587-659): shape, dtype, indices up to ties."""
+    from recsys_lite_b200 import top_n
+    g = _load(golden_dir, "topn_cases")
+    est, known, n, ref_out = g[case + "_est"], g[case + "_known"], int(g[case + "_n"]), g[case + "_out"]
+    out = top_n(est, known, n=n)
+    assert out.shape == ref_out.shape and out.dtype == ref_out.dtype
+    res = compare.topn_matches(out, ref_out, lambda row: est[row].astype(np.float64),
+                               lambda row: np.nonzero(known[row] > 0)[0], rtol=0.0)
+    assert not res["bad"], res
+    assert np.array_equal(out, o_topn.top_n(est, known, n=n))      # same tie rule as the oracle: bit-exact
+
+
+def test_top_n_api_reference_kats():
+    """literal cases of the reference's tests (tests/test_algo.py:138-232, :774-780, :880-892)."""
+    from recsys_lite_b200 import top_n
+    est = np.array([[0.1, 0.5, 0.9, 0.7]], dtype=np.float32)
+    known = np.array([[1, 0, 0, 0]], dtype=np.float32)
+    assert top_n(est, known, n=3).tolist() == [[2, 3, 1]]
+    assert top_n(np.ones((2, 3)), np.ones((2, 3)), n=2).shape == (2, 0)
+    assert top_n(np.empty((0, 0)), np.empty((0, 0)), n=2).shape == (0, 0)
+    out = top_n(sparse.csr_matrix(est), sparse.csr_matrix(known), n=10)      # n > items, sparse inputs
+    assert out.tolist() == [[2, 3, 1]] and out.dtype == np.int32
+    est = np.array([[1, 2, 2, 2, .5, 2, 3]], dtype=np.float64)
+    assert top_n(est, np.zeros_like(est), n=3).tolist() == [[6, 1, 2]]      # documented tie rule
+    big = np.random.default_rng(1).random((5, 300))
+    assert top_n(big, np.zeros_like(big), n=100).shape == (5, 100)          # n up to 128 on chip
+    with pytest.raises(ValueError, match="n must be positive"):
+        top_n(est, est, n=0)
+    with pytest.raises(ValueError, match="must have the same shape"):
+        top_n(est, np.ones((2, 7)), n=1)
+
+
+# ------------------------------------------------------------------------------------------------- SVD
+@pytest.mark.parametrize("case", ["lit", "rank3", "rnd", "samp"])
+def test_svd_reconstruct_matches_reference_golden(golden_dir, case):
+    from recsys_lite_b200 import svd_reconstruct
+    g = _load(golden_dir, "svd_cases")
+    m, k, ref_out = g[case + "_in"], int(g[case + "_k"]), g[case + "_out"]
+    out = svd_reconstruct(m, k=k, use_sparse=False)
+    assert out.dtype == np.float32 and out.shape == ref_out.shape
+    scale = max(1.0, float(np.abs(ref_out).max()))
+    assert np.max(np.abs(out - ref_out)) <= 2e-6 * scale            # reference itself is fp32 LAPACK
+    assert np.max(np.abs(out - o_svd.reconstruct_f64(m, k))) <= 3e-7 * scale   # we round a float64 result once
+    sp = svd_reconstruct(sparse.csr_matrix(m), k=k)
+    assert sparse.issparse(sp) and np.array_equal(sp.toarray(), out)
+
+
+def test_svd_quality_kat_and_wide_matrix():
+    """tests/test_algo.py:88-107: exact rank-3 matrix reproduced with max |diff| < 1e-6; wide (m < n) input."""
+    from recsys_lite_b200 import svd_reconstruct
+    rng = np.random.RandomState(0)
+    u = rng.rand(10, 3).astype(np.float32)
+    s = np.array([5.0, 3.0, 1.0], dtype=np.float32)
+    v = rng.rand(3, 8).astype(np.float32)
+    original = u @ (s[:, None] * v)
+    rec = svd_reconstruct(original, k=3, use_sparse=False)
+    assert np.max(np.abs(original - rec)) < 1e-6
+    wide = rng.rand(6, 40).astype(np.float32)
+    out = svd_reconstruct(wide, k=4, use_sparse=False)
+    assert np.max(np.abs(out - o_svd.reconstruct_f64(wide, 4))) <= 3e-7 * 2
+    assert not svd_reconstruct(np.zeros((3, 4), np.float32), k=2).any()
+    with pytest.raises(ValueError, match="k must be between"):
+        svd_reconstruct(wide, k=7)
+    with pytest.raises(ValueError, match="must be 2D"):
+        svd_reconstruct(np.ones(4), k=1)
+
+
+def test_svd_config2_scaled(golden_dir):
+    """C2 shape scaled down (2000 x 500, k = 10): reconstruction vs the float64 ground truth; then top_n."""
+    from recsys_lite_b200 import svd_reconstruct, top_n
+    m = gen.sample_ratings(2000, 500, sparsity=0.9, random_state=0)
+    out = svd_reconstruct(m, k=10, use_sparse=False)
+    truth = o_svd.reconstruct_f64(m, 10)
+    assert np.max(np.abs(out - truth)) <= 2e-5
+    rec = top_n(out, m, n=10)
+    assert rec.shape == (2000, 10) and rec.dtype == np.int32
+    assert np.array_equal(rec, o_topn.top_n(out, m, n=10))
+
+
+def test_svd_class_path_matches_reference_golden(golden_dir):
+    from recsys_lite_b200 import RecommenderSystem
+    g = _load(golden_dir, "svd_class")
+    m, k = g["ratings"], int(g["k"])
+    model = RecommenderSystem(algorithm="svd", use_sparse=False).fit(m, k=k)
+    md = model._model
+    assert set(md) == {"u", "s", "vt", "k", "global_bias", "user_bias", "item_bias"}
+    assert md["u"].shape == (120, k) and md["s"].shape == (k,) and md["vt"].shape == (k, 30)
+    assert abs(float(md["global_bias"]) - float(g["global_bias"])) < 1e-5
+    pred = model.predict(m)
+    assert pred.dtype == g["pred"].dtype and np.max(np.abs(pred - g["pred"])) < 5e-5
+    rec = model.recommend(m, n=5)
+    assert rec.shape == g["recommend"].shape and rec.dtype == g["recommend"].dtype
+    truth = o_svd.fit_predict_svd_dense(m, k)
+    res = compare.topn_matches(rec, g["recommend"], lambda row: truth[row], lambda row: np.nonzero(m[row] > 0)[0], rtol=2e-5)
+    assert not res["bad"], res
+    sp = RecommenderSystem(algorithm="svd").fit(m, k=k).predict(m)
+    assert sparse.issparse(sp)
+
+
+# ---------------------------------------------------------------------------------------------- metrics
+def test_observed_error_dev_vs_oracle(h):
+    from devbuf import Dev, padded
+    k, n_users, n_items = 64, 500, 400
+    rng = np.random.default_rng(9)
+    uf, vf = _f32(rng.random((n_users, k)) * 0.2), _f32(rng.random((n_items, k)) * 0.2)
+    indptr, indices = gen.synth_pattern(n_users, n_items, mean_deg=20, seed=9)
+    d_u, d_v, d_ip, d_ix = padded(h, uf, k), padded(h, vf, k), Dev(h, indptr), Dev(h, indices)
+    d_out = Dev(h, shape=(2,), dtype=np.float64)
+    h.call("rl_observed_error_dev", d_u.ptr, d_v.ptr, k, n_users, d_ip.ptr, d_ix.ptr, None, d_out.ptr)
+    sse, _ = d_out.get()
+    assert abs(np.sqrt(sse / len(indices)) - o_metrics.rmse_observed_csr(uf, vf, indptr, indices)) < 1e-12
+
+
+def test_api_lifecycle_and_errors():
+    """error strings pinned by the reference's tests (tests/test_algo.py:423-478)."""
+    from recsys_lite_b200 import RecommenderSystem
+    with pytest.raises(ValueError, match="Unsupported algorithm: 'invalid'"):
+        RecommenderSystem(algorithm="invalid")
+    m = RecommenderSystem(algorithm="als")
+    r = np.array([[1, 0, 1], [0, 1, 0]], dtype=np.float32)
+    with pytest.raises(RuntimeError, match="Model must be fitted"):
+        m.predict(r)
+    with pytest.raises(RuntimeError, match="Model must be fitted"):
+        m.recommend(r)
+    m.fit(r, k=2)
+    assert m.is_fitted() and m._model["user_factors"].shape == (2, 2) and m.predict(r).shape == (2, 3)
+    with pytest.raises(ValueError, match="n must be positive"):
+        m.recommend(r, n=0)
+    assert m.recommend(r, n=2, exclude_rated=False).dtype == np.int64
+    assert RecommenderSystem("als").fit(r)._model["factors"] == 10            # default factors (algo.py:107)
+    m.reset()
+    assert not m.is_fitted()
