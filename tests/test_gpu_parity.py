@@ -189,6 +189,7 @@ def test_score_topn_ragged_ties_and_bias(h):
     dense = (rng.random((n_users, n_items)) < 0.3)
     dense[3, :] = True                                     # everything seen -> all -1
     dense[5, :85] = True                                   # 5 unseen < n
+    dense[5, 85:] = False
     dense[7, :] = False
     indptr, indices = o_als.pattern_to_csr(dense.astype(np.float32))
     ub = rng.standard_normal(n_users).astype(np.float32)
