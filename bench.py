@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the recsys-lite hot path on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C4|C3|tiny]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one full ALS iteration (user half-step, factor exchange, item half-step, factor exchange;
+reference algo.py:312-332) followed by top-10 scoring of ALL users with seen items masked (algo.py:172-201), on
+the BASELINE.json configuration the metric is quoted on: C4 = 1 M users x 100 K items, ~50 M nnz, k = 64
+(fits one GPU).  Inputs are synthetic (recsys_lite_b200.synth, seed 4) and much larger than L2 (indices
+2 x 200 MB, U 256 MB), so no L2 flush is needed between timed iterations.
+
+value        whole-job iterations/s with every input resident in HBM (CUDA events, max over ranks)
+e2e          the same step through the host-buffer C ABI (rl_als_fit_host + rl_recommend_host at N = 1; the
+             same kernels with per-rank H2D / D2H at N > 1), host<->device copies inside the timed region
+roofline     dominant kernel of the step (the scoring kernel); roofline_als: the two gather/solve launches
+cpu_baseline the oracle's CSR restatement of the reference on a bounded sample, extrapolated linearly in rows
+--impl reference: the CPU leg alone, as its own JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ALS iterations/sec (both half-steps + top-10 recs for all users)"
+UNIT = "iterations/s"
+
+WORKLOADS = {
+    "C4": dict(n_users=1_000_000, n_items=100_000, mean_deg=50, k=64, seed=4, init_seed=4, n=10, lam=0.01),
+    "C3": dict(n_users=100_000, n_items=20_000, mean_deg=50, k=64, seed=3, init_seed=3, n=10, lam=0.01),
+    "tiny": dict(n_users=20_000, n_items=4_000, mean_deg=30, k=64, seed=1, init_seed=1, n=10, lam=0.01),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback")
+
+
+def make_inputs(w):
+    from recsys_lite_b200 import synth
+    from recsys_lite_b200.csr import transpose_pattern
+    indptr, indices = synth.synth_pattern(w["n_users"], w["n_items"], w["mean_deg"], w["seed"])
+    indptr_t, indices_t = transpose_pattern(indptr, indices, w["n_items"])
+    rng = np.random.default_rng(w["init_seed"])          # float32 uniform [0,1) like np.random.rand, drawn U then V
+    u0 = rng.random((w["n_users"], w["k"]), dtype=np.float32)
+    v0 = rng.random((w["n_items"], w["k"]), dtype=np.float32)
+    return indptr, indices, indptr_t, indices_t, u0, v0
+
+
+def als_bytes(n_rows, nnz, k):
+    """algorithmic bytes of one half-step: gathered rows + indices + indptr + output, fp32 factors."""
+    return nnz * k * 4 + nnz * 4 + (n_rows + 1) * 8 + n_rows * k * 4
+
+
+# ------------------------------------------------------------------------------------------- clocks sampling
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU leg
+def cpu_reference_leg(w, inputs, n_user_rows, n_item_rows, n_topn_users):
+    """The oracle's CSR restatement of algo.py:314-332 + blocked predict/top_n (algo.py:143-147, :533-659) on a
+    bounded contiguous sample, extrapolated linearly in rows.  Returns (iterations/s, seconds, description)."""
+    from oracle import als as o_als, topn as o_topn       # the CPU legs are the only place bench.py touches oracle/
+    indptr, indices, indptr_t, indices_t, u0, v0 = inputs
+    nu, ni = w["n_users"], w["n_items"]
+    n_user_rows, n_item_rows, n_topn_users = min(n_user_rows, nu), min(n_item_rows, ni), min(n_topn_users, nu)
+    u = u0.astype(np.float64)
+    v = v0.astype(np.float64)
+    t0 = time.perf_counter()
+    o_als.half_step_csr(indptr, indices, v, u, w["lam"], rows=range(n_user_rows))
+    t1 = time.perf_counter()
+    o_als.half_step_csr(indptr_t, indices_t, u, v, w["lam"], rows=range(n_item_rows))
+    t2 = time.perf_counter()
+    o_topn.recommend_blocked(u, v, indptr, indices, n=w["n"], users=np.arange(n_topn_users), block=256)
+    t3 = time.perf_counter()
+    t_iter = (t1 - t0) * nu / n_user_rows + (t2 - t1) * ni / n_item_rows + (t3 - t2) * nu / n_topn_users
+    desc = (f"oracle CSR restatement of algo.py:314-332 on the first {n_user_rows} users ({t1 - t0:.2f}s) and "
+            f"{n_item_rows} items ({t2 - t1:.2f}s) + blocked U@V.T/top-{w['n']} for {n_topn_users} users ({t3 - t2:.2f}s), "
+            f"extrapolated linearly in rows to {nu} x {ni}; single Python process, BLAS threads as configured")
+    return 1.0 / t_iter, t3 - t0, desc
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    inputs = make_inputs(w)
+    budget = 150.0 / max(1, args.steps + args.warmup)      # seconds of CPU work per step
+    scale = min(1.0, budget / 12.0)                        # 12 s ~ the (20K, 20K, 2K) sample on a 2 GHz core
+    nu_s, ni_s, nt_s = max(512, int(20_000 * scale)), max(128, int(20_000 * scale)), max(64, int(2_000 * scale))
+    vals, secs, desc = [], [], ""
+    for i in range(args.warmup + args.steps):
+        v, s, desc = cpu_reference_leg(w, inputs, nu_s, ni_s, nt_s)
+        if i >= args.warmup:
+            vals.append(v)
+            secs.append(s)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, w, "host CPU"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": blas_threads(), "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sample_seconds_per_step": float(np.mean(secs)),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, w, where):
+    return {"workload": f"{args.workload}: implicit ALS k={w['k']} one full iteration + top-{w['n']} for all users, "
+                        f"{w['n_users']} users x {w['n_items']} items, ~{w['mean_deg']} nnz/user (uniform synthetic, seed {w['seed']})",
+            "lambda": w["lam"], "where": where,
+            "l2": "inputs larger than L2 (indices 2x%d MB, U %d MB); no flush" % (
+                w["n_users"] * w["mean_deg"] * 4 // 2**20, w["n_users"] * w["k"] * 4 // 2**20)}
+
+
+# ----------------------------------------------------------------------------------------------- GPU leg
+def run_b200(args, w):
+    import torch
+    import torch.distributed as dist
+    from recsys_lite_b200 import _ffi
+    from recsys_lite_b200.sharding import ShardedProblem, make_plan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    h = _ffi.Handle(local)
+    stream = torch.cuda.Stream(device=device)               # everything (kernels, events, NCCL sync) on one stream
+    torch.cuda.set_stream(stream)
+    h.set_stream(stream.cuda_stream)
+    peaks = load_peaks()
+    prec = _ffi.RL_PREC_FP64 if args.precision == "fp64" else _ffi.RL_PREC_FP32_IR
+
+    inputs = make_inputs(w)
+    indptr, indices, indptr_t, indices_t, u0, v0 = inputs
+    nu, ni, k, n = w["n_users"], w["n_items"], w["k"], w["n"]
+    plan = make_plan(indptr, indptr_t, rank, world)
+    prob = ShardedProblem(h, plan, indptr, indices, indptr_t, indices_t, k, device)
+    prob.set_factors(u0, v0)
+    ulo, uhi = plan.users
+    ilo, ihi = plan.items
+    idx_out = torch.empty((uhi - ulo, n), dtype=torch.int32, device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)      # noqa: E731
+    marks = []
+
+    def step(record):
+        e = [ev() for _ in range(5)] if record else None
+        if record:
+            e[0].record()
+        prob.user_half_step(w["lam"], prec, args.ir_steps)
+        if record:
+            e[1].record()
+        from recsys_lite_b200.sharding import exchange_rows
+        exchange_rows(prob.U, plan.user_bounds, rank, world)
+        prob.item_half_step(w["lam"], prec, args.ir_steps)
+        if record:
+            e[2].record()
+        exchange_rows(prob.V, plan.item_bounds, rank, world)
+        if record:
+            e[3].record()
+        prob.recommend(n, idx_out, args.score_mode)
+        if record:
+            e[4].record()
+            marks.append(e)
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = h.launches
+    t_begin, t_end = ev(), ev()
+    barrier()
+    t_begin.record()
+    for _ in range(args.steps):
+        step(True)
+    t_end.record()
+    barrier()
+    clk = clocks.stop()
+    launches = h.launches - launches0
+    total_ms = t_begin.elapsed_time(t_end)
+    seg = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in marks])   # user(+0), xchg+item, xchg, score
+    t_user, t_item_x, t_x2, t_score = seg.mean(axis=0)
+    if world > 1:
+        tt = torch.tensor([total_ms, t_user, t_item_x, t_x2, t_score], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms, t_user, t_item_x, t_x2, t_score = tt.tolist()
+    ms_per_step = total_ms / args.steps
+    value = 1000.0 / ms_per_step
+
+    # ---- end-to-end leg: host buffers, copies inside the timed region -------------------------------------
+    e2e = run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier)
+
+    line = None
+    if rank == 0:
+        flops_score = 2.0 * (uhi - ulo) * ni * k
+        b_user = als_bytes(uhi - ulo, prob.nnz_users, k)
+        b_item = als_bytes(ihi - ilo, prob.nnz_items, k)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 factors; ALS solve " + ("f64" if prec else f"f32 + {args.ir_steps} f64 refinement steps")
+                     + "; scores f64",
+            "data": "synthetic", "config": workload_config(args, w, f"{world} x B200"),
+            "als_iterations_per_s": 1000.0 / (t_user + t_item_x + t_x2),
+            "top10_users_per_s": nu / (t_score / 1000.0),
+            "ms": {"user_half_step": t_user, "exchange_U_plus_item_half_step": t_item_x, "exchange_V": t_x2, "score_topn": t_score},
+            "roofline": {"kernel": "score_topn (rank 0 shard)", "bound": "tensor",
+                         "achieved": flops_score / (t_score * 1e-3) / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": flops_score / (t_score * 1e-3) / 1e12 / peaks["tflops"], "traffic": None,
+                         "peak_source": peaks["source"] + " bf16 sustained"},
+            "roofline_als": {
+                "bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_source": peaks["source"],
+                "user_half_step": {"bytes": b_user, "achieved": b_user / (t_user * 1e-3) / 1e9,
+                                   "frac": b_user / (t_user * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                "item_half_step_incl_exchange": {"bytes": b_item, "achieved": b_item / (t_item_x * 1e-3) / 1e9,
+                                                 "frac": b_item / (t_item_x * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                "traffic": None},
+            "clocks": clk, "gpu_launches": int(launches), "e2e": e2e,
+        }
+        if world == 1 and not args.no_cpu:
+            v, s, desc = cpu_reference_leg(w, inputs, 20_000, 20_000, 2_000)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": blas_threads(), "kind": "port", "sample": desc,
+                                    "seconds": s}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
+    """The step through host buffers.  N = 1: the host-buffer C ABI calls a reference binding would make
+    (rl_als_fit_host + rl_recommend_host) on pinned float32 buffers.  N > 1: per-rank H2D of its CSR / CSC ranges
+    and the initial factors, the same kernels + exchanges, D2H of its factor ranges and top-n rows."""
+    import torch
+    from recsys_lite_b200 import _ffi
+    indptr, indices, indptr_t, indices_t, u0, v0 = inputs
+    nu, ni, k, n = w["n_users"], w["n_items"], w["k"], w["n"]
+    steps = max(1, min(args.steps, 3))
+    if world == 1:
+        pin = lambda a: _pinned_copy(a)                    # noqa: E731
+        p_ip, p_ix, p_tp, p_tx = pin(indptr), pin(indices), pin(indptr_t), pin(indices_t)
+        p_u, p_v = pin(u0), pin(v0)
+        idx = _ffi.pinned_empty((nu, n), np.int32)
+        h2d = p_ip.nbytes + p_ix.nbytes + p_tp.nbytes + p_tx.nbytes + 2 * (p_u.nbytes + p_v.nbytes) + p_ip.nbytes + p_ix.nbytes
+        d2h = p_u.nbytes + p_v.nbytes + idx.nbytes
+        times = []
+        for i in range(1 + steps):
+            p_u[:] = u0
+            p_v[:] = v0
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            h.call("rl_als_fit_host", nu, ni, k, _ffi.ptr(p_ip), _ffi.ptr(p_ix), _ffi.ptr(p_tp), _ffi.ptr(p_tx), 1,
+                   float(w["lam"]), prec, args.ir_steps, _ffi.ptr(p_u), _ffi.ptr(p_v), _ffi.RL_F32)
+            h.call("rl_recommend_host", _ffi.ptr(p_u), _ffi.ptr(p_v), _ffi.RL_F32, nu, ni, k, _ffi.ptr(p_ip), _ffi.ptr(p_ix),
+                   0.0, None, None, n, _ffi.ptr(idx), None, args.score_mode)
+            torch.cuda.synchronize()
+            if i > 0:
+                times.append(time.perf_counter() - t0)
+        sec = float(np.mean(times))
+        return {"value": 1.0 / sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": sec * 1e3, "steps": steps,
+                "api": "rl_als_fit_host(iterations=1) + rl_recommend_host(n=10), pinned float32 host buffers"}
+    import torch.distributed as dist
+    from recsys_lite_b200.sharding import exchange_rows
+    ulo, uhi = plan.users
+    ilo, ihi = plan.items
+    hp = {kk: torch.from_numpy(v).pin_memory() for kk, v in prob.host.items()}
+    hu, hv = torch.from_numpy(u0).pin_memory(), torch.from_numpy(v0).pin_memory()
+    out_u = torch.empty((uhi - ulo, k), dtype=torch.float32).pin_memory()
+    out_v = torch.empty((ihi - ilo, k), dtype=torch.float32).pin_memory()
+    out_idx = torch.empty((uhi - ulo, n), dtype=torch.int32).pin_memory()
+    idx_dev = torch.empty((uhi - ulo, n), dtype=torch.int32, device=device)
+    h2d = sum(t.numel() * t.element_size() for t in hp.values()) + hu.numel() * 4 + hv.numel() * 4
+    d2h = out_u.numel() * 4 + out_v.numel() * 4 + out_idx.numel() * 4
+    times = []
+    for i in range(1 + steps):
+        barrier()
+        t0 = time.perf_counter()
+        prob.up.copy_(hp["up"], non_blocking=True)
+        prob.ux.copy_(hp["ux"], non_blocking=True)
+        prob.ip.copy_(hp["ip"], non_blocking=True)
+        prob.ix.copy_(hp["ix"], non_blocking=True)
+        prob.U[:, :k].copy_(hu, non_blocking=True)
+        prob.V[:, :k].copy_(hv, non_blocking=True)
+        prob.user_half_step(w["lam"], prec, args.ir_steps)
+        exchange_rows(prob.U, plan.user_bounds, rank, world)
+        prob.item_half_step(w["lam"], prec, args.ir_steps)
+        exchange_rows(prob.V, plan.item_bounds, rank, world)
+        prob.recommend(n, idx_dev, args.score_mode)
+        out_u.copy_(prob.U[ulo:uhi, :k], non_blocking=True)
+        out_v.copy_(prob.V[ilo:ihi, :k], non_blocking=True)
+        out_idx.copy_(idx_dev, non_blocking=True)
+        barrier()
+        if i > 0:
+            times.append(time.perf_counter() - t0)
+    sec = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=device)
+    dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+    sec = float(sec.item())
+    tot = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=device)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    return {"value": 1.0 / sec, "unit": UNIT, "h2d_bytes_per_step": int(tot[0].item()), "d2h_bytes_per_step": int(tot[1].item()),
+            "ms_per_step": sec * 1e3, "steps": steps,
+            "api": "per-rank pinned H2D of its CSR/CSC ranges + factors, rl_als_half_step_dev/rl_score_topn_dev + exchanges, D2H of its ranges"}
+
+
+def _pinned_copy(a):
+    from recsys_lite_b200 import _ffi
+    out = _ffi.pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fp32_ir", choices=["fp32_ir", "fp64"])
+    ap.add_argument("--ir-steps", type=int, default=2)
+    ap.add_argument("--score-mode", type=int, default=0, help="0 auto, 1 exact CUDA-core, 2 tensor-core candidate pass")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200" and not os.environ.get("RL_BENCH_ALLOW_SHORT_WARMUP"):
+        args.warmup = 3
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_b200(args, w)
+
+
+if __name__ == "__main__":
+    main()

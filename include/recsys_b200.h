@@ -58,7 +58,9 @@ int rl_create(int device, rl_handle* out);
 int rl_destroy(rl_handle h);
 /* text of the last error on this handle (h may be NULL: last error of the calling thread) */
 const char* rl_last_error(rl_handle h);
-/* use an existing cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = handle's own stream */
+/* use an existing cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream; NULL is the CUDA default stream);
+ * RL_OWN_STREAM switches back to the non-blocking stream the handle created for itself */
+#define RL_OWN_STREAM ((void*)(intptr_t)-1)
 int rl_set_stream(rl_handle h, void* cuda_stream);
 int rl_synchronize(rl_handle h);
 int rl_device_info(rl_handle h, int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem_bytes);

@@ -115,7 +115,8 @@ class Handle:
         self.check(getattr(self.lib, name)(self.h, *args), name)
 
     def set_stream(self, stream_ptr: int | None):
-        self.call("rl_set_stream", _vp(stream_ptr) if stream_ptr else None)
+        """stream_ptr: a cudaStream_t as int (0 = CUDA default stream); None = the handle's own stream."""
+        self.call("rl_set_stream", _vp(-1 & 0xFFFFFFFFFFFFFFFF) if stream_ptr is None else _vp(int(stream_ptr)))
 
     def synchronize(self):
         self.call("rl_synchronize")

@@ -166,7 +166,7 @@ int rl_destroy(rl_handle h) {
 
 int rl_set_stream(rl_handle h, void* cuda_stream) {
   RL_NEED(h);
-  h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  h->stream = (cuda_stream == RL_OWN_STREAM) ? h->own_stream : static_cast<cudaStream_t>(cuda_stream);
   return RL_OK;
 }
 

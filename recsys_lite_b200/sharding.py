@@ -1,0 +1,113 @@
+"""Multi-GPU plumbing for the ALS iteration and the scoring pass: one process per GPU.
+
+The reference has no parallelism (plain Python loops, algo.py:314,324).  The loops are independent per row, so:
+
+  * user half-step: users are cut into `world` contiguous ranges balanced by nnz; rank g holds the CSR rows of
+    its users and a full replica of V, solves its range and writes U[g];
+  * the freshly solved range is exchanged once per half-step (all-gather over NCCL / NVLink) so every rank has
+    the full U again before the item half-step, and likewise V afterwards;
+  * scoring shards users with V replicated: no collective.
+
+torch is used here only for device memory, the stream and torch.distributed; all arithmetic goes through the
+C ABI (librecsys_b200.so) on raw data_ptr()s.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .csr import nnz_balanced_bounds, shard_rows
+
+
+@dataclass
+class ShardPlan:
+    """Host-side description of what one rank owns."""
+    rank: int
+    world: int
+    user_bounds: np.ndarray   # (world+1,) row boundaries of the user ranges
+    item_bounds: np.ndarray   # (world+1,)
+
+    @property
+    def users(self):
+        return int(self.user_bounds[self.rank]), int(self.user_bounds[self.rank + 1])
+
+    @property
+    def items(self):
+        return int(self.item_bounds[self.rank]), int(self.item_bounds[self.rank + 1])
+
+
+def make_plan(indptr_u, indptr_i, rank: int, world: int) -> ShardPlan:
+    return ShardPlan(rank, world, nnz_balanced_bounds(indptr_u, world), nnz_balanced_bounds(indptr_i, world))
+
+
+def exchange_rows(full, bounds, rank: int, world: int, group=None):
+    """All-gather of contiguous row ranges of `full` (a torch tensor, rows x ld) IN PLACE.
+
+    Rank r contributes rows [bounds[r], bounds[r+1]); afterwards every rank holds all rows.  Ranges may have
+    different lengths (nnz-balanced), so this is issued as `world` broadcasts of views of `full` inside one
+    coalesced group where the backend supports it -- no staging copy, no padding.
+    """
+    if world == 1:
+        return
+    import torch.distributed as dist
+    views = [full[int(bounds[r]):int(bounds[r + 1])] for r in range(world)]
+    works = []
+    for r, v in enumerate(views):
+        if v.numel():
+            works.append(dist.broadcast(v, src=dist.get_global_rank(group, r) if group is not None else r,
+                                        group=group, async_op=True))
+    for w in works:
+        w.wait()
+
+
+class ShardedProblem:
+    """Device-resident ALS problem of one rank: its CSR / CSC row ranges and full factor replicas."""
+
+    def __init__(self, handle, plan: ShardPlan, indptr_u, indices_u, indptr_i, indices_i, k: int, device):
+        import torch
+        self.h, self.plan, self.k = handle, plan, int(k)
+        self.kp = handle.lib.rl_padded_k(self.k)
+        self.n_users, self.n_items = len(indptr_u) - 1, len(indptr_i) - 1
+        self.device = device
+        ulo, uhi = plan.users
+        ilo, ihi = plan.items
+        up, ux = shard_rows(indptr_u, indices_u, ulo, uhi)
+        ip, ix = shard_rows(indptr_i, indices_i, ilo, ihi)
+        self.host = {"up": up, "ux": ux, "ip": ip, "ix": ix}   # kept for the end-to-end (H2D inside) leg
+        self.nnz_users, self.nnz_items = len(ux), len(ix)
+        t = lambda a: torch.from_numpy(a).to(device)           # noqa: E731
+        self.up, self.ux, self.ip, self.ix = t(up), t(ux), t(ip), t(ix)
+        self.U = torch.zeros((self.n_users, self.kp), dtype=torch.float32, device=device)
+        self.V = torch.zeros((self.n_items, self.kp), dtype=torch.float32, device=device)
+
+    def set_factors(self, u_host, v_host):
+        import torch
+        self.U[:, : self.k].copy_(torch.from_numpy(np.ascontiguousarray(u_host, dtype=np.float32)))
+        self.V[:, : self.k].copy_(torch.from_numpy(np.ascontiguousarray(v_host, dtype=np.float32)))
+
+    # -- one ALS half-step on this rank's rows, then the exchange -------------------------------------------
+    def user_half_step(self, lam, precision, ir_steps):
+        ulo, uhi = self.plan.users
+        self.h.call("rl_als_half_step_dev", uhi - ulo, self.n_items, self.k, self.up.data_ptr(), self.ux.data_ptr(),
+                    None, None, self.V.data_ptr(), self.U[ulo:].data_ptr(), float(lam), 0.0, None, precision,
+                    ir_steps, None)
+
+    def item_half_step(self, lam, precision, ir_steps):
+        ilo, ihi = self.plan.items
+        self.h.call("rl_als_half_step_dev", ihi - ilo, self.n_users, self.k, self.ip.data_ptr(), self.ix.data_ptr(),
+                    None, None, self.U.data_ptr(), self.V[ilo:].data_ptr(), float(lam), 0.0, None, precision,
+                    ir_steps, None)
+
+    def iteration(self, lam=0.01, precision=0, ir_steps=2):
+        p = self.plan
+        self.user_half_step(lam, precision, ir_steps)
+        exchange_rows(self.U, p.user_bounds, p.rank, p.world)
+        self.item_half_step(lam, precision, ir_steps)
+        exchange_rows(self.V, p.item_bounds, p.rank, p.world)
+
+    def recommend(self, n, idx_out, mode=0):
+        """top-n for this rank's users (seen items = its CSR rows) into idx_out (users_local x n int32 tensor)."""
+        ulo, uhi = self.plan.users
+        self.h.call("rl_score_topn_dev", self.U[ulo:].data_ptr(), uhi - ulo, self.V.data_ptr(), self.n_items, self.k,
+                    self.up.data_ptr(), self.ux.data_ptr(), 0.0, None, None, int(n), idx_out.data_ptr(), None, mode)
