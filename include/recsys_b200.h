@@ -126,6 +126,13 @@ int rl_score_topn_dev(rl_handle h, const float* user_f_dev, int64_t n_users,
 #define RL_SCORE_EXACT 1  /* CUDA-core float64 scoring of every pair                                       */
 #define RL_SCORE_TENSOR 2 /* force the tcgen05 candidate pass (error if unsupported shape)                 */
 
+/* debug / validation of the tensor-core path: raw tf32 tensor-core scores U V^T, out (n_users x ld) float32 with
+ * ld >= n_items rounded up to 256 (the padding columns receive the zero-filled tail of the last tile). */
+int rl_score_dump_dev(rl_handle h, const float* user_f_dev, int64_t n_users, const float* item_f_dev, int64_t n_items,
+                      int k, float* out_dev, int64_t ld);
+/* number of user rows the last tensor-core rl_score_topn_dev call handed to the exact kernel (candidate overflow) */
+int64_t rl_last_overflow_rows(rl_handle h);
+
 int rl_recommend_host(rl_handle h, const void* user_f, const void* item_f, int factor_dtype,
                       int64_t n_users, int64_t n_items, int k,
                       const int64_t* seen_indptr, const int32_t* seen_indices,

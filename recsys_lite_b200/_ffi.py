@@ -41,6 +41,8 @@ SIGNATURES = {
     "rl_gram_dev": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "rl_als_fit_host": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _dbl, _i32, _i32, _vp, _vp, _i32]),
     "rl_score_topn_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _dbl, _vp, _vp, _i32, _vp, _vp, _i32]),
+    "rl_score_dump_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64]),
+    "rl_last_overflow_rows": (_i64, [_vp]),
     "rl_recommend_host": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i32, _vp, _vp, _dbl, _vp, _vp, _i32, _vp, _vp, _i32]),
     "rl_topn_dense_dev": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i32, _vp, _vp]),
     "rl_topn_dense_host": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i32, _vp, _vp]),

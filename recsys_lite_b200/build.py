@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, sources()))
     cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs,
-           "-Xcompiler", "-fPIC", "-lcuda"]
+           "-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -311,6 +311,14 @@ int rl_score_topn_dev(rl_handle h, const float* user_f_dev, int64_t n_users, con
                            user_bias_dev, item_bias_dev, n, idx_out_dev, score_out_dev, mode);
 }
 
+int rl_score_dump_dev(rl_handle h, const float* user_f_dev, int64_t n_users, const float* item_f_dev, int64_t n_items, int k,
+                      float* out_dev, int64_t ld) {
+  RL_NEED(h);
+  return launch_score_dump(h, user_f_dev, n_users, item_f_dev, n_items, k, out_dev, ld);
+}
+
+int64_t rl_last_overflow_rows(rl_handle h) { return h ? static_cast<int64_t>(h->last_overflow) : -1; }
+
 int rl_recommend_host(rl_handle h, const void* user_f, const void* item_f, int factor_dtype, int64_t n_users,
                       int64_t n_items, int k, const int64_t* seen_indptr, const int32_t* seen_indices, double global_bias,
                       const float* user_bias, const float* item_bias, int n, int32_t* idx_out, double* score_out, int mode) {

@@ -102,6 +102,17 @@ __global__ void __launch_bounds__(256) observed_error_kernel(const float* __rest
 
 }  // namespace
 
+bool score_tc_supported(int kp, int n, int64_t n_users, int64_t n_items, const float* ubias, const float* ibias, double gbias);
+int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int64_t dump_ld);
+
+int launch_score_dump(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k, float* out, int64_t ld) {
+  const int kp = padded_k(k);
+  if (kp != 32 && kp != 64) return fail(h, RL_ERR_INVALID, "score_dump: padded k must be 32 or 64");
+  if (!uf || !vf || !out || ld < ((n_items + 255) / 256) * 256) return fail(h, RL_ERR_INVALID, "score_dump: bad argument");
+  ScoreArgs a{uf, vf, n_users, n_items, nullptr, nullptr, 0.0, nullptr, nullptr, 1, nullptr, nullptr, nullptr, 0, false};
+  return launch_score_tc(h, kp, a, out, ld);
+}
+
 int launch_score_topn(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k,
                       const int64_t* seen_indptr, const int32_t* seen_indices, double gbias, const float* ubias,
                       const float* ibias, int n, int32_t* idx_out, double* score_out, int mode) {
@@ -113,8 +124,11 @@ int launch_score_topn(rl_context* h, const float* uf, int64_t n_users, const flo
   if (!uf || !vf || !idx_out) return fail(h, RL_ERR_INVALID, "score_topn: null pointer");
   if ((seen_indptr == nullptr) != (seen_indices == nullptr) && seen_indptr == nullptr)
     return fail(h, RL_ERR_INVALID, "score_topn: seen_indices without seen_indptr");
-  ScoreArgs a{uf, vf, n_users, n_items, seen_indptr, seen_indices, gbias, ubias, ibias, n, idx_out, score_out, nullptr, 0};
-  if (mode == RL_SCORE_TENSOR) return fail(h, RL_ERR_INVALID, "score_topn: tensor-core candidate pass not built in this version");
+  ScoreArgs a{uf, vf, n_users, n_items, seen_indptr, seen_indices, gbias, ubias, ibias, n, idx_out, score_out, nullptr, 0, false};
+  const bool tc_ok = score_tc_supported(kp, n, n_users, n_items, ubias, ibias, gbias);
+  if (mode == RL_SCORE_TENSOR && !tc_ok)
+    return fail(h, RL_ERR_INVALID, "score_topn: tensor-core path needs padded k in {32, 64}, n <= 16, >= 1024 items and no bias terms");
+  if (mode != RL_SCORE_EXACT && tc_ok) return launch_score_tc(h, kp, a, nullptr, 0);
   return launch_score_exact(h, kp, a);
 }
 

@@ -24,8 +24,9 @@ struct ScoreArgs {
   int n;
   int32_t* idx_out;
   double* score_out;
-  const int32_t* user_list;  // optional: score only these users (rows of idx_out follow the list order)
+  const int32_t* user_list;  // optional: score only these users
   int64_t n_list;
+  bool scatter;              // with user_list: write row `user` of idx_out (true) or row `position in list` (false)
 };
 
 constexpr int SE_UT = 64, SE_IT = 64, SE_THREADS = 256, SE_UPW = 8;  // users per warp
@@ -157,7 +158,10 @@ __global__ void __launch_bounds__(SE_THREADS) score_topn_exact_kernel(const Scor
 #pragma unroll
   for (int uu = 0; uu < SE_UPW; ++uu) {
     const int64_t t = t0 + warp * SE_UPW + uu;
-    if (t < total) lists[uu].store(a.n, lane, a.idx_out + t * a.n, a.score_out ? a.score_out + t * a.n : nullptr);
+    if (t < total) {
+      const int64_t orow = (a.user_list && a.scatter) ? a.user_list[t] : t;
+      lists[uu].store(a.n, lane, a.idx_out + orow * a.n, a.score_out ? a.score_out + orow * a.n : nullptr);
+    }
   }
 }
 

@@ -345,3 +345,85 @@ def test_api_lifecycle_and_errors():
     assert RecommenderSystem("als").fit(r)._model["factors"] == 10            # default factors (algo.py:107)
     m.reset()
     assert not m.is_fitted()
+
+
+# ---------------------------------------------------------------------------- tensor-core scoring (tcgen05)
+def _tf32_trunc(x):
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)
+    return b.view(np.float32).astype(np.float64)
+
+
+@pytest.mark.parametrize("k", [64, 32, 50])
+def test_tensor_core_raw_scores(h, k):
+    """rl_score_dump_dev: the tcgen05 tf32 tile pipeline (TMA 128B swizzle, UMMA descriptors, TMEM layout) reproduces
+    U V^T within the documented bound 2.5e-3 |u||v| and matches the product of tf32-truncated operands closely."""
+    from devbuf import Dev, padded
+    n_users, n_items = 300, 1500                      # 3 user tiles (last partial), 6 item tiles (last partial)
+    rng = np.random.default_rng(k)
+    uf, vf = _f32(rng.standard_normal((n_users, k))), _f32(rng.standard_normal((n_items, k)))
+    ld = ((n_items + 255) // 256) * 256
+    d_u, d_v = padded(h, uf, k), padded(h, vf, k)
+    d_out = Dev(h, shape=(n_users, ld), dtype=np.float32)
+    h.call("rl_score_dump_dev", d_u.ptr, n_users, d_v.ptr, n_items, k, d_out.ptr, ld)
+    got = d_out.get().astype(np.float64)
+    exact = uf @ vf.T
+    bound = 2.5e-3 * np.linalg.norm(uf, axis=1)[:, None] * np.linalg.norm(vf, axis=1)[None, :]
+    assert (np.abs(got[:, :n_items] - exact) <= bound).all()
+    trunc = _tf32_trunc(uf) @ _tf32_trunc(vf).T
+    assert np.max(np.abs(got[:, :n_items] - trunc)) <= 2e-5 * np.abs(exact).max()
+    assert not got[:, n_items:].any()                 # zero-filled tail of the last item tile
+
+
+@pytest.mark.parametrize("k,n,n_users,n_items", [(64, 10, 1000, 5000), (64, 1, 130, 1024), (32, 16, 257, 3000),
+                                                  (40, 10, 500, 2049)])
+def test_tensor_core_topn_equals_exact_kernel(h, k, n, n_users, n_items):
+    """mode RL_SCORE_TENSOR must return exactly what RL_SCORE_EXACT returns (indices and float64 scores), and both
+    must match the oracle (algo.py:172-201) up to exact-score ties."""
+    from devbuf import Dev, padded
+    rng = np.random.default_rng(n_users + k)
+    uf = _f32(rng.random((n_users, k)) * 0.4)          # ALS-like: non-negative factors, crowded top scores
+    vf = _f32(rng.random((n_items, k)) * 0.4)
+    indptr, indices = gen.synth_pattern(n_users, n_items, mean_deg=45, seed=n_items)
+    d_u, d_v, d_ip, d_ix = padded(h, uf, k), padded(h, vf, k), Dev(h, indptr), Dev(h, indices)
+    outs = {}
+    for mode in (1, 2):
+        d_idx = Dev(h, shape=(n_users, n), dtype=np.int32)
+        d_val = Dev(h, shape=(n_users, n), dtype=np.float64)
+        h.call("rl_score_topn_dev", d_u.ptr, n_users, d_v.ptr, n_items, k, d_ip.ptr, d_ix.ptr, 0.0, None, None, n,
+               d_idx.ptr, d_val.ptr, mode)
+        outs[mode] = (d_idx.get(), d_val.get())
+    assert np.array_equal(outs[1][0], outs[2][0])
+    assert np.array_equal(outs[1][1], outs[2][1])
+    ref_idx, _ = o_topn.recommend_blocked(uf, vf, indptr, indices, n=n)
+    res = compare.topn_matches(outs[2][0], ref_idx, lambda row: uf[row] @ vf.T, lambda row: indices[indptr[row]:indptr[row + 1]])
+    assert not res["bad"], res
+    assert h.lib.rl_last_overflow_rows(h.h) <= n_users // 20
+
+
+def test_tensor_core_topn_heavy_users_and_overflow(h):
+    """users who have seen almost everything (ragged -1 rows), many exactly tied scores (candidate overflow ->
+    exact-kernel fallback for those rows) and no seen list at all."""
+    from devbuf import Dev, padded
+    k, n, n_users, n_items = 64, 10, 260, 2100
+    rng = np.random.default_rng(11)
+    uf = _f32(rng.integers(0, 2, (n_users, k)) * 0.5)   # few distinct score values -> massive ties
+    vf = _f32(rng.integers(0, 2, (n_items, k)) * 0.5)
+    dense = rng.random((n_users, n_items)) < 0.02
+    dense[1, :] = True
+    dense[2, :2095] = True
+    dense[2, 2095:] = False
+    indptr, indices = o_als.pattern_to_csr(dense.astype(np.float32))
+    d_u, d_v, d_ip, d_ix = padded(h, uf, k), padded(h, vf, k), Dev(h, indptr), Dev(h, indices)
+    res = {}
+    for mode in (1, 2):
+        d_idx = Dev(h, shape=(n_users, n), dtype=np.int32)
+        h.call("rl_score_topn_dev", d_u.ptr, n_users, d_v.ptr, n_items, k, d_ip.ptr, d_ix.ptr, 0.0, None, None, n,
+               d_idx.ptr, None, mode)
+        res[mode] = d_idx.get()
+    assert np.array_equal(res[1], res[2])
+    assert (res[2][1] == -1).all() and (res[2][2, 5:] == -1).all() and (res[2][2, :5] >= 2095).all()
+    assert h.lib.rl_last_overflow_rows(h.h) > 0          # the tie-heavy rows went through the exact kernel
+    d_idx = Dev(h, shape=(n_users, n), dtype=np.int32)
+    h.call("rl_score_topn_dev", d_u.ptr, n_users, d_v.ptr, n_items, k, None, None, 0.0, None, None, n, d_idx.ptr, None, 2)
+    ref, _ = o_topn.recommend_blocked(uf, vf, indptr, indices, n=n, exclude_rated=False)
+    assert np.array_equal(d_idx.get(), ref)
