@@ -124,12 +124,14 @@ int rl_score_topn_dev(rl_handle h, const float* user_f_dev, int64_t n_users,
                       int n, int32_t* idx_out_dev, double* score_out_dev, int mode);
 #define RL_SCORE_AUTO 0   /* tensor-core candidate pass + exact rescoring when shapes allow, else exact   */
 #define RL_SCORE_EXACT 1  /* CUDA-core float64 scoring of every pair                                       */
-#define RL_SCORE_TENSOR 2 /* force the tcgen05 candidate pass (error if unsupported shape)                 */
+#define RL_SCORE_TENSOR 2 /* force the tcgen05 candidate pass, split-operand 3 x tf32 (error if unsupported shape) */
+#define RL_SCORE_TENSOR_TF32X1 3 /* same with a single tf32 product: wider candidate window, more exact-kernel fallbacks */
 
-/* debug / validation of the tensor-core path: raw tf32 tensor-core scores U V^T, out (n_users x ld) float32 with
- * ld >= n_items rounded up to 256 (the padding columns receive the zero-filled tail of the last tile). */
+/* debug / validation of the tensor-core path: raw tensor-core scores U V^T (terms = 1: one tf32 product, 3: split
+ * operands), out (n_users x ld) float32 with ld >= n_items rounded up to 128 (the padding columns receive the
+ * zero-filled tail of the last tile). */
 int rl_score_dump_dev(rl_handle h, const float* user_f_dev, int64_t n_users, const float* item_f_dev, int64_t n_items,
-                      int k, float* out_dev, int64_t ld);
+                      int k, float* out_dev, int64_t ld, int terms);
 /* number of user rows the last tensor-core rl_score_topn_dev call handed to the exact kernel (candidate overflow) */
 int64_t rl_last_overflow_rows(rl_handle h);
 

@@ -312,9 +312,9 @@ int rl_score_topn_dev(rl_handle h, const float* user_f_dev, int64_t n_users, con
 }
 
 int rl_score_dump_dev(rl_handle h, const float* user_f_dev, int64_t n_users, const float* item_f_dev, int64_t n_items, int k,
-                      float* out_dev, int64_t ld) {
+                      float* out_dev, int64_t ld, int terms) {
   RL_NEED(h);
-  return launch_score_dump(h, user_f_dev, n_users, item_f_dev, n_items, k, out_dev, ld);
+  return launch_score_dump(h, user_f_dev, n_users, item_f_dev, n_items, k, out_dev, ld, terms);
 }
 
 int64_t rl_last_overflow_rows(rl_handle h) { return h ? static_cast<int64_t>(h->last_overflow) : -1; }

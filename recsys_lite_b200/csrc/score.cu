@@ -103,14 +103,15 @@ __global__ void __launch_bounds__(256) observed_error_kernel(const float* __rest
 }  // namespace
 
 bool score_tc_supported(int kp, int n, int64_t n_users, int64_t n_items, const float* ubias, const float* ibias, double gbias);
-int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int64_t dump_ld);
+int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int64_t dump_ld, int terms);
 
-int launch_score_dump(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k, float* out, int64_t ld) {
+int launch_score_dump(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k, float* out, int64_t ld,
+                      int terms) {
   const int kp = padded_k(k);
   if (kp != 32 && kp != 64) return fail(h, RL_ERR_INVALID, "score_dump: padded k must be 32 or 64");
-  if (!uf || !vf || !out || ld < ((n_items + 255) / 256) * 256) return fail(h, RL_ERR_INVALID, "score_dump: bad argument");
+  if (!uf || !vf || !out || ld < ((n_items + 127) / 128) * 128) return fail(h, RL_ERR_INVALID, "score_dump: bad argument");
   ScoreArgs a{uf, vf, n_users, n_items, nullptr, nullptr, 0.0, nullptr, nullptr, 1, nullptr, nullptr, nullptr, 0, false};
-  return launch_score_tc(h, kp, a, out, ld);
+  return launch_score_tc(h, kp, a, out, ld, terms);
 }
 
 int launch_score_topn(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k,
@@ -126,9 +127,10 @@ int launch_score_topn(rl_context* h, const float* uf, int64_t n_users, const flo
     return fail(h, RL_ERR_INVALID, "score_topn: seen_indices without seen_indptr");
   ScoreArgs a{uf, vf, n_users, n_items, seen_indptr, seen_indices, gbias, ubias, ibias, n, idx_out, score_out, nullptr, 0, false};
   const bool tc_ok = score_tc_supported(kp, n, n_users, n_items, ubias, ibias, gbias);
-  if (mode == RL_SCORE_TENSOR && !tc_ok)
+  if (mode < RL_SCORE_AUTO || mode > RL_SCORE_TENSOR_TF32X1) return fail(h, RL_ERR_INVALID, "score_topn: unknown mode %d", mode);
+  if ((mode == RL_SCORE_TENSOR || mode == RL_SCORE_TENSOR_TF32X1) && !tc_ok)
     return fail(h, RL_ERR_INVALID, "score_topn: tensor-core path needs padded k in {32, 64}, n <= 16, >= 1024 items and no bias terms");
-  if (mode != RL_SCORE_EXACT && tc_ok) return launch_score_tc(h, kp, a, nullptr, 0);
+  if (mode != RL_SCORE_EXACT && tc_ok) return launch_score_tc(h, kp, a, nullptr, 0, mode == RL_SCORE_TENSOR_TF32X1 ? 1 : 3);
   return launch_score_exact(h, kp, a);
 }
 

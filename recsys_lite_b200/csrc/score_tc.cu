@@ -2,24 +2,31 @@
 //
 // Replaces predict + top_n of the reference (algo.py:143-147 `U @ V.T`, algo.py:533-659) for ALS factors without
 // ever writing the n_users x n_items score matrix.  One persistent CTA per SM owns 128 users at a time (one TMEM
-// lane = one user) and sweeps all items in tiles of 256:
+// lane = one user) and sweeps all items in tiles of 128:
 //
-//   warp 0   TMA producer: U tile (128 x KP fp32) once per user tile, V tiles (256 x KP fp32) through a
-//            2-stage shared-memory ring (128B swizzle, K-major), mbarrier complete_tx signalling;
-//   warp 1   MMA issuer: KP/8 tcgen05.mma.kind::tf32 (M=128, N=256, K=8) per item tile straight from the fp32
-//            tiles (the tensor core reads the upper 19 bits), accumulators in TMEM, two 256-column stages;
+//   warp 0   TMA producer: U tile(s) (128 x KP fp32) once per user tile, V tiles (128 x KP fp32) through a
+//            shared-memory slot ring (128B swizzle, K-major), mbarrier complete_tx signalling;
+//   warp 1   MMA issuer: tcgen05.mma.kind::tf32 (M=128, N=128, K=8) straight from the fp32 tiles (the tensor core
+//            reads the upper 19 bits of each operand), accumulators in TMEM, four 128-column stages;
 //   warp 2   TMEM allocation (512 columns);
 //   warps 4-7 epilogue: tcgen05.ld 32 columns at a time, 3-input max over groups of 8 scores and ONE compare
 //            against the row threshold per group (the common case costs ~0.6 instructions per score); rare hits
 //            are checked against the row's seen-item cursor (CSR, ascending) and appended to a per-row candidate
 //            buffer in shared memory.
 //
-// Exactness.  The tf32 scores s~ satisfy |s~ - s| <= eps_u = ERR * |u|_2 * max_i |v_i|_2 (operand truncation to
-// 10 mantissa bits; fp32 accumulation error is two orders smaller).  Each row tracks the n best approximate
-// scores of UNSEEN items; a score is kept iff it exceeds (n-th best so far) - 2 eps_u.  Every item of the exact
-// top-n therefore is among the candidates; they are re-scored in float64 (same summation order as the exact
-// kernel) and ranked by (score desc, index asc).  Rows whose candidate buffer overflows are listed for the exact
-// CUDA-core kernel.  The result is identical to rl_score_topn_dev(mode = RL_SCORE_EXACT).
+// Precision (TERMS).  A single tf32 product is only good to 2^-9 |u||v|: with 10^5 items the top scores of ALS
+// factors are ~3e-5 apart, so the candidate window would hold hundreds of items.  TERMS = 3 is the split-operand
+// scheme: x = x_hi + x_lo with x_hi = the 19 upper bits (what the tensor core reads anyway) and x_lo = x - x_hi
+// (exact in fp32, precomputed once per call), and  u.v ~ u_hi.v_hi + u_lo.v_hi + u_hi.v_lo  accumulated in the
+// same TMEM tile (3 x KP/8 MMAs per item tile).  The dropped u_lo.v_lo term and the re-truncation of the lo parts
+// are each below 2^-20 |u||v|.
+//
+// Exactness.  The approximate scores s~ satisfy |s~ - s| <= eps_u = ERR * |u|_2 * max_i |v_i|_2 (ERR covers the
+// operand terms above plus fp32 accumulation).  Each row tracks the n best approximate scores of UNSEEN items; a
+// score is kept iff it exceeds (n-th best so far) - 2 eps_u.  Every item of the exact top-n therefore is among
+// the candidates; they are re-scored in float64 (same summation order as the exact kernel) and ranked by (score
+// desc, index asc).  Rows whose candidate buffer overflows are listed for the exact CUDA-core kernel.  The
+// result is identical to rl_score_topn_dev(mode = RL_SCORE_EXACT).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -30,26 +37,32 @@ namespace rl {
 namespace {
 
 constexpr int TC_BM = 128;      // users per tile (TMEM lanes)
-constexpr int TC_BN = 256;      // items per tile (TMEM columns per accumulator stage)
-constexpr int TC_STAGES = 2;    // shared-memory stages of the V ring
+constexpr int TC_BN = 128;      // items per tile (TMEM columns per accumulator stage)
+constexpr int TC_ACC = 4;       // TMEM accumulator stages (4 x 128 columns = all of TMEM)
+constexpr int TC_SLOTS = 3;     // shared-memory slots of the V ring
 constexpr int TC_THREADS = 256;
 constexpr int TC_CAND = 40;     // candidate slots per row
 constexpr int TC_NTOP = 16;     // largest n served by this path
-constexpr float TC_ERR = 2.5e-3f;  // > 2^-9: bound on |tf32 dot - exact dot| / (|u| |v|)
+// bounds on |tensor-core dot - exact dot| / (|u| |v|), checked by tests/test_gpu_parity.py::test_tensor_core_raw_scores
+constexpr float TC_ERR1 = 2.5e-3f;   // one tf32 product: 2^-9 operand truncation (+ accumulation)
+constexpr float TC_ERR3 = 1.2e-5f;   // split operands: 3 * 2^-20 operand terms + fp32 accumulation over 3*KP products
 
-template <int KP>
+template <int KP, int TERMS>
 struct TcSmem {
   static constexpr int NKH = KP / 32;                          // 128-byte K sub-tiles
-  static constexpr uint32_t A_BYTES = TC_BM * KP * 4;
-  static constexpr uint32_t B_BYTES = TC_BN * KP * 4;
+  static constexpr int NA = TERMS == 3 ? 2 : 1;                // U tile, U_lo tile
+  static constexpr int SPT = TERMS == 3 ? 2 : 1;               // ring slots per item tile (V, V_lo)
+  static constexpr uint32_t A_BYTES = TC_BM * KP * 4;          // one U tile
+  static constexpr uint32_t B_BYTES = TC_BN * KP * 4;          // one ring slot
   static constexpr uint32_t off_a = 0;
-  static constexpr uint32_t off_b = off_a + A_BYTES;
-  static constexpr uint32_t off_cs = off_b + TC_STAGES * B_BYTES;   // float [TC_CAND][128]
+  static constexpr uint32_t off_b = off_a + NA * A_BYTES;
+  static constexpr uint32_t off_cs = off_b + TC_SLOTS * B_BYTES;    // float [TC_CAND][128]
   static constexpr uint32_t off_ci = off_cs + TC_CAND * TC_BM * 4;  // int   [TC_CAND][128]
   static constexpr uint32_t off_top = off_ci + TC_CAND * TC_BM * 4; // float [TC_NTOP][128]
-  static constexpr uint32_t off_state = off_top + TC_NTOP * TC_BM * 4;  // per-row cursors / counters, 8 x [128] words
+  static constexpr uint32_t off_state = off_top + TC_NTOP * TC_BM * 4;  // per-row cursors / counters, [field][128]
   static constexpr uint32_t off_bar = off_state + 10 * TC_BM * 4;
-  static constexpr uint32_t total = off_bar + 128 + 1024;           // + alignment slack
+  static constexpr uint32_t total = off_bar + 256 + 1024;           // + alignment slack
+  static_assert(total <= 227 * 1024, "tensor-core scoring kernel exceeds shared memory");
 };
 
 struct TcArgs {
@@ -63,6 +76,7 @@ struct TcArgs {
   int32_t* idx_out;
   double* score_out;
   const float* vmax;        // max_i |v_i|_2
+  float err;                // relative error bound of the approximate scores (TC_ERR1 / TC_ERR3)
   int32_t* overflow_rows;   // rows that need the exact kernel
   unsigned int* overflow_count;
   float* dump;              // debug: raw tensor-core scores, (n_users_padded x dump_ld)
@@ -149,7 +163,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
          (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
 }
 
-// instruction descriptor: D fp32, A/B tf32, both K-major, N = 256, M = 128
+// instruction descriptor: D fp32, A/B tf32, both K-major, N = TC_BN, M = 128
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(TC_BN >> 3) << 17) |
                               (static_cast<uint32_t>(TC_BM >> 4) << 24);
 
@@ -221,10 +235,11 @@ __device__ __noinline__ float row_hit(float s, int col, int row, float tau, RowM
   return tau;
 }
 
-template <int KP, bool DUMP>
+template <int KP, int TERMS, bool DUMP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_v, const TcArgs a) {
-  using S = TcSmem<KP>;
+score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_ulo,
+                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_vlo, const TcArgs a) {
+  using S = TcSmem<KP, TERMS>;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // 128B-swizzled tiles need 1024-byte alignment
@@ -239,20 +254,21 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_con
     rm.end_lo = st + 5 * TC_BM; rm.end_hi = st + 6 * TC_BM; rm.delta = reinterpret_cast<float*>(st + 7 * TC_BM);
     rm.flags = st + 8 * TC_BM;
   }
-  float* cs = rm.cs;
   int* ci = rm.ci;
   float* top = rm.top;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::off_bar);
-  // barrier slots: 0,1 full_b  2,3 empty_b  4 a_full  5 a_empty  6,7 tmem_full  8,9 tmem_empty  ; 10: tmem base
+  // barrier slots: [0,3) slot full  [3,6) slot empty  6 a_full  7 a_empty  [8,12) tmem_full  [12,16) tmem_empty ; 16: tmem base
   const uint32_t bar0 = base + S::off_bar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 10);
+  constexpr int B_FULL = 0, B_EMPTY = TC_SLOTS, A_FULL = 2 * TC_SLOTS, A_EMPTY = A_FULL + 1, T_FULL = A_FULL + 2, T_EMPTY = T_FULL + TC_ACC;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + T_EMPTY + TC_ACC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(0 + i), 1); mbar_init(BAR(2 + i), 1); mbar_init(BAR(6 + i), 1); mbar_init(BAR(8 + i), 4); }
-    mbar_init(BAR(4), 1);
-    mbar_init(BAR(5), 1);
+    for (int i = 0; i < TC_SLOTS; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+    for (int i = 0; i < TC_ACC; ++i) { mbar_init(BAR(T_FULL + i), 1); mbar_init(BAR(T_EMPTY + i), 4); }
+    mbar_init(BAR(A_FULL), 1);
+    mbar_init(BAR(A_EMPTY), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -267,47 +283,62 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_con
   if (warp == 0) {
     // =========================================== TMA producer ==============================================
     if (lane == 0) {
-      uint32_t it_global = 0, ut_local = 0;
+      uint32_t slot_global = 0, ut_local = 0;
       for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x, ++ut_local) {
-        mbar_wait(BAR(5), (ut_local & 1) ^ 1);  // A tile free (first pass succeeds immediately)
-        mbar_expect_tx(BAR(4), S::A_BYTES);
+        mbar_wait(BAR(A_EMPTY), (ut_local & 1) ^ 1);  // U tile(s) free (first pass succeeds immediately)
+        mbar_expect_tx(BAR(A_FULL), S::NA * S::A_BYTES);
 #pragma unroll
-        for (int kh = 0; kh < S::NKH; ++kh)
-          tma_load_2d(base + S::off_a + kh * (TC_BM * 128), &map_u, BAR(4), kh * 32, ut * TC_BM);
-        for (int it = 0; it < a.n_item_tiles; ++it, ++it_global) {
-          const uint32_t stage = it_global & 1, ph = (it_global >> 1) & 1;
-          mbar_wait(BAR(2 + stage), ph ^ 1);
-          mbar_expect_tx(BAR(0 + stage), S::B_BYTES);
+        for (int kh = 0; kh < S::NKH; ++kh) {
+          tma_load_2d(base + S::off_a + kh * (TC_BM * 128), &map_u, BAR(A_FULL), kh * 32, ut * TC_BM);
+          if (TERMS == 3) tma_load_2d(base + S::off_a + S::A_BYTES + kh * (TC_BM * 128), &map_ulo, BAR(A_FULL), kh * 32, ut * TC_BM);
+        }
+        for (int it = 0; it < a.n_item_tiles; ++it) {
 #pragma unroll
-          for (int kh = 0; kh < S::NKH; ++kh)
-            tma_load_2d(base + S::off_b + stage * S::B_BYTES + kh * (TC_BN * 128), &map_v, BAR(0 + stage), kh * 32, it * TC_BN);
+          for (int part = 0; part < S::SPT; ++part, ++slot_global) {
+            const uint32_t slot = slot_global % TC_SLOTS, ph = (slot_global / TC_SLOTS) & 1;
+            mbar_wait(BAR(B_EMPTY + slot), ph ^ 1);
+            mbar_expect_tx(BAR(B_FULL + slot), S::B_BYTES);
+#pragma unroll
+            for (int kh = 0; kh < S::NKH; ++kh)
+              tma_load_2d(base + S::off_b + slot * S::B_BYTES + kh * (TC_BN * 128), part == 0 ? &map_v : &map_vlo,
+                          BAR(B_FULL + slot), kh * 32, it * TC_BN);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // =========================================== MMA issuer ================================================
     if (lane == 0) {
-      uint32_t it_global = 0, ut_local = 0;
+      uint32_t slot_global = 0, it_global = 0, ut_local = 0;
       for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x, ++ut_local) {
-        mbar_wait(BAR(4), ut_local & 1);
+        mbar_wait(BAR(A_FULL), ut_local & 1);
         for (int it = 0; it < a.n_item_tiles; ++it, ++it_global) {
-          const uint32_t stage = it_global & 1, ph = (it_global >> 1) & 1;
-          mbar_wait(BAR(0 + stage), ph);        // V tile landed
-          mbar_wait(BAR(8 + stage), ph ^ 1);    // accumulator stage drained by the epilogue
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + stage * TC_BN;
+          const uint32_t acc = it_global % TC_ACC, aph = (it_global / TC_ACC) & 1;
+          const uint32_t d_tmem = tmem_base + acc * TC_BN;
+          mbar_wait(BAR(T_EMPTY + acc), aph ^ 1);    // accumulator stage drained by the epilogue
 #pragma unroll
-          for (int kk = 0; kk < KP / 8; ++kk) {
-            const uint32_t koff = (kk >> 2) * 128u * 1u, kin = (kk & 3) * 32u;
-            const uint64_t ad = make_desc(base + S::off_a + (kk >> 2) * (TC_BM * 128) + kin);
-            const uint64_t bd = make_desc(base + S::off_b + stage * S::B_BYTES + (kk >> 2) * (TC_BN * 128) + kin);
-            (void)koff;
-            tc_mma_tf32(d_tmem, ad, bd, TC_IDESC, kk > 0 ? 1u : 0u);
+          for (int part = 0; part < S::SPT; ++part, ++slot_global) {
+            const uint32_t slot = slot_global % TC_SLOTS, ph = (slot_global / TC_SLOTS) & 1;
+            mbar_wait(BAR(B_FULL + slot), ph);       // V (part 0) or V_lo (part 1) tile landed
+            tc_fence_after();
+            const uint32_t b_base = base + S::off_b + slot * S::B_BYTES;
+            // part 0: U.V (+ U_lo.V when TERMS == 3)      part 1: U.V_lo
+            const int n_a = (part == 0) ? S::NA : 1;
+            for (int ta = 0; ta < n_a; ++ta) {
+              const uint32_t a_base = base + S::off_a + ta * S::A_BYTES;
+#pragma unroll
+              for (int kk = 0; kk < KP / 8; ++kk) {
+                const uint32_t kin = (kk & 3) * 32u;
+                const uint64_t ad = make_desc(a_base + (kk >> 2) * (TC_BM * 128) + kin);
+                const uint64_t bd = make_desc(b_base + (kk >> 2) * (TC_BN * 128) + kin);
+                tc_mma_tf32(d_tmem, ad, bd, TC_IDESC, (part | ta | kk) != 0 ? 1u : 0u);
+              }
+            }
+            tc_commit(BAR(B_EMPTY + slot));          // slot reusable once these MMAs retire
           }
-          tc_commit(BAR(2 + stage));   // V stage reusable once these MMAs retire
-          tc_commit(BAR(6 + stage));   // accumulator ready for the epilogue
+          tc_commit(BAR(T_FULL + acc));              // accumulator ready for the epilogue
         }
-        tc_commit(BAR(5));             // U tile reusable
+        tc_commit(BAR(A_EMPTY));                     // U tile(s) reusable
       }
     }
   } else if (warp >= 4) {
@@ -334,7 +365,7 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_con
             const float4 x = up[c];
             nn += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
           }
-          delta = 2.0f * TC_ERR * sqrtf(nn) * vmax + 1e-30f;
+          delta = 2.0f * a.err * sqrtf(nn) * vmax + 1e-30f;
           if (a.seen_indptr) {
             cur = a.seen_indptr[user];
             end = a.seen_indptr[user + 1];
@@ -347,10 +378,10 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_con
         rm.end_lo[row] = static_cast<int>(end & 0xffffffff); rm.end_hi[row] = static_cast<int>(end >> 32);
       }
       for (int it = 0; it < a.n_item_tiles; ++it, ++it_global) {
-        const uint32_t stage = it_global & 1, ph = (it_global >> 1) & 1;
-        mbar_wait(BAR(6 + stage), ph);
+        const uint32_t acc = it_global % TC_ACC, aph = (it_global / TC_ACC) & 1;
+        mbar_wait(BAR(T_FULL + acc), aph);
         tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + stage * TC_BN;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * TC_BN;
 #pragma unroll 1
         for (int g = 0; g < TC_BN / 32; ++g) {
           float s[32];
@@ -376,7 +407,7 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_con
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(8 + stage));
+        if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
       }
       if (DUMP) continue;
       // ---- exact float64 re-scoring of the candidates, ranking by (score desc, index asc) ------------------
@@ -390,17 +421,17 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_con
           const float* up = a.uf + user * KP;
           for (int c = 0; c < cnt; ++c) {
             const float* vp = a.vf + static_cast<int64_t>(ci[c * TC_BM + row]) * KP;
-            double acc = 0.0;
+            double accd = 0.0;
 #pragma unroll 4
             for (int k4 = 0; k4 < KP / 4; ++k4) {
               const float4 x = *reinterpret_cast<const float4*>(up + 4 * k4);
               const float4 y = *reinterpret_cast<const float4*>(vp + 4 * k4);
-              acc = fma(static_cast<double>(x.x), static_cast<double>(y.x), acc);
-              acc = fma(static_cast<double>(x.y), static_cast<double>(y.y), acc);
-              acc = fma(static_cast<double>(x.z), static_cast<double>(y.z), acc);
-              acc = fma(static_cast<double>(x.w), static_cast<double>(y.w), acc);
+              accd = fma(static_cast<double>(x.x), static_cast<double>(y.x), accd);
+              accd = fma(static_cast<double>(x.y), static_cast<double>(y.y), accd);
+              accd = fma(static_cast<double>(x.z), static_cast<double>(y.z), accd);
+              accd = fma(static_cast<double>(x.w), static_cast<double>(y.w), accd);
             }
-            ex[c] = acc;
+            ex[c] = accd;
           }
           for (int p = 0; p < a.n; ++p) {
             int best = -1;
@@ -426,6 +457,19 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_con
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// x_lo = x - (x with the 13 low mantissa bits cleared): the part of x the tf32 datapath does not see
+__global__ void __launch_bounds__(256) split_lo_kernel(const float* __restrict__ x, int64_t n4, float* __restrict__ lo) {
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < n4; p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[p];
+    float4 r;
+    r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    reinterpret_cast<float4*>(lo)[p] = r;
   }
 }
 
@@ -474,15 +518,23 @@ int make_map(rl_context* h, CUtensorMap* map, const float* ptr, int64_t rows, in
   return RL_OK;
 }
 
-template <int KP, bool DUMP>
-int launch_tc(rl_context* h, const CUtensorMap& mu, const CUtensorMap& mv, const TcArgs& a) {
-  auto kern = score_topn_tc_kernel<KP, DUMP>;
-  const size_t smem = TcSmem<KP>::total;
+template <int KP, int TERMS, bool DUMP>
+int launch_tc(rl_context* h, const CUtensorMap& mu, const CUtensorMap& mulo, const CUtensorMap& mv, const CUtensorMap& mvlo,
+              const TcArgs& a) {
+  auto kern = score_topn_tc_kernel<KP, TERMS, DUMP>;
+  const size_t smem = TcSmem<KP, TERMS>::total;
   RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int grid = a.n_user_tiles < h->sm_count ? a.n_user_tiles : h->sm_count;
-  kern<<<grid, TC_THREADS, smem, h->stream>>>(mu, mv, a);
+  kern<<<grid, TC_THREADS, smem, h->stream>>>(mu, mulo, mv, mvlo, a);
   RL_LAUNCH_CHECK(h, "score_topn_tc_kernel");
   return RL_OK;
+}
+
+template <int KP>
+int launch_tc_k(rl_context* h, int terms, bool dump, const CUtensorMap& mu, const CUtensorMap& mulo, const CUtensorMap& mv,
+                const CUtensorMap& mvlo, const TcArgs& a) {
+  if (terms == 3) return dump ? launch_tc<KP, 3, true>(h, mu, mulo, mv, mvlo, a) : launch_tc<KP, 3, false>(h, mu, mulo, mv, mvlo, a);
+  return dump ? launch_tc<KP, 1, true>(h, mu, mulo, mv, mvlo, a) : launch_tc<KP, 1, false>(h, mu, mulo, mv, mvlo, a);
 }
 
 }  // namespace
@@ -491,25 +543,44 @@ bool score_tc_supported(int kp, int n, int64_t n_users, int64_t n_items, const f
   return (kp == 32 || kp == 64) && n <= TC_NTOP && n_items >= 1024 && n_users >= 1 && !ubias && !ibias && gbias == 0.0;
 }
 
-// tensor-core candidate pass + in-kernel exact re-scoring; overflow rows are finished by the exact kernel
-int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int64_t dump_ld) {
-  CUtensorMap mu, mv;
-  int rc = make_map(h, &mu, sa.uf, sa.n_users, kp, TC_BM);
-  if (rc != RL_OK) return rc;
-  rc = make_map(h, &mv, sa.vf, sa.n_items, kp, TC_BN);
-  if (rc != RL_OK) return rc;
-  // scratch: vmax (4 B) | overflow count (4 B) | overflow rows (n_users x 4 B)
+// tensor-core candidate pass + in-kernel exact re-scoring; overflow rows are finished by the exact kernel.
+// terms: 1 = single tf32 product, 3 = split operands (default).
+int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int64_t dump_ld, int terms) {
+  if (terms != 1 && terms != 3) return fail(h, RL_ERR_INVALID, "score_tc: terms must be 1 or 3");
+  // scratch: vmax (4 B) | overflow count (4 B) | overflow rows (n_users x 4 B) | U_lo | V_lo
+  const size_t rows_bytes = (sizeof(int32_t) * static_cast<size_t>(sa.n_users) + 255) & ~size_t(255);
+  const size_t ulo_bytes = terms == 3 ? sizeof(float) * static_cast<size_t>(sa.n_users) * kp : 0;
+  const size_t vlo_bytes = terms == 3 ? sizeof(float) * static_cast<size_t>(sa.n_items) * kp : 0;
   void* sc = nullptr;
-  rc = scratch(h, 256 + sizeof(int32_t) * static_cast<size_t>(sa.n_users), &sc);
+  int rc = scratch(h, 256 + rows_bytes + ulo_bytes + vlo_bytes, &sc);
   if (rc != RL_OK) return rc;
-  float* vmax = static_cast<float*>(sc);
-  unsigned int* ocount = reinterpret_cast<unsigned int*>(static_cast<char*>(sc) + 4);
-  int32_t* orows = reinterpret_cast<int32_t*>(static_cast<char*>(sc) + 256);
+  char* scb = static_cast<char*>(sc);
+  float* vmax = reinterpret_cast<float*>(scb);
+  unsigned int* ocount = reinterpret_cast<unsigned int*>(scb + 4);
+  int32_t* orows = reinterpret_cast<int32_t*>(scb + 256);
+  float* ulo = reinterpret_cast<float*>(scb + 256 + rows_bytes);
+  float* vlo = reinterpret_cast<float*>(scb + 256 + rows_bytes + ulo_bytes);
   RL_CUDA(h, cudaMemsetAsync(sc, 0, 256, h->stream));
+  if (terms == 3) {
+    const int64_t nu4 = sa.n_users * kp / 4, nv4 = sa.n_items * kp / 4;
+    const int64_t cap = 8 * static_cast<int64_t>(h->sm_count);
+    int64_t g = (nu4 + 255) / 256;
+    split_lo_kernel<<<static_cast<unsigned>(g < cap ? g : cap), 256, 0, h->stream>>>(sa.uf, nu4, ulo);
+    RL_LAUNCH_CHECK(h, "split_lo_kernel");
+    g = (nv4 + 255) / 256;
+    split_lo_kernel<<<static_cast<unsigned>(g < cap ? g : cap), 256, 0, h->stream>>>(sa.vf, nv4, vlo);
+    RL_LAUNCH_CHECK(h, "split_lo_kernel");
+  }
+  CUtensorMap mu, mulo, mv, mvlo;
+  if ((rc = make_map(h, &mu, sa.uf, sa.n_users, kp, TC_BM)) != RL_OK) return rc;
+  if ((rc = make_map(h, &mv, sa.vf, sa.n_items, kp, TC_BN)) != RL_OK) return rc;
+  if ((rc = make_map(h, &mulo, terms == 3 ? ulo : sa.uf, sa.n_users, kp, TC_BM)) != RL_OK) return rc;
+  if ((rc = make_map(h, &mvlo, terms == 3 ? vlo : sa.vf, sa.n_items, kp, TC_BN)) != RL_OK) return rc;
   TcArgs a{};
   a.uf = sa.uf; a.vf = sa.vf; a.n_users = sa.n_users; a.n_items = static_cast<int>(sa.n_items);
   a.seen_indptr = sa.seen_indptr; a.seen_indices = sa.seen_indices; a.n = sa.n; a.idx_out = sa.idx_out; a.score_out = sa.score_out;
-  a.vmax = vmax; a.overflow_rows = orows; a.overflow_count = ocount; a.dump = dump; a.dump_ld = dump_ld;
+  a.vmax = vmax; a.err = terms == 3 ? TC_ERR3 : TC_ERR1;
+  a.overflow_rows = orows; a.overflow_count = ocount; a.dump = dump; a.dump_ld = dump_ld;
   a.n_user_tiles = static_cast<int>((sa.n_users + TC_BM - 1) / TC_BM);
   a.n_item_tiles = static_cast<int>((sa.n_items + TC_BN - 1) / TC_BN);
   if (!dump) {
@@ -518,8 +589,8 @@ int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int
     max_row_norm_kernel<<<static_cast<unsigned>(g), 256, 0, h->stream>>>(sa.vf, sa.n_items, kp, vmax);
     RL_LAUNCH_CHECK(h, "max_row_norm_kernel");
   }
-  if (kp == 64) rc = dump ? launch_tc<64, true>(h, mu, mv, a) : launch_tc<64, false>(h, mu, mv, a);
-  else if (kp == 32) rc = dump ? launch_tc<32, true>(h, mu, mv, a) : launch_tc<32, false>(h, mu, mv, a);
+  if (kp == 64) rc = launch_tc_k<64>(h, terms, dump != nullptr, mu, mulo, mv, mvlo, a);
+  else if (kp == 32) rc = launch_tc_k<32>(h, terms, dump != nullptr, mu, mulo, mv, mvlo, a);
   else return fail(h, RL_ERR_INVALID, "score_tc: padded k %d not supported by the tensor-core path", kp);
   if (rc != RL_OK || dump) return rc;
   // rows whose candidate buffer overflowed: exact kernel on the list (needs the count on the host)
