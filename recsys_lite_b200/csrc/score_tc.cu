@@ -4,15 +4,19 @@
 // ever writing the n_users x n_items score matrix.  One persistent CTA per SM owns 128 users at a time (one TMEM
 // lane = one user) and sweeps all items in tiles of 128:
 //
-//   warp 0   TMA producer: U tile(s) (128 x KP fp32) once per user tile, V tiles (128 x KP fp32) through a
-//            shared-memory slot ring (128B swizzle, K-major), mbarrier complete_tx signalling;
-//   warp 1   MMA issuer: tcgen05.mma.kind::tf32 (M=128, N=128, K=8) straight from the fp32 tiles (the tensor core
-//            reads the upper 19 bits of each operand), accumulators in TMEM, four 128-column stages;
-//   warp 2   TMEM allocation (512 columns);
-//   warps 4-7 epilogue: tcgen05.ld 32 columns at a time, 3-input max over groups of 8 scores and ONE compare
-//            against the row threshold per group (the common case costs ~0.6 instructions per score); rare hits
-//            are checked against the row's seen-item cursor (CSR, ascending) and appended to a per-row candidate
-//            buffer in shared memory.
+//   warp 0     TMA producer: V (and V_lo) tiles (128 x KP fp32) through a shared-memory slot ring (128B swizzle,
+//              K-major), mbarrier complete_tx signalling;
+//   warp 1     MMA issuer: tcgen05.mma.kind::tf32 (M=128, N=128, K=8), A operand (the user tile) from TMEM, B from the
+//              fp32 tiles in shared memory (the tensor core reads the upper 19 bits), three 128-column accumulator
+//              stages in TMEM;
+//   warp 2     TMEM allocation (512 columns: 128 for the user tile hi|lo, 3 x 128 accumulators);
+//   warps 4-7  user-tile loaders: each thread reads its user's factor row from global memory and writes it (and its
+//              low part) into its TMEM lane with tcgen05.st -- no shared-memory copy of U, no U_lo array;
+//   warps 8-15 two epilogue sets that take alternate item tiles: tcgen05.ld 32 columns at a time, 3-input max over
+//              groups of 8 scores and ONE compare against the row threshold per group (~0.6 instructions per score);
+//              scores above the threshold are pushed to a small per-row FIFO and drained at the end of the tile by
+//              all 32 rows of the warp in parallel: seen-item cursor check (CSR, ascending), top-n tracker, candidate
+//              buffer in shared memory.
 //
 // Precision (TERMS).  A single tf32 product is only good to 2^-9 |u||v|: with 10^5 items the top scores of ALS
 // factors are ~3e-5 apart, so the candidate window would hold hundreds of items.  TERMS = 3 is the split-operand
@@ -28,6 +32,7 @@
 // desc, index asc).  Rows whose candidate buffer overflows are listed for the exact CUDA-core kernel.  The
 // result is identical to rl_score_topn_dev(mode = RL_SCORE_EXACT).
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "score_exact.cuh"
@@ -38,29 +43,31 @@ namespace {
 
 constexpr int TC_BM = 128;      // users per tile (TMEM lanes)
 constexpr int TC_BN = 128;      // items per tile (TMEM columns per accumulator stage)
-constexpr int TC_ACC = 4;       // TMEM accumulator stages (4 x 128 columns = all of TMEM)
-constexpr int TC_SLOTS = 3;     // shared-memory slots of the V ring
-constexpr int TC_THREADS = 256;
-constexpr int TC_CAND = 40;     // candidate slots per row
+constexpr int TC_ACC = 3;       // TMEM accumulator stages (columns 128..511; columns 0..127 hold the user tile hi|lo)
+constexpr int TC_SLOTS = 4;     // shared-memory slots of the V ring
+constexpr int TC_SETS = 2;      // epilogue warp sets (each 4 warps = 128 rows), alternating item tiles
+constexpr int TC_THREADS = 32 * (8 + 4 * TC_SETS);
+constexpr int TC_CAND = 32;     // candidate / raw-hit slots per row and set
 constexpr int TC_NTOP = 16;     // largest n served by this path
+constexpr int TC_TRIG = 20;     // a row asks for a batch pass once it holds this many entries
 // bounds on |tensor-core dot - exact dot| / (|u| |v|), checked by tests/test_gpu_parity.py::test_tensor_core_raw_scores
 constexpr float TC_ERR1 = 2.5e-3f;   // one tf32 product: 2^-9 operand truncation (+ accumulation)
-constexpr float TC_ERR3 = 1.2e-5f;   // split operands: 3 * 2^-20 operand terms + fp32 accumulation over 3*KP products
+constexpr float TC_ERR3 = 6.0e-6f;   // split operands: 3 * 2^-20 = 2.9e-6 operand terms + fp32 accumulation; measured <= 1.8e-6
 
 template <int KP, int TERMS>
 struct TcSmem {
   static constexpr int NKH = KP / 32;                          // 128-byte K sub-tiles
-  static constexpr int NA = TERMS == 3 ? 2 : 1;                // U tile, U_lo tile
   static constexpr int SPT = TERMS == 3 ? 2 : 1;               // ring slots per item tile (V, V_lo)
-  static constexpr uint32_t A_BYTES = TC_BM * KP * 4;          // one U tile
   static constexpr uint32_t B_BYTES = TC_BN * KP * 4;          // one ring slot
-  static constexpr uint32_t off_a = 0;
-  static constexpr uint32_t off_b = off_a + NA * A_BYTES;
-  static constexpr uint32_t off_cs = off_b + TC_SLOTS * B_BYTES;    // float [TC_CAND][128]
-  static constexpr uint32_t off_ci = off_cs + TC_CAND * TC_BM * 4;  // int   [TC_CAND][128]
-  static constexpr uint32_t off_top = off_ci + TC_CAND * TC_BM * 4; // float [TC_NTOP][128]
-  static constexpr uint32_t off_state = off_top + TC_NTOP * TC_BM * 4;  // per-row cursors / counters, [field][128]
-  static constexpr uint32_t off_bar = off_state + 10 * TC_BM * 4;
+  static constexpr uint32_t off_b = 0;
+  // per epilogue set: cs [CAND][128] f32 | ci [CAND][128] i32 | top [NTOP][128] f32 | state 12 x [128]
+  static constexpr uint32_t SET_CS = 0;
+  static constexpr uint32_t SET_CI = SET_CS + TC_CAND * TC_BM * 4;
+  static constexpr uint32_t SET_TOP = SET_CI + TC_CAND * TC_BM * 4;
+  static constexpr uint32_t SET_STATE = SET_TOP + TC_NTOP * TC_BM * 4;
+  static constexpr uint32_t SET_BYTES = SET_STATE + 12 * TC_BM * 4;
+  static constexpr uint32_t off_sets = off_b + TC_SLOTS * B_BYTES;
+  static constexpr uint32_t off_bar = off_sets + TC_SETS * SET_BYTES;
   static constexpr uint32_t total = off_bar + 256 + 1024;           // + alignment slack
   static_assert(total <= 227 * 1024, "tensor-core scoring kernel exceeds shared memory");
 };
@@ -82,6 +89,7 @@ struct TcArgs {
   float* dump;              // debug: raw tensor-core scores, (n_users_padded x dump_ld)
   int64_t dump_ld;
   int n_user_tiles, n_item_tiles;
+  long long* dbg;           // optional (block 0 only): cycle counters per role, see tools/run_kernel.py
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -115,6 +123,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -151,6 +164,32 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -169,10 +208,10 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<
 
 // ---- per-row selection state: thread-private slices of shared memory ([field][row], conflict free) ------------
 struct RowMem {
-  float* cs;        // [TC_CAND][128] candidate approximate scores
-  int* ci;          // [TC_CAND][128] candidate item ids
+  float* cs;        // [TC_CAND][128] approximate scores: entries [0, keep) are checked candidates, [keep, cnt) raw hits
+  int* ci;          // [TC_CAND][128] their item ids (ascending inside each of the two runs)
   float* top;       // [TC_NTOP][128] n best approximate scores of unseen items, descending
-  int* cnt;         // [128] candidates stored
+  int* keep;        // [128]
   int* nxt;         // [128] next seen item id >= current column (INT_MAX: none)
   int* nxt2;        // [128] the one after (prefetched)
   int* cur_lo;      // [128] low / high words of the cursor into seen_indices
@@ -181,93 +220,104 @@ struct RowMem {
   int* end_hi;
   float* delta;     // [128] 2 * eps_u
   int* flags;       // [128] bit 0: candidate buffer overflowed
+  float* tau_pub;   // [128] this set's threshold, readable by the other set
 };
 
-// one score above the row threshold: returns the (possibly raised) threshold
-__device__ __noinline__ float row_hit(float s, int col, int row, float tau, RowMem m, const int32_t* __restrict__ seen_indices,
-                                      int n_items, int n) {
-  int nxt = m.nxt[row];
-  if (nxt < col) {  // move the seen cursor up to this column
-    int64_t cur = (static_cast<int64_t>(m.cur_hi[row]) << 32) | static_cast<uint32_t>(m.cur_lo[row]);
-    const int64_t end = (static_cast<int64_t>(m.end_hi[row]) << 32) | static_cast<uint32_t>(m.end_lo[row]);
-    int nxt2 = m.nxt2[row];
-    while (nxt < col) {
+__device__ __forceinline__ RowMem row_mem(unsigned char* set_base, uint32_t set_cs, uint32_t set_ci, uint32_t set_top,
+                                          uint32_t set_state) {
+  RowMem m;
+  m.cs = reinterpret_cast<float*>(set_base + set_cs);
+  m.ci = reinterpret_cast<int*>(set_base + set_ci);
+  m.top = reinterpret_cast<float*>(set_base + set_top);
+  int* st = reinterpret_cast<int*>(set_base + set_state);
+  m.keep = st; m.nxt = st + TC_BM; m.nxt2 = st + 2 * TC_BM; m.cur_lo = st + 3 * TC_BM; m.cur_hi = st + 4 * TC_BM;
+  m.end_lo = st + 5 * TC_BM; m.end_hi = st + 6 * TC_BM; m.delta = reinterpret_cast<float*>(st + 7 * TC_BM);
+  m.flags = st + 8 * TC_BM; m.tau_pub = reinterpret_cast<float*>(st + 9 * TC_BM);
+  return m;
+}
+
+// Batch pass over a row's buffer: (1) the raw hits [keep, cnt) are checked against the seen-item cursor (columns
+// ascend) and folded into the top-n tracker with a branch-free sorted insert, (2) the threshold is raised (also to
+// the other set's published threshold: any set's n-th best is a lower bound of the global one), (3) entries at or
+// below the threshold are dropped.  Returns the new threshold; the new entry count is left in m.keep[row].
+__device__ __noinline__ float row_batch(int cnt, int row, float tau, RowMem m, const float* __restrict__ other_tau,
+                                        const int32_t* __restrict__ seen_indices, int n_items, int n) {
+  int nxt = m.nxt[row], nxt2 = m.nxt2[row];
+  int64_t cur = (static_cast<int64_t>(m.cur_hi[row]) << 32) | static_cast<uint32_t>(m.cur_lo[row]);
+  const int64_t end = (static_cast<int64_t>(m.end_hi[row]) << 32) | static_cast<uint32_t>(m.end_lo[row]);
+  const int keep = m.keep[row];
+  float t[TC_NTOP];
+#pragma unroll
+  for (int i = 0; i < TC_NTOP; ++i) t[i] = m.top[i * TC_BM + row];
+  for (int f = keep; f < cnt; ++f) {
+    float sc = m.cs[f * TC_BM + row];
+    const int col = m.ci[f * TC_BM + row];
+    while (nxt < col) {  // move the seen cursor up to this column
       nxt = nxt2;
       ++cur;
       nxt2 = (cur + 1 < end) ? seen_indices[cur + 1] : INT_MAX;
     }
-    m.nxt[row] = nxt;
-    m.nxt2[row] = nxt2;
-    m.cur_lo[row] = static_cast<int>(cur & 0xffffffff);
-    m.cur_hi[row] = static_cast<int>(cur >> 32);
-  }
-  if (col == nxt || col >= n_items) return tau;
-  int cnt = m.cnt[row];
-  if (cnt == TC_CAND) {  // drop everything the current threshold has made obsolete
-    int j = 0;
-    for (int i = 0; i < TC_CAND; ++i) {
-      const float v = m.cs[i * TC_BM + row];
-      if (v > tau) {
-        m.cs[j * TC_BM + row] = v;
-        m.ci[j * TC_BM + row] = m.ci[i * TC_BM + row];
-        ++j;
-      }
+    if (col == nxt || col >= n_items) {
+      sc = -CUDART_INF_F;
+      m.cs[f * TC_BM + row] = sc;
     }
-    cnt = j;
+    // descending sorted insert without branches: new[i] = max(old[i], min(old[i-1], sc))
+#pragma unroll
+    for (int i = TC_NTOP - 1; i > 0; --i) t[i] = fmaxf(t[i], fminf(t[i - 1], sc));
+    t[0] = fmaxf(t[0], sc);
   }
-  if (cnt < TC_CAND) {
-    m.cs[cnt * TC_BM + row] = s;
-    m.ci[cnt * TC_BM + row] = col;
-    ++cnt;
-  } else {
+#pragma unroll
+  for (int i = 0; i < TC_NTOP; ++i) m.top[i * TC_BM + row] = t[i];
+  float tn = t[0];
+#pragma unroll
+  for (int i = 1; i < TC_NTOP; ++i)
+    if (i == n - 1) tn = t[i];
+  tau = fmaxf(tau, tn - m.delta[row]);
+  tau = fmaxf(tau, other_tau[row]);
+  m.tau_pub[row] = tau;
+  int j = 0;
+  for (int f = 0; f < cnt; ++f) {
+    const float v = m.cs[f * TC_BM + row];
+    if (v > tau) {
+      m.cs[j * TC_BM + row] = v;
+      m.ci[j * TC_BM + row] = m.ci[f * TC_BM + row];
+      ++j;
+    }
+  }
+  if (j > TC_CAND - 9) {  // the window is too crowded for this path: hand the row to the exact kernel
     m.flags[row] |= 1;
+    j = 0;
   }
-  m.cnt[row] = cnt;
-  if (s > m.top[(n - 1) * TC_BM + row]) {  // sorted insertion into the n best approximate scores
-    int i = n - 1;
-    while (i > 0 && m.top[(i - 1) * TC_BM + row] < s) {
-      m.top[i * TC_BM + row] = m.top[(i - 1) * TC_BM + row];
-      --i;
-    }
-    m.top[i * TC_BM + row] = s;
-    tau = m.top[(n - 1) * TC_BM + row] - m.delta[row];
-  }
+  m.keep[row] = j;
+  m.nxt[row] = nxt;
+  m.nxt2[row] = nxt2;
+  m.cur_lo[row] = static_cast<int>(cur & 0xffffffff);
+  m.cur_hi[row] = static_cast<int>(cur >> 32);
   return tau;
 }
 
 template <int KP, int TERMS, bool DUMP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_ulo,
-                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_vlo, const TcArgs a) {
+score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_vlo, const TcArgs a) {
   using S = TcSmem<KP, TERMS>;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // 128B-swizzled tiles need 1024-byte alignment
   unsigned char* sm = smem_raw + (base - raw);
-  RowMem rm;
-  rm.cs = reinterpret_cast<float*>(sm + S::off_cs);
-  rm.ci = reinterpret_cast<int*>(sm + S::off_ci);
-  rm.top = reinterpret_cast<float*>(sm + S::off_top);
-  {
-    int* st = reinterpret_cast<int*>(sm + S::off_state);
-    rm.cnt = st; rm.nxt = st + TC_BM; rm.nxt2 = st + 2 * TC_BM; rm.cur_lo = st + 3 * TC_BM; rm.cur_hi = st + 4 * TC_BM;
-    rm.end_lo = st + 5 * TC_BM; rm.end_hi = st + 6 * TC_BM; rm.delta = reinterpret_cast<float*>(st + 7 * TC_BM);
-    rm.flags = st + 8 * TC_BM;
-  }
-  int* ci = rm.ci;
-  float* top = rm.top;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::off_bar);
-  // barrier slots: [0,3) slot full  [3,6) slot empty  6 a_full  7 a_empty  [8,12) tmem_full  [12,16) tmem_empty ; 16: tmem base
+  // barriers: [0,S) slot full  [S,2S) slot empty  a_full  a_empty  [.., +ACC) tmem_full  [.., +ACC) tmem_empty ; then: tmem base
   const uint32_t bar0 = base + S::off_bar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   constexpr int B_FULL = 0, B_EMPTY = TC_SLOTS, A_FULL = 2 * TC_SLOTS, A_EMPTY = A_FULL + 1, T_FULL = A_FULL + 2, T_EMPTY = T_FULL + TC_ACC;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + T_EMPTY + TC_ACC);
+  constexpr uint32_t A_LO_COL = KP;          // TMEM columns [0, KP): user rows as given; [KP, 2 KP): their low parts
+  constexpr uint32_t ACC_COL0 = 128;         // accumulator stage s lives in columns [128 + 128 s, 256 + 128 s)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_SLOTS; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
     for (int i = 0; i < TC_ACC; ++i) { mbar_init(BAR(T_FULL + i), 1); mbar_init(BAR(T_EMPTY + i), 4); }
-    mbar_init(BAR(A_FULL), 1);
+    mbar_init(BAR(A_FULL), 4);
     mbar_init(BAR(A_EMPTY), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -283,20 +333,15 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_con
   if (warp == 0) {
     // =========================================== TMA producer ==============================================
     if (lane == 0) {
-      uint32_t slot_global = 0, ut_local = 0;
-      for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x, ++ut_local) {
-        mbar_wait(BAR(A_EMPTY), (ut_local & 1) ^ 1);  // U tile(s) free (first pass succeeds immediately)
-        mbar_expect_tx(BAR(A_FULL), S::NA * S::A_BYTES);
-#pragma unroll
-        for (int kh = 0; kh < S::NKH; ++kh) {
-          tma_load_2d(base + S::off_a + kh * (TC_BM * 128), &map_u, BAR(A_FULL), kh * 32, ut * TC_BM);
-          if (TERMS == 3) tma_load_2d(base + S::off_a + S::A_BYTES + kh * (TC_BM * 128), &map_ulo, BAR(A_FULL), kh * 32, ut * TC_BM);
-        }
+      uint32_t slot_global = 0;
+      long long w_empty = 0;
+      const long long t_start = clock64();
+      for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x) {
         for (int it = 0; it < a.n_item_tiles; ++it) {
 #pragma unroll
           for (int part = 0; part < S::SPT; ++part, ++slot_global) {
             const uint32_t slot = slot_global % TC_SLOTS, ph = (slot_global / TC_SLOTS) & 1;
-            mbar_wait(BAR(B_EMPTY + slot), ph ^ 1);
+            mbar_wait_t(BAR(B_EMPTY + slot), ph ^ 1, w_empty);
             mbar_expect_tx(BAR(B_FULL + slot), S::B_BYTES);
 #pragma unroll
             for (int kh = 0; kh < S::NKH; ++kh)
@@ -305,55 +350,97 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_con
           }
         }
       }
+      if (a.dbg && blockIdx.x == 0) { a.dbg[0] = clock64() - t_start; a.dbg[1] = w_empty; }
     }
   } else if (warp == 1) {
     // =========================================== MMA issuer ================================================
     if (lane == 0) {
       uint32_t slot_global = 0, it_global = 0, ut_local = 0;
+      long long w_a = 0, w_t = 0, w_b = 0;
+      const long long t_start = clock64();
       for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x, ++ut_local) {
-        mbar_wait(BAR(A_FULL), ut_local & 1);
+        mbar_wait_t(BAR(A_FULL), ut_local & 1, w_a);        // user tile written to TMEM by the loader warps
+        tc_fence_after();
         for (int it = 0; it < a.n_item_tiles; ++it, ++it_global) {
           const uint32_t acc = it_global % TC_ACC, aph = (it_global / TC_ACC) & 1;
-          const uint32_t d_tmem = tmem_base + acc * TC_BN;
-          mbar_wait(BAR(T_EMPTY + acc), aph ^ 1);    // accumulator stage drained by the epilogue
+          const uint32_t d_tmem = tmem_base + ACC_COL0 + acc * TC_BN;
+          mbar_wait_t(BAR(T_EMPTY + acc), aph ^ 1, w_t);    // accumulator stage drained by the epilogue
 #pragma unroll
           for (int part = 0; part < S::SPT; ++part, ++slot_global) {
             const uint32_t slot = slot_global % TC_SLOTS, ph = (slot_global / TC_SLOTS) & 1;
-            mbar_wait(BAR(B_FULL + slot), ph);       // V (part 0) or V_lo (part 1) tile landed
+            mbar_wait_t(BAR(B_FULL + slot), ph, w_b);       // V (part 0) or V_lo (part 1) tile landed
             tc_fence_after();
             const uint32_t b_base = base + S::off_b + slot * S::B_BYTES;
             // part 0: U.V (+ U_lo.V when TERMS == 3)      part 1: U.V_lo
-            const int n_a = (part == 0) ? S::NA : 1;
+            const int n_a = (part == 0 && TERMS == 3) ? 2 : 1;
             for (int ta = 0; ta < n_a; ++ta) {
-              const uint32_t a_base = base + S::off_a + ta * S::A_BYTES;
 #pragma unroll
               for (int kk = 0; kk < KP / 8; ++kk) {
-                const uint32_t kin = (kk & 3) * 32u;
-                const uint64_t ad = make_desc(a_base + (kk >> 2) * (TC_BM * 128) + kin);
-                const uint64_t bd = make_desc(b_base + (kk >> 2) * (TC_BN * 128) + kin);
-                tc_mma_tf32(d_tmem, ad, bd, TC_IDESC, (part | ta | kk) != 0 ? 1u : 0u);
+                const uint64_t bd = make_desc(b_base + (kk >> 2) * (TC_BN * 128) + (kk & 3) * 32u);
+                tc_mma_tf32_ts(d_tmem, tmem_base + ta * A_LO_COL + kk * 8, bd, TC_IDESC, (part | ta | kk) != 0 ? 1u : 0u);
               }
             }
             tc_commit(BAR(B_EMPTY + slot));          // slot reusable once these MMAs retire
           }
           tc_commit(BAR(T_FULL + acc));              // accumulator ready for the epilogue
         }
-        tc_commit(BAR(A_EMPTY));                     // U tile(s) reusable
+        tc_commit(BAR(A_EMPTY));                     // user tile in TMEM may be overwritten
       }
+      if (a.dbg && blockIdx.x == 0) { a.dbg[2] = clock64() - t_start; a.dbg[3] = w_a; a.dbg[4] = w_t; a.dbg[5] = w_b; }
     }
-  } else if (warp >= 4) {
-    // =========================================== epilogue ==================================================
+  } else if (warp >= 4 && warp < 8) {
+    // =========================================== user-tile loaders =========================================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t ut_local = 0;
+    for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x, ++ut_local) {
+      const int64_t user = static_cast<int64_t>(ut) * TC_BM + row;
+      mbar_wait(BAR(A_EMPTY), (ut_local & 1) ^ 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < KP; c0 += 32) {
+        float x[32], lo[32];
+        if (user < a.n_users) {
+          const float4* up = reinterpret_cast<const float4*>(a.uf + user * KP + c0);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = up[c];
+            x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) x[c] = 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) lo[c] = x[c] - __uint_as_float(__float_as_uint(x[c]) & 0xFFFFE000u);
+        tc_st32(t_row + c0, x);
+        if (TERMS == 3) tc_st32(t_row + A_LO_COL + c0, lo);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(A_FULL));
+    }
+  } else if (warp >= 8) {
+    // =========================================== epilogue sets =============================================
+    const int set = (warp - 8) >> 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;          // row inside the user tile == TMEM lane
     const float vmax = DUMP ? 0.f : *a.vmax;
+    const RowMem rm = row_mem(sm + S::off_sets + set * S::SET_BYTES, S::SET_CS, S::SET_CI, S::SET_TOP, S::SET_STATE);
+    const RowMem other = row_mem(sm + S::off_sets + (set ^ 1) * S::SET_BYTES, S::SET_CS, S::SET_CI, S::SET_TOP, S::SET_STATE);
     uint32_t it_global = 0;
+    long long w_full = 0, c_batch = 0, c_final = 0, n_batch = 0;
+    const long long t_start = clock64();
     for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x) {
       const int64_t user = static_cast<int64_t>(ut) * TC_BM + row;
       const bool valid = user < a.n_users;
       float tau = -CUDART_INF_F;
+      int cnt = 0;
       if (!DUMP) {
 #pragma unroll
-        for (int i = 0; i < TC_NTOP; ++i) top[i * TC_BM + row] = -CUDART_INF_F;
+        for (int i = 0; i < TC_NTOP; ++i) rm.top[i * TC_BM + row] = -CUDART_INF_F;
         int64_t cur = 0, end = 0;
         int nxt = INT_MAX, nxt2 = INT_MAX;
         float delta = 0.f;
@@ -373,15 +460,18 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_con
             if (cur + 1 < end) nxt2 = a.seen_indices[cur + 1];
           }
         }
-        rm.cnt[row] = 0; rm.nxt[row] = nxt; rm.nxt2[row] = nxt2; rm.delta[row] = delta; rm.flags[row] = 0;
+        rm.keep[row] = 0; rm.nxt[row] = nxt; rm.nxt2[row] = nxt2; rm.delta[row] = delta; rm.flags[row] = 0;
+        rm.tau_pub[row] = -CUDART_INF_F;
         rm.cur_lo[row] = static_cast<int>(cur & 0xffffffff); rm.cur_hi[row] = static_cast<int>(cur >> 32);
         rm.end_lo[row] = static_cast<int>(end & 0xffffffff); rm.end_hi[row] = static_cast<int>(end >> 32);
+        named_bar_sync(1, 128 * TC_SETS);   // both sets have reset (tau_pub is read across sets)
       }
       for (int it = 0; it < a.n_item_tiles; ++it, ++it_global) {
+        if (static_cast<int>(it_global % TC_SETS) != set) continue;
         const uint32_t acc = it_global % TC_ACC, aph = (it_global / TC_ACC) & 1;
-        mbar_wait(BAR(T_FULL + acc), aph);
+        mbar_wait_t(BAR(T_FULL + acc), aph, w_full);
         tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * TC_BN;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ACC_COL0 + acc * TC_BN;
 #pragma unroll 1
         for (int g = 0; g < TC_BN / 32; ++g) {
           float s[32];
@@ -399,8 +489,17 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_con
                                     fmaxf(s[8 * b + 6], s[8 * b + 7]));
               if (m8 > tau) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (s[8 * b + j] > tau) tau = row_hit(s[8 * b + j], col0 + 8 * b + j, row, tau, rm, a.seen_indices, a.n_items, a.n);
+                for (int j = 0; j < 8; ++j) {
+                  if (s[8 * b + j] > tau) {
+                    rm.cs[cnt * TC_BM + row] = s[8 * b + j];
+                    rm.ci[cnt * TC_BM + row] = col0 + 8 * b + j;
+                    ++cnt;
+                  }
+                }
+                if (cnt > TC_CAND - 8) {   // no room for another group of 8: batch pass right now (start of a sweep)
+                  tau = row_batch(cnt, row, tau, rm, other.tau_pub, a.seen_indices, a.n_items, a.n);
+                  cnt = rm.keep[row];
+                }
               }
             }
           }
@@ -408,19 +507,44 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
+        if (!DUMP && __any_sync(FULL_MASK, cnt >= TC_TRIG)) {   // one row is filling up: every row of the warp tidies
+          const long long t0 = clock64();
+          if (cnt > rm.keep[row]) {
+            tau = row_batch(cnt, row, tau, rm, other.tau_pub, a.seen_indices, a.n_items, a.n);
+            cnt = rm.keep[row];
+          }
+          __syncwarp();
+          c_batch += clock64() - t0;
+          ++n_batch;
+        }
       }
       if (DUMP) continue;
-      // ---- exact float64 re-scoring of the candidates, ranking by (score desc, index asc) ------------------
-      if (valid) {
-        const int cnt = rm.cnt[row];
-        if (rm.flags[row] & 1) {
+      if (cnt > rm.keep[row]) {
+        tau = row_batch(cnt, row, tau, rm, other.tau_pub, a.seen_indices, a.n_items, a.n);
+        cnt = rm.keep[row];
+      }
+      // ---- merge the sets: exact float64 re-scoring of all candidates, ranking by (score desc, index asc) -------
+      const long long t_fin = clock64();
+      named_bar_sync(1, 128 * TC_SETS);
+      if (set == 0 && valid) {
+        bool overflow = false;
+        int total = 0;
+        int ids[TC_SETS * TC_CAND];
+        double ex[TC_SETS * TC_CAND];
+#pragma unroll
+        for (int e = 0; e < TC_SETS; ++e) {
+          const RowMem& om = (e == 0) ? rm : other;
+          overflow |= (om.flags[row] & 1) != 0;
+          const int c_e = om.keep[row];
+          for (int c = 0; c < c_e; ++c) ids[total++] = om.ci[c * TC_BM + row];
+        }
+        if (overflow) {
           const unsigned slot = atomicAdd(a.overflow_count, 1u);
           a.overflow_rows[slot] = static_cast<int32_t>(user);
         } else {
-          double ex[TC_CAND];
           const float* up = a.uf + user * KP;
-          for (int c = 0; c < cnt; ++c) {
-            const float* vp = a.vf + static_cast<int64_t>(ci[c * TC_BM + row]) * KP;
+          for (int c = 0; c < total; ++c) {
+            const float* vp = a.vf + static_cast<int64_t>(ids[c]) * KP;
             double accd = 0.0;
 #pragma unroll 4
             for (int k4 = 0; k4 < KP / 4; ++k4) {
@@ -435,15 +559,14 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_con
           }
           for (int p = 0; p < a.n; ++p) {
             int best = -1;
-            for (int c = 0; c < cnt; ++c) {
-              const int id = ci[c * TC_BM + row];
-              if (id < 0) continue;
-              if (best < 0 || beats(ex[c], id, ex[best], ci[best * TC_BM + row])) best = c;
+            for (int c = 0; c < total; ++c) {
+              if (ids[c] < 0) continue;
+              if (best < 0 || beats(ex[c], ids[c], ex[best], ids[best])) best = c;
             }
             if (best >= 0) {
-              a.idx_out[user * a.n + p] = ci[best * TC_BM + row];
+              a.idx_out[user * a.n + p] = ids[best];
               if (a.score_out) a.score_out[user * a.n + p] = ex[best];
-              ci[best * TC_BM + row] = -1;
+              ids[best] = -1;
             } else {
               a.idx_out[user * a.n + p] = -1;
               if (a.score_out) a.score_out[user * a.n + p] = -CUDART_INF;
@@ -451,6 +574,12 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_con
           }
         }
       }
+      named_bar_sync(1, 128 * TC_SETS);   // set 0 has read every set's candidates: state may be reset
+      c_final += clock64() - t_fin;
+    }
+    if (a.dbg && blockIdx.x == 0 && q == 0 && lane == 0) {
+      long long* d = a.dbg + 8 + 8 * set;
+      d[0] = clock64() - t_start; d[1] = w_full; d[2] = c_batch; d[3] = c_final; d[4] = n_batch;
     }
   }
   tc_fence_before();
@@ -519,22 +648,20 @@ int make_map(rl_context* h, CUtensorMap* map, const float* ptr, int64_t rows, in
 }
 
 template <int KP, int TERMS, bool DUMP>
-int launch_tc(rl_context* h, const CUtensorMap& mu, const CUtensorMap& mulo, const CUtensorMap& mv, const CUtensorMap& mvlo,
-              const TcArgs& a) {
+int launch_tc(rl_context* h, const CUtensorMap& mv, const CUtensorMap& mvlo, const TcArgs& a) {
   auto kern = score_topn_tc_kernel<KP, TERMS, DUMP>;
   const size_t smem = TcSmem<KP, TERMS>::total;
   RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int grid = a.n_user_tiles < h->sm_count ? a.n_user_tiles : h->sm_count;
-  kern<<<grid, TC_THREADS, smem, h->stream>>>(mu, mulo, mv, mvlo, a);
+  kern<<<grid, TC_THREADS, smem, h->stream>>>(mv, mvlo, a);
   RL_LAUNCH_CHECK(h, "score_topn_tc_kernel");
   return RL_OK;
 }
 
 template <int KP>
-int launch_tc_k(rl_context* h, int terms, bool dump, const CUtensorMap& mu, const CUtensorMap& mulo, const CUtensorMap& mv,
-                const CUtensorMap& mvlo, const TcArgs& a) {
-  if (terms == 3) return dump ? launch_tc<KP, 3, true>(h, mu, mulo, mv, mvlo, a) : launch_tc<KP, 3, false>(h, mu, mulo, mv, mvlo, a);
-  return dump ? launch_tc<KP, 1, true>(h, mu, mulo, mv, mvlo, a) : launch_tc<KP, 1, false>(h, mu, mulo, mv, mvlo, a);
+int launch_tc_k(rl_context* h, int terms, bool dump, const CUtensorMap& mv, const CUtensorMap& mvlo, const TcArgs& a) {
+  if (terms == 3) return dump ? launch_tc<KP, 3, true>(h, mv, mvlo, a) : launch_tc<KP, 3, false>(h, mv, mvlo, a);
+  return dump ? launch_tc<KP, 1, true>(h, mv, mvlo, a) : launch_tc<KP, 1, false>(h, mv, mvlo, a);
 }
 
 }  // namespace
@@ -547,9 +674,9 @@ bool score_tc_supported(int kp, int n, int64_t n_users, int64_t n_items, const f
 // terms: 1 = single tf32 product, 3 = split operands (default).
 int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int64_t dump_ld, int terms) {
   if (terms != 1 && terms != 3) return fail(h, RL_ERR_INVALID, "score_tc: terms must be 1 or 3");
-  // scratch: vmax (4 B) | overflow count (4 B) | overflow rows (n_users x 4 B) | U_lo | V_lo
+  // scratch: vmax (4 B) | overflow count (4 B) | overflow rows (n_users x 4 B) | V_lo
   const size_t rows_bytes = (sizeof(int32_t) * static_cast<size_t>(sa.n_users) + 255) & ~size_t(255);
-  const size_t ulo_bytes = terms == 3 ? sizeof(float) * static_cast<size_t>(sa.n_users) * kp : 0;
+  const size_t ulo_bytes = 0;
   const size_t vlo_bytes = terms == 3 ? sizeof(float) * static_cast<size_t>(sa.n_items) * kp : 0;
   void* sc = nullptr;
   int rc = scratch(h, 256 + rows_bytes + ulo_bytes + vlo_bytes, &sc);
@@ -562,19 +689,15 @@ int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int
   float* vlo = reinterpret_cast<float*>(scb + 256 + rows_bytes + ulo_bytes);
   RL_CUDA(h, cudaMemsetAsync(sc, 0, 256, h->stream));
   if (terms == 3) {
-    const int64_t nu4 = sa.n_users * kp / 4, nv4 = sa.n_items * kp / 4;
+    const int64_t nv4 = sa.n_items * kp / 4;
     const int64_t cap = 8 * static_cast<int64_t>(h->sm_count);
-    int64_t g = (nu4 + 255) / 256;
-    split_lo_kernel<<<static_cast<unsigned>(g < cap ? g : cap), 256, 0, h->stream>>>(sa.uf, nu4, ulo);
-    RL_LAUNCH_CHECK(h, "split_lo_kernel");
-    g = (nv4 + 255) / 256;
+    int64_t g = (nv4 + 255) / 256;
     split_lo_kernel<<<static_cast<unsigned>(g < cap ? g : cap), 256, 0, h->stream>>>(sa.vf, nv4, vlo);
     RL_LAUNCH_CHECK(h, "split_lo_kernel");
   }
-  CUtensorMap mu, mulo, mv, mvlo;
-  if ((rc = make_map(h, &mu, sa.uf, sa.n_users, kp, TC_BM)) != RL_OK) return rc;
+  (void)ulo;
+  CUtensorMap mv, mvlo;
   if ((rc = make_map(h, &mv, sa.vf, sa.n_items, kp, TC_BN)) != RL_OK) return rc;
-  if ((rc = make_map(h, &mulo, terms == 3 ? ulo : sa.uf, sa.n_users, kp, TC_BM)) != RL_OK) return rc;
   if ((rc = make_map(h, &mvlo, terms == 3 ? vlo : sa.vf, sa.n_items, kp, TC_BN)) != RL_OK) return rc;
   TcArgs a{};
   a.uf = sa.uf; a.vf = sa.vf; a.n_users = sa.n_users; a.n_items = static_cast<int>(sa.n_items);
@@ -583,14 +706,16 @@ int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int
   a.overflow_rows = orows; a.overflow_count = ocount; a.dump = dump; a.dump_ld = dump_ld;
   a.n_user_tiles = static_cast<int>((sa.n_users + TC_BM - 1) / TC_BM);
   a.n_item_tiles = static_cast<int>((sa.n_items + TC_BN - 1) / TC_BN);
+  const bool want_dbg = getenv("RL_TC_DEBUG") != nullptr;
+  a.dbg = want_dbg ? reinterpret_cast<long long*>(scb + 8) : nullptr;   // 30 x 8 B inside the 256-byte header
   if (!dump) {
     int64_t g = (sa.n_items + 255) / 256;
     if (g > 4 * h->sm_count) g = 4 * h->sm_count;
     max_row_norm_kernel<<<static_cast<unsigned>(g), 256, 0, h->stream>>>(sa.vf, sa.n_items, kp, vmax);
     RL_LAUNCH_CHECK(h, "max_row_norm_kernel");
   }
-  if (kp == 64) rc = launch_tc_k<64>(h, terms, dump != nullptr, mu, mulo, mv, mvlo, a);
-  else if (kp == 32) rc = launch_tc_k<32>(h, terms, dump != nullptr, mu, mulo, mv, mvlo, a);
+  if (kp == 64) rc = launch_tc_k<64>(h, terms, dump != nullptr, mv, mvlo, a);
+  else if (kp == 32) rc = launch_tc_k<32>(h, terms, dump != nullptr, mv, mvlo, a);
   else return fail(h, RL_ERR_INVALID, "score_tc: padded k %d not supported by the tensor-core path", kp);
   if (rc != RL_OK || dump) return rc;
   // rows whose candidate buffer overflowed: exact kernel on the list (needs the count on the host)
@@ -598,6 +723,15 @@ int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int
   RL_CUDA(h, cudaMemcpyAsync(&n_over, ocount, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
   RL_CUDA(h, cudaStreamSynchronize(h->stream));
   h->last_overflow = n_over;
+  if (want_dbg) {
+    long long d[30];
+    RL_CUDA(h, cudaMemcpy(d, scb + 8, sizeof(d), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "score_tc dbg (block 0, cycles): producer total %lld wait_empty %lld | mma total %lld wait_A %lld wait_Tempty %lld wait_Bfull %lld\n",
+            d[0], d[1], d[2], d[3], d[4], d[5]);
+    for (int e = 0; e < TC_SETS; ++e)
+      fprintf(stderr, "  epilogue set %d: total %lld wait_Tfull %lld batch passes %lld (%lld) finalize %lld\n", e, d[8 + 8 * e], d[9 + 8 * e],
+              d[10 + 8 * e], d[12 + 8 * e], d[11 + 8 * e]);
+  }
   if (n_over > 0) {
     ScoreArgs ea = sa;
     ea.user_list = orows;
