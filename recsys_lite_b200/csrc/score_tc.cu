@@ -11,8 +11,9 @@
 //              stages in TMEM;
 //   warp 2     TMEM allocation (512 columns: 128 for the user tile hi|lo, 3 x 128 accumulators);
 //   warps 4-7  user-tile loaders: each thread reads its user's factor row from global memory and writes it (and its
-//              low part) into its TMEM lane with tcgen05.st -- no shared-memory copy of U, no U_lo array;
-//   warps 8-15 two epilogue sets that take alternate item tiles: tcgen05.ld 32 columns at a time, 3-input max over
+//              low part) into its TMEM lane with tcgen05.st -- no shared-memory copy of U, no U_lo array; the same
+//              threads finish the PREVIOUS user tile (exact re-scoring of its candidates) while the next sweep runs;
+//   warps 8-19 three epilogue sets that take item tiles round robin: tcgen05.ld 32 columns at a time, 3-input max over
 //              groups of 8 scores and ONE compare against the row threshold per group (~0.6 instructions per score);
 //              scores above the threshold are pushed to a small per-row FIFO and drained at the end of the tile by
 //              all 32 rows of the warp in parallel: seen-item cursor check (CSR, ascending), top-n tracker, candidate
@@ -45,11 +46,11 @@ constexpr int TC_BM = 128;      // users per tile (TMEM lanes)
 constexpr int TC_BN = 128;      // items per tile (TMEM columns per accumulator stage)
 constexpr int TC_ACC = 3;       // TMEM accumulator stages (columns 128..511; columns 0..127 hold the user tile hi|lo)
 constexpr int TC_SLOTS = 4;     // shared-memory slots of the V ring
-constexpr int TC_SETS = 2;      // epilogue warp sets (each 4 warps = 128 rows), alternating item tiles
+constexpr int TC_SETS = 2;      // epilogue warp sets (each 4 warps = 128 rows), taking item tiles round robin
 constexpr int TC_THREADS = 32 * (8 + 4 * TC_SETS);
 constexpr int TC_CAND = 32;     // candidate / raw-hit slots per row and set
 constexpr int TC_NTOP = 16;     // largest n served by this path
-constexpr int TC_TRIG = 20;     // a row asks for a batch pass once it holds this many entries
+constexpr int TC_TRIG = 22;     // a row asks for a batch pass once it holds this many entries
 // bounds on |tensor-core dot - exact dot| / (|u| |v|), checked by tests/test_gpu_parity.py::test_tensor_core_raw_scores
 constexpr float TC_ERR1 = 2.5e-3f;   // one tf32 product: 2^-9 operand truncation (+ accumulation)
 constexpr float TC_ERR3 = 6.0e-6f;   // split operands: 3 * 2^-20 = 2.9e-6 operand terms + fp32 accumulation; measured <= 1.8e-6
@@ -90,6 +91,7 @@ struct TcArgs {
   int64_t dump_ld;
   int n_user_tiles, n_item_tiles;
   long long* dbg;           // optional (block 0 only): cycle counters per role, see tools/run_kernel.py
+  int skip_scan;            // debug: epilogue releases every accumulator stage unread (MMA / TMA pipeline ceiling)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -120,6 +122,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
     if (spin > (1u << 26)) {
       printf("score_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+// for roles that wait a whole sweep (user-tile loaders) or are far ahead of their consumer (TMA producer): do not
+// compete for issue slots with the epilogue warps while waiting
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    __nanosleep(ns);
+    if (spin > (1u << 24)) {
+      printf("score_tc: mbarrier timeout (relaxed; block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
   }
@@ -160,10 +173,10 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -240,7 +253,7 @@ __device__ __forceinline__ RowMem row_mem(unsigned char* set_base, uint32_t set_
 // ascend) and folded into the top-n tracker with a branch-free sorted insert, (2) the threshold is raised (also to
 // the other set's published threshold: any set's n-th best is a lower bound of the global one), (3) entries at or
 // below the threshold are dropped.  Returns the new threshold; the new entry count is left in m.keep[row].
-__device__ __noinline__ float row_batch(int cnt, int row, float tau, RowMem m, const float* __restrict__ other_tau,
+__device__ __noinline__ float row_batch(int cnt, int row, float tau, RowMem m, const float* other_tau0, const float* other_tau1,
                                         const int32_t* __restrict__ seen_indices, int n_items, int n) {
   int nxt = m.nxt[row], nxt2 = m.nxt2[row];
   int64_t cur = (static_cast<int64_t>(m.cur_hi[row]) << 32) | static_cast<uint32_t>(m.cur_lo[row]);
@@ -273,7 +286,7 @@ __device__ __noinline__ float row_batch(int cnt, int row, float tau, RowMem m, c
   for (int i = 1; i < TC_NTOP; ++i)
     if (i == n - 1) tn = t[i];
   tau = fmaxf(tau, tn - m.delta[row]);
-  tau = fmaxf(tau, other_tau[row]);
+  tau = fmaxf(tau, fmaxf(other_tau0[row], other_tau1[row]));
   m.tau_pub[row] = tau;
   int j = 0;
   for (int f = 0; f < cnt; ++f) {
@@ -284,7 +297,7 @@ __device__ __noinline__ float row_batch(int cnt, int row, float tau, RowMem m, c
       ++j;
     }
   }
-  if (j > TC_CAND - 9) {  // the window is too crowded for this path: hand the row to the exact kernel
+  if (j > TC_CAND - 8) {  // the window is too crowded for this path: hand the row to the exact kernel
     m.flags[row] |= 1;
     j = 0;
   }
@@ -310,6 +323,7 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   constexpr int B_FULL = 0, B_EMPTY = TC_SLOTS, A_FULL = 2 * TC_SLOTS, A_EMPTY = A_FULL + 1, T_FULL = A_FULL + 2, T_EMPTY = T_FULL + TC_ACC;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + T_EMPTY + TC_ACC);
+  int* claim = reinterpret_cast<int*>(bars + T_EMPTY + TC_ACC + 1);   // [2 parities][4 lane quarters] item-tile tickets
   constexpr uint32_t A_LO_COL = KP;          // TMEM columns [0, KP): user rows as given; [KP, 2 KP): their low parts
   constexpr uint32_t ACC_COL0 = 128;         // accumulator stage s lives in columns [128 + 128 s, 256 + 128 s)
 
@@ -319,6 +333,7 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
     for (int i = 0; i < TC_ACC; ++i) { mbar_init(BAR(T_FULL + i), 1); mbar_init(BAR(T_EMPTY + i), 4); }
     mbar_init(BAR(A_FULL), 4);
     mbar_init(BAR(A_EMPTY), 1);
+    for (int i = 0; i < 8; ++i) claim[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -341,7 +356,11 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
 #pragma unroll
           for (int part = 0; part < S::SPT; ++part, ++slot_global) {
             const uint32_t slot = slot_global % TC_SLOTS, ph = (slot_global / TC_SLOTS) & 1;
-            mbar_wait_t(BAR(B_EMPTY + slot), ph ^ 1, w_empty);
+            {
+              const long long t0 = clock64();
+              mbar_wait_relaxed(BAR(B_EMPTY + slot), ph ^ 1, 64);
+              w_empty += clock64() - t0;
+            }
             mbar_expect_tx(BAR(B_FULL + slot), S::B_BYTES);
 #pragma unroll
             for (int kh = 0; kh < S::NKH; ++kh)
@@ -393,10 +412,9 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    uint32_t ut_local = 0;
-    for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x, ++ut_local) {
+    auto load_tile = [&](int ut, uint32_t ut_local) {
       const int64_t user = static_cast<int64_t>(ut) * TC_BM + row;
-      mbar_wait(BAR(A_EMPTY), (ut_local & 1) ^ 1);
+      mbar_wait_relaxed(BAR(A_EMPTY), (ut_local & 1) ^ 1, 200);
       tc_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < KP; c0 += 32) {
@@ -421,6 +439,68 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(A_FULL));
+    };
+    uint32_t ut_local = 0;
+    if (static_cast<int>(blockIdx.x) < a.n_user_tiles) load_tile(blockIdx.x, 0);
+    for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x, ++ut_local) {
+      if (DUMP) {
+        if (ut + static_cast<int>(gridDim.x) < a.n_user_tiles) load_tile(ut + gridDim.x, ut_local + 1);
+        continue;
+      }
+      const int64_t user = static_cast<int64_t>(ut) * TC_BM + row;
+      const bool valid = user < a.n_users;
+      // ---- take over the candidates of this user tile from the epilogue sets -----------------------------------
+      named_bar_sync(1, 128 * (TC_SETS + 1));     // every set has finished its last tile of the sweep
+      bool overflow = false;
+      int total = 0;
+      int ids[TC_SETS * TC_CAND];
+#pragma unroll
+      for (int e = 0; e < TC_SETS; ++e) {
+        const RowMem om = row_mem(sm + S::off_sets + e * S::SET_BYTES, S::SET_CS, S::SET_CI, S::SET_TOP, S::SET_STATE);
+        overflow |= (om.flags[row] & 1) != 0;
+        const int c_e = om.keep[row];
+        for (int c = 0; c < c_e; ++c) ids[total++] = om.ci[c * TC_BM + row];
+      }
+      named_bar_sync(2, 128 * (TC_SETS + 1));     // candidates copied: the sets may reset and start the next sweep
+      if (ut + static_cast<int>(gridDim.x) < a.n_user_tiles) load_tile(ut + gridDim.x, ut_local + 1);
+      // ---- exact float64 re-scoring, ranking by (score desc, index asc); overlaps the next sweep ----------------
+      if (!valid) continue;
+      if (overflow) {
+        const unsigned slot = atomicAdd(a.overflow_count, 1u);
+        a.overflow_rows[slot] = static_cast<int32_t>(user);
+        continue;
+      }
+      double ex[TC_SETS * TC_CAND];
+      const float* up = a.uf + user * KP;
+      for (int c = 0; c < total; ++c) {
+        const float* vp = a.vf + static_cast<int64_t>(ids[c]) * KP;
+        double accd = 0.0;
+#pragma unroll 4
+        for (int k4 = 0; k4 < KP / 4; ++k4) {
+          const float4 x = *reinterpret_cast<const float4*>(up + 4 * k4);
+          const float4 y = *reinterpret_cast<const float4*>(vp + 4 * k4);
+          accd = fma(static_cast<double>(x.x), static_cast<double>(y.x), accd);
+          accd = fma(static_cast<double>(x.y), static_cast<double>(y.y), accd);
+          accd = fma(static_cast<double>(x.z), static_cast<double>(y.z), accd);
+          accd = fma(static_cast<double>(x.w), static_cast<double>(y.w), accd);
+        }
+        ex[c] = accd;
+      }
+      for (int p = 0; p < a.n; ++p) {
+        int best = -1;
+        for (int c = 0; c < total; ++c) {
+          if (ids[c] < 0) continue;
+          if (best < 0 || beats(ex[c], ids[c], ex[best], ids[best])) best = c;
+        }
+        if (best >= 0) {
+          a.idx_out[user * a.n + p] = ids[best];
+          if (a.score_out) a.score_out[user * a.n + p] = ex[best];
+          ids[best] = -1;
+        } else {
+          a.idx_out[user * a.n + p] = -1;
+          if (a.score_out) a.score_out[user * a.n + p] = -CUDART_INF;
+        }
+      }
     }
   } else if (warp >= 8) {
     // =========================================== epilogue sets =============================================
@@ -429,14 +509,15 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
     const int row = q * 32 + lane;          // row inside the user tile == TMEM lane
     const float vmax = DUMP ? 0.f : *a.vmax;
     const RowMem rm = row_mem(sm + S::off_sets + set * S::SET_BYTES, S::SET_CS, S::SET_CI, S::SET_TOP, S::SET_STATE);
-    const RowMem other = row_mem(sm + S::off_sets + (set ^ 1) * S::SET_BYTES, S::SET_CS, S::SET_CI, S::SET_TOP, S::SET_STATE);
-    uint32_t it_global = 0;
+    const float* other0 = row_mem(sm + S::off_sets + ((set + 1) % TC_SETS) * S::SET_BYTES, S::SET_CS, S::SET_CI, S::SET_TOP, S::SET_STATE).tau_pub;
+    const float* other1 = row_mem(sm + S::off_sets + ((set + TC_SETS - 1) % TC_SETS) * S::SET_BYTES, S::SET_CS, S::SET_CI, S::SET_TOP, S::SET_STATE).tau_pub;
+    uint32_t ut_local = 0;
     long long w_full = 0, c_batch = 0, c_final = 0, n_batch = 0;
     const long long t_start = clock64();
-    for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x) {
+    for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x, ++ut_local) {
       const int64_t user = static_cast<int64_t>(ut) * TC_BM + row;
       const bool valid = user < a.n_users;
-      float tau = -CUDART_INF_F;
+      float tau = (a.skip_scan == 2) ? CUDART_INF_F : -CUDART_INF_F;
       int cnt = 0;
       if (!DUMP) {
 #pragma unroll
@@ -464,18 +545,26 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
         rm.tau_pub[row] = -CUDART_INF_F;
         rm.cur_lo[row] = static_cast<int>(cur & 0xffffffff); rm.cur_hi[row] = static_cast<int>(cur >> 32);
         rm.end_lo[row] = static_cast<int>(end & 0xffffffff); rm.end_hi[row] = static_cast<int>(end >> 32);
-        named_bar_sync(1, 128 * TC_SETS);   // both sets have reset (tau_pub is read across sets)
+        named_bar_sync(3, 128 * TC_SETS);   // every set has reset (tau_pub is read across sets)
       }
-      for (int it = 0; it < a.n_item_tiles; ++it, ++it_global) {
-        if (static_cast<int>(it_global % TC_SETS) != set) continue;
+      if (set == 0 && lane == 0) claim[((ut_local + 1) & 1) * 4 + q] = 0;   // tickets of the NEXT user tile (unused right now)
+      // The two warps that own this lane quarter take item tiles by ticket: while one of them is busy with a batch
+      // pass the other keeps draining accumulator stages, so the MMA pipeline is not held up.
+      for (;;) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(&claim[(ut_local & 1) * 4 + q], 1);
+        it = __shfl_sync(FULL_MASK, it, 0);
+        if (it >= a.n_item_tiles) break;
+        const uint32_t it_global = ut_local * static_cast<uint32_t>(a.n_item_tiles) + static_cast<uint32_t>(it);
         const uint32_t acc = it_global % TC_ACC, aph = (it_global / TC_ACC) & 1;
         mbar_wait_t(BAR(T_FULL + acc), aph, w_full);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ACC_COL0 + acc * TC_BN;
 #pragma unroll 1
-        for (int g = 0; g < TC_BN / 32; ++g) {
+        for (int g = 0; g < (a.skip_scan == 1 ? 0 : TC_BN / 32); ++g) {
           float s[32];
           tc_ld32(t_row + g * 32, s);
+          tc_wait_ld();
           const int col0 = it * TC_BN + g * 32;
           if (DUMP) {
             if (valid) {
@@ -497,7 +586,7 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
                   }
                 }
                 if (cnt > TC_CAND - 8) {   // no room for another group of 8: batch pass right now (start of a sweep)
-                  tau = row_batch(cnt, row, tau, rm, other.tau_pub, a.seen_indices, a.n_items, a.n);
+                  tau = row_batch(cnt, row, tau, rm, other0, other1, a.seen_indices, a.n_items, a.n);
                   cnt = rm.keep[row];
                 }
               }
@@ -510,7 +599,7 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
         if (!DUMP && __any_sync(FULL_MASK, cnt >= TC_TRIG)) {   // one row is filling up: every row of the warp tidies
           const long long t0 = clock64();
           if (cnt > rm.keep[row]) {
-            tau = row_batch(cnt, row, tau, rm, other.tau_pub, a.seen_indices, a.n_items, a.n);
+            tau = row_batch(cnt, row, tau, rm, other0, other1, a.seen_indices, a.n_items, a.n);
             cnt = rm.keep[row];
           }
           __syncwarp();
@@ -520,61 +609,13 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
       }
       if (DUMP) continue;
       if (cnt > rm.keep[row]) {
-        tau = row_batch(cnt, row, tau, rm, other.tau_pub, a.seen_indices, a.n_items, a.n);
+        tau = row_batch(cnt, row, tau, rm, other0, other1, a.seen_indices, a.n_items, a.n);
         cnt = rm.keep[row];
       }
-      // ---- merge the sets: exact float64 re-scoring of all candidates, ranking by (score desc, index asc) -------
+      // ---- hand the candidates to the loader warps (they re-score and write the result during the next sweep) ---
       const long long t_fin = clock64();
-      named_bar_sync(1, 128 * TC_SETS);
-      if (set == 0 && valid) {
-        bool overflow = false;
-        int total = 0;
-        int ids[TC_SETS * TC_CAND];
-        double ex[TC_SETS * TC_CAND];
-#pragma unroll
-        for (int e = 0; e < TC_SETS; ++e) {
-          const RowMem& om = (e == 0) ? rm : other;
-          overflow |= (om.flags[row] & 1) != 0;
-          const int c_e = om.keep[row];
-          for (int c = 0; c < c_e; ++c) ids[total++] = om.ci[c * TC_BM + row];
-        }
-        if (overflow) {
-          const unsigned slot = atomicAdd(a.overflow_count, 1u);
-          a.overflow_rows[slot] = static_cast<int32_t>(user);
-        } else {
-          const float* up = a.uf + user * KP;
-          for (int c = 0; c < total; ++c) {
-            const float* vp = a.vf + static_cast<int64_t>(ids[c]) * KP;
-            double accd = 0.0;
-#pragma unroll 4
-            for (int k4 = 0; k4 < KP / 4; ++k4) {
-              const float4 x = *reinterpret_cast<const float4*>(up + 4 * k4);
-              const float4 y = *reinterpret_cast<const float4*>(vp + 4 * k4);
-              accd = fma(static_cast<double>(x.x), static_cast<double>(y.x), accd);
-              accd = fma(static_cast<double>(x.y), static_cast<double>(y.y), accd);
-              accd = fma(static_cast<double>(x.z), static_cast<double>(y.z), accd);
-              accd = fma(static_cast<double>(x.w), static_cast<double>(y.w), accd);
-            }
-            ex[c] = accd;
-          }
-          for (int p = 0; p < a.n; ++p) {
-            int best = -1;
-            for (int c = 0; c < total; ++c) {
-              if (ids[c] < 0) continue;
-              if (best < 0 || beats(ex[c], ids[c], ex[best], ids[best])) best = c;
-            }
-            if (best >= 0) {
-              a.idx_out[user * a.n + p] = ids[best];
-              if (a.score_out) a.score_out[user * a.n + p] = ex[best];
-              ids[best] = -1;
-            } else {
-              a.idx_out[user * a.n + p] = -1;
-              if (a.score_out) a.score_out[user * a.n + p] = -CUDART_INF;
-            }
-          }
-        }
-      }
-      named_bar_sync(1, 128 * TC_SETS);   // set 0 has read every set's candidates: state may be reset
+      named_bar_sync(1, 128 * (TC_SETS + 1));
+      named_bar_sync(2, 128 * (TC_SETS + 1));
       c_final += clock64() - t_fin;
     }
     if (a.dbg && blockIdx.x == 0 && q == 0 && lane == 0) {
@@ -667,7 +708,7 @@ int launch_tc_k(rl_context* h, int terms, bool dump, const CUtensorMap& mv, cons
 }  // namespace
 
 bool score_tc_supported(int kp, int n, int64_t n_users, int64_t n_items, const float* ubias, const float* ibias, double gbias) {
-  return (kp == 32 || kp == 64) && n <= TC_NTOP && n_items >= 1024 && n_users >= 1 && !ubias && !ibias && gbias == 0.0;
+  return (kp == 32 || kp == 64) && n <= TC_NTOP && n <= TC_CAND - 16 && n_items >= 1024 && n_users >= 1 && !ubias && !ibias && gbias == 0.0;
 }
 
 // tensor-core candidate pass + in-kernel exact re-scoring; overflow rows are finished by the exact kernel.
@@ -707,6 +748,7 @@ int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int
   a.n_user_tiles = static_cast<int>((sa.n_users + TC_BM - 1) / TC_BM);
   a.n_item_tiles = static_cast<int>((sa.n_items + TC_BN - 1) / TC_BN);
   const bool want_dbg = getenv("RL_TC_DEBUG") != nullptr;
+  a.skip_scan = getenv("RL_TC_SKIPSCAN") ? atoi(getenv("RL_TC_SKIPSCAN")) : 0;
   a.dbg = want_dbg ? reinterpret_cast<long long*>(scb + 8) : nullptr;   // 30 x 8 B inside the 256-byte header
   if (!dump) {
     int64_t g = (sa.n_items + 255) / 256;
@@ -728,7 +770,7 @@ int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int
     RL_CUDA(h, cudaMemcpy(d, scb + 8, sizeof(d), cudaMemcpyDeviceToHost));
     fprintf(stderr, "score_tc dbg (block 0, cycles): producer total %lld wait_empty %lld | mma total %lld wait_A %lld wait_Tempty %lld wait_Bfull %lld\n",
             d[0], d[1], d[2], d[3], d[4], d[5]);
-    for (int e = 0; e < TC_SETS; ++e)
+    for (int e = 0; e < (TC_SETS < 2 ? TC_SETS : 2); ++e)
       fprintf(stderr, "  epilogue set %d: total %lld wait_Tfull %lld batch passes %lld (%lld) finalize %lld\n", e, d[8 + 8 * e], d[9 + 8 * e],
               d[10 + 8 * e], d[12 + 8 * e], d[11 + 8 * e]);
   }

@@ -383,7 +383,7 @@ def test_tensor_core_raw_scores(h, k, terms):
     assert not got[:, n_items:].any()                 # zero-filled tail of the last item tile
 
 
-@pytest.mark.parametrize("k,n,n_users,n_items", [(64, 10, 1000, 5000), (64, 1, 130, 1024), (32, 16, 257, 3000),
+@pytest.mark.parametrize("k,n,n_users,n_items", [(64, 10, 1000, 5000), (64, 1, 130, 1024), (32, 12, 257, 3000),
                                                   (40, 10, 500, 2049)])
 def test_tensor_core_topn_equals_exact_kernel(h, k, n, n_users, n_items):
     """mode RL_SCORE_TENSOR must return exactly what RL_SCORE_EXACT returns (indices and float64 scores), and both
