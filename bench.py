@@ -404,7 +404,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="fp32_ir", choices=["fp32_ir", "fp64"])
-    ap.add_argument("--ir-steps", type=int, default=2)
+    ap.add_argument("--ir-steps", type=int, default=1)
     ap.add_argument("--score-mode", type=int, default=0, help="0 auto, 1 exact CUDA-core, 2 tensor-core candidate pass")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()

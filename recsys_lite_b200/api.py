@@ -82,7 +82,7 @@ class RecommenderSystem:
             factors = kwargs.get("factors", k or 10)
             self._model = self._fit_als(
                 ratings, factors, kwargs.get("iterations", 10), kwargs.get("lambda_", 0.01),
-                precision=kwargs.get("precision", "fp32_ir"), ir_steps=kwargs.get("ir_steps", 2),
+                precision=kwargs.get("precision", "fp32_ir"), ir_steps=kwargs.get("ir_steps", 1),
                 init=kwargs.get("init"),
             )
         elif self.algorithm == "svd":
@@ -95,7 +95,7 @@ class RecommenderSystem:
         return self
 
     def _fit_als(self, ratings, factors: int, iterations: int = 10, lambda_: float = 0.01, *,
-                 precision: str = "fp32_ir", ir_steps: int = 2, init=None) -> Dict[str, Any]:
+                 precision: str = "fp32_ir", ir_steps: int = 1, init=None) -> Dict[str, Any]:
         """algo.py:300-337: init from the GLOBAL NumPy RNG (U then V), binarise, `iterations` sweeps."""
         if ratings.ndim != 2:
             raise ValueError(f"Input matrix must be 2D (users x items), got {ratings.ndim}D.")

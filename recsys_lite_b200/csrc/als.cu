@@ -21,6 +21,8 @@
 //
 // Algorithmic bytes per row: nnz_r * (kp*4 + 4) gathered + 16 indptr + kp*4 written.
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rl {
@@ -513,6 +515,8 @@ __global__ void __launch_bounds__(WarpSmem<real, KP>::warps * 32) als_half_step_
   }
 }
 
+#include "als_k64.cuh"
+
 template <typename real, int KP, bool WEIGHTED>
 int launch_one(rl_context* h, const AlsArgs& args) {
   auto kern = als_half_step_kernel<real, KP, WEIGHTED>;
@@ -601,7 +605,10 @@ int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, 
     a.ir_steps = 0;
     return weighted ? launch_kp<double, true>(h, kp, a) : launch_kp<double, false>(h, kp, a);
   }
-  if (precision == RL_PREC_FP32_IR) return weighted ? launch_kp<float, true>(h, kp, a) : launch_kp<float, false>(h, kp, a);
+  if (precision == RL_PREC_FP32_IR) {
+    if (kp == 64 && !getenv("RL_ALS_GENERIC")) return weighted ? launch_k64<true>(h, a) : launch_k64<false>(h, a);
+    return weighted ? launch_kp<float, true>(h, kp, a) : launch_kp<float, false>(h, kp, a);
+  }
   return fail(h, RL_ERR_INVALID, "als_half_step: unknown precision %d", precision);
 }
 

@@ -99,7 +99,7 @@ class ShardedProblem:
                     None, None, self.U.data_ptr(), self.V[ilo:].data_ptr(), float(lam), 0.0, None, precision,
                     ir_steps, None)
 
-    def iteration(self, lam=0.01, precision=0, ir_steps=2):
+    def iteration(self, lam=0.01, precision=0, ir_steps=1):
         p = self.plan
         self.user_half_step(lam, precision, ir_steps)
         exchange_rows(self.U, p.user_bounds, p.rank, p.world)
