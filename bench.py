@@ -50,6 +50,12 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback")
 
 
+def load_traffic():
+    """dram bytes per launch from the committed ncu --set full capture (profiles/), or None per kernel."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 def make_inputs(w):
     from recsys_lite_b200 import synth
     from recsys_lite_b200.csr import transpose_pattern
@@ -277,6 +283,7 @@ def run_b200(args, w):
 
     line = None
     if rank == 0:
+        traffic = load_traffic() if (world == 1 and args.workload == "C4") else {}
         flops_score = 2.0 * (uhi - ulo) * ni * k
         b_user = als_bytes(uhi - ulo, prob.nnz_users, k)
         b_item = als_bytes(ihi - ilo, prob.nnz_items, k)
@@ -291,15 +298,19 @@ def run_b200(args, w):
             "ms": {"user_half_step": t_user, "exchange_U_plus_item_half_step": t_item_x, "exchange_V": t_x2, "score_topn": t_score},
             "roofline": {"kernel": "score_topn (rank 0 shard)", "bound": "tensor",
                          "achieved": flops_score / (t_score * 1e-3) / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": flops_score / (t_score * 1e-3) / 1e12 / peaks["tflops"], "traffic": None,
+                         "frac": flops_score / (t_score * 1e-3) / 1e12 / peaks["tflops"], "traffic": traffic.get("score_topn"),
+                         "tensor_pipe_active_pct_ncu": (traffic.get("tensor_pipe_active_pct") or {}).get("score_topn"),
+                         "note": "algorithmic flops 2*n_users*n_items*k; the kernel issues 3 tf32 MMAs per product term (split operands)",
                          "peak_source": peaks["source"] + " bf16 sustained"},
             "roofline_als": {
                 "bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_source": peaks["source"],
                 "user_half_step": {"bytes": b_user, "achieved": b_user / (t_user * 1e-3) / 1e9,
-                                   "frac": b_user / (t_user * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                                   "frac": b_user / (t_user * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                   "traffic": traffic.get("als_user_half_step"),
+                                   "note": "V (25.6 MB) is L2-resident: the gather is served by L2, dram traffic is indices + output"},
                 "item_half_step_incl_exchange": {"bytes": b_item, "achieved": b_item / (t_item_x * 1e-3) / 1e9,
-                                                 "frac": b_item / (t_item_x * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-                "traffic": None},
+                                                 "frac": b_item / (t_item_x * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                                 "traffic": traffic.get("als_item_half_step")}},
             "clocks": clk, "gpu_launches": int(launches), "e2e": e2e,
         }
         if world == 1 and not args.no_cpu:
