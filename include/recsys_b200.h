@@ -179,6 +179,12 @@ int rl_predict_host(rl_handle h, const void* user_f, const void* item_f, int fac
                     double global_bias, const float* user_bias, const float* item_bias,
                     void* out, int out_dtype);
 
+/* ---- compute_rmse / compute_mae on dense HOST matrices (algo.py:662-743): out3 = {sum sq err, sum |err|, #cells with
+ *      actual > 0}; flags_out bit 0: an infinite value was seen, bit 1: a NaN (the adapter raises the reference's
+ *      ValueError texts). */
+int rl_dense_error_host(rl_handle h, const void* pred, int pred_dtype, const void* actual, int actual_dtype,
+                        int64_t n_cells, double* out3, int* flags_out);
+
 /* ---- observed-entry error: replaces compute_rmse / compute_mae, algo.py:662-743, for predictions U V^T over a
  *      CSR pattern (values NULL = all ones).  out_host[0] = sum of squared errors, out_host[1] = sum |err|. */
 int rl_observed_error_dev(rl_handle h, const float* user_f_dev, const float* item_f_dev, int k,

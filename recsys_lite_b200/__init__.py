@@ -6,7 +6,9 @@ BASELINE.json: ``RecommenderSystem`` (algorithm "als" | "svd"), ``svd_reconstruc
 include/recsys_b200.h) -- there is no CPU fallback.
 """
 from .api import RecommenderSystem, compute_mae, compute_rmse, svd_reconstruct, top_n
+from .benchmark import benchmark_algorithm, quick_benchmark
 
 __version__ = "0.1.0"
 
-__all__ = ["RecommenderSystem", "svd_reconstruct", "top_n", "compute_rmse", "compute_mae", "__version__"]
+__all__ = ["RecommenderSystem", "svd_reconstruct", "top_n", "compute_rmse", "compute_mae", "benchmark_algorithm",
+           "quick_benchmark", "__version__"]

@@ -50,6 +50,7 @@ SIGNATURES = {
     "rl_lowrank_dev": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i32, _dbl, _vp, _vp, _vp, _i32]),
     "rl_svd_reconstruct_host": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
     "rl_predict_host": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i32, _dbl, _vp, _vp, _vp, _i32]),
+    "rl_dense_error_host": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _vp, _vp]),
     "rl_observed_error_dev": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
 }
 

@@ -322,38 +322,37 @@ def top_n(est, known, *, n: int = 10) -> np.ndarray:
     return _finish_topn(idx, n_valid)
 
 
-def _metric_inputs(predictions, actual):
+def _dense_errors(predictions, actual):
+    """(sum sq err, sum |err|, #observed) over cells with actual > 0, on the device (algo.py:662-743 semantics)."""
     if predictions.shape != actual.shape:
         raise ValueError(
             "Predictions and actual matrices must have the same shape. "
             f"Got {predictions.shape} and {actual.shape}."
         )
-    p, a = np.asarray(_dense(predictions)), np.asarray(_dense(actual))
-    if np.any(np.isinf(p)) or np.any(np.isinf(a)):
+    p, a = _as_float_matrix(predictions), _as_float_matrix(actual)
+    out3 = np.zeros(3, dtype=np.float64)
+    flags = np.zeros(1, dtype=np.int32)
+    if p.size:
+        h = _ffi.default_handle()
+        h.call("rl_dense_error_host", _ffi.ptr(p), _rl_dtype(p), _ffi.ptr(a), _rl_dtype(a), p.size, _ffi.ptr(out3),
+               _ffi.ptr(flags))
+    if flags[0] & 1:
         raise ValueError("Input matrices must not contain infinite values.")
-    if np.any(np.isnan(p)) or np.any(np.isnan(a)):
+    if flags[0] & 2:
         raise ValueError("Input matrices must not contain NaN values.")
-    return p, a
+    return out3
 
 
 def compute_rmse(predictions, actual) -> float:
-    """RMSE over cells with ``actual > 0`` (algo.py:662-701).  Host-side reduction, as in the reference; the
-    device version for factor models is ``observed_error`` (no score matrix)."""
-    p, a = _metric_inputs(predictions, actual)
-    m = a > 0
-    if not np.any(m):
-        return 0.0
-    d = p[m] - a[m]
-    return float(np.sqrt(np.mean(d ** 2)))
+    """RMSE over cells with ``actual > 0`` (algo.py:662-701); 0.0 when there is none."""
+    sse, _, cnt = _dense_errors(predictions, actual)
+    return float(np.sqrt(sse / cnt)) if cnt > 0 else 0.0
 
 
 def compute_mae(predictions, actual) -> float:
     """MAE over cells with ``actual > 0`` (algo.py:704-743)."""
-    p, a = _metric_inputs(predictions, actual)
-    m = a > 0
-    if not np.any(m):
-        return 0.0
-    return float(np.mean(np.abs(p[m] - a[m])))
+    _, sae, cnt = _dense_errors(predictions, actual)
+    return float(sae / cnt) if cnt > 0 else 0.0
 
 
 __all__ = ["RecommenderSystem", "svd_reconstruct", "top_n", "compute_rmse", "compute_mae"]

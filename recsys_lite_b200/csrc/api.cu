@@ -450,6 +450,29 @@ int rl_predict_host(rl_handle h, const void* user_f, const void* item_f, int fac
   return RL_OK;
 }
 
+int rl_dense_error_host(rl_handle h, const void* pred, int pred_dtype, const void* actual, int actual_dtype, int64_t n_cells,
+                        double* out3, int* flags_out) {
+  RL_NEED(h);
+  if (n_cells < 0 || !out3 || !flags_out) return fail(h, RL_ERR_INVALID, "rl_dense_error_host: bad argument");
+  out3[0] = out3[1] = out3[2] = 0.0;
+  *flags_out = 0;
+  if (n_cells == 0) return RL_OK;
+  if (!pred || !actual) return fail(h, RL_ERR_INVALID, "rl_dense_error_host: null pointer");
+  DevBuf d_p, d_a, d_o;
+  RL_TRY(upload(h, d_p, pred, static_cast<size_t>(n_cells) * (pred_dtype == RL_F64 ? 8 : 4)));
+  RL_TRY(upload(h, d_a, actual, static_cast<size_t>(n_cells) * (actual_dtype == RL_F64 ? 8 : 4)));
+  RL_TRY(d_o.alloc(h, 64));
+  double* o4 = d_o.as<double>();
+  int* fl = reinterpret_cast<int*>(o4 + 4);
+  RL_TRY(launch_dense_error(h, d_p.p, pred_dtype, d_a.p, actual_dtype, n_cells, o4, fl));
+  double host[5];
+  RL_CUDA(h, cudaMemcpyAsync(host, d_o.p, 40, cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  out3[0] = host[0]; out3[1] = host[1]; out3[2] = host[2];
+  memcpy(flags_out, &host[4], sizeof(int));
+  return RL_OK;
+}
+
 int rl_observed_error_dev(rl_handle h, const float* user_f_dev, const float* item_f_dev, int k, int64_t n_users,
                           const int64_t* indptr_dev, const int32_t* indices_dev, const float* values_dev, double* out2_dev) {
   RL_NEED(h);

@@ -73,6 +73,8 @@ int launch_lowrank(rl_context* h, const void* a, const void* b, int in_dtype, in
                    const float* rbias, const float* cbias, void* out, int out_dtype);
 int launch_observed_error(rl_context* h, const float* uf, const float* vf, int k, int64_t n_users,
                           const int64_t* indptr, const int32_t* indices, const float* values, double* out2);
+int launch_dense_error(rl_context* h, const void* pred, int pdtype, const void* actual, int adtype, int64_t n, double* out4,
+                       int* flags);
 int launch_factors_convert(rl_context* h, const void* src, int src_dtype, int64_t rows, int k, int src_ld,
                            void* dst, int dst_dtype, int dst_ld);
 

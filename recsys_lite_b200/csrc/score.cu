@@ -100,7 +100,57 @@ __global__ void __launch_bounds__(256) observed_error_kernel(const float* __rest
   }
 }
 
+// ---- compute_rmse / compute_mae on dense matrices (reference algo.py:662-743): one streaming pass, float64 sums --------
+// out4: [0] sum of squared errors, [1] sum |err|, [2] number of cells with actual > 0; flags: bit 0 = inf seen, bit 1 = NaN
+template <typename TP, typename TA>
+__global__ void __launch_bounds__(256) dense_error_kernel(const TP* __restrict__ pred, const TA* __restrict__ actual, int64_t n,
+                                                          double* __restrict__ out4, int* __restrict__ flags) {
+  double se = 0.0, ae = 0.0, cnt = 0.0;
+  int fl = 0;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < n; p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double pv = static_cast<double>(pred[p]), av = static_cast<double>(actual[p]);
+    if (isinf(pv) || isinf(av)) fl |= 1;
+    if (isnan(pv) || isnan(av)) fl |= 2;
+    if (av > 0.0) {
+      const double d = pv - av;
+      se += d * d;
+      ae += fabs(d);
+      cnt += 1.0;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    se += __shfl_xor_sync(FULL_MASK, se, o);
+    ae += __shfl_xor_sync(FULL_MASK, ae, o);
+    cnt += __shfl_xor_sync(FULL_MASK, cnt, o);
+    fl |= __shfl_xor_sync(FULL_MASK, fl, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out4, se);
+    atomicAdd(out4 + 1, ae);
+    atomicAdd(out4 + 2, cnt);
+    if (fl) atomicOr(flags, fl);
+  }
+}
+
 }  // namespace
+
+int launch_dense_error(rl_context* h, const void* pred, int pdtype, const void* actual, int adtype, int64_t n, double* out4, int* flags) {
+  if (!pred || !actual || !out4 || !flags || n < 0) return fail(h, RL_ERR_INVALID, "dense_error: bad argument");
+  RL_CUDA(h, cudaMemsetAsync(out4, 0, 4 * sizeof(double), h->stream));
+  RL_CUDA(h, cudaMemsetAsync(flags, 0, sizeof(int), h->stream));
+  if (n == 0) return RL_OK;
+  int64_t grid = (n + 255) / 256;
+  if (grid > 16 * h->sm_count) grid = 16 * h->sm_count;
+  const unsigned g = static_cast<unsigned>(grid);
+  if (pdtype == RL_F32 && adtype == RL_F32) dense_error_kernel<float, float><<<g, 256, 0, h->stream>>>(static_cast<const float*>(pred), static_cast<const float*>(actual), n, out4, flags);
+  else if (pdtype == RL_F32 && adtype == RL_F64) dense_error_kernel<float, double><<<g, 256, 0, h->stream>>>(static_cast<const float*>(pred), static_cast<const double*>(actual), n, out4, flags);
+  else if (pdtype == RL_F64 && adtype == RL_F32) dense_error_kernel<double, float><<<g, 256, 0, h->stream>>>(static_cast<const double*>(pred), static_cast<const float*>(actual), n, out4, flags);
+  else if (pdtype == RL_F64 && adtype == RL_F64) dense_error_kernel<double, double><<<g, 256, 0, h->stream>>>(static_cast<const double*>(pred), static_cast<const double*>(actual), n, out4, flags);
+  else return fail(h, RL_ERR_INVALID, "dense_error: unknown dtype");
+  RL_LAUNCH_CHECK(h, "dense_error_kernel");
+  return RL_OK;
+}
 
 bool score_tc_supported(int kp, int n, int64_t n_users, int64_t n_items, const float* ubias, const float* ibias, double gbias);
 int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int64_t dump_ld, int terms);

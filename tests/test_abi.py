@@ -97,11 +97,6 @@ def test_validation_precedes_device_calls():
         r.svd_reconstruct(x, k=9)
     assert r.top_n(np.empty((0, 0)), np.empty((0, 0)), n=3).shape == (0, 0)
     assert not r.svd_reconstruct(np.zeros((3, 4)), k=2).any()           # all-zero guard needs no device
-    assert r.compute_rmse(x + 1, x) == 1.0 and r.compute_mae(x + 1, x) == 1.0
-    with pytest.raises(ValueError, match="infinite"):
-        r.compute_rmse(x * np.inf, x)
-    with pytest.raises(ValueError, match="NaN"):
-        r.compute_mae(x * np.nan, x)
     with pytest.raises(ValueError, match="must have the same shape"):
         r.compute_rmse(x, np.ones((2, 2)))
     m = r.RecommenderSystem("als")
