@@ -11,8 +11,8 @@
 //     shared-memory descriptors and a TMEM round trip per user; at 50 gathered rows per user the per-row
 //     warp-level MMA is the better fit -- see DESIGN.md.)
 //
-//   * the Gram tiles are written once to shared memory, then every lane pulls "its" two rows (l and l + 32) of
-//     the lower triangle into registers;
+//   * the Gram fragments are written once to shared memory (packed lower triangle), then every lane pulls "its" two
+//     rows (l and l + 32) into registers; the same 8.7 KB then receive the factor (packed, column-major);
 //   * right-looking Cholesky entirely in registers: at column j the pivot lane broadcasts a_jj, everyone scales
 //     its rows (L_ij = a_ij * rsqrt(a_jj)), the column goes to shared memory (it is row j of the column-major
 //     factor kept for the refinement solves) and the rank-1 update a_ik -= L_ij L_kj runs as straight FMAs on
@@ -25,19 +25,28 @@
 // rsqrt.approx is good enough here: the factor is only a preconditioner for the float64-residual refinement.
 
 constexpr int K64 = 64;
-constexpr int K64_LD = 68;  // row stride of the column-major factor: 16-byte aligned rows, float4 loads conflict free
+constexpr int K64_TRI = 2176;  // floats of a packed 64 x 64 lower triangle with 4-aligned rows (or 4-column groups)
 constexpr int K64_LDY = 72; // row stride of a gathered row: 8 t + g is a bijection onto the banks for the mma fragments
 constexpr int K64_CH = 16;  // gathered rows per chunk (two k = 8 mma steps)
 
+// Gram staging: row-major packed lower triangle, row i at k64_row(i) (rows padded to a multiple of 4 entries).
+__host__ __device__ constexpr int k64_row(int i) { return 8 * (i >> 2) * ((i >> 2) + 1) + (i & 3) * (4 * (i >> 2) + 4); }
+// Factor: column-major packed lower triangle.  The four columns of group g = j >> 2 all start at row 4g, so that
+// column j holds rows 4g .. 63 at k64_col(j) + (i - 4g): 16-byte aligned, float4 loads of L[4g + 4m ..][j] need no shuffling.
+__host__ __device__ constexpr int k64_col(int j) { return 256 * (j >> 2) - 8 * (j >> 2) * ((j >> 2) - 1) + (j & 3) * (64 - 4 * (j >> 2)); }
+static_assert(k64_row(63) + 64 == K64_TRI && k64_col(63) + 4 == K64_TRI, "packed triangle size");
+
+template <bool WEIGHTED>
 struct K64Smem {
-  static constexpr size_t lt_bytes = sizeof(float) * K64 * K64_LD;
+  static constexpr size_t lt_bytes = sizeof(float) * K64_TRI;
   static constexpr size_t invd_bytes = sizeof(float) * K64;
   static constexpr size_t xs_bytes = sizeof(double) * K64;
-  static constexpr size_t ts_bytes = sizeof(double) * 32;
+  static constexpr size_t ts_bytes = sizeof(double) * K64_CH;
   static constexpr size_t y_bytes = sizeof(float) * 2 * K64_CH * K64_LDY;
-  static constexpr size_t w_bytes = sizeof(float2) * 2 * K64_CH;
+  static constexpr size_t w_bytes = WEIGHTED ? sizeof(float2) * 2 * K64_CH : 0;
   static constexpr size_t bytes = lt_bytes + invd_bytes + xs_bytes + ts_bytes + y_bytes + w_bytes;
-  static constexpr int warps = 4;
+  static constexpr int warps = 4;   // 3 CTAs per SM: 3 x (4 x 18.4 KB + 1 KB) < 228 KB, registers <= 168
+  static_assert(bytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
 };
 
 // cp.async gather of chunk c (16-byte pieces); rows up to the next multiple of 8 are zero-filled for the k = 8 mma
@@ -95,9 +104,9 @@ __device__ __forceinline__ void chol_group4(float (&a0)[32], float (&a1)[64], fl
     const float inv = rsqrtf(fmaxf(piv, 1e-30f));
     const float l0 = PHASE_A ? a0[c] * inv : 0.f;
     const float l1 = a1[c] * inv;
-    float* col = Lt + j * K64_LD;
-    if (PHASE_A) col[lane] = l0;
-    col[32 + lane] = l1;
+    float* col = Lt + k64_col(j) - j0;          // col[i] = L_ij for rows i >= j0
+    if (PHASE_A) { if (lane >= j0) col[lane] = l0; }
+    if (PHASE_A || lane + 32 >= j0) col[32 + lane] = l1;
     if (lane == 0) invd[j] = inv;
     // forward substitution rides along: z_j = b_j / L_jj, b_i -= L_ij z_j for i > j
     const float zj = __shfl_sync(FULL_MASK, PHASE_A ? b0 : b1, owner) * inv;
@@ -119,6 +128,8 @@ __device__ __forceinline__ void chol_group4(float (&a0)[32], float (&a1)[64], fl
     }
 #pragma unroll
     for (int m = 1; m < W1 / 4; ++m) {
+      // rows j0 + 4m .. of column j; beyond row 63 this reads the next column's storage: finite junk that only
+      // ever reaches window slots of the (unused) upper triangle
       const float4 lk = *reinterpret_cast<const float4*>(col + j0 + 4 * m);
       const int d = (c == 3) ? 4 * m - 4 : 4 * m;  // the last pivot of the group writes the window shifted by four
       if (PHASE_A && m < 8) {
@@ -138,51 +149,55 @@ __device__ __forceinline__ void chol_group4(float (&a0)[32], float (&a1)[64], fl
   a1[W1 - 4] = a1[W1 - 3] = a1[W1 - 2] = a1[W1 - 1] = 0.f;
 }
 
-// v <- L^{-T} v   (v0: entry l, v1: entry l + 32); L_ji = Lt[i * LD + j]
+// v <- L^{-T} v   (v0: entry l, v1: entry l + 32); L_ji (j > i) sits in column i: Lt[k64_col(i) - 4 (i >> 2) + j]
 __device__ __forceinline__ void k64_backward(const float* __restrict__ Lt, const float* __restrict__ invd, float& v0, float& v1, int lane) {
+  const float* c0 = Lt + k64_col(lane) - (lane & ~3);
+  const float* c1 = Lt + k64_col(lane + 32) - ((lane + 32) & ~3);
 #pragma unroll 4
   for (int j = 63; j >= 32; --j) {
     const float xj = __shfl_sync(FULL_MASK, v1, j - 32) * invd[j];
     if (lane == j - 32) v1 = xj;
-    else if (lane + 32 < j) v1 = fmaf(-Lt[(lane + 32) * K64_LD + j], xj, v1);
-    v0 = fmaf(-Lt[lane * K64_LD + j], xj, v0);
+    else if (lane + 32 < j) v1 = fmaf(-c1[j], xj, v1);
+    v0 = fmaf(-c0[j], xj, v0);
   }
 #pragma unroll 4
   for (int j = 31; j >= 0; --j) {
     const float xj = __shfl_sync(FULL_MASK, v0, j) * invd[j];
     if (lane == j) v0 = xj;
-    else if (lane < j) v0 = fmaf(-Lt[lane * K64_LD + j], xj, v0);
+    else if (lane < j) v0 = fmaf(-c0[j], xj, v0);
   }
 }
 
-// v <- L^{-1} v ; L_ij = Lt[j * LD + i]
+// v <- L^{-1} v ; L_ij (i > j) = Lt[k64_col(j) - 4 (j >> 2) + i]
 __device__ __forceinline__ void k64_forward(const float* __restrict__ Lt, const float* __restrict__ invd, float& v0, float& v1, int lane) {
 #pragma unroll 4
   for (int j = 0; j < 32; ++j) {
+    const float* col = Lt + k64_col(j) - (j & ~3);
     const float zj = __shfl_sync(FULL_MASK, v0, j) * invd[j];
     if (lane == j) v0 = zj;
-    else if (lane > j) v0 = fmaf(-Lt[j * K64_LD + lane], zj, v0);
-    v1 = fmaf(-Lt[j * K64_LD + 32 + lane], zj, v1);
+    else if (lane > j) v0 = fmaf(-col[lane], zj, v0);
+    v1 = fmaf(-col[32 + lane], zj, v1);
   }
 #pragma unroll 4
   for (int j = 32; j < 64; ++j) {
+    const float* col = Lt + k64_col(j) - (j & ~3);
     const float zj = __shfl_sync(FULL_MASK, v1, j - 32) * invd[j];
     if (lane == j - 32) v1 = zj;
-    else if (lane + 32 > j) v1 = fmaf(-Lt[j * K64_LD + 32 + lane], zj, v1);
+    else if (lane + 32 > j) v1 = fmaf(-col[32 + lane], zj, v1);
   }
 }
 
 template <bool WEIGHTED>
-__global__ void __launch_bounds__(K64Smem::warps * 32) als_k64_kernel(const AlsArgs a) {
+__global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, 3) als_k64_kernel(const AlsArgs a) {
   constexpr int KP = K64, CH = K64_CH, LDY = K64_LDY;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* wbase = smem_raw + static_cast<size_t>(warp) * K64Smem::bytes;
+  unsigned char* wbase = smem_raw + static_cast<size_t>(warp) * K64Smem<WEIGHTED>::bytes;
   float* Lt = reinterpret_cast<float*>(wbase);
-  float* invd = Lt + K64 * K64_LD;
+  float* invd = Lt + K64_TRI;
   double* xs = reinterpret_cast<double*>(invd + K64);
   double* ts = xs + K64;
-  float* ybuf = reinterpret_cast<float*>(ts + 32);
+  float* ybuf = reinterpret_cast<float*>(ts + K64_CH);
   float2* wbuf = reinterpret_cast<float2*>(ybuf + 2 * CH * LDY);
 
   const float lam = static_cast<float>(a.lambda);
@@ -280,7 +295,7 @@ __global__ void __launch_bounds__(K64Smem::warps * 32) als_k64_kernel(const AlsA
       __syncwarp();
     }
 
-    // ---- Gram fragments -> shared (row-major lower triangle, stride K64_LD) -> two rows per lane in registers ------
+    // ---- Gram fragments -> shared (packed row-major lower triangle) -> two rows per lane in registers ------
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -293,7 +308,7 @@ __global__ void __launch_bounds__(K64Smem::warps * 32) als_k64_kernel(const AlsA
             float v = d[e];
             if (hkv) v += static_cast<float>(a.w0 * a.gram0[gi * KP + gj]);
             if (gi == gj) v += (gi < a.k) ? lam : 1.0f;
-            Lt[gi * K64_LD + gj] = v;
+            Lt[k64_row(gi) + gj] = v;
           }
         }
       }
@@ -301,12 +316,12 @@ __global__ void __launch_bounds__(K64Smem::warps * 32) als_k64_kernel(const AlsA
     float a0[32], a1[64];
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
-      const float4 v = *reinterpret_cast<const float4*>(Lt + lane * K64_LD + 4 * m);
+      const float4 v = *reinterpret_cast<const float4*>(Lt + k64_row(lane) + 4 * m);
       a0[4 * m] = v.x; a0[4 * m + 1] = v.y; a0[4 * m + 2] = v.z; a0[4 * m + 3] = v.w;
     }
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-      const float4 v = *reinterpret_cast<const float4*>(Lt + (32 + lane) * K64_LD + 4 * m);
+      const float4 v = *reinterpret_cast<const float4*>(Lt + k64_row(32 + lane) + 4 * m);
       a1[4 * m] = v.x; a1[4 * m + 1] = v.y; a1[4 * m + 2] = v.z; a1[4 * m + 3] = v.w;
     }
     __syncwarp();
@@ -395,8 +410,8 @@ __global__ void __launch_bounds__(K64Smem::warps * 32) als_k64_kernel(const AlsA
 template <bool WEIGHTED>
 int launch_k64(rl_context* h, const AlsArgs& args) {
   auto kern = als_k64_kernel<WEIGHTED>;
-  constexpr int W = K64Smem::warps;
-  const size_t smem = K64Smem::bytes * W;
+  constexpr int W = K64Smem<WEIGHTED>::warps;
+  const size_t smem = K64Smem<WEIGHTED>::bytes * W;
   RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;
   RL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, smem));
