@@ -400,15 +400,24 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
             const uint32_t slot = slot_global % TC_SLOTS, ph = (slot_global / TC_SLOTS) & 1;
             mbar_wait_t(BAR(B_FULL + slot), ph, w_b);       // V (part 0) or V_lo (part 1) tile landed
             tc_fence_after();
-            const uint32_t b_base = base + S::off_b + slot * S::B_BYTES;
-            // part 0: U.V (+ U_lo.V when TERMS == 3)      part 1: U.V_lo
-            const int n_a = (part == 0 && TERMS == 3) ? 2 : 1;
-            for (int ta = 0; ta < n_a; ++ta) {
+            // one descriptor per slot; the K steps only add compile-time constants to its address field (the single
+            // issuing thread must spend fewer cycles per MMA than the 64 cycles the tensor core needs for it)
+            const uint64_t bd0 = make_desc(base + S::off_b + slot * S::B_BYTES);
+            if (part == 0) {
 #pragma unroll
-              for (int kk = 0; kk < KP / 8; ++kk) {
-                const uint64_t bd = make_desc(b_base + (kk >> 2) * (TC_BN * 128) + (kk & 3) * 32u);
-                tc_mma_tf32_ts(d_tmem, tmem_base + ta * A_LO_COL + kk * 8, bd, TC_IDESC, (part | ta | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < KP / 8; ++kk)
+                tc_mma_tf32_ts(d_tmem, tmem_base + kk * 8, bd0 + (((kk >> 2) * (TC_BN * 128) + (kk & 3) * 32) >> 4), TC_IDESC,
+                               kk != 0 ? 1u : 0u);
+              if (TERMS == 3) {
+#pragma unroll
+                for (int kk = 0; kk < KP / 8; ++kk)
+                  tc_mma_tf32_ts(d_tmem, tmem_base + A_LO_COL + kk * 8, bd0 + (((kk >> 2) * (TC_BN * 128) + (kk & 3) * 32) >> 4),
+                                 TC_IDESC, 1u);
               }
+            } else {
+#pragma unroll
+              for (int kk = 0; kk < KP / 8; ++kk)
+                tc_mma_tf32_ts(d_tmem, tmem_base + kk * 8, bd0 + (((kk >> 2) * (TC_BN * 128) + (kk & 3) * 32) >> 4), TC_IDESC, 1u);
             }
             tc_commit(BAR(B_EMPTY + slot));          // slot reusable once these MMAs retire
           }
