@@ -300,7 +300,7 @@ def run_b200(args, w):
                          "achieved": flops_score / (t_score * 1e-3) / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": flops_score / (t_score * 1e-3) / 1e12 / peaks["tflops"], "traffic": traffic.get("score_topn"),
                          "tensor_pipe_active_pct_ncu": (traffic.get("tensor_pipe_active_pct") or {}).get("score_topn"),
-                         "note": "algorithmic flops 2*n_users*n_items*k; the kernel issues 3 tf32 MMAs per product term (split operands)",
+                         "note": "algorithmic flops 2*n_users*n_items*k; the kernel issues 3 fp16 MMAs per product (split operands), so the tensor pipe does 3x the algorithmic flops",
                          "peak_source": peaks["source"] + " bf16 sustained"},
             "roofline_als": {
                 "bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_source": peaks["source"],

@@ -124,8 +124,8 @@ int rl_score_topn_dev(rl_handle h, const float* user_f_dev, int64_t n_users,
                       int n, int32_t* idx_out_dev, double* score_out_dev, int mode);
 #define RL_SCORE_AUTO 0   /* tensor-core candidate pass + exact rescoring when shapes allow, else exact   */
 #define RL_SCORE_EXACT 1  /* CUDA-core float64 scoring of every pair                                       */
-#define RL_SCORE_TENSOR 2 /* force the tcgen05 candidate pass, split-operand 3 x tf32 (error if unsupported shape) */
-#define RL_SCORE_TENSOR_TF32X1 3 /* same with a single tf32 product: wider candidate window, more exact-kernel fallbacks */
+#define RL_SCORE_TENSOR 2 /* force the tcgen05 candidate pass, split-operand 3 x fp16 (error if unsupported shape) */
+#define RL_SCORE_TENSOR_TF32X1 3 /* same with a single fp16 product: wider candidate window, more exact-kernel fallbacks */
 
 /* debug / validation of the tensor-core path: raw tensor-core scores U V^T (terms = 1: one tf32 product, 3: split
  * operands), out (n_users x ld) float32 with ld >= n_items rounded up to 128 (the padding columns receive the

@@ -158,7 +158,7 @@ int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int
 int launch_score_dump(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k, float* out, int64_t ld,
                       int terms) {
   const int kp = padded_k(k);
-  if (kp != 32 && kp != 64) return fail(h, RL_ERR_INVALID, "score_dump: padded k must be 32 or 64");
+  if (kp == 0) return fail(h, RL_ERR_INVALID, "score_dump: k=%d outside [1, 128]", k);
   if (!uf || !vf || !out || ld < ((n_items + 127) / 128) * 128) return fail(h, RL_ERR_INVALID, "score_dump: bad argument");
   ScoreArgs a{uf, vf, n_users, n_items, nullptr, nullptr, 0.0, nullptr, nullptr, 1, nullptr, nullptr, nullptr, 0, false};
   return launch_score_tc(h, kp, a, out, ld, terms);
@@ -179,7 +179,7 @@ int launch_score_topn(rl_context* h, const float* uf, int64_t n_users, const flo
   const bool tc_ok = score_tc_supported(kp, n, n_users, n_items, ubias, ibias, gbias);
   if (mode < RL_SCORE_AUTO || mode > RL_SCORE_TENSOR_TF32X1) return fail(h, RL_ERR_INVALID, "score_topn: unknown mode %d", mode);
   if ((mode == RL_SCORE_TENSOR || mode == RL_SCORE_TENSOR_TF32X1) && !tc_ok)
-    return fail(h, RL_ERR_INVALID, "score_topn: tensor-core path needs padded k in {32, 64}, n <= 16, >= 1024 items and no bias terms");
+    return fail(h, RL_ERR_INVALID, "score_topn: tensor-core path needs k <= 128, n <= 16, >= 1024 items and no bias terms");
   if (mode != RL_SCORE_EXACT && tc_ok) return launch_score_tc(h, kp, a, nullptr, 0, mode == RL_SCORE_TENSOR_TF32X1 ? 1 : 3);
   return launch_score_exact(h, kp, a);
 }

@@ -4,27 +4,31 @@
 // ever writing the n_users x n_items score matrix.  One persistent CTA per SM owns 128 users at a time (one TMEM
 // lane = one user) and sweeps all items in tiles of 128:
 //
-//   warp 0     TMA producer: V (and V_lo) tiles (128 x KP fp32) through a shared-memory slot ring (128B swizzle,
+//   warp 0     TMA producer: V_hi (and V_lo) tiles (128 x KP fp16) through a shared-memory slot ring (128B swizzle,
 //              K-major), mbarrier complete_tx signalling;
-//   warp 1     MMA issuer: tcgen05.mma.kind::tf32 (M=128, N=128, K=8), A operand (the user tile) from TMEM, B from the
-//              fp32 tiles in shared memory (the tensor core reads the upper 19 bits), three 128-column accumulator
-//              stages in TMEM;
-//   warp 2     TMEM allocation (512 columns: 128 for the user tile hi|lo, 3 x 128 accumulators);
-//   warps 4-7  user-tile loaders: each thread reads its user's factor row from global memory and writes it (and its
-//              low part) into its TMEM lane with tcgen05.st -- no shared-memory copy of U, no U_lo array; the same
-//              threads finish the PREVIOUS user tile (exact re-scoring of its candidates) while the next sweep runs;
+//   warp 1     MMA issuer: tcgen05.mma.kind::f16 (M=128, N=128, K=16), A operand (the user tile) from TMEM, B from the
+//              fp16 tiles in shared memory, three 128-column fp32 accumulator stages in TMEM;
+//   warp 2     TMEM allocation (512 columns: up to 128 for the user tile hi|lo, 3 x 128 accumulators);
+//   warps 4-7  user-tile loaders: each thread reads its user's factor row from global memory, scales it by a power of
+//              two, splits it into two fp16 numbers and writes both (packed two per column) into its TMEM lane with
+//              tcgen05.st -- no shared-memory copy of U; the same threads finish the PREVIOUS user tile (exact
+//              re-scoring of its candidates) while the next sweep runs;
 //   warps 8-19 three epilogue sets that take item tiles round robin: tcgen05.ld 32 columns at a time, 3-input max over
 //              groups of 8 scores and ONE compare against the row threshold per group (~0.6 instructions per score);
 //              scores above the threshold are pushed to a small per-row FIFO and drained at the end of the tile by
 //              all 32 rows of the warp in parallel: seen-item cursor check (CSR, ascending), top-n tracker, candidate
 //              buffer in shared memory.
 //
-// Precision (TERMS).  A single tf32 product is only good to 2^-9 |u||v|: with 10^5 items the top scores of ALS
+// Precision (TERMS).  A single fp16 product is only good to 2^-10 |u||v|: with 10^5 items the top scores of ALS
 // factors are ~3e-5 apart, so the candidate window would hold hundreds of items.  TERMS = 3 is the split-operand
-// scheme: x = x_hi + x_lo with x_hi = the 19 upper bits (what the tensor core reads anyway) and x_lo = x - x_hi
-// (exact in fp32, precomputed once per call), and  u.v ~ u_hi.v_hi + u_lo.v_hi + u_hi.v_lo  accumulated in the
-// same TMEM tile (3 x KP/8 MMAs per item tile).  The dropped u_lo.v_lo term and the re-truncation of the lo parts
-// are each below 2^-20 |u||v|.
+// scheme: x s = x_hi + x_lo + r with s a power of two that puts max|x| at <= 2^14 (one s for all of V, one per
+// user row: a per-row scale multiplies that row's scores by a constant and changes no ranking), x_hi = fp16(x s),
+// x_lo = fp16(x s - x_hi), |r| <= 2^-22 |x s| (22 significant bits; entries more than 2^17 below the row maximum
+// lose low bits to fp16 subnormals, which is < 2^-38 of the row norm), and
+//     u.v ~ u_hi.v_hi + u_lo.v_hi + u_hi.v_lo
+// accumulated in the same fp32 TMEM tile (3 x KP/16 MMAs per item tile).  fp16 x fp16 products are exact in fp32;
+// the dropped u_lo.v_lo term and the two residuals r are each below 2^-22 |u||v|.  The fp16 kind runs at twice
+// the tf32 rate on the tensor pipe, so this costs half of a 3 x tf32 split at (slightly better than) the same accuracy.
 //
 // Exactness.  The approximate scores s~ satisfy |s~ - s| <= eps_u = ERR * |u|_2 * max_i |v_i|_2 (ERR covers the
 // operand terms above plus fp32 accumulation).  Each row tracks the n best approximate scores of UNSEEN items; a
@@ -33,6 +37,7 @@
 // desc, index asc).  Rows whose candidate buffer overflows are listed for the exact CUDA-core kernel.  The
 // result is identical to rl_score_topn_dev(mode = RL_SCORE_EXACT).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -45,21 +50,21 @@ namespace {
 constexpr int TC_BM = 128;      // users per tile (TMEM lanes)
 constexpr int TC_BN = 128;      // items per tile (TMEM columns per accumulator stage)
 constexpr int TC_ACC = 3;       // TMEM accumulator stages (columns 128..511; columns 0..127 hold the user tile hi|lo)
-constexpr int TC_SLOTS = 4;     // shared-memory slots of the V ring
 constexpr int TC_SETS = 2;      // epilogue warp sets (each 4 warps = 128 rows), taking item tiles round robin
 constexpr int TC_THREADS = 32 * (8 + 4 * TC_SETS);
-constexpr int TC_CAND = 32;     // candidate / raw-hit slots per row and set
+constexpr int TC_CAND = 40;     // candidate / raw-hit slots per row and set
 constexpr int TC_NTOP = 16;     // largest n served by this path
-constexpr int TC_TRIG = 22;     // a row asks for a batch pass once it holds this many entries
+constexpr int TC_TRIG = 20;     // a row asks for a batch pass (at the end of a tile) once it holds this many entries
 // bounds on |tensor-core dot - exact dot| / (|u| |v|), checked by tests/test_gpu_parity.py::test_tensor_core_raw_scores
-constexpr float TC_ERR1 = 2.5e-3f;   // one tf32 product: 2^-9 operand truncation (+ accumulation)
-constexpr float TC_ERR3 = 6.0e-6f;   // split operands: 3 * 2^-20 = 2.9e-6 operand terms + fp32 accumulation; measured <= 1.8e-6
+constexpr float TC_ERR1 = 1.5e-3f;   // one fp16 product: 2 x 2^-11 operand rounding (+ accumulation)
+constexpr float TC_ERR3 = 6.0e-6f;   // split operands: 3 * 2^-22 = 7.2e-7 operand terms + fp32 accumulation (64 .. 128 terms)
 
 template <int KP, int TERMS>
 struct TcSmem {
-  static constexpr int NKH = KP / 32;                          // 128-byte K sub-tiles
-  static constexpr int SPT = TERMS == 3 ? 2 : 1;               // ring slots per item tile (V, V_lo)
-  static constexpr uint32_t B_BYTES = TC_BN * KP * 4;          // one ring slot
+  static constexpr int SLOTS = KP > 64 ? 3 : 4;                // shared-memory slots of the V ring (hi and lo tiles alternate)
+  static constexpr int NKH = KP / 64;                          // 128-byte K sub-tiles (64 fp16)
+  static constexpr int SPT = TERMS == 3 ? 2 : 1;               // ring slots per item tile (V_hi, V_lo)
+  static constexpr uint32_t B_BYTES = TC_BN * KP * 2;          // one ring slot
   static constexpr uint32_t off_b = 0;
   // per epilogue set: cs [CAND][128] f32 | ci [CAND][128] i32 | top [NTOP][128] f32 | state 12 x [128]
   static constexpr uint32_t SET_CS = 0;
@@ -67,7 +72,7 @@ struct TcSmem {
   static constexpr uint32_t SET_TOP = SET_CI + TC_CAND * TC_BM * 4;
   static constexpr uint32_t SET_STATE = SET_TOP + TC_NTOP * TC_BM * 4;
   static constexpr uint32_t SET_BYTES = SET_STATE + 12 * TC_BM * 4;
-  static constexpr uint32_t off_sets = off_b + TC_SLOTS * B_BYTES;
+  static constexpr uint32_t off_sets = off_b + SLOTS * B_BYTES;
   static constexpr uint32_t off_bar = off_sets + TC_SETS * SET_BYTES;
   static constexpr uint32_t total = off_bar + 256 + 1024;           // + alignment slack
   static_assert(total <= 227 * 1024, "tensor-core scoring kernel exceeds shared memory");
@@ -76,6 +81,7 @@ struct TcSmem {
 struct TcArgs {
   const float* uf;
   const float* vf;
+  int ldf;                  // row stride (floats) of uf / vf: the padded k of the caller, <= KP
   int64_t n_users;
   int n_items;
   const int64_t* seen_indptr;
@@ -153,14 +159,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -177,28 +175,34 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
+// the same, with the loaded registers tied to the wait so that no use of them can be scheduled above it
+__device__ __forceinline__ void tc_wait_ld_dep(float (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]),
+                 "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]),
+                 "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]),
+                 "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
       "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
-        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
-        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
-        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
-        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+        "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+        "r"(v[30]), "r"(v[31])
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem], fp16 operands, fp32 accumulate
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -215,14 +219,41 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
          (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
 }
 
-// instruction descriptor: D fp32, A/B tf32, both K-major, N = TC_BN, M = 128
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(TC_BN >> 3) << 17) |
+// instruction descriptor: D fp32 (bits 4-5 = 1), A/B fp16 (format 0), both K-major, N = TC_BN, M = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(TC_BN >> 3) << 17) |
                               (static_cast<uint32_t>(TC_BM >> 4) << 24);
+
+// power-of-two scale s with m * s <= 2^14 (fp16 headroom: hi parts stay finite, lo parts stay normal down to 2^-17 m)
+__host__ __device__ __forceinline__ float pow2_scale(float m) {
+  if (!(m > 0.f) || !(m < 3.0e38f)) return 1.0f;
+  int e;
+  frexpf(m, &e);                       // m = f * 2^e, f in [0.5, 1)
+  e = 14 - e;
+  e = e > 100 ? 100 : (e < -100 ? -100 : e);
+  return ldexpf(1.0f, e);
+}
+// (hi, lo) fp16 pairs of two scaled values, packed low half = first element (TMEM / shared-memory K order)
+__device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__device__ __forceinline__ float row_absmax(const float4* p, int ld) {
+  float mx = 0.f;
+  for (int c = 0; c < ld / 4; ++c) {
+    const float4 x = p[c];
+    mx = fmaxf(fmaxf(mx, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
+  }
+  return mx;
+}
 
 // ---- per-row selection state: thread-private slices of shared memory ([field][row], conflict free) ------------
 struct RowMem {
-  float* cs;        // [TC_CAND][128] approximate scores: entries [0, keep) are checked candidates, [keep, cnt) raw hits
-  int* ci;          // [TC_CAND][128] their item ids (ascending inside each of the two runs)
+  float2* c2;       // [TC_CAND][128] (approximate score, item id as bits): entries [0, keep) are checked candidates,
+                    // [keep, cnt) raw hits; item ids ascend inside each of the two runs.  One 8-byte store per hit.
   float* top;       // [TC_NTOP][128] n best approximate scores of unseen items, descending
   int* keep;        // [128]
   int* nxt;         // [128] next seen item id >= current column (INT_MAX: none)
@@ -239,8 +270,8 @@ struct RowMem {
 __device__ __forceinline__ RowMem row_mem(unsigned char* set_base, uint32_t set_cs, uint32_t set_ci, uint32_t set_top,
                                           uint32_t set_state) {
   RowMem m;
-  m.cs = reinterpret_cast<float*>(set_base + set_cs);
-  m.ci = reinterpret_cast<int*>(set_base + set_ci);
+  m.c2 = reinterpret_cast<float2*>(set_base + set_cs);   // spans the SET_CS and SET_CI regions
+  (void)set_ci;
   m.top = reinterpret_cast<float*>(set_base + set_top);
   int* st = reinterpret_cast<int*>(set_base + set_state);
   m.keep = st; m.nxt = st + TC_BM; m.nxt2 = st + 2 * TC_BM; m.cur_lo = st + 3 * TC_BM; m.cur_hi = st + 4 * TC_BM;
@@ -267,8 +298,9 @@ __device__ __forceinline__ float row_batch(int cnt, int row, float tau, RowMem m
 #pragma unroll
   for (int i = 0; i < TC_NTOP; ++i) t[i] = m.top[i * TC_BM + row];
   for (int f = keep; f < cnt; ++f) {
-    float sc = m.cs[f * TC_BM + row];
-    const int col = m.ci[f * TC_BM + row];
+    const float2 e = m.c2[f * TC_BM + row];
+    float sc = e.x;
+    const int col = __float_as_int(e.y);
     int nxt;
     for (;;) {                                 // move the seen cursor up to this column
       nxt = w[0];
@@ -285,7 +317,7 @@ __device__ __forceinline__ float row_batch(int cnt, int row, float tau, RowMem m
     }
     if (col == nxt || col >= n_items) {
       sc = -CUDART_INF_F;
-      m.cs[f * TC_BM + row] = sc;
+      m.c2[f * TC_BM + row].x = sc;
     }
     // descending sorted insert without branches: new[i] = max(old[i], min(old[i-1], sc))
 #pragma unroll
@@ -303,10 +335,9 @@ __device__ __forceinline__ float row_batch(int cnt, int row, float tau, RowMem m
   m.tau_pub[row] = tau;
   int j = 0;
   for (int f = 0; f < cnt; ++f) {
-    const float v = m.cs[f * TC_BM + row];
-    if (v > tau) {
-      m.cs[j * TC_BM + row] = v;
-      m.ci[j * TC_BM + row] = m.ci[f * TC_BM + row];
+    const float2 e = m.c2[f * TC_BM + row];
+    if (e.x > tau) {
+      m.c2[j * TC_BM + row] = e;
       ++j;
     }
   }
@@ -332,10 +363,11 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
   // barriers: [0,S) slot full  [S,2S) slot empty  a_full  a_empty  [.., +ACC) tmem_full  [.., +ACC) tmem_empty ; then: tmem base
   const uint32_t bar0 = base + S::off_bar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
+  constexpr int TC_SLOTS = S::SLOTS;
   constexpr int B_FULL = 0, B_EMPTY = TC_SLOTS, A_FULL = 2 * TC_SLOTS, A_EMPTY = A_FULL + 1, T_FULL = A_FULL + 2, T_EMPTY = T_FULL + TC_ACC;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + T_EMPTY + TC_ACC);
   int* claim = reinterpret_cast<int*>(bars + T_EMPTY + TC_ACC + 1);   // [2 parities][4 lane quarters] item-tile tickets
-  constexpr uint32_t A_LO_COL = KP;          // TMEM columns [0, KP): user rows as given; [KP, 2 KP): their low parts
+  constexpr uint32_t A_LO_COL = KP / 2;      // TMEM columns [0, KP/2): user rows, hi parts (two fp16 per column); [KP/2, KP): lo parts
   constexpr uint32_t ACC_COL0 = 128;         // accumulator stage s lives in columns [128 + 128 s, 256 + 128 s)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -376,7 +408,7 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
 #pragma unroll
             for (int kh = 0; kh < S::NKH; ++kh)
               tma_load_2d(base + S::off_b + slot * S::B_BYTES + kh * (TC_BN * 128), part == 0 ? &map_v : &map_vlo,
-                          BAR(B_FULL + slot), kh * 32, it * TC_BN);
+                          BAR(B_FULL + slot), kh * 64, it * TC_BN);
           }
         }
       }
@@ -403,22 +435,23 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
             // one descriptor per slot; the K steps only add compile-time constants to its address field (the single
             // issuing thread must spend fewer cycles per MMA than the 64 cycles the tensor core needs for it)
             const uint64_t bd0 = make_desc(base + S::off_b + slot * S::B_BYTES);
-            if (part == 0) {
+            // K step kk (16 fp16 = 32 bytes of the 128-byte swizzled row, 8 TMEM columns of the A operand)
+#define RL_BOFF(kk) (static_cast<uint64_t>((((kk) >> 2) * (TC_BN * 128) + ((kk) & 3) * 32) >> 4))
+            if (part == 0) {                         // U_hi . V_hi  (+ U_lo . V_hi)
 #pragma unroll
-              for (int kk = 0; kk < KP / 8; ++kk)
-                tc_mma_tf32_ts(d_tmem, tmem_base + kk * 8, bd0 + (((kk >> 2) * (TC_BN * 128) + (kk & 3) * 32) >> 4), TC_IDESC,
-                               kk != 0 ? 1u : 0u);
+              for (int kk = 0; kk < KP / 16; ++kk)
+                tc_mma_f16_ts(d_tmem, tmem_base + kk * 8, bd0 + RL_BOFF(kk), TC_IDESC, kk != 0 ? 1u : 0u);
               if (TERMS == 3) {
 #pragma unroll
-                for (int kk = 0; kk < KP / 8; ++kk)
-                  tc_mma_tf32_ts(d_tmem, tmem_base + A_LO_COL + kk * 8, bd0 + (((kk >> 2) * (TC_BN * 128) + (kk & 3) * 32) >> 4),
-                                 TC_IDESC, 1u);
+                for (int kk = 0; kk < KP / 16; ++kk)
+                  tc_mma_f16_ts(d_tmem, tmem_base + A_LO_COL + kk * 8, bd0 + RL_BOFF(kk), TC_IDESC, 1u);
               }
-            } else {
+            } else {                                 // U_hi . V_lo
 #pragma unroll
-              for (int kk = 0; kk < KP / 8; ++kk)
-                tc_mma_tf32_ts(d_tmem, tmem_base + kk * 8, bd0 + (((kk >> 2) * (TC_BN * 128) + (kk & 3) * 32) >> 4), TC_IDESC, 1u);
+              for (int kk = 0; kk < KP / 16; ++kk)
+                tc_mma_f16_ts(d_tmem, tmem_base + kk * 8, bd0 + RL_BOFF(kk), TC_IDESC, 1u);
             }
+#undef RL_BOFF
             tc_commit(BAR(B_EMPTY + slot));          // slot reusable once these MMAs retire
           }
           tc_commit(BAR(T_FULL + acc));              // accumulator ready for the epilogue
@@ -436,24 +469,21 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
       const int64_t user = static_cast<int64_t>(ut) * TC_BM + row;
       mbar_wait_relaxed(BAR(A_EMPTY), (ut_local & 1) ^ 1, 200);
       tc_fence_after();
+      const float4* up = reinterpret_cast<const float4*>(a.uf + user * a.ldf);
+      float su = 1.0f;
+      if (user < a.n_users) su = pow2_scale(row_absmax(up, a.ldf));
 #pragma unroll
-      for (int c0 = 0; c0 < KP; c0 += 32) {
-        float x[32], lo[32];
-        if (user < a.n_users) {
-          const float4* up = reinterpret_cast<const float4*>(a.uf + user * KP + c0);
+      for (int c0 = 0; c0 < KP; c0 += 64) {        // 64 factors = 32 packed TMEM columns per tcgen05.st
+        uint32_t hi[32], lo[32];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 v = up[c];
-            x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) x[c] = 0.f;
+        for (int c = 0; c < 16; ++c) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (user < a.n_users && c0 + 4 * c < a.ldf) v = up[c0 / 4 + c];
+          split_h2(v.x * su, v.y * su, hi[2 * c], lo[2 * c]);
+          split_h2(v.z * su, v.w * su, hi[2 * c + 1], lo[2 * c + 1]);
         }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) lo[c] = x[c] - __uint_as_float(__float_as_uint(x[c]) & 0xFFFFE000u);
-        tc_st32(t_row + c0, x);
-        if (TERMS == 3) tc_st32(t_row + A_LO_COL + c0, lo);
+        tc_st32(t_row + c0 / 2, hi);
+        if (TERMS == 3) tc_st32(t_row + A_LO_COL + c0 / 2, lo);
       }
       tc_wait_st();
       tc_fence_before();
@@ -479,7 +509,7 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
         const RowMem om = row_mem(sm + S::off_sets + e * S::SET_BYTES, S::SET_CS, S::SET_CI, S::SET_TOP, S::SET_STATE);
         overflow |= (om.flags[row] & 1) != 0;
         const int c_e = om.keep[row];
-        for (int c = 0; c < c_e; ++c) ids[total++] = om.ci[c * TC_BM + row];
+        for (int c = 0; c < c_e; ++c) ids[total++] = __float_as_int(om.c2[c * TC_BM + row].y);
       }
       named_bar_sync(2, 128 * (TC_SETS + 1));     // candidates copied: the sets may reset and start the next sweep
       if (ut + static_cast<int>(gridDim.x) < a.n_user_tiles) load_tile(ut + gridDim.x, ut_local + 1);
@@ -491,12 +521,12 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
         continue;
       }
       double ex[TC_SETS * TC_CAND];
-      const float* up = a.uf + user * KP;
+      const float* up = a.uf + user * a.ldf;
       for (int c = 0; c < total; ++c) {
-        const float* vp = a.vf + static_cast<int64_t>(ids[c]) * KP;
+        const float* vp = a.vf + static_cast<int64_t>(ids[c]) * a.ldf;
         double accd = 0.0;
 #pragma unroll 4
-        for (int k4 = 0; k4 < KP / 4; ++k4) {
+        for (int k4 = 0; k4 < a.ldf / 4; ++k4) {
           const float4 x = *reinterpret_cast<const float4*>(up + 4 * k4);
           const float4 y = *reinterpret_cast<const float4*>(vp + 4 * k4);
           accd = fma(static_cast<double>(x.x), static_cast<double>(y.x), accd);
@@ -527,7 +557,8 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
     const int set = (warp - 8) >> 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;          // row inside the user tile == TMEM lane
-    const float vmax = DUMP ? 0.f : *a.vmax;
+    const float vmax = *a.vmax;
+    const float sv = pow2_scale(vmax);           // the scale the V_hi / V_lo arrays were built with
     const RowMem rm = row_mem(sm + S::off_sets + set * S::SET_BYTES, S::SET_CS, S::SET_CI, S::SET_TOP, S::SET_STATE);
     const float* other0 = row_mem(sm + S::off_sets + ((set + 1) % TC_SETS) * S::SET_BYTES, S::SET_CS, S::SET_CI, S::SET_TOP, S::SET_STATE).tau_pub;
     const float* other1 = row_mem(sm + S::off_sets + ((set + TC_SETS - 1) % TC_SETS) * S::SET_BYTES, S::SET_CS, S::SET_CI, S::SET_TOP, S::SET_STATE).tau_pub;
@@ -539,20 +570,24 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
       const bool valid = user < a.n_users;
       float tau = (a.skip_scan == 2) ? CUDART_INF_F : -CUDART_INF_F;
       int cnt = 0;
+      bool careful = true, gave_up = false;
+      float unscale = 1.0f;                      // DUMP: tensor-core scores are (s_u s_v) u.v
+      if (DUMP && valid) unscale = 1.0f / (pow2_scale(row_absmax(reinterpret_cast<const float4*>(a.uf + user * a.ldf), a.ldf)) * sv);
       if (!DUMP) {
 #pragma unroll
         for (int i = 0; i < TC_NTOP; ++i) rm.top[i * TC_BM + row] = -CUDART_INF_F;
         int64_t cur = 0, end = 0;
         float delta = 0.f;
         if (valid) {
-          float nn = 0.f;
-          const float4* up = reinterpret_cast<const float4*>(a.uf + user * KP);
-#pragma unroll
-          for (int c = 0; c < KP / 4; ++c) {
+          float nn = 0.f, mx = 0.f;
+          const float4* up = reinterpret_cast<const float4*>(a.uf + user * a.ldf);
+          for (int c = 0; c < a.ldf / 4; ++c) {
             const float4 x = up[c];
             nn += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
           }
-          delta = 2.0f * a.err * sqrtf(nn) * vmax + 1e-30f;
+          // scores of this row come out of the tensor core multiplied by s_u s_v: so does the window
+          delta = 2.0f * a.err * (sqrtf(nn) * 1.000001f * pow2_scale(mx)) * (vmax * sv) + 1e-30f;
           if (a.seen_indptr) {
             cur = a.seen_indptr[user];
             end = a.seen_indptr[user + 1];
@@ -577,42 +612,96 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
         mbar_wait_t(BAR(T_FULL + acc), aph, w_full);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ACC_COL0 + acc * TC_BN;
+        auto release_stage = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
+        };
+        const int cnt_in = cnt;
+        bool heavy = false;                      // this row took a batch pass in the middle of the tile
+        if (a.skip_scan == 1) {
+          release_stage();
+        } else if (DUMP || careful) {
+          // ---- careful scan (start of a sweep, or the last tile was crowded): any row may run a batch pass after
+          //      any group of 8 scores, so no row can run out of buffer space
 #pragma unroll 1
-        for (int g = 0; g < (a.skip_scan == 1 ? 0 : TC_BN / 32); ++g) {
-          float s[32];
-          tc_ld32(t_row + g * 32, s);
-          tc_wait_ld();
-          const int col0 = it * TC_BN + g * 32;
-          if (DUMP) {
-            if (valid) {
+          for (int g = 0; g < TC_BN / 32; ++g) {
+            float sg[32];
+            tc_ld32(t_row + g * 32, sg);
+            tc_wait_ld_dep(sg);
+            const int col0 = it * TC_BN + g * 32;
+            if (DUMP) {
+              if (valid) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) a.dump[user * a.dump_ld + col0 + j] = s[j];
-            }
-          } else {
+                for (int j = 0; j < 32; ++j) a.dump[user * a.dump_ld + col0 + j] = sg[j] * unscale;
+              }
+            } else {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const float m8 = max3(max3(s[8 * b], s[8 * b + 1], s[8 * b + 2]), max3(s[8 * b + 3], s[8 * b + 4], s[8 * b + 5]),
-                                    fmaxf(s[8 * b + 6], s[8 * b + 7]));
-              if (m8 > tau) {
+              for (int b = 0; b < 4; ++b) {
+                const float m8 = max3(max3(sg[8 * b], sg[8 * b + 1], sg[8 * b + 2]), max3(sg[8 * b + 3], sg[8 * b + 4], sg[8 * b + 5]),
+                                      fmaxf(sg[8 * b + 6], sg[8 * b + 7]));
+                if (m8 > tau) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  if (s[8 * b + j] > tau) {
-                    rm.cs[cnt * TC_BM + row] = s[8 * b + j];
-                    rm.ci[cnt * TC_BM + row] = col0 + 8 * b + j;
-                    ++cnt;
+                  for (int j = 0; j < 8; ++j) {
+                    if (sg[8 * b + j] > tau) {
+                      rm.c2[cnt * TC_BM + row] = make_float2(sg[8 * b + j], __int_as_float(col0 + 8 * b + j));
+                      ++cnt;
+                    }
                   }
-                }
-                if (cnt > TC_CAND - 8) {   // no room for another group of 8: batch pass right now (start of a sweep)
-                  tau = row_batch(cnt, row, tau, rm, other0, other1, a.seen_indices, a.n_items, a.n);
-                  cnt = rm.keep[row];
+                  if (cnt > TC_CAND - 8) {   // no room for another group of 8: batch pass right now
+                    tau = row_batch(cnt, row, tau, rm, other0, other1, a.seen_indices, a.n_items, a.n);
+                    cnt = rm.keep[row];
+                    heavy = true;
+                  }
                 }
               }
             }
           }
+          release_stage();
+        } else {
+          // ---- steady-state scan: software pipeline over the four 32-column groups (the tcgen05.ld of the next group
+          //      is in flight while this one is scanned -- TMEM reads, 64 B/clk per SM, are what bounds the epilogue),
+          //      the accumulator stage goes back to the MMA warp as soon as the last group sits in registers.  No
+          //      batch pass inside the tile: a row that would run out of buffer space (> 20 hits in one tile right
+          //      after a quiet tile) is handed to the exact kernel.
+          float s0[32], s1[32];
+          auto scan32 = [&](const float (&sg)[32], const int col0) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const float m8 = max3(max3(sg[8 * b], sg[8 * b + 1], sg[8 * b + 2]), max3(sg[8 * b + 3], sg[8 * b + 4], sg[8 * b + 5]),
+                                    fmaxf(sg[8 * b + 6], sg[8 * b + 7]));
+              if (m8 > tau) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  if (sg[8 * b + j] > tau) {
+                    rm.c2[cnt * TC_BM + row] = make_float2(sg[8 * b + j], __int_as_float(col0 + 8 * b + j));
+                    ++cnt;
+                  }
+                }
+                if (cnt > TC_CAND - 8) {     // out of space: stop collecting, the exact kernel finishes this row
+                  gave_up = true;
+                  tau = CUDART_INF_F;
+                  cnt = 0;
+                }
+              }
+            }
+          };
+          tc_ld32(t_row, s0);
+#pragma unroll 1
+          for (int gp = 0; gp < TC_BN / 64; ++gp) {
+            const int col0 = it * TC_BN + gp * 64;
+            tc_wait_ld_dep(s0);
+            tc_ld32(t_row + gp * 64 + 32, s1);
+            scan32(s0, col0);
+            tc_wait_ld_dep(s1);
+            if (gp + 1 < TC_BN / 64) tc_ld32(t_row + gp * 64 + 64, s0);
+            else release_stage();
+            scan32(s1, col0 + 32);
+          }
+          if (gave_up) { rm.flags[row] |= 1; rm.keep[row] = 0; }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
+        // the next tile is scanned carefully if this one was crowded for some row of the warp
+        careful = __any_sync(FULL_MASK, heavy || cnt - cnt_in >= 8);
         if (!DUMP && __any_sync(FULL_MASK, cnt >= TC_TRIG)) {   // one row is filling up: every row of the warp tidies
           const long long t0 = clock64();
           if (cnt > rm.keep[row]) {
@@ -647,16 +736,23 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
   }
 }
 
-// x_lo = x - (x with the 13 low mantissa bits cleared): the part of x the tf32 datapath does not see
-__global__ void __launch_bounds__(256) split_lo_kernel(const float* __restrict__ x, int64_t n4, float* __restrict__ lo) {
-  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < n4; p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const float4 v = reinterpret_cast<const float4*>(x)[p];
-    float4 r;
-    r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-    r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-    r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-    r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-    reinterpret_cast<float4*>(lo)[p] = r;
+// V -> (V_hi, V_lo): fp16 pairs of the scaled entries (scale from the largest row norm, see pow2_scale), rows padded
+// with zeros from ld_src to kp_dst columns
+__global__ void __launch_bounds__(256) split_half_kernel(const float* __restrict__ x, int64_t n_rows, int ld_src, int kp_dst,
+                                                         const float* __restrict__ vmax, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const float sc = pow2_scale(*vmax);
+  const int ppr = kp_dst / 4;
+  const int64_t total = n_rows * ppr;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < total; p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = p / ppr;
+    const int c4 = static_cast<int>(p - r * ppr);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (4 * c4 < ld_src) v = *reinterpret_cast<const float4*>(x + r * ld_src + 4 * c4);
+    uint2 h, l;
+    split_h2(v.x * sc, v.y * sc, h.x, l.x);
+    split_h2(v.z * sc, v.w * sc, h.y, l.y);
+    *reinterpret_cast<uint2*>(hi + r * kp_dst + 4 * c4) = h;
+    if (lo) *reinterpret_cast<uint2*>(lo + r * kp_dst + 4 * c4) = l;
   }
 }
 
@@ -691,14 +787,14 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_map(rl_context* h, CUtensorMap* map, const float* ptr, int64_t rows, int kp, int box_rows) {
+int make_map(rl_context* h, CUtensorMap* map, const __half* ptr, int64_t rows, int kp, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(h, RL_ERR_CUDA, "score_tc: cuTensorMapEncodeTiled not available from the driver");
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kp), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kp) * 4};
-  const cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kp) * 2};
+  const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};   // 64 fp16 = one 128-byte swizzled row
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(h, RL_ERR_CUDA, "score_tc: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
@@ -725,40 +821,45 @@ int launch_tc_k(rl_context* h, int terms, bool dump, const CUtensorMap& mv, cons
 }  // namespace
 
 bool score_tc_supported(int kp, int n, int64_t n_users, int64_t n_items, const float* ubias, const float* ibias, double gbias) {
-  return (kp == 32 || kp == 64) && n <= TC_NTOP && n <= TC_CAND - 16 && n_items >= 1024 && n_users >= 1 && !ubias && !ibias && gbias == 0.0;
+  return (kp == 16 || kp == 32 || kp == 64 || kp == 128) && n <= TC_NTOP && n <= TC_CAND - 16 && n_items >= 1024 && n_users >= 1 &&
+         !ubias && !ibias && gbias == 0.0;
 }
 
 // tensor-core candidate pass + in-kernel exact re-scoring; overflow rows are finished by the exact kernel.
-// terms: 1 = single tf32 product, 3 = split operands (default).
+// terms: 1 = single fp16 product, 3 = split operands (default).  kp: padded k of the caller's factor rows.
 int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int64_t dump_ld, int terms) {
   if (terms != 1 && terms != 3) return fail(h, RL_ERR_INVALID, "score_tc: terms must be 1 or 3");
-  // scratch: vmax (4 B) | overflow count (4 B) | overflow rows (n_users x 4 B) | V_lo
+  const int kph = kp <= 64 ? 64 : 128;         // fp16 row width of the tensor-core operands (zero padded)
+  // scratch: vmax (4 B) | overflow count (4 B) | debug counters | overflow rows (n_users x 4 B) | V_hi | V_lo
   const size_t rows_bytes = (sizeof(int32_t) * static_cast<size_t>(sa.n_users) + 255) & ~size_t(255);
-  const size_t ulo_bytes = 0;
-  const size_t vlo_bytes = terms == 3 ? sizeof(float) * static_cast<size_t>(sa.n_items) * kp : 0;
+  const size_t vh_bytes = sizeof(__half) * static_cast<size_t>(sa.n_items) * kph;
   void* sc = nullptr;
-  int rc = scratch(h, 256 + rows_bytes + ulo_bytes + vlo_bytes, &sc);
+  int rc = scratch(h, 256 + rows_bytes + 2 * vh_bytes, &sc);
   if (rc != RL_OK) return rc;
   char* scb = static_cast<char*>(sc);
   float* vmax = reinterpret_cast<float*>(scb);
   unsigned int* ocount = reinterpret_cast<unsigned int*>(scb + 4);
   int32_t* orows = reinterpret_cast<int32_t*>(scb + 256);
-  float* ulo = reinterpret_cast<float*>(scb + 256 + rows_bytes);
-  float* vlo = reinterpret_cast<float*>(scb + 256 + rows_bytes + ulo_bytes);
+  __half* vhi = reinterpret_cast<__half*>(scb + 256 + rows_bytes);
+  __half* vlo = reinterpret_cast<__half*>(scb + 256 + rows_bytes + vh_bytes);
   RL_CUDA(h, cudaMemsetAsync(sc, 0, 256, h->stream));
-  if (terms == 3) {
-    const int64_t nv4 = sa.n_items * kp / 4;
+  {
+    int64_t g = (sa.n_items + 255) / 256;
+    if (g > 4 * h->sm_count) g = 4 * h->sm_count;
+    max_row_norm_kernel<<<static_cast<unsigned>(g), 256, 0, h->stream>>>(sa.vf, sa.n_items, kp, vmax);
+    RL_LAUNCH_CHECK(h, "max_row_norm_kernel");
+    const int64_t np = sa.n_items * (kph / 4);
     const int64_t cap = 8 * static_cast<int64_t>(h->sm_count);
-    int64_t g = (nv4 + 255) / 256;
-    split_lo_kernel<<<static_cast<unsigned>(g < cap ? g : cap), 256, 0, h->stream>>>(sa.vf, nv4, vlo);
-    RL_LAUNCH_CHECK(h, "split_lo_kernel");
+    g = (np + 255) / 256;
+    split_half_kernel<<<static_cast<unsigned>(g < cap ? g : cap), 256, 0, h->stream>>>(sa.vf, sa.n_items, kp, kph, vmax, vhi,
+                                                                                     terms == 3 ? vlo : nullptr);
+    RL_LAUNCH_CHECK(h, "split_half_kernel");
   }
-  (void)ulo;
   CUtensorMap mv, mvlo;
-  if ((rc = make_map(h, &mv, sa.vf, sa.n_items, kp, TC_BN)) != RL_OK) return rc;
-  if ((rc = make_map(h, &mvlo, terms == 3 ? vlo : sa.vf, sa.n_items, kp, TC_BN)) != RL_OK) return rc;
+  if ((rc = make_map(h, &mv, vhi, sa.n_items, kph, TC_BN)) != RL_OK) return rc;
+  if ((rc = make_map(h, &mvlo, terms == 3 ? vlo : vhi, sa.n_items, kph, TC_BN)) != RL_OK) return rc;
   TcArgs a{};
-  a.uf = sa.uf; a.vf = sa.vf; a.n_users = sa.n_users; a.n_items = static_cast<int>(sa.n_items);
+  a.uf = sa.uf; a.vf = sa.vf; a.ldf = kp; a.n_users = sa.n_users; a.n_items = static_cast<int>(sa.n_items);
   a.seen_indptr = sa.seen_indptr; a.seen_indices = sa.seen_indices; a.n = sa.n; a.idx_out = sa.idx_out; a.score_out = sa.score_out;
   a.vmax = vmax; a.err = terms == 3 ? TC_ERR3 : TC_ERR1;
   a.overflow_rows = orows; a.overflow_count = ocount; a.dump = dump; a.dump_ld = dump_ld;
@@ -767,15 +868,8 @@ int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int
   const bool want_dbg = getenv("RL_TC_DEBUG") != nullptr;
   a.skip_scan = getenv("RL_TC_SKIPSCAN") ? atoi(getenv("RL_TC_SKIPSCAN")) : 0;
   a.dbg = want_dbg ? reinterpret_cast<long long*>(scb + 8) : nullptr;   // 30 x 8 B inside the 256-byte header
-  if (!dump) {
-    int64_t g = (sa.n_items + 255) / 256;
-    if (g > 4 * h->sm_count) g = 4 * h->sm_count;
-    max_row_norm_kernel<<<static_cast<unsigned>(g), 256, 0, h->stream>>>(sa.vf, sa.n_items, kp, vmax);
-    RL_LAUNCH_CHECK(h, "max_row_norm_kernel");
-  }
-  if (kp == 64) rc = launch_tc_k<64>(h, terms, dump != nullptr, mv, mvlo, a);
-  else if (kp == 32) rc = launch_tc_k<32>(h, terms, dump != nullptr, mv, mvlo, a);
-  else return fail(h, RL_ERR_INVALID, "score_tc: padded k %d not supported by the tensor-core path", kp);
+  if (kph == 64) rc = launch_tc_k<64>(h, terms, dump != nullptr, mv, mvlo, a);
+  else rc = launch_tc_k<128>(h, terms, dump != nullptr, mv, mvlo, a);
   if (rc != RL_OK || dump) return rc;
   // rows whose candidate buffer overflowed: exact kernel on the list (needs the count on the host)
   unsigned int n_over = 0;

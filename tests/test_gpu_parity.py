@@ -365,23 +365,34 @@ def test_api_lifecycle_and_errors():
 
 
 # ---------------------------------------------------------------------------- tensor-core scoring (tcgen05)
-def _tf32_trunc(x):
-    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)
-    return b.view(np.float32).astype(np.float64)
+def _pow2_scale(m):
+    """score_tc.cu pow2_scale: the power of two s with m * s <= 2^14 (s = 1 for m = 0)."""
+    m = np.asarray(m, dtype=np.float32)
+    _, e = np.frexp(np.where(m > 0, m, 1.0))
+    return np.where(m > 0, np.ldexp(1.0, np.clip(14 - e, -100, 100)), 1.0)
+
+
+def _fp16_round(x, scale):
+    """x rounded the way the tensor-core operands are: fp16(x * scale) / scale (scale a power of two)."""
+    xs = (np.asarray(x, dtype=np.float32) * np.asarray(scale, dtype=np.float32)).astype(np.float32)
+    return xs.astype(np.float16).astype(np.float64) / scale
 
 
 @pytest.mark.parametrize("terms", [1, 3])
-@pytest.mark.parametrize("k", [64, 32, 50])
+@pytest.mark.parametrize("k", [64, 32, 50, 128, 100, 10])
 def test_tensor_core_raw_scores(h, k, terms):
-    """rl_score_dump_dev: the tcgen05 tile pipeline (TMA 128B swizzle, UMMA descriptors, TMEM layout) reproduces
-    U V^T within the error bound the selection relies on: 2.5e-3 |u||v| for one tf32 product (and it matches the
-    product of tf32-truncated operands), 1.2e-5 |u||v| for the split-operand scheme -- with a 4x safety margin."""
+    """rl_score_dump_dev: the tcgen05 tile pipeline (TMA 128B swizzle, UMMA descriptors, packed fp16 TMEM operand)
+    reproduces U V^T within the error bound the selection relies on: 1.5e-3 |u||v| for one fp16 product (and it
+    matches the product of the fp16-rounded scaled operands), 6e-6 |u||v| for the split-operand scheme."""
     from devbuf import Dev, padded
     n_users, n_items = 300, 1500                      # 3 user tiles (last partial), 12 item tiles (last partial)
     rng = np.random.default_rng(k)
     uf, vf = _f32(rng.standard_normal((n_users, k))), _f32(rng.standard_normal((n_items, k)))
-    if k == 32:                                       # ALS-like all-positive factors: no cancellation in the sums
+    if k in (32, 128):                                # ALS-like all-positive factors: no cancellation in the sums
         uf, vf = np.abs(uf), np.abs(vf)
+    if k == 100:                                      # wide dynamic range across rows and inside a row
+        uf = _f32(uf * np.exp(rng.uniform(-20, 20, (n_users, 1))))
+        vf = _f32(vf * np.exp(rng.uniform(-3, 3, (n_items, k))) * 1e-6)
     ld = ((n_items + 127) // 128) * 128
     d_u, d_v = padded(h, uf, k), padded(h, vf, k)
     d_out = Dev(h, shape=(n_users, ld), dtype=np.float32)
@@ -390,18 +401,21 @@ def test_tensor_core_raw_scores(h, k, terms):
     exact = uf @ vf.T
     norms = np.linalg.norm(uf, axis=1)[:, None] * np.linalg.norm(vf, axis=1)[None, :]
     ratio = float(np.max(np.abs(got[:, :n_items] - exact) / norms))
-    # rigorous operand bounds: 2^-9 (one product), 3 * 2^-20 (split operands); the kernel constants add headroom for
-    # fp32 accumulation.  All-positive factors (k = 32 case) are the worst case: every truncation error has one sign.
+    # rigorous operand bounds: 2 * 2^-11 (one product), 3 * 2^-22 (split operands); the kernel constants (TC_ERR1 =
+    # 1.5e-3, TC_ERR3 = 6e-6) add headroom for the fp32 accumulation, the asserts below keep a margin to them.
     print(f"tensor-core score error / (|u||v|): k={k} terms={terms}: {ratio:.3e}")
-    assert ratio <= (2.0e-3 if terms == 1 else 4.0e-6), ratio
+    assert ratio <= (1.0e-3 if terms == 1 else 3.0e-6), ratio
     if terms == 1:
-        trunc = _tf32_trunc(uf) @ _tf32_trunc(vf).T
-        assert np.max(np.abs(got[:, :n_items] - trunc)) <= 2e-5 * np.abs(exact).max()
+        su = _pow2_scale(np.abs(uf).max(axis=1))[:, None]
+        sv = _pow2_scale(np.float32(np.linalg.norm(vf.astype(np.float64), axis=1).max() * 1.0000002))
+        rounded = _fp16_round(uf, su) @ _fp16_round(vf, sv).T
+        assert np.max(np.abs(got[:, :n_items] - rounded) / norms) <= 2e-6
     assert not got[:, n_items:].any()                 # zero-filled tail of the last item tile
 
 
 @pytest.mark.parametrize("k,n,n_users,n_items", [(64, 10, 1000, 5000), (64, 1, 130, 1024), (32, 12, 257, 3000),
-                                                  (40, 10, 500, 2049)])
+                                                  (40, 10, 500, 2049), (128, 10, 700, 4000), (100, 5, 300, 1500),
+                                                  (16, 10, 300, 1200)])
 def test_tensor_core_topn_equals_exact_kernel(h, k, n, n_users, n_items):
     """mode RL_SCORE_TENSOR must return exactly what RL_SCORE_EXACT returns (indices and float64 scores), and both
     must match the oracle (algo.py:172-201) up to exact-score ties."""
@@ -412,7 +426,7 @@ def test_tensor_core_topn_equals_exact_kernel(h, k, n, n_users, n_items):
     indptr, indices = gen.synth_pattern(n_users, n_items, mean_deg=45, seed=n_items)
     d_u, d_v, d_ip, d_ix = padded(h, uf, k), padded(h, vf, k), Dev(h, indptr), Dev(h, indices)
     outs, over = {}, {}
-    for mode in (1, 2, 3):                              # exact, split-operand tensor path, single-tf32 tensor path
+    for mode in (1, 2, 3):                              # exact, split-operand tensor path, single-fp16 tensor path
         d_idx = Dev(h, shape=(n_users, n), dtype=np.int32)
         d_val = Dev(h, shape=(n_users, n), dtype=np.float64)
         h.call("rl_score_topn_dev", d_u.ptr, n_users, d_v.ptr, n_items, k, d_ip.ptr, d_ix.ptr, 0.0, None, None, n,
