@@ -515,6 +515,9 @@ __global__ void __launch_bounds__(WarpSmem<real, KP>::warps * 32) als_half_step_
   }
 }
 
+namespace k64v1 {
+#include "als_k64_v1.cuh"
+}
 #include "als_k64.cuh"
 
 template <typename real, int KP, bool WEIGHTED>
@@ -606,6 +609,7 @@ int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, 
     return weighted ? launch_kp<double, true>(h, kp, a) : launch_kp<double, false>(h, kp, a);
   }
   if (precision == RL_PREC_FP32_IR) {
+    if (kp == 64 && getenv("RL_ALS_K64_V1")) return weighted ? k64v1::launch_k64o<true>(h, a) : k64v1::launch_k64o<false>(h, a);
     if (kp == 64 && !getenv("RL_ALS_GENERIC")) return weighted ? launch_k64<true>(h, a) : launch_k64<false>(h, a);
     return weighted ? launch_kp<float, true>(h, kp, a) : launch_kp<float, false>(h, kp, a);
   }

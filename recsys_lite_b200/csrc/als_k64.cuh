@@ -1,55 +1,54 @@
 // als_k64.cuh -- ALS half-step, fp32 + refinement path for padded k = 64 (the C3 / C4 configurations).
 // Included by als.cu inside its anonymous namespace (uses AlsArgs and the cp.async helpers).
 //
-// Same algorithm as als_half_step_kernel (reference algo.py:314-322 / :324-332), different Gram and solve phases:
+// Same algorithm as als_half_step_kernel (reference algo.py:314-322 / :324-332): per row with observations S,
+//   x = (Y_S^T Y_S + lambda I)^-1 Y_S^T 1,
+// one warp per row.  Everything that is a matrix product runs on the tensor cores (mma.sync m16n8k8, every
+// operand split x = hi + lo with hi = upper 19 bits, products hi.hi + hi.lo + lo.hi: fp32-accurate):
 //
-//   * Gram on the tensor cores: per chunk of 8 gathered rows the 64 x 64 update Y_c^T Y_c is 20 lower-triangle
-//     m16n8k8 tiles; every element is split x = hi + lo (hi = upper 19 bits) and each tile gets hi.hi + hi.lo +
-//     lo.hi (3 x tf32, fp32 accumulate), which keeps the Gram at fp32 accuracy.  The A
-//     and B fragments are the SAME 16 registers (A = Y_c^T, B = Y_c), so a chunk costs 16 shared-memory loads,
-//     32 split ops and 60 mma.sync instead of 8 x 72 FMAs + 8 x 36 loads.  (tcgen05 needs M >= 64 tiles fed by
-//     shared-memory descriptors and a TMEM round trip per user; at 50 gathered rows per user the per-row
-//     warp-level MMA is the better fit -- see DESIGN.md.)
+//   * Gram: per 8 gathered rows the 64 x 64 update Y_c^T Y_c is 20 lower-triangle 16 x 8 tiles whose A and B
+//     fragments are the SAME 16 registers (A = Y_c^T, B = Y_c).  The right-hand side sum is kept in float64.
+//   * Cholesky, blocked left-looking and in place in shared memory, block columns of 8:
+//     A[:, J] -= L[:, 0:8J] L[J, 0:8J]^T   is J k-steps of the same m16n8k8 per 16 x 8 tile (fragments read back from
+//     the factor), the 8-column panel goes through shared memory to turn "mma layout" into "one row per lane"
+//     and is factored row-locally (Crout inside the panel: lane i needs the finished row c of the 8 x 8 diagonal
+//     block for column c, eight shuffle rounds per panel).  The forward substitution of the right-hand side rides
+//     along while the panel rows are in registers.  ~2.4 K instructions per system instead of ~5.8 K for the
+//     register-window rank-1 version, and one copy of the code for all block columns (instruction cache).
+//   * the factor is stored panel by panel (block column K: rows 8K .. 63, 8 floats per row), the two 16-byte halves
+//     of a row swapped when bit 2 of the row index is set and panel bases skewed by 8 floats: conflict-free for
+//     the mma fragment loads (8 rows x 4 columns), for row loads (one row per lane, LDS.128) and for "row i across
+//     all columns" (the backward substitution).
+//   * refinement: x += L^-T L^-1 (b - A x) with the residual evaluated in float64 directly from the re-gathered
+//     rows (matrix-free), ir_steps times.
 //
-//   * the Gram fragments are written once to shared memory (packed lower triangle), then every lane pulls "its" two
-//     rows (l and l + 32) into registers; the same 8.7 KB then receive the factor (packed, column-major);
-//   * right-looking Cholesky entirely in registers: at column j the pivot lane broadcasts a_jj, everyone scales
-//     its rows (L_ij = a_ij * rsqrt(a_jj)), the column goes to shared memory (it is row j of the column-major
-//     factor kept for the refinement solves) and the rank-1 update a_ik -= L_ij L_kj runs as straight FMAs on
-//     register windows that are shifted by four columns after every group of four pivots, so the same code is
-//     reused for all groups of a phase (phase A: columns 0..31, windows 32 / 64; phase B: columns 32..63,
-//     window 32) -- no index arithmetic, no triangular packing, ~4.1 K FMA per system instead of ~16 K
-//     instructions of the left-looking shared-memory version;
-//   * the forward substitution of the right-hand side rides along with the factorisation.
-//
-// rsqrt.approx is good enough here: the factor is only a preconditioner for the float64-residual refinement.
+// rsqrt.approx pivots are good enough: the factor is only a preconditioner for the float64-residual refinement.
 
 constexpr int K64 = 64;
-constexpr int K64_TRI = 2176;  // floats of a packed 64 x 64 lower triangle with 4-aligned rows (or 4-column groups)
-constexpr int K64_LDY = 72; // row stride of a gathered row: 8 t + g is a bijection onto the banks for the mma fragments
-constexpr int K64_CH = 16;  // gathered rows per chunk (two k = 8 mma steps)
+constexpr int K64_LDY = 72;   // row stride of a gathered row: 8 t + g is a bijection onto the banks for the mma fragments
+constexpr int K64_CH = 8;     // gathered rows per chunk (one k = 8 mma step), double buffered
+constexpr int K64_LSZ = 2368; // floats of the factor storage (8 panels, 8 floats of skew each)
 
-// Gram staging: row-major packed lower triangle, row i at k64_row(i) (rows padded to a multiple of 4 entries).
-__host__ __device__ constexpr int k64_row(int i) { return 8 * (i >> 2) * ((i >> 2) + 1) + (i & 3) * (4 * (i >> 2) + 4); }
-// Factor: column-major packed lower triangle.  The four columns of group g = j >> 2 all start at row 4g, so that
-// column j holds rows 4g .. 63 at k64_col(j) + (i - 4g): 16-byte aligned, float4 loads of L[4g + 4m ..][j] need no shuffling.
-__host__ __device__ constexpr int k64_col(int j) { return 256 * (j >> 2) - 8 * (j >> 2) * ((j >> 2) - 1) + (j & 3) * (64 - 4 * (j >> 2)); }
-static_assert(k64_row(63) + 64 == K64_TRI && k64_col(63) + 4 == K64_TRI, "packed triangle size");
+// element (i, j) of the factor, i >= 8 (j >> 3):  Lt[k64_pb0(j >> 3) + 8 i + ((j & 7) ^ k64_swz(i))]
+__host__ __device__ constexpr int k64_pb0(int K) { return K * (488 - 32 * K); }
+__host__ __device__ constexpr int k64_swz(int i) { return ((i >> 2) & 1) << 2; }
+static_assert(k64_pb0(7) + 8 * 63 + 7 < K64_LSZ && k64_pb0(1) + 8 * 8 == 520, "factor storage layout");
 
 template <bool WEIGHTED>
 struct K64Smem {
-  static constexpr size_t lt_bytes = sizeof(float) * K64_TRI;
+  static constexpr size_t lt_bytes = sizeof(float) * K64_LSZ;
   static constexpr size_t invd_bytes = sizeof(float) * K64;
-  static constexpr size_t xs_bytes = sizeof(double) * K64;
-  static constexpr size_t ts_bytes = sizeof(double) * K64_CH;
+  static constexpr size_t xs_bytes = sizeof(double) * K64;       // x in float64 (residual pass); aliased by the float right-hand side
+  static constexpr size_t ts_bytes = sizeof(double) * 16;
   static constexpr size_t y_bytes = sizeof(float) * 2 * K64_CH * K64_LDY;
   static constexpr size_t w_bytes = WEIGHTED ? sizeof(float2) * 2 * K64_CH : 0;
   static constexpr size_t bytes = lt_bytes + invd_bytes + xs_bytes + ts_bytes + y_bytes + w_bytes;
-  static constexpr int warps = 4;   // 3 CTAs per SM: 3 x (4 x 18.4 KB + 1 KB) < 228 KB, registers <= 168
+  static constexpr int warps = 2;   // 7 CTAs per SM: 7 x (2 x 15.1 KB + 1 KB) < 228 KB, registers <= 144
+  static constexpr int ctas = 7;
   static_assert(bytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
 };
 
-// cp.async gather of chunk c (16-byte pieces); rows up to the next multiple of 8 are zero-filled for the k = 8 mma
+// cp.async gather of chunk c (16-byte pieces); a short last chunk is zero-filled up to 8 rows for the k = 8 mma
 template <bool WEIGHTED>
 __device__ __forceinline__ void k64_gather(const AlsArgs& a, int64_t s, int nnz, int c, float* yb, float2* wb, int lane) {
   const int base = c * K64_CH;
@@ -64,16 +63,16 @@ __device__ __forceinline__ void k64_gather(const AlsArgs& a, int64_t s, int nnz,
     }
   }
   constexpr int PPR = K64 / 4;  // 16-byte pieces per gathered row
-  const int total = cnt * PPR, padded = ((cnt + 7) & ~7) * PPR;
-  for (int p0 = 0; p0 < padded; p0 += 32) {
+#pragma unroll
+  for (int p0 = 0; p0 < K64_CH * PPR; p0 += 32) {
     const int p = p0 + lane;
     const int r = p / PPR;
-    const int idx = __shfl_sync(FULL_MASK, my, r & 31);
+    const int idx = __shfl_sync(FULL_MASK, my, r);
     const int c4 = p - r * PPR;
     const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(yb + r * K64_LDY + 4 * c4));
-    if (p < total) {
+    if (r < cnt) {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(a.other + static_cast<int64_t>(idx) * K64 + 4 * c4));
-    } else if (p < padded) {
+    } else {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 0;\n" ::"r"(dst), "l"(a.other));  // src-size 0: zero fill
     }
   }
@@ -87,121 +86,198 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t a0, const
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// lower-triangle 16 x 8 tiles of the 64 x 64 Gram: tile (mi, nj) is needed iff nj <= 2 mi + 1  ->  2 + 4 + 6 + 8 = 20 tiles
+// lower-triangle 16 x 8 tiles of a 64 x 64 symmetric matrix: tile (mi, nj) is needed iff nj <= 2 mi + 1  ->  2 + 4 + 6 + 8 = 20
 __device__ __forceinline__ constexpr int k64_tile(int mi, int nj) { return mi * (mi + 1) + nj; }
 
-// four pivots j0 .. j0+3.  Phase A (j0 < 32): rows l (window a0, 32 wide) and l + 32 (window a1, 64 wide) are live.
-// Phase B (j0 >= 32): only rows l + 32 (window a1, first 32 positions).  Window position p holds column j0 + p.
-template <bool PHASE_A>
-__device__ __forceinline__ void chol_group4(float (&a0)[32], float (&a1)[64], float& b0, float& b1, float* __restrict__ Lt,
-                                            float* __restrict__ invd, int j0, int lane) {
-  constexpr int W1 = PHASE_A ? 64 : 32;
+__device__ __forceinline__ void k64_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void k64_split_neg(float x, uint32_t& hi, uint32_t& lo) {   // parts of -x
+  const uint32_t h = __float_as_uint(x) & 0xFFFFE000u;
+  hi = h ^ 0x80000000u;
+  lo = __float_as_uint(__uint_as_float(h) - x);
+}
+
+// One panel (block column J): rows 8J .. 63 of columns 8J .. 8J+7 sit in shared memory.  Lane l takes rows 8J + l and
+// (TWO, i.e. J < 4) 8J + 32 + l.  FACTOR: the rows hold updated values of A and are factored against the 8 x 8 diagonal
+// block (rows of lanes 0..7; Crout inside the panel), the factor is written back and 1 / L_cc goes to invd.  In both
+// modes the right-hand side bs[] is carried along:  z_c = b_c / L_cc,  b_i -= L_ic z_c  (forward substitution).
+template <bool TWO, bool FACTOR>
+__device__ __forceinline__ void k64_panel(float* __restrict__ Lt, float* __restrict__ invd, float* __restrict__ bs, int J, int lane) {
+  const int NR = 64 - 8 * J;                   // rows in this panel
+  float* pj = Lt + k64_pb0(J) + 64 * J;        // row r of the panel (global row 8J + r) at pj + 8 r
+  const int r0 = min(lane, NR - 1);            // lanes beyond the panel shadow its last row (their results are dropped)
+  const bool v0 = lane < NR;
+  const int r1 = TWO ? min(lane + 32, NR - 1) : 0;
+  const bool v1 = TWO && lane + 32 < NR;
+  const int s0 = k64_swz(r0), s1 = k64_swz(r1);   // 8J is a multiple of 8: the swizzle bit of row 8J + r is that of r
+  float a[8], c1[8], iv[8];
+  {
+    const float4 lo = *reinterpret_cast<const float4*>(pj + 8 * r0 + s0);
+    const float4 hi = *reinterpret_cast<const float4*>(pj + 8 * r0 + (s0 ^ 4));
+    a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+  }
+  if (TWO) {
+    const float4 lo = *reinterpret_cast<const float4*>(pj + 8 * r1 + s1);
+    const float4 hi = *reinterpret_cast<const float4*>(pj + 8 * r1 + (s1 ^ 4));
+    c1[0] = lo.x; c1[1] = lo.y; c1[2] = lo.z; c1[3] = lo.w; c1[4] = hi.x; c1[5] = hi.y; c1[6] = hi.z; c1[7] = hi.w;
+  }
+  if (!FACTOR) {
+    const float4 i0 = *reinterpret_cast<const float4*>(invd + 8 * J);
+    const float4 i1 = *reinterpret_cast<const float4*>(invd + 8 * J + 4);
+    iv[0] = i0.x; iv[1] = i0.y; iv[2] = i0.z; iv[3] = i0.w; iv[4] = i1.x; iv[5] = i1.y; iv[6] = i1.z; iv[7] = i1.w;
+  }
+  float bb0 = bs[8 * J + r0];
+  float bb1 = TWO ? bs[8 * J + r1] : 0.f;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int j = j0 + c;
-    const int owner = j & 31;
-    const float piv = __shfl_sync(FULL_MASK, PHASE_A ? a0[c] : a1[c], owner);
-    const float inv = rsqrtf(fmaxf(piv, 1e-30f));
-    const float l0 = PHASE_A ? a0[c] * inv : 0.f;
-    const float l1 = a1[c] * inv;
-    float* col = Lt + k64_col(j) - j0;          // col[i] = L_ij for rows i >= j0
-    if (PHASE_A) { if (lane >= j0) col[lane] = l0; }
-    if (PHASE_A || lane + 32 >= j0) col[32 + lane] = l1;
-    if (lane == 0) invd[j] = inv;
-    // forward substitution rides along: z_j = b_j / L_jj, b_i -= L_ij z_j for i > j
-    const float zj = __shfl_sync(FULL_MASK, PHASE_A ? b0 : b1, owner) * inv;
-    if (PHASE_A) {
-      if (lane == owner) b0 = zj;
-      else if (lane > j) b0 = fmaf(-l0, zj, b0);
-      b1 = fmaf(-l1, zj, b1);
+  for (int c = 0; c < 8; ++c) {
+    float inv;
+    if (FACTOR) {
+      // column c: v = a_c - sum_{c' < c} a_c' D[c][c'], D = finished rows of the diagonal block (lane c holds row c)
+      float acc0 = a[c], acc1 = TWO ? c1[c] : 0.f;
+#pragma unroll
+      for (int cp = 0; cp < c; ++cp) {
+        const float d = __shfl_sync(FULL_MASK, a[cp], c);
+        acc0 = fmaf(-a[cp], d, acc0);
+        if (TWO) acc1 = fmaf(-c1[cp], d, acc1);
+      }
+      const float piv = __shfl_sync(FULL_MASK, acc0, c);
+      inv = rsqrtf(fmaxf(piv, 1e-30f));
+      a[c] = acc0 * inv;                           // lane c: piv * rsqrt(piv) = L_cc
+      if (TWO) c1[c] = acc1 * inv;
+      iv[c] = inv;
     } else {
-      if (lane == owner) b1 = zj;
-      else if (lane + 32 > j) b1 = fmaf(-l1, zj, b1);
+      inv = iv[c];
+    }
+    const float zc = __shfl_sync(FULL_MASK, bb0, c) * inv;
+    if (lane == c) bb0 = zc;
+    else if (lane > c) bb0 = fmaf(-a[c], zc, bb0);
+    if (TWO) bb1 = fmaf(-c1[c], zc, bb1);
+  }
+  if (FACTOR) {
+    if (lane == 0) {
+      *reinterpret_cast<float4*>(invd + 8 * J) = make_float4(iv[0], iv[1], iv[2], iv[3]);
+      *reinterpret_cast<float4*>(invd + 8 * J + 4) = make_float4(iv[4], iv[5], iv[6], iv[7]);
+    }
+    if (v0) {
+      *reinterpret_cast<float4*>(pj + 8 * r0 + s0) = make_float4(a[0], a[1], a[2], a[3]);
+      *reinterpret_cast<float4*>(pj + 8 * r0 + (s0 ^ 4)) = make_float4(a[4], a[5], a[6], a[7]);
+    }
+    if (v1) {
+      *reinterpret_cast<float4*>(pj + 8 * r1 + s1) = make_float4(c1[0], c1[1], c1[2], c1[3]);
+      *reinterpret_cast<float4*>(pj + 8 * r1 + (s1 ^ 4)) = make_float4(c1[4], c1[5], c1[6], c1[7]);
+    }
+  }
+  if (v0) bs[8 * J + r0] = bb0;
+  if (v1) bs[8 * J + r1] = bb1;
+  __syncwarp();
+}
+
+// Blocked left-looking Cholesky, in place in the panel storage (which holds A on entry, written there from the Gram
+// accumulators); L -> Lt, 1 / L_jj -> invd, and bs <- L^-1 bs on the way.  One copy of the code for all block columns
+// (the kernel is instruction-cache bound otherwise: every warp of an SM is in a different phase).
+__device__ __forceinline__ void k64_chol(float* __restrict__ Lt, float* __restrict__ invd, float* __restrict__ bs, int lane) {
+  const int g = lane >> 2, tq = lane & 3;
+  const int sg = ((g >> 2) & 1) << 2;          // swizzle bit of rows 8 m + g
+  const int o0 = tq ^ sg, o1 = o0 ^ 4;         // physical positions of panel columns tq and tq + 4 in such a row
+  const int oc = (2 * tq) ^ sg;                // ... of the accumulator columns 2 tq, 2 tq + 1
+#pragma unroll 1
+  for (int J = 0; J < 8; ++J) {
+    float* pj = Lt + k64_pb0(J);
+    const int m0 = J >> 1;
+    float d[4][4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      if (mi >= m0) {       // rows 16 mi + g of the odd-J first tile lie above the panel: junk in, never stored
+        const float2 t0 = *reinterpret_cast<const float2*>(pj + 8 * (16 * mi + g) + oc);
+        const float2 t1 = *reinterpret_cast<const float2*>(pj + 8 * (16 * mi + 8 + g) + oc);
+        d[mi][0] = t0.x; d[mi][1] = t0.y; d[mi][2] = t1.x; d[mi][3] = t1.y;
+      }
+    }
+#pragma unroll 1
+    for (int K = 0; K < J; ++K) {
+      const float* pk = Lt + K * (488 - 32 * K);
+      uint32_t bh[2], bl[2];                   // B(k, n) = L[8J + n][8K + k]
+      k64_split(pk[8 * (8 * J + g) + o0], bh[0], bl[0]);
+      k64_split(pk[8 * (8 * J + g) + o1], bh[1], bl[1]);
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        if (mi >= m0) {
+          const float* pa = pk + 8 * (16 * mi + g);
+          uint32_t ah[4], al[4];               // A(m, k) = -L[16 mi + m][8K + k]
+          k64_split_neg(pa[o0], ah[0], al[0]);
+          k64_split_neg(pa[64 + o0], ah[1], al[1]);
+          k64_split_neg(pa[o1], ah[2], al[2]);
+          k64_split_neg(pa[64 + o1], ah[3], al[3]);
+          mma_tf32(d[mi], ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+          mma_tf32(d[mi], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+          mma_tf32(d[mi], al[0], al[1], al[2], al[3], bh[0], bh[1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      if (mi >= m0) {
+        if (mi > m0 || !(J & 1)) *reinterpret_cast<float2*>(pj + 8 * (16 * mi + g) + oc) = make_float2(d[mi][0], d[mi][1]);
+        *reinterpret_cast<float2*>(pj + 8 * (16 * mi + 8 + g) + oc) = make_float2(d[mi][2], d[mi][3]);
+      }
     }
     __syncwarp();
-    // rank-1 update of the remaining window: a_i[p] -= L_ij * L_{j0+p, j}
-#pragma unroll
-    for (int p = c + 1; p < 4; ++p) {
-      const float lk = col[j0 + p];
-      if (PHASE_A) a0[p] = fmaf(-l0, lk, a0[p]);
-      a1[p] = fmaf(-l1, lk, a1[p]);
-    }
-#pragma unroll
-    for (int m = 1; m < W1 / 4; ++m) {
-      // rows j0 + 4m .. of column j; beyond row 63 this reads the next column's storage: finite junk that only
-      // ever reaches window slots of the (unused) upper triangle
-      const float4 lk = *reinterpret_cast<const float4*>(col + j0 + 4 * m);
-      const int d = (c == 3) ? 4 * m - 4 : 4 * m;  // the last pivot of the group writes the window shifted by four
-      if (PHASE_A && m < 8) {
-        a0[d + 0] = fmaf(-l0, lk.x, a0[4 * m + 0]);
-        a0[d + 1] = fmaf(-l0, lk.y, a0[4 * m + 1]);
-        a0[d + 2] = fmaf(-l0, lk.z, a0[4 * m + 2]);
-        a0[d + 3] = fmaf(-l0, lk.w, a0[4 * m + 3]);
-      }
-      a1[d + 0] = fmaf(-l1, lk.x, a1[4 * m + 0]);
-      a1[d + 1] = fmaf(-l1, lk.y, a1[4 * m + 1]);
-      a1[d + 2] = fmaf(-l1, lk.z, a1[4 * m + 2]);
-      a1[d + 3] = fmaf(-l1, lk.w, a1[4 * m + 3]);
-    }
+    if (J < 4) k64_panel<true, true>(Lt, invd, bs, J, lane);
+    else k64_panel<false, true>(Lt, invd, bs, J, lane);
   }
-  // columns that slid into the window belong to the (unused) upper triangle
-  if (PHASE_A) { a0[28] = a0[29] = a0[30] = a0[31] = 0.f; }
-  a1[W1 - 4] = a1[W1 - 3] = a1[W1 - 2] = a1[W1 - 1] = 0.f;
 }
 
-// v <- L^{-T} v   (v0: entry l, v1: entry l + 32); L_ji (j > i) sits in column i: Lt[k64_col(i) - 4 (i >> 2) + j]
+// bs <- L^-1 bs with the stored factor (the sweep of k64_panel with the rows loaded instead of computed)
+__device__ __forceinline__ void k64_forward(float* __restrict__ Lt, float* __restrict__ invd, float* __restrict__ bs, int lane) {
+#pragma unroll 1
+  for (int J = 0; J < 4; ++J) k64_panel<true, false>(Lt, invd, bs, J, lane);
+#pragma unroll 1
+  for (int J = 4; J < 8; ++J) k64_panel<false, false>(Lt, invd, bs, J, lane);
+}
+
+// v <- L^-T v   (v0: entry l, v1: entry l + 32), row i of the factor read across the lanes
 __device__ __forceinline__ void k64_backward(const float* __restrict__ Lt, const float* __restrict__ invd, float& v0, float& v1, int lane) {
-  const float* c0 = Lt + k64_col(lane) - (lane & ~3);
-  const float* c1 = Lt + k64_col(lane + 32) - ((lane + 32) & ~3);
-#pragma unroll 4
-  for (int j = 63; j >= 32; --j) {
-    const float xj = __shfl_sync(FULL_MASK, v1, j - 32) * invd[j];
-    if (lane == j - 32) v1 = xj;
-    else if (lane + 32 < j) v1 = fmaf(-c1[j], xj, v1);
-    v0 = fmaf(-c0[j], xj, v0);
+  const float* c0 = Lt + k64_pb0(lane >> 3);            // L[i][l]      = c0[8 i + ((l & 7) ^ swz(i))]
+  const float* c1 = Lt + k64_pb0(4 + (lane >> 3));      // L[i][l + 32] = c1[8 i + ((l & 7) ^ swz(i))]
+  const int q0 = lane & 7, q1 = q0 ^ 4;
+#pragma unroll 8
+  for (int i = 63; i >= 32; --i) {
+    const int q = (i & 4) ? q1 : q0;
+    const float xi = __shfl_sync(FULL_MASK, v1, i - 32) * invd[i];
+    const float l1 = c1[8 * i + q], l0 = c0[8 * i + q];
+    if (lane == i - 32) v1 = xi;
+    else if (lane + 32 < i) v1 = fmaf(-l1, xi, v1);
+    v0 = fmaf(-l0, xi, v0);
   }
-#pragma unroll 4
-  for (int j = 31; j >= 0; --j) {
-    const float xj = __shfl_sync(FULL_MASK, v0, j) * invd[j];
-    if (lane == j) v0 = xj;
-    else if (lane < j) v0 = fmaf(-c0[j], xj, v0);
-  }
-}
-
-// v <- L^{-1} v ; L_ij (i > j) = Lt[k64_col(j) - 4 (j >> 2) + i]
-__device__ __forceinline__ void k64_forward(const float* __restrict__ Lt, const float* __restrict__ invd, float& v0, float& v1, int lane) {
-#pragma unroll 4
-  for (int j = 0; j < 32; ++j) {
-    const float* col = Lt + k64_col(j) - (j & ~3);
-    const float zj = __shfl_sync(FULL_MASK, v0, j) * invd[j];
-    if (lane == j) v0 = zj;
-    else if (lane > j) v0 = fmaf(-col[lane], zj, v0);
-    v1 = fmaf(-col[32 + lane], zj, v1);
-  }
-#pragma unroll 4
-  for (int j = 32; j < 64; ++j) {
-    const float* col = Lt + k64_col(j) - (j & ~3);
-    const float zj = __shfl_sync(FULL_MASK, v1, j - 32) * invd[j];
-    if (lane == j - 32) v1 = zj;
-    else if (lane + 32 > j) v1 = fmaf(-col[32 + lane], zj, v1);
+#pragma unroll 8
+  for (int i = 31; i >= 0; --i) {
+    const int q = (i & 4) ? q1 : q0;
+    const float xi = __shfl_sync(FULL_MASK, v0, i) * invd[i];
+    const float l0 = c0[8 * i + q];               // lanes >= i read below their panel: finite junk, not used
+    if (lane == i) v0 = xi;
+    else if (lane < i) v0 = fmaf(-l0, xi, v0);
   }
 }
 
 template <bool WEIGHTED>
-__global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, 3) als_k64_kernel(const AlsArgs a) {
+__global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTED>::ctas) als_k64_kernel(const AlsArgs a) {
   constexpr int KP = K64, CH = K64_CH, LDY = K64_LDY;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* wbase = smem_raw + static_cast<size_t>(warp) * K64Smem<WEIGHTED>::bytes;
   float* Lt = reinterpret_cast<float*>(wbase);
-  float* invd = Lt + K64_TRI;
+  float* invd = Lt + K64_LSZ;
   double* xs = reinterpret_cast<double*>(invd + K64);
+  float* bs = reinterpret_cast<float*>(xs);               // the float right-hand side of a solve lives in the same 512 bytes
   double* ts = xs + K64;
-  float* ybuf = reinterpret_cast<float*>(ts + K64_CH);
+  float* ybuf = reinterpret_cast<float*>(ts + 16);
   float2* wbuf = reinterpret_cast<float2*>(ybuf + 2 * CH * LDY);
 
   const float lam = static_cast<float>(a.lambda);
-  const bool hkv = a.w0 != 0.0;
+  const bool hkv = WEIGHTED && a.w0 != 0.0;   // w0 != 0 always runs the WEIGHTED instantiation
+  const int g = lane >> 2, tq = lane & 3;
 
   for (;;) {
     unsigned int ticket = 0;
@@ -226,7 +302,6 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, 3) als_k64_kern
     double bq0 = 0.0, bq1 = 0.0;
 #pragma unroll
     for (int t = 0; t < 20; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
-    const int g = lane >> 2, tq = lane & 3;
     k64_gather<WEIGHTED>(a, s, nnz, 0, ybuf, wbuf, lane);
     for (int c = 0; c < nchunk; ++c) {
       const int buf = c & 1;
@@ -240,28 +315,28 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, 3) als_k64_kern
       const float* yb = ybuf + buf * CH * LDY;
       const float2* wb = wbuf + buf * CH;
       const int cnt = min(CH, nnz - c * CH);
-      for (int r = 0; r < cnt; ++r) {   // right-hand side in float64 (an fp32 sum would be amplified by 1 / lambda)
+      // right-hand side in float64 (an fp32 sum would be amplified by 1 / lambda); zero-filled rows add nothing
+#pragma unroll
+      for (int r = 0; r < CH; ++r) {
         const float* yr = yb + r * LDY;
-        double wr = 1.0;
-        if constexpr (WEIGHTED) wr = static_cast<double>(wb[r].y);
-        bq0 += wr * static_cast<double>(yr[lane]);
-        bq1 += wr * static_cast<double>(yr[32 + lane]);
+        if constexpr (WEIGHTED) {
+          const double wr = (r < cnt) ? static_cast<double>(wb[r].y) : 0.0;
+          bq0 += wr * static_cast<double>(yr[lane]);
+          bq1 += wr * static_cast<double>(yr[32 + lane]);
+        } else {
+          bq0 += static_cast<double>(yr[lane]);
+          bq1 += static_cast<double>(yr[32 + lane]);
+        }
       }
-      for (int k0 = 0; k0 < cnt; k0 += 8) {
-        // fragments: hi[mi][0..3] = A(mi) a0..a3 = Y[k0 + tq (+4)][16 mi + g (+8)]; B(nj = 2mi) = (a0, a2), B(2mi+1) = (a1, a3)
+      {
+        // fragments: v = A(mi) a0..a3 = Y[tq (+4)][16 mi + g (+8)]; B(nj = 2mi) = (a0, a2), B(2mi+1) = (a1, a3)
         uint32_t hi[4][4], lo[4][4];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
-          float v[4];
-          v[0] = yb[(k0 + tq) * LDY + 16 * mi + g];
-          v[1] = yb[(k0 + tq) * LDY + 16 * mi + g + 8];
-          v[2] = yb[(k0 + tq + 4) * LDY + 16 * mi + g];
-          v[3] = yb[(k0 + tq + 4) * LDY + 16 * mi + g + 8];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            hi[mi][e] = __float_as_uint(v[e]) & 0xFFFFE000u;
-            lo[mi][e] = __float_as_uint(v[e] - __uint_as_float(hi[mi][e]));
-          }
+          k64_split(yb[tq * LDY + 16 * mi + g], hi[mi][0], lo[mi][0]);
+          k64_split(yb[tq * LDY + 16 * mi + g + 8], hi[mi][1], lo[mi][1]);
+          k64_split(yb[(tq + 4) * LDY + 16 * mi + g], hi[mi][2], lo[mi][2]);
+          k64_split(yb[(tq + 4) * LDY + 16 * mi + g + 8], hi[mi][3], lo[mi][3]);
         }
         uint32_t ahi[4][4], alo[4][4];
 #pragma unroll
@@ -269,16 +344,15 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, 3) als_k64_kern
 #pragma unroll
           for (int e = 0; e < 4; ++e) { ahi[mi][e] = hi[mi][e]; alo[mi][e] = lo[mi][e]; }
         if constexpr (WEIGHTED) {     // scale the A side by the Gram weight of its gathered row (rows tq and tq + 4)
-          const float w0 = (k0 + tq < cnt) ? wb[k0 + tq].x : 0.f;
-          const float w1 = (k0 + tq + 4 < cnt) ? wb[k0 + tq + 4].x : 0.f;
+          const float w0 = (tq < cnt) ? wb[tq].x : 0.f;
+          const float w1 = (tq + 4 < cnt) ? wb[tq + 4].x : 0.f;
 #pragma unroll
           for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float w = (e < 2) ? w0 : w1;
               const float full = (__uint_as_float(hi[mi][e]) + __uint_as_float(lo[mi][e])) * w;
-              ahi[mi][e] = __float_as_uint(full) & 0xFFFFE000u;
-              alo[mi][e] = __float_as_uint(full - __uint_as_float(ahi[mi][e]));
+              k64_split(full, ahi[mi][e], alo[mi][e]);
             }
         }
 #pragma unroll
@@ -295,49 +369,40 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, 3) als_k64_kern
       __syncwarp();
     }
 
-    // ---- Gram fragments -> shared (packed row-major lower triangle) -> two rows per lane in registers ------
+    // ---- + lambda I (+ w0 Y^T Y), accumulator tiles -> panel storage: element e of tile (mi, nj) is
+    //      A[16 mi + g + 8 (e >> 1)][8 nj + 2 tq + (e & 1)]; the first 8 rows of the odd tiles nj = 2 mi + 1 lie above the diagonal
+    {
+      const int oc = (2 * tq) ^ (((g >> 2) & 1) << 2);
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
+      for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-      for (int nj = 0; nj <= 2 * mi + 1; ++nj) {
-        const float (&d)[4] = acc[k64_tile(mi, nj)];
+        for (int nj = 0; nj <= 2 * mi + 1; ++nj) {
+          float (&d)[4] = acc[k64_tile(mi, nj)];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int gi = 16 * mi + g + ((e & 2) ? 8 : 0), gj = 8 * nj + 2 * tq + (e & 1);
-          if (gj <= gi) {
-            float v = d[e];
-            if (hkv) v += static_cast<float>(a.w0 * a.gram0[gi * KP + gj]);
-            if (gi == gj) v += (gi < a.k) ? lam : 1.0f;
-            Lt[k64_row(gi) + gj] = v;
+          for (int e = 0; e < 4; ++e) {
+            const int gi = 16 * mi + g + ((e & 2) ? 8 : 0), gj = 8 * nj + 2 * tq + (e & 1);
+            if (hkv) d[e] += static_cast<float>(a.w0 * a.gram0[gi * KP + gj]);
+            if (nj >= 2 * mi && gi == gj) d[e] += (gi < a.k) ? lam : 1.0f;
           }
+          float* pn = Lt + k64_pb0(nj);
+          if (nj <= 2 * mi) *reinterpret_cast<float2*>(pn + 8 * (16 * mi + g) + oc) = make_float2(d[0], d[1]);
+          *reinterpret_cast<float2*>(pn + 8 * (16 * mi + 8 + g) + oc) = make_float2(d[2], d[3]);
         }
-      }
-    __syncwarp();
-    float a0[32], a1[64];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      const float4 v = *reinterpret_cast<const float4*>(Lt + k64_row(lane) + 4 * m);
-      a0[4 * m] = v.x; a0[4 * m + 1] = v.y; a0[4 * m + 2] = v.z; a0[4 * m + 3] = v.w;
     }
-#pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      const float4 v = *reinterpret_cast<const float4*>(Lt + k64_row(32 + lane) + 4 * m);
-      a1[4 * m] = v.x; a1[4 * m + 1] = v.y; a1[4 * m + 2] = v.z; a1[4 * m + 3] = v.w;
-    }
+    // ---- blocked Cholesky on the tensor cores, forward substitution fused ------------------------------------
+    bs[lane] = static_cast<float>(bq0);
+    bs[32 + lane] = static_cast<float>(bq1);
     __syncwarp();
-
-    // ---- Cholesky in registers, forward substitution fused ------------------------------------------------------
-    float b0 = static_cast<float>(bq0), b1 = static_cast<float>(bq1);
-#pragma unroll 1
-    for (int j0 = 0; j0 < 32; j0 += 4) chol_group4<true>(a0, a1, b0, b1, Lt, invd, j0, lane);
-#pragma unroll 1
-    for (int j0 = 32; j0 < 64; j0 += 4) chol_group4<false>(a0, a1, b0, b1, Lt, invd, j0, lane);
-    __syncwarp();
-    k64_backward(Lt, invd, b0, b1, lane);
-    double xd0 = static_cast<double>(b0), xd1 = static_cast<double>(b1);
-
-    // ---- iterative refinement with a float64 matrix-free residual ---------------------------------------------
-    for (int it = 0; it < a.ir_steps; ++it) {
+    k64_chol(Lt, invd, bs, lane);
+    // ---- back substitution, then refinement steps  x += L^-T L^-1 (b - A x)  with a float64 matrix-free residual ----
+    double xd0 = 0.0, xd1 = 0.0;
+    for (int it = 0;; ++it) {
+      float v0 = bs[lane], v1 = bs[32 + lane];    // L^-1 (right-hand side or residual)
+      __syncwarp();
+      k64_backward(Lt, invd, v0, v1, lane);
+      xd0 += static_cast<double>(v0);
+      xd1 += static_cast<double>(v1);
+      if (it >= a.ir_steps) break;
       xs[lane] = xd0;
       xs[32 + lane] = xd1;
       double r0 = bq0 - ((lane < a.k) ? a.lambda : 1.0) * xd0;
@@ -365,41 +430,39 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, 3) als_k64_kern
         const float* yb = ybuf + buf * CH * LDY;
         const float2* wb = wbuf + buf * CH;
         const int cnt = min(CH, nnz - c * CH);
-        // t_i = w_i <y_i, x>: two lanes per gathered row (each half of the factor dimension), then a shuffle add
+        // t_i = w_i <y_i, x>: four lanes per gathered row (a quarter of the factor dimension each), then two shuffle adds
         {
-          const int i = lane & 15, half = lane >> 4;
-          double t = 0.0;
-          if (i < cnt) {
-            const float* yr = yb + i * LDY + 32 * half;
-            const double* xh = xs + 32 * half;
-            double t0 = 0.0, t1 = 0.0;
+          const int i = lane & 7, quarter = lane >> 3;
+          const float* yr = yb + i * LDY + 16 * quarter;
+          const double* xh = xs + 16 * quarter;
+          double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-            for (int cc = 0; cc < 32; cc += 4) {
-              const float4 y4 = *reinterpret_cast<const float4*>(yr + cc);
-              t0 = fma(static_cast<double>(y4.x), xh[cc], t0);
-              t1 = fma(static_cast<double>(y4.y), xh[cc + 1], t1);
-              t0 = fma(static_cast<double>(y4.z), xh[cc + 2], t0);
-              t1 = fma(static_cast<double>(y4.w), xh[cc + 3], t1);
-            }
-            t = t0 + t1;
+          for (int cc = 0; cc < 16; cc += 4) {
+            const float4 y4 = *reinterpret_cast<const float4*>(yr + cc);
+            t0 = fma(static_cast<double>(y4.x), xh[cc], t0);
+            t1 = fma(static_cast<double>(y4.y), xh[cc + 1], t1);
+            t0 = fma(static_cast<double>(y4.z), xh[cc + 2], t0);
+            t1 = fma(static_cast<double>(y4.w), xh[cc + 3], t1);
           }
+          double t = t0 + t1;
+          t += __shfl_xor_sync(FULL_MASK, t, 8);
           t += __shfl_xor_sync(FULL_MASK, t, 16);
-          if constexpr (WEIGHTED) { if (i < cnt) t *= static_cast<double>(wb[i].x); }
-          if (lane < 16) ts[lane] = t;
+          if constexpr (WEIGHTED) t *= (i < cnt) ? static_cast<double>(wb[i].x) : 0.0;
+          if (lane < 8) ts[lane] = t;     // zero-filled rows give t = 0
         }
         __syncwarp();
-        for (int i = 0; i < cnt; ++i) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
           const double ti = ts[i];
           r0 = fma(-ti, static_cast<double>(yb[i * LDY + lane]), r0);
           r1 = fma(-ti, static_cast<double>(yb[i * LDY + 32 + lane]), r1);
         }
         __syncwarp();
       }
-      float v0 = static_cast<float>(r0), v1 = static_cast<float>(r1);
-      k64_forward(Lt, invd, v0, v1, lane);
-      k64_backward(Lt, invd, v0, v1, lane);
-      xd0 += static_cast<double>(v0);
-      xd1 += static_cast<double>(v1);
+      bs[lane] = static_cast<float>(r0);        // xs is dead from here on: its bytes take the right-hand side
+      bs[32 + lane] = static_cast<float>(r1);
+      __syncwarp();
+      k64_forward(Lt, invd, bs, lane);
     }
     a.mine[row * KP + lane] = (lane < a.k) ? static_cast<float>(xd0) : 0.0f;
     a.mine[row * KP + 32 + lane] = (32 + lane < a.k) ? static_cast<float>(xd1) : 0.0f;
