@@ -174,6 +174,34 @@ __device__ __forceinline__ void k64_panel(float* __restrict__ Lt, float* __restr
   __syncwarp();
 }
 
+// d[mi] -= L[16 mi .. 16 mi + 15][0 : 8J] L[8J .. 8J + 7][0 : 8J]^T for the tiles mi >= M0 of block column J
+template <int M0>
+__device__ __forceinline__ void k64_update(float (&d)[4][4], const float* __restrict__ Lt, int J, int g, int o0, int o1) {
+#pragma unroll 1
+  for (int K = 0; K < J; ++K) {
+    const float* pk = Lt + K * (488 - 32 * K);
+    uint32_t bh[2], bl[2];                     // B(k, n) = L[8J + n][8K + k]
+    k64_split(pk[8 * (8 * J + g) + o0], bh[0], bl[0]);
+    k64_split(pk[8 * (8 * J + g) + o1], bh[1], bl[1]);
+    uint32_t ah[4][4], al[4][4];               // A(m, k) = -L[16 mi + m][8K + k]
+#pragma unroll
+    for (int mi = M0; mi < 4; ++mi) {
+      const float* pa = pk + 8 * (16 * mi + g);
+      k64_split_neg(pa[o0], ah[mi][0], al[mi][0]);
+      k64_split_neg(pa[64 + o0], ah[mi][1], al[mi][1]);
+      k64_split_neg(pa[o1], ah[mi][2], al[mi][2]);
+      k64_split_neg(pa[64 + o1], ah[mi][3], al[mi][3]);
+    }
+    // term by term across the tiles: consecutive HMMAs are independent
+#pragma unroll
+    for (int mi = M0; mi < 4; ++mi) mma_tf32(d[mi], ah[mi][0], ah[mi][1], ah[mi][2], ah[mi][3], bh[0], bh[1]);
+#pragma unroll
+    for (int mi = M0; mi < 4; ++mi) mma_tf32(d[mi], ah[mi][0], ah[mi][1], ah[mi][2], ah[mi][3], bl[0], bl[1]);
+#pragma unroll
+    for (int mi = M0; mi < 4; ++mi) mma_tf32(d[mi], al[mi][0], al[mi][1], al[mi][2], al[mi][3], bh[0], bh[1]);
+  }
+}
+
 // Blocked left-looking Cholesky, in place in the panel storage (which holds A on entry, written there from the Gram
 // accumulators); L -> Lt, 1 / L_jj -> invd, and bs <- L^-1 bs on the way.  One copy of the code for all block columns
 // (the kernel is instruction-cache bound otherwise: every warp of an SM is in a different phase).
@@ -195,26 +223,11 @@ __device__ __forceinline__ void k64_chol(float* __restrict__ Lt, float* __restri
         d[mi][0] = t0.x; d[mi][1] = t0.y; d[mi][2] = t1.x; d[mi][3] = t1.y;
       }
     }
-#pragma unroll 1
-    for (int K = 0; K < J; ++K) {
-      const float* pk = Lt + K * (488 - 32 * K);
-      uint32_t bh[2], bl[2];                   // B(k, n) = L[8J + n][8K + k]
-      k64_split(pk[8 * (8 * J + g) + o0], bh[0], bl[0]);
-      k64_split(pk[8 * (8 * J + g) + o1], bh[1], bl[1]);
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi) {
-        if (mi >= m0) {
-          const float* pa = pk + 8 * (16 * mi + g);
-          uint32_t ah[4], al[4];               // A(m, k) = -L[16 mi + m][8K + k]
-          k64_split_neg(pa[o0], ah[0], al[0]);
-          k64_split_neg(pa[64 + o0], ah[1], al[1]);
-          k64_split_neg(pa[o1], ah[2], al[2]);
-          k64_split_neg(pa[64 + o1], ah[3], al[3]);
-          mma_tf32(d[mi], ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
-          mma_tf32(d[mi], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
-          mma_tf32(d[mi], al[0], al[1], al[2], al[3], bh[0], bh[1]);
-        }
-      }
+    switch (m0) {      // the set of 16-row tiles below the diagonal is fixed per block column: no predicates in the K loop
+      case 0: k64_update<0>(d, Lt, J, g, o0, o1); break;
+      case 1: k64_update<1>(d, Lt, J, g, o0, o1); break;
+      case 2: k64_update<2>(d, Lt, J, g, o0, o1); break;
+      default: k64_update<3>(d, Lt, J, g, o0, o1); break;
     }
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
@@ -242,22 +255,24 @@ __device__ __forceinline__ void k64_backward(const float* __restrict__ Lt, const
   const float* c0 = Lt + k64_pb0(lane >> 3);            // L[i][l]      = c0[8 i + ((l & 7) ^ swz(i))]
   const float* c1 = Lt + k64_pb0(4 + (lane >> 3));      // L[i][l + 32] = c1[8 i + ((l & 7) ^ swz(i))]
   const int q0 = lane & 7, q1 = q0 ^ 4;
-#pragma unroll 8
+  const float* c0a = c0 + q0; const float* c0b = c0 + q1;   // rows with swizzle bit 0 / 1
+  const float* c1a = c1 + q0; const float* c1b = c1 + q1;
+  const float inv0 = invd[lane], inv1 = invd[32 + lane];
+#pragma unroll 16
   for (int i = 63; i >= 32; --i) {
-    const int q = (i & 4) ? q1 : q0;
-    const float xi = __shfl_sync(FULL_MASK, v1, i - 32) * invd[i];
-    const float l1 = c1[8 * i + q], l0 = c0[8 * i + q];
-    if (lane == i - 32) v1 = xi;
-    else if (lane + 32 < i) v1 = fmaf(-l1, xi, v1);
+    const float xi = __shfl_sync(FULL_MASK, v1 * inv1, i - 32);     // the owner lane's product is the one that counts
+    const float l1 = (i & 4) ? c1b[8 * i] : c1a[8 * i];
+    const float l0 = (i & 4) ? c0b[8 * i] : c0a[8 * i];
+    const float upd = fmaf(-l1, xi, v1);
+    v1 = (lane < i - 32) ? upd : ((lane == i - 32) ? xi : v1);
     v0 = fmaf(-l0, xi, v0);
   }
-#pragma unroll 8
+#pragma unroll 16
   for (int i = 31; i >= 0; --i) {
-    const int q = (i & 4) ? q1 : q0;
-    const float xi = __shfl_sync(FULL_MASK, v0, i) * invd[i];
-    const float l0 = c0[8 * i + q];               // lanes >= i read below their panel: finite junk, not used
-    if (lane == i) v0 = xi;
-    else if (lane < i) v0 = fmaf(-l0, xi, v0);
+    const float xi = __shfl_sync(FULL_MASK, v0 * inv0, i);
+    const float l0 = (i & 4) ? c0b[8 * i] : c0a[8 * i];             // lanes >= i read below their panel: finite junk, not used
+    const float upd = fmaf(-l0, xi, v0);
+    v0 = (lane < i) ? upd : ((lane == i) ? xi : v0);
   }
 }
 
@@ -355,16 +370,22 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
               k64_split(full, ahi[mi][e], alo[mi][e]);
             }
         }
+        // B(nj) = (a[bo], a[bo + 2]) of m-tile bm = nj >> 1, bo = nj & 1; term by term: consecutive HMMAs are independent
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-          for (int nj = 0; nj <= 2 * mi + 1; ++nj) {
-            const int bm = nj >> 1, bo = nj & 1;   // B(nj) = (a[bo], a[bo + 2]) of m-tile bm
-            float (&d)[4] = acc[k64_tile(mi, nj)];
-            mma_tf32(d, ahi[mi][0], ahi[mi][1], ahi[mi][2], ahi[mi][3], hi[bm][bo], hi[bm][bo + 2]);
-            mma_tf32(d, ahi[mi][0], ahi[mi][1], ahi[mi][2], ahi[mi][3], lo[bm][bo], lo[bm][bo + 2]);
-            mma_tf32(d, alo[mi][0], alo[mi][1], alo[mi][2], alo[mi][3], hi[bm][bo], hi[bm][bo + 2]);
-          }
+          for (int nj = 0; nj <= 2 * mi + 1; ++nj)
+            mma_tf32(acc[k64_tile(mi, nj)], ahi[mi][0], ahi[mi][1], ahi[mi][2], ahi[mi][3], hi[nj >> 1][nj & 1], hi[nj >> 1][(nj & 1) + 2]);
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int nj = 0; nj <= 2 * mi + 1; ++nj)
+            mma_tf32(acc[k64_tile(mi, nj)], ahi[mi][0], ahi[mi][1], ahi[mi][2], ahi[mi][3], lo[nj >> 1][nj & 1], lo[nj >> 1][(nj & 1) + 2]);
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int nj = 0; nj <= 2 * mi + 1; ++nj)
+            mma_tf32(acc[k64_tile(mi, nj)], alo[mi][0], alo[mi][1], alo[mi][2], alo[mi][3], hi[nj >> 1][nj & 1], hi[nj >> 1][(nj & 1) + 2]);
       }
       __syncwarp();
     }
