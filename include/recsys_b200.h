@@ -66,6 +66,10 @@ int rl_synchronize(rl_handle h);
 int rl_device_info(rl_handle h, int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem_bytes);
 /* number of kernels this library has launched on the handle since creation (bench: "gpu_launches") */
 int64_t rl_launch_count(rl_handle h);
+/* The *_host entry points allocate their device staging buffers from the device's stream-ordered memory pool and leave
+ * them cached there between calls (no cudaMalloc / cudaFree per call).  rl_trim returns the cached memory and the
+ * handle's scratch buffer to the driver. */
+int rl_trim(rl_handle h);
 
 /* row stride (floats) of device factor matrices for `k` factors: 16, 32, 64 or 128; 0 if k is unsupported */
 int rl_padded_k(int k);

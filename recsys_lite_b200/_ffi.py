@@ -28,6 +28,7 @@ SIGNATURES = {
     "rl_synchronize": (_i32, [_vp]),
     "rl_device_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64)]),
     "rl_launch_count": (_i64, [_vp]),
+    "rl_trim": (_i32, [_vp]),
     "rl_padded_k": (_i32, [_i32]),
     "rl_pinned_alloc": (_i32, [_i64, C.POINTER(_vp)]),
     "rl_pinned_free": (_i32, [_vp]),

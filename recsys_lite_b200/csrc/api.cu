@@ -54,11 +54,16 @@ __global__ void convert_kernel(const TS* __restrict__ src, int64_t rows, int k, 
   }
 }
 
-struct DevBuf {  // RAII device allocation for the host wrappers
+// RAII device allocation for the host wrappers.  Stream-ordered (cudaMallocAsync on the handle's stream): the device's
+// default memory pool keeps freed blocks (release threshold set in rl_create), so repeated host-buffer calls neither
+// pay cudaMalloc / cudaFree nor synchronise the device.
+struct DevBuf {
   void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
+  rl_context* ctx = nullptr;
+  ~DevBuf() { if (p) cudaFreeAsync(p, ctx->stream); }
   int alloc(rl_context* h, size_t bytes) {
-    RL_CUDA(h, cudaMalloc(&p, bytes ? bytes : 16));
+    ctx = h;
+    RL_CUDA(h, cudaMallocAsync(&p, bytes ? bytes : 16, h->stream));
     return RL_OK;
   }
   template <typename T> T* as() { return static_cast<T*>(p); }
@@ -149,6 +154,13 @@ int rl_create(int device, rl_handle* out) {
     return cuda_fail(nullptr, e, "cudaMalloc(counter)");
   }
   cudaMemset(h->counter, 0, 64 * sizeof(unsigned int));
+  {  // keep the stream-ordered pool's memory between calls (see DevBuf); rl_trim() gives it back
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   *out = h;
   return RL_OK;
 }
@@ -161,6 +173,20 @@ int rl_destroy(rl_handle h) {
   if (h->counter) cudaFree(h->counter);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
+  return RL_OK;
+}
+
+int rl_trim(rl_handle h) {
+  RL_NEED(h);
+  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->scratch) {
+    RL_CUDA(h, cudaFree(h->scratch));
+    h->scratch = nullptr;
+    h->scratch_bytes = 0;
+  }
+  cudaMemPool_t pool;
+  RL_CUDA(h, cudaDeviceGetDefaultMemPool(&pool, h->device));
+  RL_CUDA(h, cudaMemPoolTrimTo(pool, 0));
   return RL_OK;
 }
 

@@ -27,6 +27,12 @@ struct ScoreArgs {
   const int32_t* user_list;  // optional: score only these users
   int64_t n_list;
   bool scatter;              // with user_list: write row `user` of idx_out (true) or row `position in list` (false)
+  // item slicing (short user lists: one CTA per 64 users would sweep all items alone).  slices > 1: CTA (x, y) scores
+  // items [y * slice_items, (y + 1) * slice_items) and writes its list to row (position * slices + y) of part_*.
+  int slices = 1;
+  int64_t slice_items = 0;
+  int32_t* part_idx = nullptr;
+  double* part_score = nullptr;
 };
 
 constexpr int SE_UT = 64, SE_IT = 64, SE_THREADS = 256, SE_UPW = 8;  // users per warp
@@ -76,8 +82,23 @@ __global__ void __launch_bounds__(SE_THREADS) score_topn_exact_kernel(const Scor
     }
   }
   const int tu = tid >> 4, ti = tid & 15;
+  int64_t j_begin = 0, j_end = a.n_items;
+  if (a.slices > 1) {
+    j_begin = static_cast<int64_t>(blockIdx.y) * a.slice_items;     // a multiple of SE_IT
+    j_end = min(a.n_items, j_begin + a.slice_items);
+#pragma unroll
+    for (int uu = 0; uu < SE_UPW; ++uu) {       // skip the seen items in front of this slice (ascending list)
+      for (;;) {
+        const int64_t p = cur[uu] + lane;
+        const int idx = (p < end[uu]) ? a.seen_indices[p] : INT_MAX;
+        const unsigned b = __ballot_sync(FULL_MASK, idx < j_begin);
+        cur[uu] += __popc(b);
+        if (b != FULL_MASK) break;
+      }
+    }
+  }
 
-  for (int64_t j0 = 0; j0 < a.n_items; j0 += SE_IT) {
+  for (int64_t j0 = j_begin; j0 < j_end; j0 += SE_IT) {
     __syncthreads();  // previous tile fully consumed (and Ut visible on the first trip)
     for (int p = tid; p < SE_IT * (KP / 4); p += SE_THREADS) {
       const int i = p % SE_IT, c4 = p / SE_IT;
@@ -159,22 +180,82 @@ __global__ void __launch_bounds__(SE_THREADS) score_topn_exact_kernel(const Scor
   for (int uu = 0; uu < SE_UPW; ++uu) {
     const int64_t t = t0 + warp * SE_UPW + uu;
     if (t < total) {
-      const int64_t orow = (a.user_list && a.scatter) ? a.user_list[t] : t;
-      lists[uu].store(a.n, lane, a.idx_out + orow * a.n, a.score_out ? a.score_out + orow * a.n : nullptr);
+      if (a.slices > 1) {
+        const int64_t prow = t * a.slices + blockIdx.y;
+        lists[uu].store(a.n, lane, a.part_idx + prow * a.n, a.part_score + prow * a.n);
+      } else {
+        const int64_t orow = (a.user_list && a.scatter) ? a.user_list[t] : t;
+        lists[uu].store(a.n, lane, a.idx_out + orow * a.n, a.score_out ? a.score_out + orow * a.n : nullptr);
+      }
     }
   }
 }
 
+// merge of the per-slice lists: one warp per user, same order contract (score desc, index asc)
+template <int R>
+__global__ void __launch_bounds__(128) score_merge_kernel(const ScoreArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t total = a.user_list ? a.n_list : a.n_users;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (t >= total) return;
+  WarpTopK<R> list;
+  list.init();
+  double tv;
+  int tix;
+  list.threshold(a.n, tv, tix);
+  const int64_t cand = static_cast<int64_t>(a.slices) * a.n;
+  for (int64_t c0 = 0; c0 < cand; c0 += 32) {
+    const int64_t c = c0 + lane;
+    const int id = (c < cand) ? a.part_idx[t * cand + c] : -1;
+    const double sc = (c < cand) ? a.part_score[t * cand + c] : -CUDART_INF;
+    unsigned m = __ballot_sync(FULL_MASK, id >= 0 && beats(sc, id, tv, tix));
+    while (m) {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      const double cs = __shfl_sync(FULL_MASK, sc, l);
+      const int cj = __shfl_sync(FULL_MASK, id, l);
+      if (beats(cs, cj, tv, tix)) {
+        list.insert(cs, cj, lane);
+        list.threshold(a.n, tv, tix);
+      }
+    }
+  }
+  const int64_t orow = (a.user_list && a.scatter) ? a.user_list[t] : t;
+  list.store(a.n, lane, a.idx_out + orow * a.n, a.score_out ? a.score_out + orow * a.n : nullptr);
+}
+
 template <int KP, int R>
-int launch_score_exact_kr(rl_context* h, const ScoreArgs& a) {
+int launch_score_exact_kr(rl_context* h, const ScoreArgs& a_in) {
+  ScoreArgs a = a_in;
   auto kern = score_topn_exact_kernel<KP, R>;
   constexpr size_t smem = score_exact_smem<KP>();
   RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int64_t total = a.user_list ? a.n_list : a.n_users;
   const int64_t grid = (total + SE_UT - 1) / SE_UT;
   if (grid == 0) return RL_OK;
-  kern<<<static_cast<unsigned>(grid), SE_THREADS, smem, h->stream>>>(a);
+  // few user groups and many items: slice the item range so that the whole chip works on them, then merge
+  const int64_t item_tiles = (a.n_items + SE_IT - 1) / SE_IT;
+  void* part = nullptr;
+  if (grid * 2 <= h->sm_count && item_tiles >= 16) {
+    int64_t slices = (2 * static_cast<int64_t>(h->sm_count) + grid - 1) / grid;
+    if (slices > item_tiles / 4) slices = item_tiles / 4;
+    if (slices > 64) slices = 64;
+    const int64_t tiles_per = (item_tiles + slices - 1) / slices;
+    a.slice_items = tiles_per * SE_IT;
+    a.slices = static_cast<int>((item_tiles + tiles_per - 1) / tiles_per);
+    const size_t rows = static_cast<size_t>(total) * a.slices * a.n;
+    const size_t idx_bytes = (rows * sizeof(int32_t) + 15) & ~size_t(15);
+    RL_CUDA(h, cudaMallocAsync(&part, idx_bytes + rows * sizeof(double), h->stream));
+    a.part_idx = static_cast<int32_t*>(part);
+    a.part_score = reinterpret_cast<double*>(static_cast<char*>(part) + idx_bytes);
+  }
+  kern<<<dim3(static_cast<unsigned>(grid), static_cast<unsigned>(a.slices)), SE_THREADS, smem, h->stream>>>(a);
   RL_LAUNCH_CHECK(h, "score_topn_exact_kernel");
+  if (a.slices > 1) {
+    score_merge_kernel<R><<<static_cast<unsigned>((total + 3) / 4), 128, 0, h->stream>>>(a);
+    RL_LAUNCH_CHECK(h, "score_merge_kernel");
+    RL_CUDA(h, cudaFreeAsync(part, h->stream));
+  }
   return RL_OK;
 }
 

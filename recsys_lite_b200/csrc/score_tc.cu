@@ -661,9 +661,7 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
         } else {
           // ---- steady-state scan: software pipeline over the four 32-column groups (the tcgen05.ld of the next group
           //      is in flight while this one is scanned -- TMEM reads, 64 B/clk per SM, are what bounds the epilogue),
-          //      the accumulator stage goes back to the MMA warp as soon as the last group sits in registers.  No
-          //      batch pass inside the tile: a row that would run out of buffer space (> 20 hits in one tile right
-          //      after a quiet tile) is handed to the exact kernel.
+          //      the accumulator stage goes back to the MMA warp as soon as the last group sits in registers.
           float s0[32], s1[32];
           auto scan32 = [&](const float (&sg)[32], const int col0) {
 #pragma unroll
@@ -678,9 +676,9 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
                     ++cnt;
                   }
                 }
-                if (cnt > TC_CAND - 8) {     // out of space: stop collecting, the exact kernel finishes this row
-                  gave_up = true;
-                  tau = CUDART_INF_F;
+                if (cnt > TC_CAND - 8) {     // out of space (a burst of > 12 hits in one tile right after a quiet one; about
+                  gave_up = true;            // one row in a million): stop collecting, the exact kernel finishes this row --
+                  tau = CUDART_INF_F;        // a batch pass here would pull its code and register pressure into the hot loop
                   cnt = 0;
                 }
               }
