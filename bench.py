@@ -179,7 +179,7 @@ def run_reference(args, w):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sample_seconds_per_step": float(np.mean(secs)),
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args, w, where):
@@ -317,7 +317,7 @@ def run_b200(args, w):
             v, s, desc = cpu_reference_leg(w, inputs, 20_000, 20_000, 2_000)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": blas_threads(), "kind": "port", "sample": desc,
                                     "seconds": s}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -400,6 +400,25 @@ def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
             "api": "per-rank pinned H2D of its CSR/CSC ranges + factors, rl_als_half_step_dev/rl_score_topn_dev + exchanges, D2H of its ranges"}
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything a library prints on fd 1 (NCCL's version banner, ...) goes to stderr: stdout carries the one JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def _pinned_copy(a):
     from recsys_lite_b200 import _ffi
     out = _ffi.pinned_empty(a.shape, a.dtype)
@@ -419,6 +438,7 @@ def main():
     ap.add_argument("--score-mode", type=int, default=0, help="0 auto, 1 exact CUDA-core, 2 tensor-core candidate pass")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
+    _quiet_stdout()
     if args.warmup < 3 and args.impl == "b200" and not os.environ.get("RL_BENCH_ALLOW_SHORT_WARMUP"):
         args.warmup = 3
     w = WORKLOADS[args.workload]
