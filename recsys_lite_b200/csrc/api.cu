@@ -81,6 +81,64 @@ int upload(rl_context* h, DevBuf& b, const void* host, size_t bytes) {
   return RL_OK;
 }
 
+// run a piece of the host wrappers on another stream of the handle (launchers enqueue on h->stream)
+struct StreamScope {
+  rl_context* h;
+  cudaStream_t saved;
+  StreamScope(rl_context* ctx, cudaStream_t s) : h(ctx), saved(ctx->stream) { h->stream = s; }
+  ~StreamScope() { h->stream = saved; }
+};
+
+struct Event {  // ordering between the handle's compute and copy streams
+  cudaEvent_t e = nullptr;
+  ~Event() { if (e) cudaEventDestroy(e); }
+  int record(rl_context* h, cudaStream_t s) {
+    if (!e) RL_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    RL_CUDA(h, cudaEventRecord(e, s));
+    return RL_OK;
+  }
+  int wait(rl_context* h, cudaStream_t s) {
+    RL_CUDA(h, cudaStreamWaitEvent(s, e, 0));
+    return RL_OK;
+  }
+};
+
+}  // namespace
+
+int launch_factors_convert(rl_context* h, const void* src, int src_dtype, int64_t rows, int k, int src_ld,
+                           void* dst, int dst_dtype, int dst_ld);
+
+namespace {
+
+// host (rows x k, f32 / f64) -> device (rows x padded k, f32) on h->stream, no synchronisation.  A float32 matrix whose
+// k is already the padded width is copied straight into place; everything else goes through a staging buffer.
+int factors_h2d(rl_context* h, const void* src, int dtype, int64_t rows, int k, float* dst, DevBuf& stage) {
+  if (rows == 0) return RL_OK;
+  const int kp = rl::padded_k(k);
+  const size_t bytes = static_cast<size_t>(rows) * k * (dtype == RL_F64 ? 8 : 4);
+  if (dtype == RL_F32 && k == kp) {
+    RL_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return RL_OK;
+  }
+  RL_TRY(stage.alloc(h, bytes));
+  RL_CUDA(h, cudaMemcpyAsync(stage.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  return launch_factors_convert(h, stage.p, dtype, rows, k, k, dst, RL_F32, kp);
+}
+
+int factors_d2h(rl_context* h, const float* src, int64_t rows, int k, void* dst, int dtype, DevBuf& stage) {
+  if (rows == 0) return RL_OK;
+  const int kp = rl::padded_k(k);
+  const size_t bytes = static_cast<size_t>(rows) * k * (dtype == RL_F64 ? 8 : 4);
+  if (dtype == RL_F32 && k == kp) {
+    RL_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    return RL_OK;
+  }
+  RL_TRY(stage.alloc(h, bytes));
+  RL_TRY(launch_factors_convert(h, src, RL_F32, rows, k, kp, stage.p, dtype, k));
+  RL_CUDA(h, cudaMemcpyAsync(dst, stage.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+  return RL_OK;
+}
+
 }  // namespace
 
 int launch_factors_convert(rl_context* h, const void* src, int src_dtype, int64_t rows, int k, int src_ld,
@@ -148,6 +206,11 @@ int rl_create(int device, rl_handle* out) {
   if ((e = cudaSetDevice(device)) != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaSetDevice"); }
   if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
   h->stream = h->own_stream;
+  if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    cudaStreamDestroy(h->own_stream);
+    delete h;
+    return cuda_fail(nullptr, e, "cudaStreamCreate(copy)");
+  }
   if ((e = cudaMalloc(&h->counter, 64 * sizeof(unsigned int))) != cudaSuccess) {
     cudaStreamDestroy(h->own_stream);
     delete h;
@@ -171,6 +234,7 @@ int rl_destroy(rl_handle h) {
   cudaStreamSynchronize(h->stream);
   if (h->scratch) cudaFree(h->scratch);
   if (h->counter) cudaFree(h->counter);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return RL_OK;
@@ -307,24 +371,53 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const 
   if (!indptr || !indptr_t || !user_f || !item_f) return fail(h, RL_ERR_INVALID, "rl_als_fit_host: null pointer");
   const int64_t nnz = indptr[n_users];
   if (nnz != indptr_t[n_items]) return fail(h, RL_ERR_INVALID, "rl_als_fit_host: CSR and transposed CSR disagree on nnz");
-  DevBuf d_ip, d_ix, d_tp, d_tx, d_u, d_v;
-  RL_TRY(upload(h, d_ip, indptr, sizeof(int64_t) * (n_users + 1)));
-  RL_TRY(upload(h, d_ix, indices, sizeof(int32_t) * nnz));
-  RL_TRY(upload(h, d_tp, indptr_t, sizeof(int64_t) * (n_items + 1)));
-  RL_TRY(upload(h, d_tx, indices_t, sizeof(int32_t) * nnz));
-  RL_TRY(d_u.alloc(h, sizeof(float) * n_users * kp));
-  RL_TRY(d_v.alloc(h, sizeof(float) * n_items * kp));
-  RL_TRY(rl_factors_upload(h, user_f, factor_dtype, n_users, k, d_u.as<float>()));
-  RL_TRY(rl_factors_upload(h, item_f, factor_dtype, n_items, k, d_v.as<float>()));
+  // Host traffic runs on the copy stream, ordered against the kernels by events:
+  //   copy:    V, user CSR, U | item CSR ........................ | U back (during the last item half-step)
+  //   compute:                 | user half-step | item half-step ... | V back
+  DevBuf d_ip, d_ix, d_tp, d_tx, d_u, d_v, st_u, st_v, st_ud, st_vd;
+  Event ev_user_ready, ev_item_ready, ev_u_done, ev_copy_done;
+  cudaStream_t cs = h->copy_stream, ks = h->stream;
+  RL_TRY(d_ip.alloc(h, sizeof(int64_t) * (n_users + 1)));
+  RL_TRY(d_ix.alloc(h, sizeof(int32_t) * (nnz ? nnz : 1)));
+  RL_TRY(d_tp.alloc(h, sizeof(int64_t) * (n_items + 1)));
+  RL_TRY(d_tx.alloc(h, sizeof(int32_t) * (nnz ? nnz : 1)));
+  RL_TRY(d_u.alloc(h, sizeof(float) * (n_users ? n_users : 1) * kp));
+  RL_TRY(d_v.alloc(h, sizeof(float) * (n_items ? n_items : 1) * kp));
+  Event ev_alloc;
+  RL_TRY(ev_alloc.record(h, ks));      // the buffers come from the stream-ordered pool on the compute stream
+  RL_TRY(ev_alloc.wait(h, cs));
+  {
+    StreamScope on_copy(h, cs);
+    RL_TRY(factors_h2d(h, item_f, factor_dtype, n_items, k, d_v.as<float>(), st_v));
+    RL_CUDA(h, cudaMemcpyAsync(d_ip.p, indptr, sizeof(int64_t) * (n_users + 1), cudaMemcpyHostToDevice, cs));
+    if (nnz) RL_CUDA(h, cudaMemcpyAsync(d_ix.p, indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, cs));
+    RL_TRY(factors_h2d(h, user_f, factor_dtype, n_users, k, d_u.as<float>(), st_u));
+    RL_TRY(ev_user_ready.record(h, cs));
+    RL_CUDA(h, cudaMemcpyAsync(d_tp.p, indptr_t, sizeof(int64_t) * (n_items + 1), cudaMemcpyHostToDevice, cs));
+    if (nnz) RL_CUDA(h, cudaMemcpyAsync(d_tx.p, indices_t, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, cs));
+    RL_TRY(ev_item_ready.record(h, cs));
+  }
+  RL_TRY(ev_user_ready.wait(h, ks));
+  bool u_on_copy = false;
   for (int it = 0; it < iterations; ++it) {
     RL_TRY(launch_als_half_step(h, n_users, n_items, k, d_ip.as<int64_t>(), d_ix.as<int32_t>(), nullptr, nullptr,
                                 d_v.as<float>(), d_u.as<float>(), lambda, 0.0, nullptr, precision, ir_steps, nullptr));
+    if (it == 0) RL_TRY(ev_item_ready.wait(h, ks));
+    if (it == iterations - 1) {        // U is final: send it home while the item half-step runs
+      RL_TRY(ev_u_done.record(h, ks));
+      RL_TRY(ev_u_done.wait(h, cs));
+      StreamScope on_copy(h, cs);
+      RL_TRY(factors_d2h(h, d_u.as<float>(), n_users, k, user_f, factor_dtype, st_ud));
+      u_on_copy = true;
+    }
     RL_TRY(launch_als_half_step(h, n_items, n_users, k, d_tp.as<int64_t>(), d_tx.as<int32_t>(), nullptr, nullptr,
                                 d_u.as<float>(), d_v.as<float>(), lambda, 0.0, nullptr, precision, ir_steps, nullptr));
   }
-  RL_TRY(rl_factors_download(h, d_u.as<float>(), n_users, k, user_f, factor_dtype));
-  RL_TRY(rl_factors_download(h, d_v.as<float>(), n_items, k, item_f, factor_dtype));
-  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (!u_on_copy) RL_TRY(factors_d2h(h, d_u.as<float>(), n_users, k, user_f, factor_dtype, st_ud));
+  RL_TRY(factors_d2h(h, d_v.as<float>(), n_items, k, item_f, factor_dtype, st_vd));
+  RL_TRY(ev_copy_done.record(h, cs));  // the buffers are freed on the compute stream: it has to see the copy stream's work
+  RL_TRY(ev_copy_done.wait(h, ks));
+  RL_CUDA(h, cudaStreamSynchronize(ks));
   return RL_OK;
 }
 
@@ -355,26 +448,67 @@ int rl_recommend_host(rl_handle h, const void* user_f, const void* item_f, int f
   if (n_users < 0 || n_items < 0) return fail(h, RL_ERR_INVALID, "rl_recommend_host: negative size");
   if (n_users == 0) return RL_OK;
   if (!user_f || !item_f || !idx_out) return fail(h, RL_ERR_INVALID, "rl_recommend_host: null pointer");
-  DevBuf d_u, d_v, d_sp, d_sx, d_ub, d_ib, d_idx, d_sc;
+  // Users are processed in a few chunks (whole sweeps of the scoring kernel: multiples of 128 users x SM count) so that
+  // the copy stream uploads chunk c + 1 (factor rows + its part of the seen lists) while chunk c is being scored, and
+  // the results of chunk c travel back during chunk c + 1.
+  DevBuf d_u, d_v, d_sp, d_sx, d_ub, d_ib, d_idx, d_sc, st_v;
+  const int64_t nnz = seen_indptr ? seen_indptr[n_users] : 0;
   RL_TRY(d_u.alloc(h, sizeof(float) * n_users * kp));
-  RL_TRY(d_v.alloc(h, sizeof(float) * n_items * kp));
-  RL_TRY(rl_factors_upload(h, user_f, factor_dtype, n_users, k, d_u.as<float>()));
-  RL_TRY(rl_factors_upload(h, item_f, factor_dtype, n_items, k, d_v.as<float>()));
+  RL_TRY(d_v.alloc(h, sizeof(float) * (n_items ? n_items : 1) * kp));
   if (seen_indptr) {
-    const int64_t nnz = seen_indptr[n_users];
-    RL_TRY(upload(h, d_sp, seen_indptr, sizeof(int64_t) * (n_users + 1)));
-    RL_TRY(upload(h, d_sx, seen_indices, sizeof(int32_t) * nnz));
+    RL_TRY(d_sp.alloc(h, sizeof(int64_t) * (n_users + 1)));
+    RL_TRY(d_sx.alloc(h, sizeof(int32_t) * (nnz ? nnz : 1)));
   }
-  if (user_bias) RL_TRY(upload(h, d_ub, user_bias, sizeof(float) * n_users));
-  if (item_bias) RL_TRY(upload(h, d_ib, item_bias, sizeof(float) * n_items));
   RL_TRY(d_idx.alloc(h, sizeof(int32_t) * n_users * n));
   if (score_out) RL_TRY(d_sc.alloc(h, sizeof(double) * n_users * n));
-  RL_TRY(launch_score_topn(h, d_u.as<float>(), n_users, d_v.as<float>(), n_items, k, seen_indptr ? d_sp.as<int64_t>() : nullptr,
-                           seen_indptr ? d_sx.as<int32_t>() : nullptr, global_bias, user_bias ? d_ub.as<float>() : nullptr,
-                           item_bias ? d_ib.as<float>() : nullptr, n, d_idx.as<int32_t>(), score_out ? d_sc.as<double>() : nullptr, mode));
-  RL_CUDA(h, cudaMemcpyAsync(idx_out, d_idx.p, sizeof(int32_t) * n_users * n, cudaMemcpyDeviceToHost, h->stream));
-  if (score_out) RL_CUDA(h, cudaMemcpyAsync(score_out, d_sc.p, sizeof(double) * n_users * n, cudaMemcpyDeviceToHost, h->stream));
-  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (user_bias) RL_TRY(upload(h, d_ub, user_bias, sizeof(float) * n_users));
+  if (item_bias) RL_TRY(upload(h, d_ib, item_bias, sizeof(float) * n_items));
+  cudaStream_t cs = h->copy_stream, ks = h->stream;
+  const int64_t sweep = static_cast<int64_t>(128) * h->sm_count;
+  int64_t per = ((n_users / 4 + sweep - 1) / sweep) * sweep;            // about four chunks, never a fraction of a sweep
+  if (per <= 0 || n_users < 2 * sweep) per = n_users;
+  const int n_chunks = static_cast<int>((n_users + per - 1) / per);
+  std::vector<Event> ready(n_chunks), done(n_chunks);
+  std::vector<DevBuf> stage(n_chunks);
+  Event ev_alloc, ev_copy_done;
+  RL_TRY(ev_alloc.record(h, ks));
+  RL_TRY(ev_alloc.wait(h, cs));
+  {
+    StreamScope on_copy(h, cs);
+    RL_TRY(factors_h2d(h, item_f, factor_dtype, n_items, k, d_v.as<float>(), st_v));
+    if (seen_indptr) RL_CUDA(h, cudaMemcpyAsync(d_sp.p, seen_indptr, sizeof(int64_t) * (n_users + 1), cudaMemcpyHostToDevice, cs));
+    for (int c = 0; c < n_chunks; ++c) {
+      const int64_t r0 = c * per, r1 = (r0 + per < n_users) ? r0 + per : n_users;
+      const size_t es = factor_dtype == RL_F64 ? 8 : 4;
+      RL_TRY(factors_h2d(h, static_cast<const char*>(user_f) + static_cast<size_t>(r0) * k * es, factor_dtype, r1 - r0, k,
+                         d_u.as<float>() + r0 * kp, stage[c]));
+      if (seen_indptr && seen_indptr[r1] > seen_indptr[r0])
+        RL_CUDA(h, cudaMemcpyAsync(d_sx.as<int32_t>() + seen_indptr[r0], seen_indices + seen_indptr[r0],
+                                   sizeof(int32_t) * (seen_indptr[r1] - seen_indptr[r0]), cudaMemcpyHostToDevice, cs));
+      RL_TRY(ready[c].record(h, cs));
+    }
+  }
+  unsigned int overflow_total = 0;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int64_t r0 = c * per, r1 = (r0 + per < n_users) ? r0 + per : n_users;
+    RL_TRY(ready[c].wait(h, ks));
+    h->last_overflow = 0;
+    // seen_indptr holds absolute offsets into the full seen_indices array: pass its window, keep the indices whole
+    RL_TRY(launch_score_topn(h, d_u.as<float>() + r0 * kp, r1 - r0, d_v.as<float>(), n_items, k,
+                             seen_indptr ? d_sp.as<int64_t>() + r0 : nullptr, seen_indptr ? d_sx.as<int32_t>() : nullptr, global_bias,
+                             user_bias ? d_ub.as<float>() + r0 : nullptr, item_bias ? d_ib.as<float>() : nullptr, n,
+                             d_idx.as<int32_t>() + r0 * n, score_out ? d_sc.as<double>() + r0 * n : nullptr, mode));
+    overflow_total += h->last_overflow;
+    RL_TRY(done[c].record(h, ks));
+    RL_TRY(done[c].wait(h, cs));
+    RL_CUDA(h, cudaMemcpyAsync(idx_out + r0 * n, d_idx.as<int32_t>() + r0 * n, sizeof(int32_t) * (r1 - r0) * n, cudaMemcpyDeviceToHost, cs));
+    if (score_out)
+      RL_CUDA(h, cudaMemcpyAsync(score_out + r0 * n, d_sc.as<double>() + r0 * n, sizeof(double) * (r1 - r0) * n, cudaMemcpyDeviceToHost, cs));
+  }
+  h->last_overflow = overflow_total;
+  RL_TRY(ev_copy_done.record(h, cs));
+  RL_TRY(ev_copy_done.wait(h, ks));
+  RL_CUDA(h, cudaStreamSynchronize(ks));
   return RL_OK;
 }
 

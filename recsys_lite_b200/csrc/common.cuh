@@ -17,6 +17,7 @@ struct rl_context {
   size_t total_mem = 0;
   cudaStream_t stream = nullptr;      // stream kernels are enqueued on
   cudaStream_t own_stream = nullptr;  // created by rl_create
+  cudaStream_t copy_stream = nullptr; // host <-> device traffic of the *_host entry points, overlapped with the kernels
   unsigned int* counter = nullptr;    // device work counters (row schedulers), 64 x u32
   int64_t launches = 0;
   std::string err;

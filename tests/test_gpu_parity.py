@@ -211,6 +211,44 @@ def test_score_topn_ragged_ties_and_bias(h):
     assert np.allclose(val[ref_idx >= 0], ref_val[ref_idx >= 0], rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("k,dtype,bias", [(64, np.float32, False), (20, np.float64, True)])
+def test_host_entry_points_overlapped_chunks_equal_device_path(h, k, dtype, bias):
+    """rl_recommend_host splits the users into chunks (upload of chunk c+1 / download of chunk c overlap the scoring of
+    chunk c) and rl_als_fit_host overlaps its transfers with the half-steps: results must equal the single-stream device
+    path bit for bit (same kernels, same inputs)."""
+    from devbuf import Dev, padded, unpadded
+    from recsys_lite_b200 import _ffi
+    n_users, n_items, n = 40000, 1100, 10          # > 2 sweeps of 128 users x 148 SMs: three chunks, the last one ragged
+    rng = np.random.default_rng(k)
+    indptr, indices = gen.synth_pattern(n_users, n_items, mean_deg=12, seed=k)
+    ti, tx = o_als.transpose_pattern(indptr, indices, n_items)
+    u0 = rng.random((n_users, k)).astype(dtype)
+    v0 = rng.random((n_items, k)).astype(dtype)
+    code = _ffi.RL_F64 if dtype == np.float64 else _ffi.RL_F32
+    # ---- fit: host entry point vs the same two half-steps on device buffers
+    uh, vh = u0.copy(), v0.copy()
+    h.call("rl_als_fit_host", n_users, n_items, k, _ffi.ptr(indptr), _ffi.ptr(indices), _ffi.ptr(ti), _ffi.ptr(tx), 2, 0.01, 0, 1,
+           _ffi.ptr(uh), _ffi.ptr(vh), code)
+    d_u, d_v = padded(h, u0, k), padded(h, v0, k)
+    d_ip, d_ix, d_tp, d_tx = Dev(h, indptr), Dev(h, indices), Dev(h, ti), Dev(h, tx)
+    for _ in range(2):
+        h.call("rl_als_half_step_dev", n_users, n_items, k, d_ip.ptr, d_ix.ptr, None, None, d_v.ptr, d_u.ptr, 0.01, 0.0, None, 0, 1, None)
+        h.call("rl_als_half_step_dev", n_items, n_users, k, d_tp.ptr, d_tx.ptr, None, None, d_u.ptr, d_v.ptr, 0.01, 0.0, None, 0, 1, None)
+    assert np.array_equal(uh, unpadded(h, d_u, k, dtype)) and np.array_equal(vh, unpadded(h, d_v, k, dtype))
+    # ---- recommend: chunked host entry point vs one device call
+    ub = rng.standard_normal(n_users).astype(np.float32) if bias else None
+    ib = rng.standard_normal(n_items).astype(np.float32) if bias else None
+    idx = np.empty((n_users, n), np.int32)
+    val = np.empty((n_users, n), np.float64)
+    h.call("rl_recommend_host", _ffi.ptr(uh), _ffi.ptr(vh), code, n_users, n_items, k, _ffi.ptr(indptr), _ffi.ptr(indices),
+           0.25 if bias else 0.0, _ffi.ptr(ub) if bias else None, _ffi.ptr(ib) if bias else None, n, _ffi.ptr(idx), _ffi.ptr(val), 0)
+    d_idx, d_val = Dev(h, shape=(n_users, n), dtype=np.int32), Dev(h, shape=(n_users, n), dtype=np.float64)
+    d_ub, d_ib = (Dev(h, ub), Dev(h, ib)) if bias else (None, None)
+    h.call("rl_score_topn_dev", d_u.ptr, n_users, d_v.ptr, n_items, k, d_ip.ptr, d_ix.ptr, 0.25 if bias else 0.0,
+           d_ub.ptr if bias else None, d_ib.ptr if bias else None, n, d_idx.ptr, d_val.ptr, 0)
+    assert np.array_equal(idx, d_idx.get()) and np.array_equal(val, d_val.get())
+
+
 @pytest.mark.parametrize("case", ["lit", "order", "ragged", "rand_f64", "rand_f32"])
 def test_top_n_api_matches_reference_golden(golden_dir, case):
     """top_n(est, known, n) vs the reference's output (algo.py:587-659): shape, dtype, indices up to ties."""
