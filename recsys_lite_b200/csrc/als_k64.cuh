@@ -43,8 +43,8 @@ struct K64Smem {
   static constexpr size_t y_bytes = sizeof(float) * 2 * K64_CH * K64_LDY;
   static constexpr size_t w_bytes = WEIGHTED ? sizeof(float2) * 2 * K64_CH : 0;
   static constexpr size_t bytes = lt_bytes + invd_bytes + xs_bytes + ts_bytes + y_bytes + w_bytes;
-  static constexpr int warps = 2;   // 7 CTAs per SM: 7 x (2 x 15.1 KB + 1 KB) < 228 KB, registers <= 144
-  static constexpr int ctas = 7;
+  static constexpr int warps = 3;   // 5 CTAs per SM: 5 x (3 x 14.6 KB + 1 KB) < 227 KB, registers <= 136
+  static constexpr int ctas = 5;
   static_assert(bytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
 };
 
