@@ -221,6 +221,7 @@ def run_b200(args, w):
     plan = make_plan(indptr, indptr_t, rank, world)
     prob = ShardedProblem(h, plan, indptr, indices, indptr_t, indices_t, k, device)
     prob.set_factors(u0, v0)
+    fused = prob.enable_peer_stores() if (world > 1 and not args.no_peer_stores) else False
     ulo, uhi = plan.users
     ilo, ihi = plan.items
     idx_out = torch.empty((uhi - ulo, n), dtype=torch.int32, device=device)
@@ -240,12 +241,11 @@ def run_b200(args, w):
         prob.user_half_step(w["lam"], prec, args.ir_steps)
         if record:
             e[1].record()
-        from recsys_lite_b200.sharding import exchange_rows
-        exchange_rows(prob.U, plan.user_bounds, rank, world)
+        prob.exchange_users()
         prob.item_half_step(w["lam"], prec, args.ir_steps)
         if record:
             e[2].record()
-        exchange_rows(prob.V, plan.item_bounds, rank, world)
+        prob.exchange_items()
         if record:
             e[3].record()
         prob.recommend(n, idx_out, args.score_mode)
@@ -271,8 +271,12 @@ def run_b200(args, w):
     total_ms = t_begin.elapsed_time(t_end)
     seg = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in marks])   # user(+0), xchg+item, xchg, score
     t_user, t_item_x, t_x2, t_score = seg.mean(axis=0)
+    per_rank = None
     if world > 1:
         tt = torch.tensor([total_ms, t_user, t_item_x, t_x2, t_score], dtype=torch.float64, device=device)
+        allt = [torch.empty_like(tt) for _ in range(world)]
+        dist.all_gather(allt, tt)
+        per_rank = [[round(float(x), 3) for x in t.tolist()[1:]] for t in allt]     # diagnostics: stragglers show up here
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms, t_user, t_item_x, t_x2, t_score = tt.tolist()
     ms_per_step = total_ms / args.steps
@@ -292,7 +296,9 @@ def run_b200(args, w):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 factors; ALS solve " + ("f64" if prec else f"f32 + {args.ir_steps} f64 refinement steps")
                      + "; scores f64",
-            "data": "synthetic", "config": workload_config(args, w, f"{world} x B200"),
+            "data": "synthetic", "config": dict(workload_config(args, w, f"{world} x B200"), exchange=(
+                "none (1 GPU)" if world == 1 else "fused: solve kernel stores rows into the peers' replicas over NVLink (CUDA IPC) + "
+                "one-element all-reduce as barrier" if fused else "NCCL broadcasts of the row ranges")),
             "als_iterations_per_s": 1000.0 / (t_user + t_item_x + t_x2),
             "top10_users_per_s": nu / (t_score / 1000.0),
             "ms": {"user_half_step": t_user, "exchange_U_plus_item_half_step": t_item_x, "exchange_V": t_x2, "score_topn": t_score},
@@ -311,7 +317,7 @@ def run_b200(args, w):
                 "item_half_step_incl_exchange": {"bytes": b_item, "achieved": b_item / (t_item_x * 1e-3) / 1e9,
                                                  "frac": b_item / (t_item_x * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                                  "traffic": traffic.get("als_item_half_step")}},
-            "clocks": clk, "gpu_launches": int(launches), "e2e": e2e,
+            "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "ms_per_rank": per_rank,
         }
         if world == 1 and not args.no_cpu:
             v, s, desc = cpu_reference_leg(w, inputs, 20_000, 20_000, 2_000)
@@ -358,7 +364,6 @@ def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
                 "ms_per_step": sec * 1e3, "steps": steps,
                 "api": "rl_als_fit_host(iterations=1) + rl_recommend_host(n=10), pinned float32 host buffers"}
     import torch.distributed as dist
-    from recsys_lite_b200.sharding import exchange_rows
     ulo, uhi = plan.users
     ilo, ihi = plan.items
     hp = {kk: torch.from_numpy(v).pin_memory() for kk, v in prob.host.items()}
@@ -379,10 +384,12 @@ def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
         prob.ix.copy_(hp["ix"], non_blocking=True)
         prob.U[:, :k].copy_(hu, non_blocking=True)
         prob.V[:, :k].copy_(hv, non_blocking=True)
+        if getattr(prob, "peer_stores", False):
+            prob.peer_barrier()       # no peer may store into this replica before its upload has landed
         prob.user_half_step(w["lam"], prec, args.ir_steps)
-        exchange_rows(prob.U, plan.user_bounds, rank, world)
+        prob.exchange_users()
         prob.item_half_step(w["lam"], prec, args.ir_steps)
-        exchange_rows(prob.V, plan.item_bounds, rank, world)
+        prob.exchange_items()
         prob.recommend(n, idx_dev, args.score_mode)
         out_u.copy_(prob.U[ulo:uhi, :k], non_blocking=True)
         out_v.copy_(prob.V[ilo:ihi, :k], non_blocking=True)
@@ -397,7 +404,7 @@ def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     return {"value": 1.0 / sec, "unit": UNIT, "h2d_bytes_per_step": int(tot[0].item()), "d2h_bytes_per_step": int(tot[1].item()),
             "ms_per_step": sec * 1e3, "steps": steps,
-            "api": "per-rank pinned H2D of its CSR/CSC ranges + factors, rl_als_half_step_dev/rl_score_topn_dev + exchanges, D2H of its ranges"}
+            "api": "per-rank pinned H2D of its CSR/CSC ranges + factors, rl_als_half_step(_peers)_dev/rl_score_topn_dev + exchanges, D2H of its ranges"}
 
 
 _REAL_STDOUT = None
@@ -436,6 +443,7 @@ def main():
     ap.add_argument("--precision", default="fp32_ir", choices=["fp32_ir", "fp64"])
     ap.add_argument("--ir-steps", type=int, default=1)
     ap.add_argument("--score-mode", type=int, default=0, help="0 auto, 1 exact CUDA-core, 2 tensor-core candidate pass")
+    ap.add_argument("--no-peer-stores", action="store_true", help="N > 1: exchange with NCCL broadcasts instead of the fused NVLink stores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     _quiet_stdout()

@@ -102,6 +102,27 @@ int rl_als_half_step_dev(rl_handle h, int64_t n_rows, int64_t n_other, int k,
                          double lambda, double w0, const double* gram0_dev,
                          int precision, int ir_steps, const int32_t* row_order_dev);
 
+/* The same half-step fused with the multi-GPU exchange ("all-gather of the factor matrix once per
+ * half-step"): every solved row is stored into mine_dev AND, over NVLink, into the replicas of the other ranks.
+ * peer_mine_dev: host array of n_peers (<= RL_MAX_PEERS) device pointers, each the address in a PEER's replica that
+ * corresponds to mine_dev (same row range), mapped into this process with rl_ipc_open.  The stores are complete when
+ * the kernel is; ranks still need one barrier on the stream (e.g. a one-element all-reduce) before the replica is read. */
+#define RL_MAX_PEERS 15
+int rl_als_half_step_peers_dev(rl_handle h, int64_t n_rows, int64_t n_other, int k,
+                               const int64_t* indptr_dev, const int32_t* indices_dev,
+                               const float* conf_dev, const float* pref_dev,
+                               const float* other_dev, float* mine_dev,
+                               double lambda, double w0, const double* gram0_dev,
+                               int precision, int ir_steps, const int32_t* row_order_dev,
+                               int n_peers, float* const* peer_mine_dev);
+/* CUDA IPC plumbing for the peer replicas (one process per GPU).  rl_ipc_export: 64-byte handle of the allocation that
+ * contains dev_ptr + the offset of dev_ptr inside it (framework allocators sub-allocate).  rl_ipc_open: maps a peer's
+ * allocation into this process (peer access over NVLink) and returns base + offset; rl_ipc_close takes that pointer. */
+#define RL_IPC_HANDLE_BYTES 64
+int rl_ipc_export(rl_handle h, const void* dev_ptr, void* handle_out, int64_t* offset_out);
+int rl_ipc_open(rl_handle h, const void* handle, int64_t offset, void** dev_ptr_out);
+int rl_ipc_close(rl_handle h, void* dev_ptr);
+
 /* G = Y^T Y, float64 (kp x kp row-major), Y (n x kp) float32.  Used for the w0 term above. */
 int rl_gram_dev(rl_handle h, const float* y_dev, int64_t n, int k, double* gram_dev);
 

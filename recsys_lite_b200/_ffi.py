@@ -39,6 +39,11 @@ SIGNATURES = {
     "rl_factors_upload": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp]),
     "rl_factors_download": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32]),
     "rl_als_half_step_dev": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _vp, _i32, _i32, _vp]),
+    "rl_als_half_step_peers_dev": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _vp, _i32, _i32, _vp,
+                                          _i32, _vp]),
+    "rl_ipc_export": (_i32, [_vp, _vp, _vp, C.POINTER(_i64)]),
+    "rl_ipc_open": (_i32, [_vp, _vp, _i64, C.POINTER(_vp)]),
+    "rl_ipc_close": (_i32, [_vp, _vp]),
     "rl_gram_dev": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "rl_als_fit_host": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _dbl, _i32, _i32, _vp, _vp, _i32]),
     "rl_score_topn_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _dbl, _vp, _vp, _i32, _vp, _vp, _i32]),

@@ -84,6 +84,10 @@ struct AlsArgs {
   int ir_steps;
   unsigned int* counter;
   const int32_t* row_order;
+  // fused exchange (multi-GPU): the solved row is also stored into the replicas of the other ranks, which are mapped
+  // into this process (CUDA IPC) and reached over NVLink -- same row offset as `mine`
+  int n_peers;
+  float* peers[RL_MAX_PEERS];
 };
 
 template <typename real, int T>
@@ -282,7 +286,10 @@ __global__ void __launch_bounds__(WarpSmem<real, KP>::warps * 32) als_half_step_
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
           const int col = lane + 32 * q;
-          if (col < KP) a.mine[row * KP + col] = 0.0f;
+          if (col < KP) {
+            a.mine[row * KP + col] = 0.0f;
+            for (int pr = 0; pr < a.n_peers; ++pr) a.peers[pr][row * KP + col] = 0.0f;
+          }
         }
       }
       continue;  // reference: rows with no observation keep their previous value (algo.py:316-317)
@@ -509,7 +516,11 @@ __global__ void __launch_bounds__(WarpSmem<real, KP>::warps * 32) als_half_step_
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
       const int col = lane + 32 * q;
-      if (col < KP) a.mine[row * KP + col] = (col < a.k) ? static_cast<float>(xd[q]) : 0.0f;
+      if (col < KP) {
+        const float xo = (col < a.k) ? static_cast<float>(xd[q]) : 0.0f;
+        a.mine[row * KP + col] = xo;
+        for (int pr = 0; pr < a.n_peers; ++pr) a.peers[pr][row * KP + col] = xo;
+      }
     }
     __syncwarp();
   }
@@ -592,9 +603,11 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ y, 
 int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, const int64_t* indptr,
                          const int32_t* indices, const float* conf, const float* pref, const float* other,
                          float* mine, double lambda, double w0, const double* gram0, int precision,
-                         int ir_steps, const int32_t* row_order) {
+                         int ir_steps, const int32_t* row_order, int n_peers, float* const* peers) {
   const int kp = padded_k(k);
   if (kp == 0) return fail(h, RL_ERR_INVALID, "als_half_step: k=%d outside [1, 128]", k);
+  if (n_peers < 0 || n_peers > RL_MAX_PEERS || (n_peers > 0 && !peers))
+    return fail(h, RL_ERR_INVALID, "als_half_step: n_peers=%d outside [0, %d] or null peer list", n_peers, RL_MAX_PEERS);
   if (n_rows < 0 || n_other < 0) return fail(h, RL_ERR_INVALID, "als_half_step: negative size");
   if (n_rows >= (1ll << 32) - 1) return fail(h, RL_ERR_INVALID, "als_half_step: n_rows too large for the row ticket");
   if (n_rows == 0) return RL_OK;
@@ -602,7 +615,11 @@ int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, 
   if (w0 != 0.0 && !gram0) return fail(h, RL_ERR_INVALID, "als_half_step: w0 != 0 needs gram0 (rl_gram_dev)");
   if (!(lambda >= 0.0)) return fail(h, RL_ERR_INVALID, "als_half_step: lambda must be >= 0");
   if (ir_steps < 0 || ir_steps > 8) return fail(h, RL_ERR_INVALID, "als_half_step: ir_steps outside [0, 8]");
-  AlsArgs a{indptr, indices, conf, pref, other, mine, n_rows, k, lambda, w0, gram0, ir_steps, h->counter, row_order};
+  AlsArgs a{indptr, indices, conf, pref, other, mine, n_rows, k, lambda, w0, gram0, ir_steps, h->counter, row_order, n_peers, {}};
+  for (int pr = 0; pr < n_peers; ++pr) {
+    if (!peers[pr]) return fail(h, RL_ERR_INVALID, "als_half_step: peer pointer %d is null", pr);
+    a.peers[pr] = peers[pr];
+  }
   const bool weighted = conf != nullptr || pref != nullptr || w0 != 0.0;
   if (precision == RL_PREC_FP64) {
     a.ir_steps = 0;

@@ -306,6 +306,10 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
       if (hkv) {
         a.mine[row * KP + lane] = 0.0f;
         a.mine[row * KP + 32 + lane] = 0.0f;
+        for (int pr = 0; pr < a.n_peers; ++pr) {
+          a.peers[pr][row * KP + lane] = 0.0f;
+          a.peers[pr][row * KP + 32 + lane] = 0.0f;
+        }
       }
       continue;  // reference: rows with no observation keep their previous value (algo.py:316-317)
     }
@@ -485,8 +489,14 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
       __syncwarp();
       k64_forward(Lt, invd, bs, lane);
     }
-    a.mine[row * KP + lane] = (lane < a.k) ? static_cast<float>(xd0) : 0.0f;
-    a.mine[row * KP + 32 + lane] = (32 + lane < a.k) ? static_cast<float>(xd1) : 0.0f;
+    const float xo0 = (lane < a.k) ? static_cast<float>(xd0) : 0.0f;
+    const float xo1 = (32 + lane < a.k) ? static_cast<float>(xd1) : 0.0f;
+    a.mine[row * KP + lane] = xo0;
+    a.mine[row * KP + 32 + lane] = xo1;
+    for (int pr = 0; pr < a.n_peers; ++pr) {      // fused exchange: two 128-byte NVLink stores per peer replica
+      a.peers[pr][row * KP + lane] = xo0;
+      a.peers[pr][row * KP + 32 + lane] = xo1;
+    }
     __syncwarp();
   }
 }

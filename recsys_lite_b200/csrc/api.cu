@@ -1,4 +1,5 @@
 // api.cu -- the C ABI of librecsys_b200.so (include/recsys_b200.h): handle, memory helpers, host-buffer wrappers.
+#include <cuda.h>
 #include <cstdarg>
 #include <vector>
 
@@ -354,6 +355,67 @@ int rl_als_half_step_dev(rl_handle h, int64_t n_rows, int64_t n_other, int k, co
   RL_NEED(h);
   return launch_als_half_step(h, n_rows, n_other, k, indptr_dev, indices_dev, conf_dev, pref_dev, other_dev, mine_dev,
                               lambda, w0, gram0_dev, precision, ir_steps, row_order_dev);
+}
+
+int rl_als_half_step_peers_dev(rl_handle h, int64_t n_rows, int64_t n_other, int k, const int64_t* indptr_dev,
+                               const int32_t* indices_dev, const float* conf_dev, const float* pref_dev,
+                               const float* other_dev, float* mine_dev, double lambda, double w0, const double* gram0_dev,
+                               int precision, int ir_steps, const int32_t* row_order_dev, int n_peers,
+                               float* const* peer_mine_dev) {
+  RL_NEED(h);
+  return launch_als_half_step(h, n_rows, n_other, k, indptr_dev, indices_dev, conf_dev, pref_dev, other_dev, mine_dev,
+                              lambda, w0, gram0_dev, precision, ir_steps, row_order_dev, n_peers, peer_mine_dev);
+}
+
+int rl_ipc_export(rl_handle h, const void* dev_ptr, void* handle_out, int64_t* offset_out) {
+  RL_NEED(h);
+  if (!dev_ptr || !handle_out || !offset_out) return fail(h, RL_ERR_INVALID, "rl_ipc_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == RL_IPC_HANDLE_BYTES, "IPC handle size");
+  // driver entry point looked up at run time: the library itself does not link against libcuda
+  typedef CUresult (*GetRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static GetRangeFn get_range = nullptr;
+  if (!get_range) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return fail(h, RL_ERR_CUDA, "rl_ipc_export: cuMemGetAddressRange not available from the driver");
+    get_range = reinterpret_cast<GetRangeFn>(fp);
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (get_range(&base, &size, reinterpret_cast<CUdeviceptr>(dev_ptr)) != CUDA_SUCCESS)
+    return fail(h, RL_ERR_CUDA, "rl_ipc_export: cuMemGetAddressRange failed (not a device allocation?)");
+  cudaIpcMemHandle_t hd;
+  RL_CUDA(h, cudaIpcGetMemHandle(&hd, reinterpret_cast<void*>(base)));
+  memcpy(handle_out, &hd, sizeof(hd));
+  *offset_out = static_cast<int64_t>(reinterpret_cast<CUdeviceptr>(dev_ptr) - base);
+  return RL_OK;
+}
+
+int rl_ipc_open(rl_handle h, const void* handle, int64_t offset, void** dev_ptr_out) {
+  RL_NEED(h);
+  if (!handle || !dev_ptr_out || offset < 0) return fail(h, RL_ERR_INVALID, "rl_ipc_open: bad argument");
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle, sizeof(hd));
+  void* base = nullptr;
+  RL_CUDA(h, cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+  h->ipc_bases.push_back({static_cast<char*>(base) + offset, base});
+  *dev_ptr_out = static_cast<char*>(base) + offset;
+  return RL_OK;
+}
+
+int rl_ipc_close(rl_handle h, void* dev_ptr) {
+  RL_NEED(h);
+  for (size_t i = 0; i < h->ipc_bases.size(); ++i) {
+    if (h->ipc_bases[i].first == dev_ptr) {
+      void* base = h->ipc_bases[i].second;
+      h->ipc_bases.erase(h->ipc_bases.begin() + i);
+      RL_CUDA(h, cudaStreamSynchronize(h->stream));
+      RL_CUDA(h, cudaIpcCloseMemHandle(base));
+      return RL_OK;
+    }
+  }
+  return fail(h, RL_ERR_INVALID, "rl_ipc_close: pointer was not returned by rl_ipc_open");
 }
 
 int rl_gram_dev(rl_handle h, const float* y_dev, int64_t n, int k, double* gram_dev) {

@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/recsys_b200.h"
 
@@ -25,6 +27,7 @@ struct rl_context {
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
   unsigned int last_overflow = 0;  // rows the last tensor-core scoring call handed to the exact kernel
+  std::vector<std::pair<void*, void*>> ipc_bases;  // (pointer handed out by rl_ipc_open, base of the mapping)
 };
 
 namespace rl {
@@ -59,7 +62,7 @@ __host__ __device__ constexpr int padded_k(int k) {
 int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, const int64_t* indptr,
                          const int32_t* indices, const float* conf, const float* pref, const float* other,
                          float* mine, double lambda, double w0, const double* gram0, int precision,
-                         int ir_steps, const int32_t* row_order);
+                         int ir_steps, const int32_t* row_order, int n_peers = 0, float* const* peers = nullptr);
 int launch_gram(rl_context* h, const float* y, int64_t n, int k, double* gram);
 int launch_score_topn(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k,
                       const int64_t* seen_indptr, const int32_t* seen_indices, double gbias, const float* ubias,

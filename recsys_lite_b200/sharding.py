@@ -4,8 +4,11 @@ The reference has no parallelism (plain Python loops, algo.py:314,324).  The loo
 
   * user half-step: users are cut into `world` contiguous ranges balanced by nnz; rank g holds the CSR rows of
     its users and a full replica of V, solves its range and writes U[g];
-  * the freshly solved range is exchanged once per half-step (all-gather over NCCL / NVLink) so every rank has
-    the full U again before the item half-step, and likewise V afterwards;
+  * the freshly solved range is exchanged once per half-step so every rank has the full U again before the item
+    half-step, and likewise V afterwards.  On NVLink-connected GPUs the exchange is FUSED into the solve kernel
+    (`enable_peer_stores`): every rank maps the other ranks' replicas (CUDA IPC) and the kernel stores each solved
+    row into all of them, so the transfer rides under the solves and what is left of the "all-gather" is one
+    one-element all-reduce as a barrier.  `exchange_rows` (NCCL broadcasts of the row ranges) is the portable path;
   * scoring shards users with V replicated: no collective.
 
 torch is used here only for device memory, the stream and torch.distributed; all arithmetic goes through the
@@ -81,6 +84,78 @@ class ShardedProblem:
         self.U = torch.zeros((self.n_users, self.kp), dtype=torch.float32, device=device)
         self.V = torch.zeros((self.n_items, self.kp), dtype=torch.float32, device=device)
 
+    # -- fused exchange over peer memory ---------------------------------------------------------------------
+    def enable_peer_stores(self, group=None):
+        """Map every other rank's U / V replica into this process (rl_ipc_export / rl_ipc_open, all_gather_object for
+        the handles).  Afterwards the half-steps store their rows into all replicas (rl_als_half_step_peers_dev) and
+        `iteration` only needs `peer_barrier` between them.  Returns False (and changes nothing) if any rank could
+        not export or open a mapping; collective: every rank must call it."""
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _ffi
+        world, rank = self.plan.world, self.plan.rank
+        if world == 1:
+            return False
+        if world - 1 > 15:
+            return False
+        ok, mine = True, None
+        try:
+            mine = []
+            for t in (self.U, self.V):
+                hb = C.create_string_buffer(64)
+                off = C.c_int64(0)
+                self.h.call("rl_ipc_export", t.data_ptr(), hb, C.byref(off))
+                mine.append((hb.raw, int(off.value)))
+        except _ffi.RecsysB200Error:
+            ok = False
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine if ok else None, group=group)
+        if any(g is None for g in gathered):
+            return False
+        peers_u, peers_v, opened = [], [], []
+        try:
+            for r in range(world):
+                if r == rank:
+                    continue
+                for (raw, off), lst in zip(gathered[r], (peers_u, peers_v)):
+                    out = C.c_void_p()
+                    self.h.call("rl_ipc_open", C.create_string_buffer(raw, 64), off, C.byref(out))
+                    opened.append(out.value)
+                    lst.append(out.value)
+        except _ffi.RecsysB200Error:
+            ok = False
+        flags = [None] * world
+        dist.all_gather_object(flags, ok, group=group)
+        if not all(flags):
+            for ptr in opened:
+                self.h.call("rl_ipc_close", ptr)
+            return False
+        self._peer_ptrs = opened
+        ulo, _ = self.plan.users
+        ilo, _ = self.plan.items
+        row_bytes = 4 * self.kp
+        arr = C.c_void_p * (world - 1)
+        self._peers_u = arr(*[p + ulo * row_bytes for p in peers_u])     # where MY user range lives in each peer's U
+        self._peers_v = arr(*[p + ilo * row_bytes for p in peers_v])
+        self._barrier_buf = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._group = group
+        self.peer_stores = True
+        return True
+
+    def peer_barrier(self):
+        """Every rank's kernel (and with it its NVLink stores into this replica) has finished once this one-element
+        all-reduce, enqueued behind the kernel on the same stream, completes."""
+        import torch.distributed as dist
+        dist.all_reduce(self._barrier_buf, group=self._group)
+
+    def close_peer_stores(self):
+        if getattr(self, "peer_stores", False):
+            self.h.synchronize()
+            for ptr in self._peer_ptrs:
+                self.h.call("rl_ipc_close", ptr)
+            self.peer_stores = False
+
     def set_factors(self, u_host, v_host):
         import torch
         self.U[:, : self.k].copy_(torch.from_numpy(np.ascontiguousarray(u_host, dtype=np.float32)))
@@ -89,22 +164,44 @@ class ShardedProblem:
     # -- one ALS half-step on this rank's rows, then the exchange -------------------------------------------
     def user_half_step(self, lam, precision, ir_steps):
         ulo, uhi = self.plan.users
-        self.h.call("rl_als_half_step_dev", uhi - ulo, self.n_items, self.k, self.up.data_ptr(), self.ux.data_ptr(),
-                    None, None, self.V.data_ptr(), self.U[ulo:].data_ptr(), float(lam), 0.0, None, precision,
-                    ir_steps, None)
+        if getattr(self, "peer_stores", False):
+            self.h.call("rl_als_half_step_peers_dev", uhi - ulo, self.n_items, self.k, self.up.data_ptr(), self.ux.data_ptr(),
+                        None, None, self.V.data_ptr(), self.U[ulo:].data_ptr(), float(lam), 0.0, None, precision,
+                        ir_steps, None, self.plan.world - 1, self._peers_u)
+        else:
+            self.h.call("rl_als_half_step_dev", uhi - ulo, self.n_items, self.k, self.up.data_ptr(), self.ux.data_ptr(),
+                        None, None, self.V.data_ptr(), self.U[ulo:].data_ptr(), float(lam), 0.0, None, precision,
+                        ir_steps, None)
 
     def item_half_step(self, lam, precision, ir_steps):
         ilo, ihi = self.plan.items
-        self.h.call("rl_als_half_step_dev", ihi - ilo, self.n_users, self.k, self.ip.data_ptr(), self.ix.data_ptr(),
-                    None, None, self.U.data_ptr(), self.V[ilo:].data_ptr(), float(lam), 0.0, None, precision,
-                    ir_steps, None)
+        if getattr(self, "peer_stores", False):
+            self.h.call("rl_als_half_step_peers_dev", ihi - ilo, self.n_users, self.k, self.ip.data_ptr(), self.ix.data_ptr(),
+                        None, None, self.U.data_ptr(), self.V[ilo:].data_ptr(), float(lam), 0.0, None, precision,
+                        ir_steps, None, self.plan.world - 1, self._peers_v)
+        else:
+            self.h.call("rl_als_half_step_dev", ihi - ilo, self.n_users, self.k, self.ip.data_ptr(), self.ix.data_ptr(),
+                        None, None, self.U.data_ptr(), self.V[ilo:].data_ptr(), float(lam), 0.0, None, precision,
+                        ir_steps, None)
+
+    def exchange_users(self):
+        """Make U whole on every rank after the user half-step (barrier only when the kernel already stored to the peers)."""
+        if getattr(self, "peer_stores", False):
+            self.peer_barrier()
+        else:
+            exchange_rows(self.U, self.plan.user_bounds, self.plan.rank, self.plan.world)
+
+    def exchange_items(self):
+        if getattr(self, "peer_stores", False):
+            self.peer_barrier()
+        else:
+            exchange_rows(self.V, self.plan.item_bounds, self.plan.rank, self.plan.world)
 
     def iteration(self, lam=0.01, precision=0, ir_steps=1):
-        p = self.plan
         self.user_half_step(lam, precision, ir_steps)
-        exchange_rows(self.U, p.user_bounds, p.rank, p.world)
+        self.exchange_users()
         self.item_half_step(lam, precision, ir_steps)
-        exchange_rows(self.V, p.item_bounds, p.rank, p.world)
+        self.exchange_items()
 
     def recommend(self, n, idx_out, mode=0):
         """top-n for this rank's users (seen items = its CSR rows) into idx_out (users_local x n int32 tensor)."""

@@ -550,3 +550,91 @@ def test_cold_start_under_one_second():
     best = min(float(subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True,
                                     check=True).stdout.strip()) for _ in range(2))
     assert best < 1.0, best
+
+
+# ---------------------------------------------------------------------------- fused exchange (peer stores)
+def test_half_step_peer_stores_single_gpu(h):
+    """rl_als_half_step_peers_dev writes every solved row into `mine` and into each peer replica (here: two more local
+    buffers standing in for other ranks' replicas); rows without observations are left alone in all of them."""
+    import ctypes as C
+    from devbuf import Dev, padded, unpadded
+    n_rows, n_other, k = 3000, 900, 64
+    indptr, indices = gen.synth_pattern(n_rows, n_other, mean_deg=20, seed=3)
+    indptr = indptr.copy()
+    indptr[11:] -= indptr[11] - indptr[10]                       # row 10 loses its observations
+    indices = np.concatenate([indices[:indptr[10]], indices[len(indices) - (indptr[-1] - indptr[10]):]])
+    rng = np.random.default_rng(0)
+    other = rng.random((n_other, k)).astype(np.float32)
+    init = rng.random((n_rows, k)).astype(np.float32)
+    d_other, d_ip, d_ix = padded(h, other, k), Dev(h, indptr), Dev(h, indices)
+    bufs = [padded(h, init, k) for _ in range(3)]
+    peers = (C.c_void_p * 2)(bufs[1].ptr, bufs[2].ptr)
+    h.call("rl_als_half_step_peers_dev", n_rows, n_other, k, d_ip.ptr, d_ix.ptr, None, None, d_other.ptr, bufs[0].ptr, 0.01, 0.0,
+           None, 0, 1, None, 2, peers)
+    ref = padded(h, init, k)
+    h.call("rl_als_half_step_dev", n_rows, n_other, k, d_ip.ptr, d_ix.ptr, None, None, d_other.ptr, ref.ptr, 0.01, 0.0, None, 0, 1, None)
+    want = unpadded(h, ref, k, np.float32)
+    assert np.array_equal(want[10], init[10])
+    for b in bufs:
+        assert np.array_equal(unpadded(h, b, k, np.float32), want)
+    with pytest.raises(Exception):
+        h.call("rl_als_half_step_peers_dev", n_rows, n_other, k, d_ip.ptr, d_ix.ptr, None, None, d_other.ptr, bufs[0].ptr, 0.01, 0.0,
+               None, 0, 1, None, 16, peers)
+
+
+def _peer_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    from recsys_lite_b200 import _ffi
+    from recsys_lite_b200.sharding import ShardedProblem, make_plan
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        hh = _ffi.Handle(rank)
+        hh.set_stream(torch.cuda.current_stream().cuda_stream)
+        n_users, n_items, k = 6000, 1500, 64
+        indptr, indices = gen.synth_pattern(n_users, n_items, mean_deg=25, seed=5, skew=True)
+        ti, tx = o_als.transpose_pattern(indptr, indices, n_items)
+        u0, v0 = gen.seeded_factors(n_users, n_items, k, 2)
+        plan = make_plan(indptr, ti, rank, world)
+        res = {}
+        for fused in (False, True):
+            prob = ShardedProblem(hh, plan, indptr, indices, ti, tx, k, torch.device("cuda", rank))
+            prob.set_factors(u0, v0)
+            if fused:
+                assert prob.enable_peer_stores()
+            dist.barrier()
+            for _ in range(2):
+                prob.iteration(0.01, 0, 1)
+            torch.cuda.synchronize()
+            dist.barrier()
+            res[fused] = (prob.U[:, :k].cpu().numpy(), prob.V[:, :k].cpu().numpy())
+            prob.close_peer_stores()
+        assert np.array_equal(res[False][0], res[True][0]) and np.array_equal(res[False][1], res[True][1])
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), U=res[True][0], V=res[True][1])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_peer_store_exchange_two_gpus(tmp_path):
+    """2 ranks, NCCL: an iteration whose exchange is fused into the solve kernel (NVLink stores into the peer replica +
+    barrier) equals the NCCL-broadcast exchange bit for bit, on every rank, and matches the unsharded oracle."""
+    import socket
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_peer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    n_users, n_items, k = 6000, 1500, 64
+    indptr, indices = gen.synth_pattern(n_users, n_items, mean_deg=25, seed=5, skew=True)
+    ti, tx = o_als.transpose_pattern(indptr, indices, n_items)
+    u0, v0 = gen.seeded_factors(n_users, n_items, k, 2)
+    ref = o_als.fit_csr(indptr, indices, ti, tx, k, iterations=2, lam=0.01, init=(u0, v0))
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    assert np.array_equal(r0["U"], r1["U"]) and np.array_equal(r0["V"], r1["V"])
+    assert max(compare.factor_error(r0["U"], ref["user_factors"])) <= compare.FACTOR_RTOL
+    assert max(compare.factor_error(r0["V"], ref["item_factors"])) <= compare.FACTOR_RTOL
