@@ -273,10 +273,13 @@ def run_b200(args, w):
     t_user, t_item_x, t_x2, t_score = seg.mean(axis=0)
     per_rank = None
     if world > 1:
-        tt = torch.tensor([total_ms, t_user, t_item_x, t_x2, t_score], dtype=torch.float64, device=device)
+        tt = torch.tensor([total_ms, t_user, t_item_x, t_x2, t_score, float(h.lib.rl_last_overflow_rows(h.h))],
+                          dtype=torch.float64, device=device)
         allt = [torch.empty_like(tt) for _ in range(world)]
         dist.all_gather(allt, tt)
-        per_rank = [[round(float(x), 3) for x in t.tolist()[1:]] for t in allt]     # diagnostics: stragglers show up here
+        # diagnostics (stragglers show up here): per rank [user, exchange+item, exchange, score] ms, overflow rows of the last scoring call
+        per_rank = [[round(float(x), 3) for x in t.tolist()[1:]] for t in allt]
+        tt = tt[:5]
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms, t_user, t_item_x, t_x2, t_score = tt.tolist()
     ms_per_step = total_ms / args.steps
