@@ -26,6 +26,7 @@ struct rl_context {
   // grow-only device scratch (svd, scoring candidates, ...)
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  unsigned int preloaded_exact = 0;  // bit (kp >> 4): fallback kernels of the tensor-core scoring path are loaded
   unsigned int last_overflow = 0;  // rows the last tensor-core scoring call handed to the exact kernel
   std::vector<std::pair<void*, void*>> ipc_bases;  // (pointer handed out by rl_ipc_open, base of the mapping)
 };

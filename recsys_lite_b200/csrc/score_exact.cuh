@@ -267,6 +267,23 @@ int launch_score_exact_k(rl_context* h, const ScoreArgs& a) {
   return fail(h, RL_ERR_INVALID, "score_topn: n=%d exceeds the on-chip list capacity of 128", a.n);
 }
 
+// Force the (lazily loaded) fallback kernels of the tensor-core path into the context: their first use must not land
+// inside somebody's timed step as a multi-millisecond module load.
+template <int KP>
+inline void preload_score_exact_k() {
+  cudaFuncAttributes at;
+  cudaFuncGetAttributes(&at, score_topn_exact_kernel<KP, 1>);
+  cudaFuncGetAttributes(&at, score_merge_kernel<1>);
+}
+inline void preload_score_exact(int kp) {
+  switch (kp) {
+    case 16: preload_score_exact_k<16>(); break;
+    case 32: preload_score_exact_k<32>(); break;
+    case 64: preload_score_exact_k<64>(); break;
+    case 128: preload_score_exact_k<128>(); break;
+  }
+}
+
 inline int launch_score_exact(rl_context* h, int kp, const ScoreArgs& a) {
   switch (kp) {
     case 16: return launch_score_exact_k<16>(h, a);
