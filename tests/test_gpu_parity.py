@@ -638,3 +638,75 @@ def test_fused_peer_store_exchange_two_gpus(tmp_path):
     assert np.array_equal(r0["U"], r1["U"]) and np.array_equal(r0["V"], r1["V"])
     assert max(compare.factor_error(r0["U"], ref["user_factors"])) <= compare.FACTOR_RTOL
     assert max(compare.factor_error(r0["V"], ref["item_factors"])) <= compare.FACTOR_RTOL
+
+
+# ---------------------------------------------------------------------------- BASELINE.json full size (C4)
+def test_full_size_config4_sampled_properties(h):
+    """C4 at its full size (1M users x 100K items, ~50M nnz, k = 64), where the oracle cannot run as a whole: checked
+    through size-independent properties on random samples of rows -- every sampled row of a half-step solves ITS
+    normal equations (algo.py:318-322 restated in float64 on the CPU for that row), rows are independent of each other
+    (a half-step over a shuffled row order gives the same bits), and the fused top-10 of sampled users equals the
+    float64 scores ranked on the CPU (algo.py:172-201), seen items excluded, up to exact ties."""
+    from devbuf import Dev, padded, unpadded
+    from recsys_lite_b200 import synth
+    from recsys_lite_b200.csr import transpose_pattern
+    w = synth.CONFIGS["C4"]
+    nu, ni, k, lam = w["n_users"], w["n_items"], w["k"], w["lam"]
+    indptr, indices = synth.synth_pattern(nu, ni, w["mean_deg"], w["seed"])
+    ti, tx = transpose_pattern(indptr, indices, ni)
+    rng = np.random.default_rng(w["init_seed"])
+    u0 = rng.random((nu, k), dtype=np.float32)
+    v0 = rng.random((ni, k), dtype=np.float32)
+    d_u, d_v = padded(h, u0, k), padded(h, v0, k)
+    d_ip, d_ix, d_tp, d_tx = Dev(h, indptr), Dev(h, indices), Dev(h, ti), Dev(h, tx)
+
+    def solve_rows(rows, ptr, idx, other):
+        out = np.empty((len(rows), k))
+        for j, r in enumerate(rows):
+            ys = other[idx[ptr[r]:ptr[r + 1]]].astype(np.float64)
+            out[j] = np.linalg.solve(ys.T @ ys + lam * np.eye(k), ys.sum(axis=0))
+        return out
+
+    # ---- user half-step: sampled rows against their own float64 solve (incl. the shortest and longest rows)
+    h.call("rl_als_half_step_dev", nu, ni, k, d_ip.ptr, d_ix.ptr, None, None, d_v.ptr, d_u.ptr, lam, 0.0, None, 0, 1, None)
+    U = unpadded(h, d_u, k, np.float32)
+    deg = np.diff(indptr)
+    rows = np.unique(np.concatenate([rng.integers(0, nu, 300), [int(deg.argmin()), int(deg.argmax()), 0, nu - 1]]))
+    ref = solve_rows(rows, indptr, indices, v0)
+    err = np.linalg.norm(U[rows] - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert err.max() <= compare.FACTOR_RTOL, err.max()
+    # ---- rows are independent: longest-first processing order gives the same bits
+    order = np.argsort(-deg, kind="stable").astype(np.int32)
+    d_u2, d_order = padded(h, u0, k), Dev(h, order)
+    h.call("rl_als_half_step_dev", nu, ni, k, d_ip.ptr, d_ix.ptr, None, None, d_v.ptr, d_u2.ptr, lam, 0.0, None, 0, 1, d_order.ptr)
+    assert np.array_equal(unpadded(h, d_u2, k, np.float32), U)
+    del d_u2, d_order
+    # ---- item half-step (500 observations per row) on the updated U
+    h.call("rl_als_half_step_dev", ni, nu, k, d_tp.ptr, d_tx.ptr, None, None, d_u.ptr, d_v.ptr, lam, 0.0, None, 0, 1, None)
+    V = unpadded(h, d_v, k, np.float32)
+    irows = np.unique(rng.integers(0, ni, 100))
+    iref = solve_rows(irows, ti, tx, U)
+    ierr = np.linalg.norm(V[irows] - iref, axis=1) / np.linalg.norm(iref, axis=1)
+    assert ierr.max() <= compare.FACTOR_RTOL, ierr.max()
+    # ---- fused scoring + top-10 for ALL users; sampled users against float64 scores ranked on the CPU
+    n = 10
+    d_idx = Dev(h, shape=(nu, n), dtype=np.int32)
+    h.call("rl_score_topn_dev", d_u.ptr, nu, d_v.ptr, ni, k, d_ip.ptr, d_ix.ptr, 0.0, None, None, n, d_idx.ptr, None, 0)
+    idx = d_idx.get()
+    assert idx.min() >= 0 and idx.max() < ni                  # every user has >= 10 unseen items: no -1 padding
+    srt = np.sort(idx, axis=1)
+    assert (srt[:, 1:] != srt[:, :-1]).all()                   # ten distinct items per user
+    users = np.unique(rng.integers(0, nu, 200))
+    V64 = V.astype(np.float64)
+    bad = 0
+    for u in users:
+        sc = V64 @ U[u].astype(np.float64)
+        seen = indices[indptr[u]:indptr[u + 1]]
+        assert not np.isin(idx[u], seen).any()
+        sc[seen] = -np.inf
+        want = np.lexsort((np.arange(ni), -sc))[:n]            # score descending, lower index first
+        if not np.array_equal(idx[u], want):
+            # only a permutation / substitution inside a set of scores equal within 4 eps counts as a match
+            tol = 4 * np.finfo(np.float32).eps * np.abs(sc[want]).max()
+            bad += not np.allclose(np.sort(sc[idx[u]])[::-1], sc[want], rtol=0, atol=tol)
+    assert bad == 0
