@@ -23,6 +23,8 @@
 
 #include <cstdlib>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace rl {
@@ -88,6 +90,7 @@ struct AlsArgs {
   // into this process (CUDA IPC) and reached over NVLink -- same row offset as `mine`
   int n_peers;
   float* peers[RL_MAX_PEERS];
+  const float* other_absmax;   // max |entry| of `other` (device scalar), for the fp16 operand scale of the k = 64 path
 };
 
 template <typename real, int T>
@@ -526,6 +529,18 @@ __global__ void __launch_bounds__(WarpSmem<real, KP>::warps * 32) als_half_step_
   }
 }
 
+// max |x| over a float array (non-negative floats order like their bit patterns)
+__global__ void __launch_bounds__(256) absmax_kernel(const float4* __restrict__ x, int64_t n4, float* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < n4; p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = x[p];
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+
 namespace k64v1 {
 #include "als_k64_v1.cuh"
 }
@@ -615,11 +630,12 @@ int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, 
   if (w0 != 0.0 && !gram0) return fail(h, RL_ERR_INVALID, "als_half_step: w0 != 0 needs gram0 (rl_gram_dev)");
   if (!(lambda >= 0.0)) return fail(h, RL_ERR_INVALID, "als_half_step: lambda must be >= 0");
   if (ir_steps < 0 || ir_steps > 8) return fail(h, RL_ERR_INVALID, "als_half_step: ir_steps outside [0, 8]");
-  AlsArgs a{indptr, indices, conf, pref, other, mine, n_rows, k, lambda, w0, gram0, ir_steps, h->counter, row_order, n_peers, {}};
+  AlsArgs a{indptr, indices, conf, pref, other, mine, n_rows, k, lambda, w0, gram0, ir_steps, h->counter, row_order, n_peers, {}, nullptr};
   for (int pr = 0; pr < n_peers; ++pr) {
     if (!peers[pr]) return fail(h, RL_ERR_INVALID, "als_half_step: peer pointer %d is null", pr);
     a.peers[pr] = peers[pr];
   }
+  a.other_absmax = reinterpret_cast<const float*>(h->counter + 16);
   const bool weighted = conf != nullptr || pref != nullptr || w0 != 0.0;
   if (precision == RL_PREC_FP64) {
     a.ir_steps = 0;
@@ -627,7 +643,18 @@ int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, 
   }
   if (precision == RL_PREC_FP32_IR) {
     if (kp == 64 && getenv("RL_ALS_K64_V1")) return weighted ? k64v1::launch_k64o<true>(h, a) : k64v1::launch_k64o<false>(h, a);
-    if (kp == 64 && !getenv("RL_ALS_GENERIC")) return weighted ? launch_k64<true>(h, a) : launch_k64<false>(h, a);
+    if (kp == 64 && !getenv("RL_ALS_GENERIC")) {
+      RL_CUDA(h, cudaMemsetAsync(h->counter + 16, 0, sizeof(float), h->stream));
+      const int64_t n4 = n_other * (kp / 4);
+      int64_t g = (n4 + 255) / 256;
+      if (g > 8 * h->sm_count) g = 8 * h->sm_count;
+      if (g > 0) {
+        absmax_kernel<<<static_cast<unsigned>(g), 256, 0, h->stream>>>(reinterpret_cast<const float4*>(other), n4,
+                                                                      reinterpret_cast<float*>(h->counter + 16));
+        RL_LAUNCH_CHECK(h, "absmax_kernel");
+      }
+      return weighted ? launch_k64<true>(h, a) : launch_k64<false>(h, a);
+    }
     return weighted ? launch_kp<float, true>(h, kp, a) : launch_kp<float, false>(h, kp, a);
   }
   return fail(h, RL_ERR_INVALID, "als_half_step: unknown precision %d", precision);

@@ -25,7 +25,7 @@
 // rsqrt.approx pivots are good enough: the factor is only a preconditioner for the float64-residual refinement.
 
 constexpr int K64 = 64;
-constexpr int K64_LDY = 72;   // row stride of a gathered row: 8 t + g is a bijection onto the banks for the mma fragments
+constexpr int K64_LDY = 68;   // row stride of a gathered row: the fragment reads (rows 2t, 2t+1; columns g) hit banks 8 t + g (+4)
 constexpr int K64_CH = 8;     // gathered rows per chunk (one k = 8 mma step), double buffered
 constexpr int K64_LSZ = 2368; // floats of the factor storage (8 panels, 8 floats of skew each)
 
@@ -84,6 +84,20 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t a0, const
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t a0, const uint32_t a1, const uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(b0));
+}
+// (x0, x1) -> fp16 pairs hi = fp16(x), lo = fp16(x - hi): 22 significant bits, first element in the low half
+__device__ __forceinline__ void k64_split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // lower-triangle 16 x 8 tiles of a 64 x 64 symmetric matrix: tile (mi, nj) is needed iff nj <= 2 mi + 1  ->  2 + 4 + 6 + 8 = 20
@@ -292,6 +306,10 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
 
   const float lam = static_cast<float>(a.lambda);
   const bool hkv = WEIGHTED && a.w0 != 0.0;   // w0 != 0 always runs the WEIGHTED instantiation
+  // fp16 split of the Gram operands: a power-of-two scale puts max |y| at <= 2^14 (the largest |entry| of `other` was
+  // reduced by absmax_kernel just before this launch); Gram tiles are unscaled by its exact inverse square
+  const float ysc = pow2_scale(*a.other_absmax);
+  const float yunsc = (1.0f / ysc) * (1.0f / ysc);
   const int g = lane >> 2, tq = lane & 3;
 
   for (;;) {
@@ -318,7 +336,7 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
 
     // ---- gather + Gram on the tensor cores (3 x tf32 split, fp32 accumulate) -----------------------------------
     float acc[20][4];
-    double bq0 = 0.0, bq1 = 0.0;
+    float bf0 = 0.f, bf1 = 0.f;      // right-hand side in fp32: only the first solve uses it, the refinement residual is b-free
 #pragma unroll
     for (int t = 0; t < 20; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
     k64_gather<WEIGHTED>(a, s, nnz, 0, ybuf, wbuf, lane);
@@ -334,62 +352,56 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
       const float* yb = ybuf + buf * CH * LDY;
       const float2* wb = wbuf + buf * CH;
       const int cnt = min(CH, nnz - c * CH);
-      // right-hand side in float64 (an fp32 sum would be amplified by 1 / lambda); zero-filled rows add nothing
 #pragma unroll
-      for (int r = 0; r < CH; ++r) {
+      for (int r = 0; r < CH; ++r) {        // zero-filled rows add nothing
         const float* yr = yb + r * LDY;
         if constexpr (WEIGHTED) {
-          const double wr = (r < cnt) ? static_cast<double>(wb[r].y) : 0.0;
-          bq0 += wr * static_cast<double>(yr[lane]);
-          bq1 += wr * static_cast<double>(yr[32 + lane]);
+          const float wr = (r < cnt) ? wb[r].y : 0.f;
+          bf0 = fmaf(wr, yr[lane], bf0);
+          bf1 = fmaf(wr, yr[32 + lane], bf1);
         } else {
-          bq0 += static_cast<double>(yr[lane]);
-          bq1 += static_cast<double>(yr[32 + lane]);
+          bf0 += yr[lane];
+          bf1 += yr[32 + lane];
         }
       }
       {
-        // fragments: v = A(mi) a0..a3 = Y[tq (+4)][16 mi + g (+8)]; B(nj = 2mi) = (a0, a2), B(2mi+1) = (a1, a3)
-        uint32_t hi[4][4], lo[4][4];
+        // m16n8k8 fp16 fragments, k = gathered row: A(mi) = (a0, a1) = Y[2 tq, 2 tq + 1][16 mi + g (+8)] packed in pairs;
+        // B(nj) = Y[2 tq, 2 tq + 1][8 nj + g] is ONE of those registers: a[nj >> 1][nj & 1] -- no operand moves.
+        uint32_t hi[4][2], lo[4][2];
+        const float* y0 = yb + (2 * tq) * LDY + g;
+        const float* y1 = y0 + LDY;
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
-          k64_split(yb[tq * LDY + 16 * mi + g], hi[mi][0], lo[mi][0]);
-          k64_split(yb[tq * LDY + 16 * mi + g + 8], hi[mi][1], lo[mi][1]);
-          k64_split(yb[(tq + 4) * LDY + 16 * mi + g], hi[mi][2], lo[mi][2]);
-          k64_split(yb[(tq + 4) * LDY + 16 * mi + g + 8], hi[mi][3], lo[mi][3]);
+          k64_split_h2(y0[16 * mi] * ysc, y1[16 * mi] * ysc, hi[mi][0], lo[mi][0]);
+          k64_split_h2(y0[16 * mi + 8] * ysc, y1[16 * mi + 8] * ysc, hi[mi][1], lo[mi][1]);
         }
-        uint32_t ahi[4][4], alo[4][4];
+        uint32_t ahi[4][2], alo[4][2];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { ahi[mi][e] = hi[mi][e]; alo[mi][e] = lo[mi][e]; }
-        if constexpr (WEIGHTED) {     // scale the A side by the Gram weight of its gathered row (rows tq and tq + 4)
-          const float w0 = (tq < cnt) ? wb[tq].x : 0.f;
-          const float w1 = (tq + 4 < cnt) ? wb[tq + 4].x : 0.f;
+          for (int e = 0; e < 2; ++e) { ahi[mi][e] = hi[mi][e]; alo[mi][e] = lo[mi][e]; }
+        if constexpr (WEIGHTED) {     // scale the A side by the Gram weight of its gathered row (rows 2 tq and 2 tq + 1)
+          const float w0 = (2 * tq < cnt) ? wb[2 * tq].x * ysc : 0.f;
+          const float w1 = (2 * tq + 1 < cnt) ? wb[2 * tq + 1].x * ysc : 0.f;
 #pragma unroll
-          for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float w = (e < 2) ? w0 : w1;
-              const float full = (__uint_as_float(hi[mi][e]) + __uint_as_float(lo[mi][e])) * w;
-              k64_split(full, ahi[mi][e], alo[mi][e]);
-            }
+          for (int mi = 0; mi < 4; ++mi) {
+            k64_split_h2(y0[16 * mi] * w0, y1[16 * mi] * w1, ahi[mi][0], alo[mi][0]);
+            k64_split_h2(y0[16 * mi + 8] * w0, y1[16 * mi + 8] * w1, ahi[mi][1], alo[mi][1]);
+          }
         }
-        // B(nj) = (a[bo], a[bo + 2]) of m-tile bm = nj >> 1, bo = nj & 1; term by term: consecutive HMMAs are independent
+        // term by term: consecutive HMMAs are independent
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-          for (int nj = 0; nj <= 2 * mi + 1; ++nj)
-            mma_tf32(acc[k64_tile(mi, nj)], ahi[mi][0], ahi[mi][1], ahi[mi][2], ahi[mi][3], hi[nj >> 1][nj & 1], hi[nj >> 1][(nj & 1) + 2]);
+          for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], ahi[mi][0], ahi[mi][1], hi[nj >> 1][nj & 1]);
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-          for (int nj = 0; nj <= 2 * mi + 1; ++nj)
-            mma_tf32(acc[k64_tile(mi, nj)], ahi[mi][0], ahi[mi][1], ahi[mi][2], ahi[mi][3], lo[nj >> 1][nj & 1], lo[nj >> 1][(nj & 1) + 2]);
+          for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], ahi[mi][0], ahi[mi][1], lo[nj >> 1][nj & 1]);
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-          for (int nj = 0; nj <= 2 * mi + 1; ++nj)
-            mma_tf32(acc[k64_tile(mi, nj)], alo[mi][0], alo[mi][1], alo[mi][2], alo[mi][3], hi[nj >> 1][nj & 1], hi[nj >> 1][(nj & 1) + 2]);
+          for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], alo[mi][0], alo[mi][1], hi[nj >> 1][nj & 1]);
       }
       __syncwarp();
     }
@@ -406,6 +418,7 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int gi = 16 * mi + g + ((e & 2) ? 8 : 0), gj = 8 * nj + 2 * tq + (e & 1);
+            d[e] *= yunsc;                         // the operands were scaled by ysc (a power of two): exact
             if (hkv) d[e] += static_cast<float>(a.w0 * a.gram0[gi * KP + gj]);
             if (nj >= 2 * mi && gi == gj) d[e] += (gi < a.k) ? lam : 1.0f;
           }
@@ -415,8 +428,8 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
         }
     }
     // ---- blocked Cholesky on the tensor cores, forward substitution fused ------------------------------------
-    bs[lane] = static_cast<float>(bq0);
-    bs[32 + lane] = static_cast<float>(bq1);
+    bs[lane] = bf0;
+    bs[32 + lane] = bf1;
     __syncwarp();
     k64_chol(Lt, invd, bs, lane);
     // ---- back substitution, then refinement steps  x += L^-T L^-1 (b - A x)  with a float64 matrix-free residual ----
@@ -430,8 +443,9 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
       if (it >= a.ir_steps) break;
       xs[lane] = xd0;
       xs[32 + lane] = xd1;
-      double r0 = bq0 - ((lane < a.k) ? a.lambda : 1.0) * xd0;
-      double r1 = bq1 - ((32 + lane < a.k) ? a.lambda : 1.0) * xd1;
+      // r = b - A x = sum_i (p_i - w_i <y_i, x>) y_i - lambda x (- w0 G x): the right-hand side never appears on its own
+      double r0 = -((lane < a.k) ? a.lambda : 1.0) * xd0;
+      double r1 = -((32 + lane < a.k) ? a.lambda : 1.0) * xd1;
       __syncwarp();
       if (hkv) {
         double t0 = 0.0, t1 = 0.0;
@@ -472,15 +486,16 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
           double t = t0 + t1;
           t += __shfl_xor_sync(FULL_MASK, t, 8);
           t += __shfl_xor_sync(FULL_MASK, t, 16);
-          if constexpr (WEIGHTED) t *= (i < cnt) ? static_cast<double>(wb[i].x) : 0.0;
-          if (lane < 8) ts[lane] = t;     // zero-filled rows give t = 0
+          if constexpr (WEIGHTED) t = (i < cnt) ? static_cast<double>(wb[i].y) - static_cast<double>(wb[i].x) * t : 0.0;
+          else t = (i < cnt) ? 1.0 - t : 0.0;
+          if (lane < 8) ts[lane] = t;     // coefficient of y_i in the residual; zero-filled rows: 0
         }
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
           const double ti = ts[i];
-          r0 = fma(-ti, static_cast<double>(yb[i * LDY + lane]), r0);
-          r1 = fma(-ti, static_cast<double>(yb[i * LDY + 32 + lane]), r1);
+          r0 = fma(ti, static_cast<double>(yb[i * LDY + lane]), r0);
+          r1 = fma(ti, static_cast<double>(yb[i * LDY + 32 + lane]), r1);
         }
         __syncwarp();
       }

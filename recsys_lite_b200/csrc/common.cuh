@@ -59,6 +59,15 @@ __host__ __device__ constexpr int padded_k(int k) {
   return k <= 0 ? 0 : k <= 16 ? 16 : k <= 32 ? 32 : k <= 64 ? 64 : k <= 128 ? 128 : 0;
 }
 
+// power-of-two scale s with m * s <= 2^14 (fp16 headroom: hi parts stay finite, lo parts stay normal down to 2^-17 m)
+__host__ __device__ __forceinline__ float pow2_scale(float m) {
+  if (!(m > 0.f) || !(m < 3.0e38f)) return 1.0f;
+  int e;
+  frexpf(m, &e);                       // m = f * 2^e, f in [0.5, 1)
+  e = 14 - e;
+  e = e > 100 ? 100 : (e < -100 ? -100 : e);
+  return ldexpf(1.0f, e);
+}
 // ---- kernels' host launchers (one per .cu) --------------------------------------------------------------
 int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, const int64_t* indptr,
                          const int32_t* indices, const float* conf, const float* pref, const float* other,

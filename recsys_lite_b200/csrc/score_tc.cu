@@ -223,15 +223,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 constexpr uint32_t TC_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(TC_BN >> 3) << 17) |
                               (static_cast<uint32_t>(TC_BM >> 4) << 24);
 
-// power-of-two scale s with m * s <= 2^14 (fp16 headroom: hi parts stay finite, lo parts stay normal down to 2^-17 m)
-__host__ __device__ __forceinline__ float pow2_scale(float m) {
-  if (!(m > 0.f) || !(m < 3.0e38f)) return 1.0f;
-  int e;
-  frexpf(m, &e);                       // m = f * 2^e, f in [0.5, 1)
-  e = 14 - e;
-  e = e > 100 ? 100 : (e < -100 ? -100 : e);
-  return ldexpf(1.0f, e);
-}
 // (hi, lo) fp16 pairs of two scaled values, packed low half = first element (TMEM / shared-memory K order)
 __device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(x0, x1);
