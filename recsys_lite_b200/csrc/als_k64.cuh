@@ -272,7 +272,7 @@ __device__ __forceinline__ void k64_backward(const float* __restrict__ Lt, const
   const float* c0a = c0 + q0; const float* c0b = c0 + q1;   // rows with swizzle bit 0 / 1
   const float* c1a = c1 + q0; const float* c1b = c1 + q1;
   const float inv0 = invd[lane], inv1 = invd[32 + lane];
-#pragma unroll 16
+#pragma unroll 8
   for (int i = 63; i >= 32; --i) {
     const float xi = __shfl_sync(FULL_MASK, v1 * inv1, i - 32);     // the owner lane's product is the one that counts
     const float l1 = (i & 4) ? c1b[8 * i] : c1a[8 * i];
@@ -281,7 +281,7 @@ __device__ __forceinline__ void k64_backward(const float* __restrict__ Lt, const
     v1 = (lane < i - 32) ? upd : ((lane == i - 32) ? xi : v1);
     v0 = fmaf(-l0, xi, v0);
   }
-#pragma unroll 16
+#pragma unroll 8
   for (int i = 31; i >= 0; --i) {
     const float xi = __shfl_sync(FULL_MASK, v0 * inv0, i);
     const float l0 = (i & 4) ? c0b[8 * i] : c0a[8 * i];             // lanes >= i read below their panel: finite junk, not used
@@ -339,11 +339,11 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
     float bf0 = 0.f, bf1 = 0.f;      // right-hand side in fp32: only the first solve uses it, the refinement residual is b-free
 #pragma unroll
     for (int t = 0; t < 20; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
-    k64_gather<WEIGHTED>(a, s, nnz, 0, ybuf, wbuf, lane);
-    for (int c = 0; c < nchunk; ++c) {
+    for (int c = -1; c < nchunk; ++c) {       // one gather call site: chunk c + 1 is requested, then chunk c is consumed
       const int buf = c & 1;
       if (c + 1 < nchunk) {
         k64_gather<WEIGHTED>(a, s, nnz, c + 1, ybuf + (buf ^ 1) * CH * LDY, wbuf + (buf ^ 1) * CH, lane);
+        if (c < 0) continue;
         cp_async_wait<1>();
       } else {
         cp_async_wait<0>();
@@ -456,11 +456,11 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
         r0 -= a.w0 * t0;
         r1 -= a.w0 * t1;
       }
-      k64_gather<WEIGHTED>(a, s, nnz, 0, ybuf, wbuf, lane);
-      for (int c = 0; c < nchunk; ++c) {
+      for (int c = -1; c < nchunk; ++c) {
         const int buf = c & 1;
         if (c + 1 < nchunk) {
           k64_gather<WEIGHTED>(a, s, nnz, c + 1, ybuf + (buf ^ 1) * CH * LDY, wbuf + (buf ^ 1) * CH, lane);
+          if (c < 0) continue;
           cp_async_wait<1>();
         } else {
           cp_async_wait<0>();
