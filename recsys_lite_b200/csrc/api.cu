@@ -55,6 +55,19 @@ __global__ void convert_kernel(const TS* __restrict__ src, int64_t rows, int k, 
   }
 }
 
+// rows without observations keep their initial values (reference algo.py:316-317): copied from the uploaded initial
+// matrix after the half-step, so that the upload itself can run underneath the half-step
+__global__ void __launch_bounds__(256) fill_empty_rows_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, int kp,
+                                                              const float* __restrict__ init, float* __restrict__ out) {
+  const int per = kp / 4;
+  const int64_t total = n_rows * per;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < total; p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = p / per;
+    if (indptr[r + 1] == indptr[r])
+      reinterpret_cast<float4*>(out)[p] = reinterpret_cast<const float4*>(init)[p];
+  }
+}
+
 // RAII device allocation for the host wrappers.  Stream-ordered (cudaMallocAsync on the handle's stream): the device's
 // default memory pool keeps freed blocks (release threshold set in rl_create), so repeated host-buffer calls neither
 // pay cudaMalloc / cudaFree nor synchronise the device.
@@ -434,10 +447,12 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const 
   const int64_t nnz = indptr[n_users];
   if (nnz != indptr_t[n_items]) return fail(h, RL_ERR_INVALID, "rl_als_fit_host: CSR and transposed CSR disagree on nnz");
   // Host traffic runs on the copy stream, ordered against the kernels by events:
-  //   copy:    V, user CSR, U | item CSR ........................ | U back (during the last item half-step)
-  //   compute:                 | user half-step | item half-step ... | V back
-  DevBuf d_ip, d_ix, d_tp, d_tx, d_u, d_v, st_u, st_v, st_ud, st_vd;
-  Event ev_user_ready, ev_item_ready, ev_u_done, ev_copy_done;
+  //   copy:    V, user CSR | U (initial), item CSR ................... | U back (during the last item half-step)
+  //   compute:              | user half-step, empty rows <- initial U | item half-step ... | V back
+  // The first user half-step overwrites every row that has observations, so it does not wait for the initial U: that
+  // upload runs underneath it into a second buffer, from which only the rows WITHOUT observations are taken afterwards.
+  DevBuf d_ip, d_ix, d_tp, d_tx, d_u, d_u0, d_v, st_u, st_v, st_ud, st_vd;
+  Event ev_user_ready, ev_u0_ready, ev_item_ready, ev_u_done, ev_copy_done;
   cudaStream_t cs = h->copy_stream, ks = h->stream;
   RL_TRY(d_ip.alloc(h, sizeof(int64_t) * (n_users + 1)));
   RL_TRY(d_ix.alloc(h, sizeof(int32_t) * (nnz ? nnz : 1)));
@@ -445,6 +460,12 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const 
   RL_TRY(d_tx.alloc(h, sizeof(int32_t) * (nnz ? nnz : 1)));
   RL_TRY(d_u.alloc(h, sizeof(float) * (n_users ? n_users : 1) * kp));
   RL_TRY(d_v.alloc(h, sizeof(float) * (n_items ? n_items : 1) * kp));
+  const bool lazy_u = iterations > 0 && n_users > 0;
+  float* u_upload = d_u.as<float>();
+  if (lazy_u) {
+    RL_TRY(d_u0.alloc(h, sizeof(float) * n_users * kp));
+    u_upload = d_u0.as<float>();
+  }
   Event ev_alloc;
   RL_TRY(ev_alloc.record(h, ks));      // the buffers come from the stream-ordered pool on the compute stream
   RL_TRY(ev_alloc.wait(h, cs));
@@ -453,18 +474,27 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const 
     RL_TRY(factors_h2d(h, item_f, factor_dtype, n_items, k, d_v.as<float>(), st_v));
     RL_CUDA(h, cudaMemcpyAsync(d_ip.p, indptr, sizeof(int64_t) * (n_users + 1), cudaMemcpyHostToDevice, cs));
     if (nnz) RL_CUDA(h, cudaMemcpyAsync(d_ix.p, indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, cs));
-    RL_TRY(factors_h2d(h, user_f, factor_dtype, n_users, k, d_u.as<float>(), st_u));
     RL_TRY(ev_user_ready.record(h, cs));
+    RL_TRY(factors_h2d(h, user_f, factor_dtype, n_users, k, u_upload, st_u));
+    RL_TRY(ev_u0_ready.record(h, cs));
     RL_CUDA(h, cudaMemcpyAsync(d_tp.p, indptr_t, sizeof(int64_t) * (n_items + 1), cudaMemcpyHostToDevice, cs));
     if (nnz) RL_CUDA(h, cudaMemcpyAsync(d_tx.p, indices_t, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, cs));
     RL_TRY(ev_item_ready.record(h, cs));
   }
   RL_TRY(ev_user_ready.wait(h, ks));
+  if (!lazy_u) RL_TRY(ev_u0_ready.wait(h, ks));
   bool u_on_copy = false;
   for (int it = 0; it < iterations; ++it) {
     RL_TRY(launch_als_half_step(h, n_users, n_items, k, d_ip.as<int64_t>(), d_ix.as<int32_t>(), nullptr, nullptr,
                                 d_v.as<float>(), d_u.as<float>(), lambda, 0.0, nullptr, precision, ir_steps, nullptr));
-    if (it == 0) RL_TRY(ev_item_ready.wait(h, ks));
+    if (it == 0) {
+      RL_TRY(ev_u0_ready.wait(h, ks));
+      int64_t g = (n_users * (kp / 4) + 255) / 256;
+      if (g > 8 * h->sm_count) g = 8 * h->sm_count;
+      fill_empty_rows_kernel<<<static_cast<unsigned>(g), 256, 0, ks>>>(d_ip.as<int64_t>(), n_users, kp, d_u0.as<float>(), d_u.as<float>());
+      RL_LAUNCH_CHECK(h, "fill_empty_rows_kernel");
+      RL_TRY(ev_item_ready.wait(h, ks));
+    }
     if (it == iterations - 1) {        // U is final: send it home while the item half-step runs
       RL_TRY(ev_u_done.record(h, ks));
       RL_TRY(ev_u_done.wait(h, cs));

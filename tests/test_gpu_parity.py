@@ -221,6 +221,11 @@ def test_host_entry_points_overlapped_chunks_equal_device_path(h, k, dtype, bias
     n_users, n_items, n = 40000, 1100, 10          # > 2 sweeps of 128 users x 148 SMs: three chunks, the last one ragged
     rng = np.random.default_rng(k)
     indptr, indices = gen.synth_pattern(n_users, n_items, mean_deg=12, seed=k)
+    deg = np.diff(indptr)
+    deg[[5, 17, n_users - 1]] = 0                              # users without observations keep their initial factors
+    keep = np.repeat(deg > 0, np.diff(indptr))
+    indices = indices[keep]
+    indptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
     ti, tx = o_als.transpose_pattern(indptr, indices, n_items)
     u0 = rng.random((n_users, k)).astype(dtype)
     v0 = rng.random((n_items, k)).astype(dtype)
@@ -235,6 +240,7 @@ def test_host_entry_points_overlapped_chunks_equal_device_path(h, k, dtype, bias
         h.call("rl_als_half_step_dev", n_users, n_items, k, d_ip.ptr, d_ix.ptr, None, None, d_v.ptr, d_u.ptr, 0.01, 0.0, None, 0, 1, None)
         h.call("rl_als_half_step_dev", n_items, n_users, k, d_tp.ptr, d_tx.ptr, None, None, d_u.ptr, d_v.ptr, 0.01, 0.0, None, 0, 1, None)
     assert np.array_equal(uh, unpadded(h, d_u, k, dtype)) and np.array_equal(vh, unpadded(h, d_v, k, dtype))
+    assert np.array_equal(uh[[5, 17, n_users - 1]], u0[[5, 17, n_users - 1]].astype(np.float32).astype(dtype))
     # ---- recommend: chunked host entry point vs one device call
     ub = rng.standard_normal(n_users).astype(np.float32) if bias else None
     ib = rng.standard_normal(n_items).astype(np.float32) if bias else None
