@@ -63,7 +63,8 @@ def main():
     for r in range(args.reps):
         h.synchronize()
         t = time.perf_counter()
-        h.call("rl_score_topn_dev", d_u.ptr, nu, d_v.ptr, ni, k, d_ip.ptr, d_ix.ptr, 0.0, None, None, 10, d_idx.ptr, None,
+        seen = (None, None) if os.environ.get("RL_NO_SEEN") else (d_ip.ptr, d_ix.ptr)
+        h.call("rl_score_topn_dev", d_u.ptr, nu, d_v.ptr, ni, k, seen[0], seen[1], 0.0, None, None, 10, d_idx.ptr, None,
                args.mode)
         h.synchronize()
         print(f"score_topn mode {args.mode} rep {r}: {(time.perf_counter() - t) * 1e3:.3f} ms, overflow rows "
