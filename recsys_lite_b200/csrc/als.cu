@@ -541,9 +541,6 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float4* __restrict__ 
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
 }
 
-namespace k64v1 {
-#include "als_k64_v1.cuh"
-}
 #include "als_k64.cuh"
 
 template <typename real, int KP, bool WEIGHTED>
@@ -642,7 +639,6 @@ int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, 
     return weighted ? launch_kp<double, true>(h, kp, a) : launch_kp<double, false>(h, kp, a);
   }
   if (precision == RL_PREC_FP32_IR) {
-    if (kp == 64 && getenv("RL_ALS_K64_V1")) return weighted ? k64v1::launch_k64o<true>(h, a) : k64v1::launch_k64o<false>(h, a);
     if (kp == 64 && !getenv("RL_ALS_GENERIC")) {
       RL_CUDA(h, cudaMemsetAsync(h->counter + 16, 0, sizeof(float), h->stream));
       const int64_t n4 = n_other * (kp / 4);
