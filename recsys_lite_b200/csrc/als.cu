@@ -91,6 +91,7 @@ struct AlsArgs {
   int n_peers;
   float* peers[RL_MAX_PEERS];
   const float* other_absmax;   // max |entry| of `other` (device scalar), for the fp16 operand scale of the k = 64 path
+  int split_long;              // k = 64 path: rows above K64_LONG observations are left to the cooperative kernel
 };
 
 template <typename real, int T>
@@ -529,6 +530,18 @@ __global__ void __launch_bounds__(WarpSmem<real, KP>::warps * 32) als_half_step_
   }
 }
 
+// longest row of a CSR: max over r of indptr[r + 1] - indptr[r], clamped to INT_MAX
+__global__ void __launch_bounds__(256) max_degree_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, int* __restrict__ out) {
+  int m = 0;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n_rows; r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t d = indptr[r + 1] - indptr[r];
+    m = max(m, static_cast<int>(d > INT_MAX ? INT_MAX : d));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULL_MASK, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
 // max |x| over a float array (non-negative floats order like their bit patterns)
 __global__ void __launch_bounds__(256) absmax_kernel(const float4* __restrict__ x, int64_t n4, float* __restrict__ out) {
   float m = 0.f;
@@ -627,7 +640,7 @@ int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, 
   if (w0 != 0.0 && !gram0) return fail(h, RL_ERR_INVALID, "als_half_step: w0 != 0 needs gram0 (rl_gram_dev)");
   if (!(lambda >= 0.0)) return fail(h, RL_ERR_INVALID, "als_half_step: lambda must be >= 0");
   if (ir_steps < 0 || ir_steps > 8) return fail(h, RL_ERR_INVALID, "als_half_step: ir_steps outside [0, 8]");
-  AlsArgs a{indptr, indices, conf, pref, other, mine, n_rows, k, lambda, w0, gram0, ir_steps, h->counter, row_order, n_peers, {}, nullptr};
+  AlsArgs a{indptr, indices, conf, pref, other, mine, n_rows, k, lambda, w0, gram0, ir_steps, h->counter, row_order, n_peers, {}, nullptr, 0};
   for (int pr = 0; pr < n_peers; ++pr) {
     if (!peers[pr]) return fail(h, RL_ERR_INVALID, "als_half_step: peer pointer %d is null", pr);
     a.peers[pr] = peers[pr];
@@ -649,6 +662,26 @@ int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, 
                                                                       reinterpret_cast<float*>(h->counter + 16));
         RL_LAUNCH_CHECK(h, "absmax_kernel");
       }
+      // rows above K64_LONG observations need the cooperative kernel: asked once per pattern (see rl_context)
+      int has_long = -1;
+      if (!getenv("RL_ALS_NO_LONG_CACHE"))      // (tests: always ask the device)
+        for (const auto& e : h->long_rows_cache)
+          if (e.indptr == indptr && e.n_rows == n_rows) has_long = e.has_long ? 1 : 0;
+      if (has_long < 0) {
+        int* slot = reinterpret_cast<int*>(h->counter + 17);
+        RL_CUDA(h, cudaMemsetAsync(slot, 0, sizeof(int), h->stream));
+        int64_t gd = (n_rows + 255) / 256;
+        if (gd > 8 * h->sm_count) gd = 8 * h->sm_count;
+        max_degree_kernel<<<static_cast<unsigned>(gd), 256, 0, h->stream>>>(indptr, n_rows, slot);
+        RL_LAUNCH_CHECK(h, "max_degree_kernel");
+        int md = 0;
+        RL_CUDA(h, cudaMemcpyAsync(&md, slot, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        RL_CUDA(h, cudaStreamSynchronize(h->stream));
+        has_long = md > K64_LONG ? 1 : 0;
+        if (h->long_rows_cache.size() >= 64) h->long_rows_cache.clear();
+        h->long_rows_cache.push_back({indptr, n_rows, has_long != 0});
+      }
+      a.split_long = has_long;
       return weighted ? launch_k64<true>(h, a) : launch_k64<false>(h, a);
     }
     return weighted ? launch_kp<float, true>(h, kp, a) : launch_kp<float, false>(h, kp, a);

@@ -290,19 +290,37 @@ __device__ __forceinline__ void k64_backward(const float* __restrict__ Lt, const
   }
 }
 
-template <bool WEIGHTED>
-__global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTED>::ctas) als_k64_kernel(const AlsArgs a) {
+// rows longer than this are solved by a whole CTA (als_k64_kernel<.., K64_COOP_WARPS>) instead of one warp: on power-law
+// data a single row can hold a large part of all observations, and one warp gathers ~6 M rows/s
+constexpr int K64_LONG = 2048;
+constexpr int K64_COOP_WARPS = 16;
+constexpr int K64_RANGE = 1024;      // rows per ticket of the cooperative kernel (it scans indptr for long rows itself)
+
+// NW = 1: one warp per row, independent warps (the common case).  NW > 1: the NW warps of a CTA share one (long) row:
+// every warp takes the chunks c = w (mod NW), partial Gram tiles and residuals meet in shared memory (atomics), warp 0
+// factors and solves.
+template <bool WEIGHTED, int NW>
+__global__ void __launch_bounds__(NW == 1 ? K64Smem<WEIGHTED>::warps * 32 : NW * 32, NW == 1 ? K64Smem<WEIGHTED>::ctas : 1)
+als_k64_kernel(const AlsArgs a) {
   constexpr int KP = K64, CH = K64_CH, LDY = K64_LDY;
+  constexpr bool COOP = NW > 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* wbase = smem_raw + static_cast<size_t>(warp) * K64Smem<WEIGHTED>::bytes;
-  float* Lt = reinterpret_cast<float*>(wbase);
+  // solo: [Lt | invd | xs | ts | y | w] per warp.  coop: [Lt | invd | xs | rs] once, then [ts | y | w] per warp.
+  constexpr size_t SH_BYTES = K64Smem<WEIGHTED>::lt_bytes + K64Smem<WEIGHTED>::invd_bytes + K64Smem<WEIGHTED>::xs_bytes;
+  constexpr size_t PW_BYTES = K64Smem<WEIGHTED>::ts_bytes + K64Smem<WEIGHTED>::y_bytes + K64Smem<WEIGHTED>::w_bytes;
+  unsigned char* shb = COOP ? smem_raw : smem_raw + static_cast<size_t>(warp) * K64Smem<WEIGHTED>::bytes;
+  unsigned char* pwb = COOP ? smem_raw + SH_BYTES + sizeof(double) * K64 + static_cast<size_t>(warp) * PW_BYTES : shb + SH_BYTES;
+  float* Lt = reinterpret_cast<float*>(shb);
   float* invd = Lt + K64_LSZ;
   double* xs = reinterpret_cast<double*>(invd + K64);
   float* bs = reinterpret_cast<float*>(xs);               // the float right-hand side of a solve lives in the same 512 bytes
-  double* ts = xs + K64;
+  double* rs = xs + K64;                                  // coop only: residual accumulator
+  double* ts = reinterpret_cast<double*>(pwb);
   float* ybuf = reinterpret_cast<float*>(ts + 16);
   float2* wbuf = reinterpret_cast<float2*>(ybuf + 2 * CH * LDY);
+  __shared__ unsigned int s_ticket, s_nlong;
+  __shared__ int s_long[COOP ? K64_RANGE : 1];   // coop: the long rows of the current ticket (offsets inside the range)
 
   const float lam = static_cast<float>(a.lambda);
   const bool hkv = WEIGHTED && a.w0 != 0.0;   // w0 != 0 always runs the WEIGHTED instantiation
@@ -311,15 +329,41 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
   const float ysc = pow2_scale(*a.other_absmax);
   const float yunsc = (1.0f / ysc) * (1.0f / ysc);
   const int g = lane >> 2, tq = lane & 3;
+  const bool lead = !COOP || warp == 0;        // the warp that factors and solves
 
+  int64_t range_base = 0;                      // coop: first row of the current ticket
+  unsigned int list_pos = 0, list_n = 0;       //       its long rows still to be solved
   for (;;) {
-    unsigned int ticket = 0;
-    if (lane == 0) ticket = atomicAdd(a.counter, 1u);
-    ticket = __shfl_sync(FULL_MASK, ticket, 0);
-    if (static_cast<int64_t>(ticket) >= a.n_rows) break;
-    const int64_t row = a.row_order ? a.row_order[ticket] : static_cast<int64_t>(ticket);
+    int64_t row;
+    if constexpr (!COOP) {
+      unsigned int ticket = 0;
+      if (lane == 0) ticket = atomicAdd(a.counter, 1u);
+      ticket = __shfl_sync(FULL_MASK, ticket, 0);
+      if (static_cast<int64_t>(ticket) >= a.n_rows) break;
+      row = a.row_order ? a.row_order[ticket] : static_cast<int64_t>(ticket);
+    } else {
+      while (list_pos >= list_n) {            // next ticket: all threads look through its rows for long ones
+        __syncthreads();
+        if (threadIdx.x == 0) { s_ticket = atomicAdd(a.counter + 1, 1u); s_nlong = 0; }
+        __syncthreads();
+        range_base = static_cast<int64_t>(s_ticket) * K64_RANGE;
+        if (range_base >= a.n_rows) break;
+        for (int64_t r = range_base + threadIdx.x; r < min(a.n_rows, range_base + K64_RANGE); r += NW * 32)
+          if (a.indptr[r + 1] - a.indptr[r] > K64_LONG) s_long[atomicAdd(&s_nlong, 1u)] = static_cast<int>(r - range_base);
+        __syncthreads();
+        list_pos = 0;
+        list_n = s_nlong;
+      }
+      if (range_base >= a.n_rows) break;
+      row = range_base + s_long[list_pos++];
+    }
     const int64_t s = a.indptr[row];
     const int64_t nnz64 = a.indptr[row + 1] - s;
+    if constexpr (COOP) {
+      if (nnz64 <= K64_LONG) continue;         // the warp-per-row kernel has it
+    } else {
+      if (a.split_long && nnz64 > K64_LONG) continue;   // the cooperative kernel has it
+    }
     if (nnz64 <= 0) {
       if (hkv) {
         a.mine[row * KP + lane] = 0.0f;
@@ -332,9 +376,17 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
       continue;  // reference: rows with no observation keep their previous value (algo.py:316-317)
     }
     const int nnz = static_cast<int>(nnz64);
-    const int nchunk = (nnz + CH - 1) / CH;
+    const int nchunk_all = (nnz + CH - 1) / CH;
+    // chunks of this warp: w, w + NW, ...
+    const int nchunk = COOP ? (nchunk_all > warp ? (nchunk_all - warp + NW - 1) / NW : 0) : nchunk_all;
+    auto chunk_id = [&](int c) { return COOP ? warp + c * NW : c; };
+    if constexpr (COOP) {                       // the accumulators of the row start from zero
+      for (int p = threadIdx.x; p < K64_LSZ; p += NW * 32) Lt[p] = 0.f;
+      if (threadIdx.x < K64) bs[threadIdx.x] = 0.f;
+      __syncthreads();
+    }
 
-    // ---- gather + Gram on the tensor cores (3 x tf32 split, fp32 accumulate) -----------------------------------
+    // ---- gather + Gram on the tensor cores (fp16 split operands, fp32 accumulate) --------------------------------
     float acc[20][4];
     float bf0 = 0.f, bf1 = 0.f;      // right-hand side in fp32: only the first solve uses it, the refinement residual is b-free
 #pragma unroll
@@ -342,16 +394,17 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
     for (int c = -1; c < nchunk; ++c) {       // one gather call site: chunk c + 1 is requested, then chunk c is consumed
       const int buf = c & 1;
       if (c + 1 < nchunk) {
-        k64_gather<WEIGHTED>(a, s, nnz, c + 1, ybuf + (buf ^ 1) * CH * LDY, wbuf + (buf ^ 1) * CH, lane);
+        k64_gather<WEIGHTED>(a, s, nnz, chunk_id(c + 1), ybuf + (buf ^ 1) * CH * LDY, wbuf + (buf ^ 1) * CH, lane);
         if (c < 0) continue;
         cp_async_wait<1>();
       } else {
+        if (c < 0) continue;
         cp_async_wait<0>();
       }
       __syncwarp();
       const float* yb = ybuf + buf * CH * LDY;
       const float2* wb = wbuf + buf * CH;
-      const int cnt = min(CH, nnz - c * CH);
+      const int cnt = min(CH, nnz - chunk_id(c) * CH);
 #pragma unroll
       for (int r = 0; r < CH; ++r) {        // zero-filled rows add nothing
         const float* yr = yb + r * LDY;
@@ -419,35 +472,57 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
           for (int e = 0; e < 4; ++e) {
             const int gi = 16 * mi + g + ((e & 2) ? 8 : 0), gj = 8 * nj + 2 * tq + (e & 1);
             d[e] *= yunsc;                         // the operands were scaled by ysc (a power of two): exact
-            if (hkv) d[e] += static_cast<float>(a.w0 * a.gram0[gi * KP + gj]);
-            if (nj >= 2 * mi && gi == gj) d[e] += (gi < a.k) ? lam : 1.0f;
+            if (lead) {
+              if (hkv) d[e] += static_cast<float>(a.w0 * a.gram0[gi * KP + gj]);
+              if (nj >= 2 * mi && gi == gj) d[e] += (gi < a.k) ? lam : 1.0f;
+            }
           }
           float* pn = Lt + k64_pb0(nj);
-          if (nj <= 2 * mi) *reinterpret_cast<float2*>(pn + 8 * (16 * mi + g) + oc) = make_float2(d[0], d[1]);
-          *reinterpret_cast<float2*>(pn + 8 * (16 * mi + 8 + g) + oc) = make_float2(d[2], d[3]);
+          if constexpr (!COOP) {
+            if (nj <= 2 * mi) *reinterpret_cast<float2*>(pn + 8 * (16 * mi + g) + oc) = make_float2(d[0], d[1]);
+            *reinterpret_cast<float2*>(pn + 8 * (16 * mi + 8 + g) + oc) = make_float2(d[2], d[3]);
+          } else {
+            if (nj <= 2 * mi) { atomicAdd(pn + 8 * (16 * mi + g) + oc, d[0]); atomicAdd(pn + 8 * (16 * mi + g) + oc + 1, d[1]); }
+            atomicAdd(pn + 8 * (16 * mi + 8 + g) + oc, d[2]);
+            atomicAdd(pn + 8 * (16 * mi + 8 + g) + oc + 1, d[3]);
+          }
         }
     }
     // ---- blocked Cholesky on the tensor cores, forward substitution fused ------------------------------------
-    bs[lane] = bf0;
-    bs[32 + lane] = bf1;
-    __syncwarp();
-    k64_chol(Lt, invd, bs, lane);
+    if constexpr (!COOP) {
+      bs[lane] = bf0;
+      bs[32 + lane] = bf1;
+      __syncwarp();
+    } else {
+      atomicAdd(bs + lane, bf0);
+      atomicAdd(bs + 32 + lane, bf1);
+      __syncthreads();
+    }
+    if (lead) k64_chol(Lt, invd, bs, lane);
     // ---- back substitution, then refinement steps  x += L^-T L^-1 (b - A x)  with a float64 matrix-free residual ----
     double xd0 = 0.0, xd1 = 0.0;
     for (int it = 0;; ++it) {
-      float v0 = bs[lane], v1 = bs[32 + lane];    // L^-1 (right-hand side or residual)
-      __syncwarp();
-      k64_backward(Lt, invd, v0, v1, lane);
-      xd0 += static_cast<double>(v0);
-      xd1 += static_cast<double>(v1);
+      if (lead) {
+        float v0 = bs[lane], v1 = bs[32 + lane];    // L^-1 (right-hand side or residual)
+        __syncwarp();
+        k64_backward(Lt, invd, v0, v1, lane);
+        xd0 += static_cast<double>(v0);
+        xd1 += static_cast<double>(v1);
+      }
       if (it >= a.ir_steps) break;
-      xs[lane] = xd0;
-      xs[32 + lane] = xd1;
+      if (lead) {
+        xs[lane] = xd0;
+        xs[32 + lane] = xd1;
+        if constexpr (COOP) { rs[lane] = 0.0; rs[32 + lane] = 0.0; }
+      }
+      if constexpr (COOP) __syncthreads(); else __syncwarp();
       // r = b - A x = sum_i (p_i - w_i <y_i, x>) y_i - lambda x (- w0 G x): the right-hand side never appears on its own
-      double r0 = -((lane < a.k) ? a.lambda : 1.0) * xd0;
-      double r1 = -((32 + lane < a.k) ? a.lambda : 1.0) * xd1;
-      __syncwarp();
-      if (hkv) {
+      double r0 = 0.0, r1 = 0.0;
+      if (lead) {
+        r0 = -((lane < a.k) ? a.lambda : 1.0) * xd0;
+        r1 = -((32 + lane < a.k) ? a.lambda : 1.0) * xd1;
+      }
+      if (hkv && lead) {
         double t0 = 0.0, t1 = 0.0;
         for (int cc = 0; cc < KP; ++cc) {
           t0 = fma(a.gram0[lane * KP + cc], xs[cc], t0);
@@ -459,16 +534,17 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
       for (int c = -1; c < nchunk; ++c) {
         const int buf = c & 1;
         if (c + 1 < nchunk) {
-          k64_gather<WEIGHTED>(a, s, nnz, c + 1, ybuf + (buf ^ 1) * CH * LDY, wbuf + (buf ^ 1) * CH, lane);
+          k64_gather<WEIGHTED>(a, s, nnz, chunk_id(c + 1), ybuf + (buf ^ 1) * CH * LDY, wbuf + (buf ^ 1) * CH, lane);
           if (c < 0) continue;
           cp_async_wait<1>();
         } else {
+          if (c < 0) continue;
           cp_async_wait<0>();
         }
         __syncwarp();
         const float* yb = ybuf + buf * CH * LDY;
         const float2* wb = wbuf + buf * CH;
-        const int cnt = min(CH, nnz - c * CH);
+        const int cnt = min(CH, nnz - chunk_id(c) * CH);
         // t_i = w_i <y_i, x>: four lanes per gathered row (a quarter of the factor dimension each), then two shuffle adds
         {
           const int i = lane & 7, quarter = lane >> 3;
@@ -499,26 +575,51 @@ __global__ void __launch_bounds__(K64Smem<WEIGHTED>::warps * 32, K64Smem<WEIGHTE
         }
         __syncwarp();
       }
-      bs[lane] = static_cast<float>(r0);        // xs is dead from here on: its bytes take the right-hand side
-      bs[32 + lane] = static_cast<float>(r1);
-      __syncwarp();
-      k64_forward(Lt, invd, bs, lane);
+      if constexpr (COOP) {                     // partial residuals of the warps meet in shared memory
+        atomicAdd(rs + lane, r0);
+        atomicAdd(rs + 32 + lane, r1);
+        __syncthreads();
+        r0 = rs[lane];
+        r1 = rs[32 + lane];
+        __syncthreads();                        // everybody has read xs / rs before warp 0 reuses the bytes as bs
+      }
+      if (lead) {
+        bs[lane] = static_cast<float>(r0);      // xs is dead from here on: its bytes take the right-hand side
+        bs[32 + lane] = static_cast<float>(r1);
+        __syncwarp();
+        k64_forward(Lt, invd, bs, lane);
+      }
     }
-    const float xo0 = (lane < a.k) ? static_cast<float>(xd0) : 0.0f;
-    const float xo1 = (32 + lane < a.k) ? static_cast<float>(xd1) : 0.0f;
-    a.mine[row * KP + lane] = xo0;
-    a.mine[row * KP + 32 + lane] = xo1;
-    for (int pr = 0; pr < a.n_peers; ++pr) {      // fused exchange: two 128-byte NVLink stores per peer replica
-      a.peers[pr][row * KP + lane] = xo0;
-      a.peers[pr][row * KP + 32 + lane] = xo1;
+    if (lead) {
+      const float xo0 = (lane < a.k) ? static_cast<float>(xd0) : 0.0f;
+      const float xo1 = (32 + lane < a.k) ? static_cast<float>(xd1) : 0.0f;
+      a.mine[row * KP + lane] = xo0;
+      a.mine[row * KP + 32 + lane] = xo1;
+      for (int pr = 0; pr < a.n_peers; ++pr) {      // fused exchange: two 128-byte NVLink stores per peer replica
+        a.peers[pr][row * KP + lane] = xo0;
+        a.peers[pr][row * KP + 32 + lane] = xo1;
+      }
     }
-    __syncwarp();
+    if constexpr (COOP) __syncthreads(); else __syncwarp();
   }
 }
 
 template <bool WEIGHTED>
-int launch_k64(rl_context* h, const AlsArgs& args) {
-  auto kern = als_k64_kernel<WEIGHTED>;
+int launch_k64(rl_context* h, const AlsArgs& args_in) {
+  AlsArgs args = args_in;
+  RL_CUDA(h, cudaMemsetAsync(args.counter, 0, 2 * sizeof(unsigned int), h->stream));
+  if (args.split_long) {  // rows with more than K64_LONG observations: one CTA per row; it looks for them itself, in tickets of K64_RANGE rows
+    auto coop = als_k64_kernel<WEIGHTED, K64_COOP_WARPS>;
+    constexpr size_t sh = K64Smem<WEIGHTED>::lt_bytes + K64Smem<WEIGHTED>::invd_bytes + K64Smem<WEIGHTED>::xs_bytes + sizeof(double) * K64;
+    constexpr size_t pw = K64Smem<WEIGHTED>::ts_bytes + K64Smem<WEIGHTED>::y_bytes + K64Smem<WEIGHTED>::w_bytes;
+    const size_t smem = sh + pw * K64_COOP_WARPS;
+    RL_CUDA(h, cudaFuncSetAttribute(coop, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int64_t grid = (args.n_rows + K64_RANGE - 1) / K64_RANGE;
+    if (grid > h->sm_count) grid = h->sm_count;
+    coop<<<static_cast<unsigned>(grid), K64_COOP_WARPS * 32, smem, h->stream>>>(args);
+    RL_LAUNCH_CHECK(h, "als_k64_kernel(coop)");
+  }
+  auto kern = als_k64_kernel<WEIGHTED, 1>;
   constexpr int W = K64Smem<WEIGHTED>::warps;
   const size_t smem = K64Smem<WEIGHTED>::bytes * W;
   RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -529,7 +630,6 @@ int launch_k64(rl_context* h, const AlsArgs& args) {
   int64_t grid = static_cast<int64_t>(h->sm_count) * per_sm;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  RL_CUDA(h, cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), h->stream));
   kern<<<static_cast<unsigned>(grid), W * 32, smem, h->stream>>>(args);
   RL_LAUNCH_CHECK(h, "als_k64_kernel");
   return RL_OK;

@@ -26,6 +26,10 @@ struct rl_context {
   // grow-only device scratch (svd, scoring candidates, ...)
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  // ALS k = 64 path: does this CSR (keyed by its device indptr pointer and row count) hold rows long enough for the
+  // cooperative kernel?  Answered once per pattern by a reduction over indptr; a stale "no" only costs speed.
+  struct LongRowsEntry { const void* indptr; int64_t n_rows; bool has_long; };
+  std::vector<LongRowsEntry> long_rows_cache;
   unsigned int preloaded_exact = 0;  // bit (kp >> 4): fallback kernels of the tensor-core scoring path are loaded
   unsigned int last_overflow = 0;  // rows the last tensor-core scoring call handed to the exact kernel
   std::vector<std::pair<void*, void*>> ipc_bases;  // (pointer handed out by rl_ipc_open, base of the mapping)

@@ -88,9 +88,10 @@ def test_half_step_dev_vs_oracle(h, k, precision):
     assert not raw[:, k:].any()
 
 
-def test_half_step_long_and_skewed_rows(h):
+def test_half_step_long_and_skewed_rows(h, monkeypatch):
     """item-side shape: few rows with hundreds..thousands of observations (chunked gather, many chunks)."""
     from devbuf import Dev, padded, unpadded
+    monkeypatch.setenv("RL_ALS_NO_LONG_CACHE", "1")
     k, n_rows, n_other = 64, 60, 5000
     rng = np.random.default_rng(5)
     degs = np.concatenate(([1, 2, 15, 16, 17, 31, 32, 33, 4000], rng.integers(100, 900, n_rows - 9)))
@@ -134,6 +135,49 @@ def test_half_step_general_weights_vs_dense_restatement(h, precision):
            0.1, 1.0, d_g.ptr, precision, 2, None)
     fro, mx = compare.factor_error(unpadded(h, d_mine, k), ref)
     assert fro <= 5e-6 and mx <= 5e-5, (fro, mx)
+
+
+def test_half_step_cooperative_long_rows_weighted_and_peers(h, monkeypatch):
+    """rows above K64_LONG = 2048 observations are solved by a whole CTA (partial Grams / residuals of 16 warps meet in
+    shared memory): power-law shaped row lengths, k = 50 (padded 64), general weights with w0 = 1 and a peer replica;
+    checked against oracle.half_step_general and against the unweighted reference arithmetic."""
+    import ctypes as C
+    from devbuf import Dev, padded, unpadded
+    monkeypatch.setenv("RL_ALS_NO_LONG_CACHE", "1")     # the "has long rows" answer is cached per device pointer: ask afresh
+    k, n_other = 50, 30000
+    rng = np.random.default_rng(9)
+    degs = np.array([3, 2048, 2049, 2500, 9000, 25000, 40, 7, 4097, 300])
+    n_rows = len(degs)
+    rows = [np.sort(rng.choice(n_other, d, replace=False)) for d in degs]
+    indptr = np.concatenate(([0], np.cumsum(degs))).astype(np.int64)
+    indices = np.concatenate(rows).astype(np.int32)
+    other = rng.random((n_other, k)) * 0.6
+    mine0 = rng.random((n_rows, k))
+    d_other = padded(h, other, k)
+    d_ip, d_ix = Dev(h, indptr), Dev(h, indices)
+    # reference arithmetic (algo.py:318-322), one refinement step, plus a peer replica
+    ref = o_als.half_step_csr(indptr, indices, _f32(other), _f32(mine0).copy(), 0.01)
+    d_mine, d_peer = padded(h, mine0, k), padded(h, mine0, k)
+    peers = (C.c_void_p * 1)(d_peer.ptr)
+    h.call("rl_als_half_step_peers_dev", n_rows, n_other, k, d_ip.ptr, d_ix.ptr, None, None, d_other.ptr, d_mine.ptr, 0.01, 0.0,
+           None, 0, 1, None, 1, peers)
+    got = unpadded(h, d_mine, k)
+    fro, mx = compare.factor_error(got, ref)
+    assert fro <= 1e-5 and mx <= 1e-4, (fro, mx)
+    assert np.array_equal(unpadded(h, d_peer, k), got)
+    # general weights, w0 = 1 (not reference parity: against the dense restatement)
+    conf = (1.0 + 2.0 * rng.random(len(indices))).astype(np.float32)
+    pref = (0.5 + rng.random(len(indices))).astype(np.float32)
+    refw = o_als.half_step_general(indptr, indices, _f32(other), _f32(mine0).copy(), 0.1, w0=1.0,
+                                   conf=conf.astype(np.float64), pref=pref.astype(np.float64))
+    kp = h.lib.rl_padded_k(k)
+    d_g = Dev(h, shape=(kp, kp), dtype=np.float64)
+    h.call("rl_gram_dev", d_other.ptr, n_other, k, d_g.ptr)
+    d_c, d_p, d_mw = Dev(h, conf), Dev(h, pref), padded(h, mine0, k)
+    h.call("rl_als_half_step_dev", n_rows, n_other, k, d_ip.ptr, d_ix.ptr, d_c.ptr, d_p.ptr, d_other.ptr, d_mw.ptr,
+           0.1, 1.0, d_g.ptr, 0, 2, None)
+    fro, mx = compare.factor_error(unpadded(h, d_mw, k), refw)
+    assert fro <= 1e-5 and mx <= 1e-4, (fro, mx)
 
 
 def test_als_medium_config3_shape_vs_oracle():
