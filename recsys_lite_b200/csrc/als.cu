@@ -92,6 +92,8 @@ struct AlsArgs {
   float* peers[RL_MAX_PEERS];
   const float* other_absmax;   // max |entry| of `other` (device scalar), for the fp16 operand scale of the k = 64 path
   int split_long;              // k = 64 path: rows above K64_LONG observations are left to the cooperative kernel
+  const int32_t* long_list;    //   ... which takes them from this list (device), *long_count entries
+  const unsigned int* long_count;
 };
 
 template <typename real, int T>
@@ -640,7 +642,7 @@ int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, 
   if (w0 != 0.0 && !gram0) return fail(h, RL_ERR_INVALID, "als_half_step: w0 != 0 needs gram0 (rl_gram_dev)");
   if (!(lambda >= 0.0)) return fail(h, RL_ERR_INVALID, "als_half_step: lambda must be >= 0");
   if (ir_steps < 0 || ir_steps > 8) return fail(h, RL_ERR_INVALID, "als_half_step: ir_steps outside [0, 8]");
-  AlsArgs a{indptr, indices, conf, pref, other, mine, n_rows, k, lambda, w0, gram0, ir_steps, h->counter, row_order, n_peers, {}, nullptr, 0};
+  AlsArgs a{indptr, indices, conf, pref, other, mine, n_rows, k, lambda, w0, gram0, ir_steps, h->counter, row_order, n_peers, {}, nullptr, 0, nullptr, nullptr};
   for (int pr = 0; pr < n_peers; ++pr) {
     if (!peers[pr]) return fail(h, RL_ERR_INVALID, "als_half_step: peer pointer %d is null", pr);
     a.peers[pr] = peers[pr];

@@ -294,7 +294,13 @@ __device__ __forceinline__ void k64_backward(const float* __restrict__ Lt, const
 // data a single row can hold a large part of all observations, and one warp gathers ~6 M rows/s
 constexpr int K64_LONG = 2048;
 constexpr int K64_COOP_WARPS = 16;
-constexpr int K64_RANGE = 1024;      // rows per ticket of the cooperative kernel (it scans indptr for long rows itself)
+
+// the rows the cooperative kernel works on: list[0 .. *count)
+__global__ void __launch_bounds__(256) k64_find_long_rows_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, int32_t* __restrict__ list,
+                                                                 unsigned int* __restrict__ count) {
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n_rows; r += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    if (indptr[r + 1] - indptr[r] > K64_LONG) list[atomicAdd(count, 1u)] = static_cast<int32_t>(r);
+}
 
 // NW = 1: one warp per row, independent warps (the common case).  NW > 1: the NW warps of a CTA share one (long) row:
 // every warp takes the chunks c = w (mod NW), partial Gram tiles and residuals meet in shared memory (atomics), warp 0
@@ -319,8 +325,7 @@ als_k64_kernel(const AlsArgs a) {
   double* ts = reinterpret_cast<double*>(pwb);
   float* ybuf = reinterpret_cast<float*>(ts + 16);
   float2* wbuf = reinterpret_cast<float2*>(ybuf + 2 * CH * LDY);
-  __shared__ unsigned int s_ticket, s_nlong;
-  __shared__ int s_long[COOP ? K64_RANGE : 1];   // coop: the long rows of the current ticket (offsets inside the range)
+  __shared__ unsigned int s_ticket;
 
   const float lam = static_cast<float>(a.lambda);
   const bool hkv = WEIGHTED && a.w0 != 0.0;   // w0 != 0 always runs the WEIGHTED instantiation
@@ -331,8 +336,6 @@ als_k64_kernel(const AlsArgs a) {
   const int g = lane >> 2, tq = lane & 3;
   const bool lead = !COOP || warp == 0;        // the warp that factors and solves
 
-  int64_t range_base = 0;                      // coop: first row of the current ticket
-  unsigned int list_pos = 0, list_n = 0;       //       its long rows still to be solved
   for (;;) {
     int64_t row;
     if constexpr (!COOP) {
@@ -342,26 +345,15 @@ als_k64_kernel(const AlsArgs a) {
       if (static_cast<int64_t>(ticket) >= a.n_rows) break;
       row = a.row_order ? a.row_order[ticket] : static_cast<int64_t>(ticket);
     } else {
-      while (list_pos >= list_n) {            // next ticket: all threads look through its rows for long ones
-        __syncthreads();
-        if (threadIdx.x == 0) { s_ticket = atomicAdd(a.counter + 1, 1u); s_nlong = 0; }
-        __syncthreads();
-        range_base = static_cast<int64_t>(s_ticket) * K64_RANGE;
-        if (range_base >= a.n_rows) break;
-        for (int64_t r = range_base + threadIdx.x; r < min(a.n_rows, range_base + K64_RANGE); r += NW * 32)
-          if (a.indptr[r + 1] - a.indptr[r] > K64_LONG) s_long[atomicAdd(&s_nlong, 1u)] = static_cast<int>(r - range_base);
-        __syncthreads();
-        list_pos = 0;
-        list_n = s_nlong;
-      }
-      if (range_base >= a.n_rows) break;
-      row = range_base + s_long[list_pos++];
+      __syncthreads();
+      if (threadIdx.x == 0) s_ticket = atomicAdd(a.counter + 1, 1u);
+      __syncthreads();
+      if (s_ticket >= *a.long_count) break;
+      row = a.long_list[s_ticket];
     }
     const int64_t s = a.indptr[row];
     const int64_t nnz64 = a.indptr[row + 1] - s;
-    if constexpr (COOP) {
-      if (nnz64 <= K64_LONG) continue;         // the warp-per-row kernel has it
-    } else {
+    if constexpr (!COOP) {
       if (a.split_long && nnz64 > K64_LONG) continue;   // the cooperative kernel has it
     }
     if (nnz64 <= 0) {
@@ -608,16 +600,36 @@ template <bool WEIGHTED>
 int launch_k64(rl_context* h, const AlsArgs& args_in) {
   AlsArgs args = args_in;
   RL_CUDA(h, cudaMemsetAsync(args.counter, 0, 2 * sizeof(unsigned int), h->stream));
-  if (args.split_long) {  // rows with more than K64_LONG observations: one CTA per row; it looks for them itself, in tickets of K64_RANGE rows
+  if (args.split_long) {
+    // Rows with more than K64_LONG observations: listed by a small kernel, then one CTA per row by ticket.  Both run on
+    // the handle's second compute stream and are launched first, so that the cooperative kernel takes one CTA slot per
+    // SM and the warp-per-row kernel fills the rest of the chip beside it (the two write disjoint rows).
+    if (args.n_rows >= (1ll << 31)) return fail(h, RL_ERR_INVALID, "als_k64: too many rows for the long-row list");
+    if (h->long_list_rows < args.n_rows) {
+      RL_CUDA(h, cudaStreamSynchronize(h->aux_stream));
+      if (h->long_list) RL_CUDA(h, cudaFree(h->long_list));
+      h->long_list = nullptr;
+      h->long_list_rows = 0;
+      RL_CUDA(h, cudaMalloc(&h->long_list, sizeof(int32_t) * static_cast<size_t>(args.n_rows)));
+      h->long_list_rows = args.n_rows;
+    }
+    args.long_list = h->long_list;
+    args.long_count = args.counter + 2;
+    RL_CUDA(h, cudaMemsetAsync(args.counter + 2, 0, sizeof(unsigned int), h->stream));
+    RL_CUDA(h, cudaEventRecord(h->aux_fork, h->stream));
+    RL_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->aux_fork, 0));
+    int64_t gf = (args.n_rows + 255) / 256;
+    if (gf > 4 * h->sm_count) gf = 4 * h->sm_count;
+    k64_find_long_rows_kernel<<<static_cast<unsigned>(gf), 256, 0, h->aux_stream>>>(args.indptr, args.n_rows, h->long_list, args.counter + 2);
+    RL_LAUNCH_CHECK(h, "k64_find_long_rows_kernel");
     auto coop = als_k64_kernel<WEIGHTED, K64_COOP_WARPS>;
     constexpr size_t sh = K64Smem<WEIGHTED>::lt_bytes + K64Smem<WEIGHTED>::invd_bytes + K64Smem<WEIGHTED>::xs_bytes + sizeof(double) * K64;
     constexpr size_t pw = K64Smem<WEIGHTED>::ts_bytes + K64Smem<WEIGHTED>::y_bytes + K64Smem<WEIGHTED>::w_bytes;
     const size_t smem = sh + pw * K64_COOP_WARPS;
     RL_CUDA(h, cudaFuncSetAttribute(coop, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    int64_t grid = (args.n_rows + K64_RANGE - 1) / K64_RANGE;
-    if (grid > h->sm_count) grid = h->sm_count;
-    coop<<<static_cast<unsigned>(grid), K64_COOP_WARPS * 32, smem, h->stream>>>(args);
+    coop<<<static_cast<unsigned>(h->sm_count), K64_COOP_WARPS * 32, smem, h->aux_stream>>>(args);
     RL_LAUNCH_CHECK(h, "als_k64_kernel(coop)");
+    RL_CUDA(h, cudaEventRecord(h->aux_join, h->aux_stream));
   }
   auto kern = als_k64_kernel<WEIGHTED, 1>;
   constexpr int W = K64Smem<WEIGHTED>::warps;
@@ -632,5 +644,6 @@ int launch_k64(rl_context* h, const AlsArgs& args_in) {
   if (grid < 1) grid = 1;
   kern<<<static_cast<unsigned>(grid), W * 32, smem, h->stream>>>(args);
   RL_LAUNCH_CHECK(h, "als_k64_kernel");
+  if (args.split_long) RL_CUDA(h, cudaStreamWaitEvent(h->stream, h->aux_join, 0));
   return RL_OK;
 }

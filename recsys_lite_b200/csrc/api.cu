@@ -225,6 +225,14 @@ int rl_create(int device, rl_handle* out) {
     delete h;
     return cuda_fail(nullptr, e, "cudaStreamCreate(copy)");
   }
+  if ((e = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->aux_join, cudaEventDisableTiming)) != cudaSuccess) {
+    cudaStreamDestroy(h->own_stream);
+    cudaStreamDestroy(h->copy_stream);
+    delete h;
+    return cuda_fail(nullptr, e, "cudaStreamCreate(aux)");
+  }
   if ((e = cudaMalloc(&h->counter, 64 * sizeof(unsigned int))) != cudaSuccess) {
     cudaStreamDestroy(h->own_stream);
     delete h;
@@ -249,6 +257,10 @@ int rl_destroy(rl_handle h) {
   if (h->scratch) cudaFree(h->scratch);
   if (h->counter) cudaFree(h->counter);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
+  if (h->long_list) cudaFree(h->long_list);
+  if (h->aux_fork) cudaEventDestroy(h->aux_fork);
+  if (h->aux_join) cudaEventDestroy(h->aux_join);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return RL_OK;

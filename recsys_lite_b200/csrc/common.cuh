@@ -20,6 +20,10 @@ struct rl_context {
   cudaStream_t stream = nullptr;      // stream kernels are enqueued on
   cudaStream_t own_stream = nullptr;  // created by rl_create
   cudaStream_t copy_stream = nullptr; // host <-> device traffic of the *_host entry points, overlapped with the kernels
+  cudaStream_t aux_stream = nullptr;  // second compute stream: the cooperative long-row ALS kernel runs beside the warp-per-row one
+  cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+  int32_t* long_list = nullptr;       // rows for the cooperative ALS kernel (device), capacity long_list_rows
+  int64_t long_list_rows = 0;
   unsigned int* counter = nullptr;    // device work counters (row schedulers), 64 x u32
   int64_t launches = 0;
   std::string err;
