@@ -375,7 +375,10 @@ def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
     out_v = torch.empty((ihi - ilo, k), dtype=torch.float32).pin_memory()
     out_idx = torch.empty((uhi - ulo, n), dtype=torch.int32).pin_memory()
     idx_dev = torch.empty((uhi - ulo, n), dtype=torch.int32, device=device)
-    h2d = sum(t.numel() * t.element_size() for t in hp.values()) + hu.numel() * 4 + hv.numel() * 4
+    # Each rank uploads the initial factors it needs: all of V (the first user half-step gathers from it) but only ITS
+    # range of U -- every user row with observations is overwritten by its owner's half-step (and arrives through the
+    # exchange) before anyone reads it, and rows without observations are read by nobody but their owner's scoring pass.
+    h2d = sum(t.numel() * t.element_size() for t in hp.values()) + (uhi - ulo) * k * 4 + hv.numel() * 4
     d2h = out_u.numel() * 4 + out_v.numel() * 4 + out_idx.numel() * 4
     times = []
     for i in range(1 + steps):
@@ -385,7 +388,7 @@ def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
         prob.ux.copy_(hp["ux"], non_blocking=True)
         prob.ip.copy_(hp["ip"], non_blocking=True)
         prob.ix.copy_(hp["ix"], non_blocking=True)
-        prob.U[:, :k].copy_(hu, non_blocking=True)
+        prob.U[ulo:uhi, :k].copy_(hu[ulo:uhi], non_blocking=True)
         prob.V[:, :k].copy_(hv, non_blocking=True)
         if getattr(prob, "peer_stores", False):
             prob.peer_barrier()       # no peer may store into this replica before its upload has landed
