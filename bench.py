@@ -38,6 +38,9 @@ UNIT = "iterations/s"
 WORKLOADS = {
     "C4": dict(n_users=1_000_000, n_items=100_000, mean_deg=50, k=64, seed=4, init_seed=4, n=10, lam=0.01),
     "C3": dict(n_users=100_000, n_items=20_000, mean_deg=50, k=64, seed=3, init_seed=3, n=10, lam=0.01),
+    # skewed variants of SURVEY 8(d): Zipf(1.0) item popularity, log-normal user degrees (load balance, long rows)
+    "C4s": dict(n_users=1_000_000, n_items=100_000, mean_deg=50, k=64, seed=14, init_seed=4, n=10, lam=0.01, skew=True),
+    "C3s": dict(n_users=100_000, n_items=20_000, mean_deg=50, k=64, seed=13, init_seed=3, n=10, lam=0.01, skew=True),
     "tiny": dict(n_users=20_000, n_items=4_000, mean_deg=30, k=64, seed=1, init_seed=1, n=10, lam=0.01),
 }
 
@@ -59,7 +62,7 @@ def load_traffic():
 def make_inputs(w):
     from recsys_lite_b200 import synth
     from recsys_lite_b200.csr import transpose_pattern
-    indptr, indices = synth.synth_pattern(w["n_users"], w["n_items"], w["mean_deg"], w["seed"])
+    indptr, indices = synth.synth_pattern(w["n_users"], w["n_items"], w["mean_deg"], w["seed"], skew=w.get("skew", False))
     indptr_t, indices_t = transpose_pattern(indptr, indices, w["n_items"])
     rng = np.random.default_rng(w["init_seed"])          # float32 uniform [0,1) like np.random.rand, drawn U then V
     u0 = rng.random((w["n_users"], w["k"]), dtype=np.float32)
@@ -184,7 +187,7 @@ def run_reference(args, w):
 
 def workload_config(args, w, where):
     return {"workload": f"{args.workload}: implicit ALS k={w['k']} one full iteration + top-{w['n']} for all users, "
-                        f"{w['n_users']} users x {w['n_items']} items, ~{w['mean_deg']} nnz/user (uniform synthetic, seed {w['seed']})",
+                        f"{w['n_users']} users x {w['n_items']} items, ~{w['mean_deg']} nnz/user ({'skewed: Zipf item popularity, log-normal degrees' if w.get('skew') else 'uniform synthetic'}, seed {w['seed']})",
             "lambda": w["lam"], "where": where,
             "l2": "inputs larger than L2 (indices 2x%d MB, U %d MB); no flush" % (
                 w["n_users"] * w["mean_deg"] * 4 // 2**20, w["n_users"] * w["k"] * 4 // 2**20)}
