@@ -23,6 +23,7 @@
 
 #include <cstdlib>
 
+#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"

@@ -294,22 +294,35 @@ __device__ __forceinline__ void k64_backward(const float* __restrict__ Lt, const
 // data a single row can hold a large part of all observations, and one warp gathers ~6 M rows/s
 constexpr int K64_LONG = 2048;
 constexpr int K64_COOP_WARPS = 16;
+// ... and rows longer than this by a thread-block cluster of K64_CLUSTER such CTAs (partial sums meet in the leader CTA's
+// shared memory over DSMEM): one CTA gathers ~100 M rows/s, a row with a million observations would hold it for 20 ms
+constexpr int K64_GIANT = 32768;
+constexpr int K64_CLUSTER = 8;
 
-// the rows the cooperative kernel works on: list[0 .. *count)
+// the rows the cooperative kernels work on: long rows in list[0 .. count[0]), giant rows in list[n_rows - count[1] .. n_rows)
 __global__ void __launch_bounds__(256) k64_find_long_rows_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, int32_t* __restrict__ list,
                                                                  unsigned int* __restrict__ count) {
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n_rows; r += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    if (indptr[r + 1] - indptr[r] > K64_LONG) list[atomicAdd(count, 1u)] = static_cast<int32_t>(r);
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n_rows; r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t d = indptr[r + 1] - indptr[r];
+    if (d > K64_GIANT) list[n_rows - 1 - atomicAdd(count + 1, 1u)] = static_cast<int32_t>(r);
+    else if (d > K64_LONG) list[atomicAdd(count, 1u)] = static_cast<int32_t>(r);
+  }
 }
 
 // NW = 1: one warp per row, independent warps (the common case).  NW > 1: the NW warps of a CTA share one (long) row:
 // every warp takes the chunks c = w (mod NW), partial Gram tiles and residuals meet in shared memory (atomics), warp 0
 // factors and solves.
-template <bool WEIGHTED, int NW>
+// NCTA > 1 (with NW > 1): the CTAs of a thread-block cluster share one (giant) row the same way; their totals are added
+// into the leader CTA's shared memory through distributed shared memory, cluster barriers in place of __syncthreads.
+template <bool WEIGHTED, int NW, int NCTA>
 __global__ void __launch_bounds__(NW == 1 ? K64Smem<WEIGHTED>::warps * 32 : NW * 32, NW == 1 ? K64Smem<WEIGHTED>::ctas : 1)
 als_k64_kernel(const AlsArgs a) {
   constexpr int KP = K64, CH = K64_CH, LDY = K64_LDY;
   constexpr bool COOP = NW > 1;
+  constexpr bool CLUSTER = NCTA > 1;
+  static_assert(!CLUSTER || COOP, "clusters only in the cooperative mode");
+  namespace cg = cooperative_groups;
+  const unsigned int crank = CLUSTER ? cg::this_cluster().block_rank() : 0u;   // 0: the leader CTA of the cluster
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // solo: [Lt | invd | xs | ts | y | w] per warp.  coop: [Lt | invd | xs | rs] once, then [ts | y | w] per warp.
@@ -334,7 +347,23 @@ als_k64_kernel(const AlsArgs a) {
   const float ysc = pow2_scale(*a.other_absmax);
   const float yunsc = (1.0f / ysc) * (1.0f / ysc);
   const int g = lane >> 2, tq = lane & 3;
-  const bool lead = !COOP || warp == 0;        // the warp that factors and solves
+  const bool lead = !COOP || (warp == 0 && crank == 0);   // the warp that factors and solves
+  // the leader CTA's copies of the shared accumulators (DSMEM)
+  float* Lt0 = Lt;
+  float* bs0 = bs;
+  double* xs0 = xs;
+  double* rs0 = rs;
+  if constexpr (CLUSTER) {
+    cg::cluster_group cluster = cg::this_cluster();
+    Lt0 = cluster.map_shared_rank(Lt, 0);
+    bs0 = cluster.map_shared_rank(bs, 0);
+    xs0 = cluster.map_shared_rank(xs, 0);
+    rs0 = cluster.map_shared_rank(rs, 0);
+  }
+  auto block_or_cluster_sync = [&]() {
+    if constexpr (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
+  };
+  unsigned int giant_pos = CLUSTER ? blockIdx.x / NCTA : 0u;   // cluster c takes giant rows c, c + #clusters, ...
 
   for (;;) {
     int64_t row;
@@ -345,11 +374,17 @@ als_k64_kernel(const AlsArgs a) {
       if (static_cast<int64_t>(ticket) >= a.n_rows) break;
       row = a.row_order ? a.row_order[ticket] : static_cast<int64_t>(ticket);
     } else {
-      __syncthreads();
-      if (threadIdx.x == 0) s_ticket = atomicAdd(a.counter + 1, 1u);
-      __syncthreads();
-      if (s_ticket >= *a.long_count) break;
-      row = a.long_list[s_ticket];
+      if constexpr (CLUSTER) {
+        if (giant_pos >= a.long_count[1]) break;
+        row = a.long_list[a.n_rows - 1 - giant_pos];
+        giant_pos += gridDim.x / NCTA;
+      } else {
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = atomicAdd(a.counter + 1, 1u);
+        __syncthreads();
+        if (s_ticket >= a.long_count[0]) break;
+        row = a.long_list[s_ticket];
+      }
     }
     const int64_t s = a.indptr[row];
     const int64_t nnz64 = a.indptr[row + 1] - s;
@@ -370,12 +405,14 @@ als_k64_kernel(const AlsArgs a) {
     const int nnz = static_cast<int>(nnz64);
     const int nchunk_all = (nnz + CH - 1) / CH;
     // chunks of this warp: w, w + NW, ...
-    const int nchunk = COOP ? (nchunk_all > warp ? (nchunk_all - warp + NW - 1) / NW : 0) : nchunk_all;
-    auto chunk_id = [&](int c) { return COOP ? warp + c * NW : c; };
+    constexpr int NWT = NW * NCTA;               // warps sharing the row
+    const int gw = COOP ? static_cast<int>(crank) * NW + warp : 0;
+    const int nchunk = COOP ? (nchunk_all > gw ? (nchunk_all - gw + NWT - 1) / NWT : 0) : nchunk_all;
+    auto chunk_id = [&](int c) { return COOP ? gw + c * NWT : c; };
     if constexpr (COOP) {                       // the accumulators of the row start from zero
       for (int p = threadIdx.x; p < K64_LSZ; p += NW * 32) Lt[p] = 0.f;
       if (threadIdx.x < K64) bs[threadIdx.x] = 0.f;
-      __syncthreads();
+      block_or_cluster_sync();
     }
 
     // ---- gather + Gram on the tensor cores (fp16 split operands, fp32 accumulate) --------------------------------
@@ -489,6 +526,13 @@ als_k64_kernel(const AlsArgs a) {
       atomicAdd(bs + lane, bf0);
       atomicAdd(bs + 32 + lane, bf1);
       __syncthreads();
+      if constexpr (CLUSTER) {                  // this CTA's totals -> the leader's (zeroed before the barrier above)
+        if (crank != 0) {
+          for (int p = threadIdx.x; p < K64_LSZ; p += NW * 32) atomicAdd(Lt0 + p, Lt[p]);
+          if (threadIdx.x < K64) atomicAdd(bs0 + threadIdx.x, bs[threadIdx.x]);
+        }
+        cg::this_cluster().sync();
+      }
     }
     if (lead) k64_chol(Lt, invd, bs, lane);
     // ---- back substitution, then refinement steps  x += L^-T L^-1 (b - A x)  with a float64 matrix-free residual ----
@@ -505,9 +549,13 @@ als_k64_kernel(const AlsArgs a) {
       if (lead) {
         xs[lane] = xd0;
         xs[32 + lane] = xd1;
-        if constexpr (COOP) { rs[lane] = 0.0; rs[32 + lane] = 0.0; }
       }
-      if constexpr (COOP) __syncthreads(); else __syncwarp();
+      if constexpr (COOP) { if (warp == 0) { rs[lane] = 0.0; rs[32 + lane] = 0.0; } }
+      if constexpr (COOP) block_or_cluster_sync(); else __syncwarp();
+      if constexpr (CLUSTER) {                  // every CTA works from its own copy of x
+        if (crank != 0 && threadIdx.x < K64) xs[threadIdx.x] = xs0[threadIdx.x];
+        __syncthreads();
+      }
       // r = b - A x = sum_i (p_i - w_i <y_i, x>) y_i - lambda x (- w0 G x): the right-hand side never appears on its own
       double r0 = 0.0, r1 = 0.0;
       if (lead) {
@@ -571,6 +619,10 @@ als_k64_kernel(const AlsArgs a) {
         atomicAdd(rs + lane, r0);
         atomicAdd(rs + 32 + lane, r1);
         __syncthreads();
+        if constexpr (CLUSTER) {
+          if (crank != 0 && threadIdx.x < K64) atomicAdd(rs0 + threadIdx.x, rs[threadIdx.x]);
+          cg::this_cluster().sync();
+        }
         r0 = rs[lane];
         r1 = rs[32 + lane];
         __syncthreads();                        // everybody has read xs / rs before warp 0 reuses the bytes as bs
@@ -592,7 +644,7 @@ als_k64_kernel(const AlsArgs a) {
         a.peers[pr][row * KP + 32 + lane] = xo1;
       }
     }
-    if constexpr (COOP) __syncthreads(); else __syncwarp();
+    if constexpr (COOP) block_or_cluster_sync(); else __syncwarp();
   }
 }
 
@@ -615,23 +667,41 @@ int launch_k64(rl_context* h, const AlsArgs& args_in) {
     }
     args.long_list = h->long_list;
     args.long_count = args.counter + 2;
-    RL_CUDA(h, cudaMemsetAsync(args.counter + 2, 0, sizeof(unsigned int), h->stream));
+    RL_CUDA(h, cudaMemsetAsync(args.counter + 2, 0, 2 * sizeof(unsigned int), h->stream));
     RL_CUDA(h, cudaEventRecord(h->aux_fork, h->stream));
     RL_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->aux_fork, 0));
     int64_t gf = (args.n_rows + 255) / 256;
     if (gf > 4 * h->sm_count) gf = 4 * h->sm_count;
     k64_find_long_rows_kernel<<<static_cast<unsigned>(gf), 256, 0, h->aux_stream>>>(args.indptr, args.n_rows, h->long_list, args.counter + 2);
     RL_LAUNCH_CHECK(h, "k64_find_long_rows_kernel");
-    auto coop = als_k64_kernel<WEIGHTED, K64_COOP_WARPS>;
+    auto coop = als_k64_kernel<WEIGHTED, K64_COOP_WARPS, 1>;
+    auto giant = als_k64_kernel<WEIGHTED, K64_COOP_WARPS, K64_CLUSTER>;
     constexpr size_t sh = K64Smem<WEIGHTED>::lt_bytes + K64Smem<WEIGHTED>::invd_bytes + K64Smem<WEIGHTED>::xs_bytes + sizeof(double) * K64;
     constexpr size_t pw = K64Smem<WEIGHTED>::ts_bytes + K64Smem<WEIGHTED>::y_bytes + K64Smem<WEIGHTED>::w_bytes;
     const size_t smem = sh + pw * K64_COOP_WARPS;
     RL_CUDA(h, cudaFuncSetAttribute(coop, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    {  // giant rows first (clusters of K64_CLUSTER CTAs), then the long ones
+      RL_CUDA(h, cudaFuncSetAttribute(giant, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(static_cast<unsigned>((h->sm_count / K64_CLUSTER) * K64_CLUSTER));
+      cfg.blockDim = dim3(K64_COOP_WARPS * 32);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = h->aux_stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = K64_CLUSTER;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      RL_CUDA(h, cudaLaunchKernelEx(&cfg, giant, args));
+      h->launches++;
+    }
     coop<<<static_cast<unsigned>(h->sm_count), K64_COOP_WARPS * 32, smem, h->aux_stream>>>(args);
     RL_LAUNCH_CHECK(h, "als_k64_kernel(coop)");
     RL_CUDA(h, cudaEventRecord(h->aux_join, h->aux_stream));
   }
-  auto kern = als_k64_kernel<WEIGHTED, 1>;
+  auto kern = als_k64_kernel<WEIGHTED, 1, 1>;
   constexpr int W = K64Smem<WEIGHTED>::warps;
   const size_t smem = K64Smem<WEIGHTED>::bytes * W;
   RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -139,14 +139,15 @@ def test_half_step_general_weights_vs_dense_restatement(h, precision):
 
 def test_half_step_cooperative_long_rows_weighted_and_peers(h, monkeypatch):
     """rows above K64_LONG = 2048 observations are solved by a whole CTA (partial Grams / residuals of 16 warps meet in
-    shared memory): power-law shaped row lengths, k = 50 (padded 64), general weights with w0 = 1 and a peer replica;
+    shared memory), rows above K64_GIANT = 32768 by a thread-block cluster of 8 CTAs (totals meet in the leader's shared
+    memory over DSMEM): power-law shaped row lengths, k = 50 (padded 64), general weights with w0 = 1 and a peer replica;
     checked against oracle.half_step_general and against the unweighted reference arithmetic."""
     import ctypes as C
     from devbuf import Dev, padded, unpadded
     monkeypatch.setenv("RL_ALS_NO_LONG_CACHE", "1")     # the "has long rows" answer is cached per device pointer: ask afresh
-    k, n_other = 50, 30000
+    k, n_other = 50, 90000
     rng = np.random.default_rng(9)
-    degs = np.array([3, 2048, 2049, 2500, 9000, 25000, 40, 7, 4097, 300])
+    degs = np.array([3, 2048, 2049, 2500, 9000, 25000, 40, 7, 4097, 300, 32768, 32769, 70001, 33000])
     n_rows = len(degs)
     rows = [np.sort(rng.choice(n_other, d, replace=False)) for d in degs]
     indptr = np.concatenate(([0], np.cumsum(degs))).astype(np.int64)
