@@ -558,6 +558,7 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float4* __restrict__ 
 }
 
 #include "als_k64.cuh"
+#include "als_k128.cuh"
 
 template <typename real, int KP, bool WEIGHTED>
 int launch_one(rl_context* h, const AlsArgs& args) {
@@ -686,6 +687,18 @@ int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, 
       }
       a.split_long = has_long;
       return weighted ? launch_k64<true>(h, a) : launch_k64<false>(h, a);
+    }
+    if (kp == 128 && !weighted && !getenv("RL_ALS_GENERIC")) {     // 2 x 2 blocks of the k = 64 machinery, four warps per row
+      RL_CUDA(h, cudaMemsetAsync(h->counter + 16, 0, sizeof(float), h->stream));
+      const int64_t n4 = n_other * (kp / 4);
+      int64_t g = (n4 + 255) / 256;
+      if (g > 8 * h->sm_count) g = 8 * h->sm_count;
+      if (g > 0) {
+        absmax_kernel<<<static_cast<unsigned>(g), 256, 0, h->stream>>>(reinterpret_cast<const float4*>(other), n4,
+                                                                      reinterpret_cast<float*>(h->counter + 16));
+        RL_LAUNCH_CHECK(h, "absmax_kernel");
+      }
+      return launch_k128(h, a);
     }
     return weighted ? launch_kp<float, true>(h, kp, a) : launch_kp<float, false>(h, kp, a);
   }

@@ -1,0 +1,427 @@
+// als_k128.cuh -- ALS half-step, fp32 + refinement path for 64 < padded k <= 128 (the C5 configuration).
+// Included by als.cu after als_k64.cuh (uses its 64 x 64 building blocks).
+//
+// Same arithmetic as als_k64.cuh (reference algo.py:314-322 / :324-332), one CTA of four warps per row, the 128 x 128
+// normal equations as 2 x 2 blocks of 64:
+//
+//        A = [A11  .  ]      L11 = chol(A11)             (warp 0, k64_chol)
+//            [A21  A22]      L21 = A21 L11^-T            (all warps: 16 rows each; update on the tensor cores, row-local solve)
+//                            S   = A22 - L21 L21^T       (all warps: tensor cores)
+//                            L22 = chol(S)               (warp 0, k64_chol)
+//
+//   * Gram: every warp reads the same gathered chunk (8 rows, shared buffer) and owns a part of the tiles: warp 0 the
+//     lower triangle of A11 (20 tiles), warp 1 that of A22 (20), warps 2 and 3 the upper / lower half of A21 (16 each);
+//     fp16 split operands, B fragments are A registers (see als_k64.cuh);
+//   * the right-hand side rides along with both factorisations (forward substitution), the coupling term
+//     b2 -= L21 z1 with the row-local solve of L21;
+//   * back substitution and the float64 matrix-free refinement as in the k = 64 kernel (residual: one thread per
+//     factor dimension, no atomics).
+// Unweighted (reference) mode only; weights / w0 run the general kernel.
+
+constexpr int K128 = 128;
+constexpr int K128_LDY = 132;     // row stride of a gathered row (2 LDY = 8 mod 32: conflict-free fragment reads)
+constexpr int K128_CH = 8;
+constexpr int K128_FSZ = 8 * 520; // the full 64 x 64 block A21 / L21: 8 panels of 64 rows x 8 floats, 8 floats of skew each
+
+// element (i, j) of the full block: B21[k128_f0(j >> 3) + 8 i + ((j & 7) ^ k64_swz(i))]
+__host__ __device__ constexpr int k128_f0(int K) { return 520 * K; }
+
+struct K128Smem {
+  static constexpr size_t p_bytes = sizeof(float) * K64_LSZ;          // P11, P22
+  static constexpr size_t f_bytes = sizeof(float) * K128_FSZ;         // B21
+  static constexpr size_t invd_bytes = sizeof(float) * K128;
+  static constexpr size_t xs_bytes = sizeof(double) * K128;           // x in float64; aliased by the float right-hand side
+  static constexpr size_t ts_bytes = sizeof(double) * 8;
+  static constexpr size_t y_bytes = sizeof(float) * 2 * K128_CH * K128_LDY;
+  static constexpr size_t bytes = 2 * p_bytes + f_bytes + invd_bytes + xs_bytes + ts_bytes + y_bytes;
+  static_assert(bytes % 16 == 0, "shared memory layout must keep 16-byte alignment");
+};
+
+__global__ void __launch_bounds__(128, 4) als_k128_kernel(const AlsArgs a) {
+  constexpr int KP = K128, CH = K128_CH, LDY = K128_LDY;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* P11 = reinterpret_cast<float*>(smem_raw);
+  float* P22 = P11 + K64_LSZ;
+  float* B21 = P22 + K64_LSZ;
+  float* invd = B21 + K128_FSZ;
+  double* xs = reinterpret_cast<double*>(invd + K128);
+  float* bs = reinterpret_cast<float*>(xs);
+  double* ts = xs + K128;
+  float* ybuf = reinterpret_cast<float*>(ts + 8);
+  __shared__ unsigned int s_ticket;
+
+  const float lam = static_cast<float>(a.lambda);
+  const float ysc = pow2_scale(*a.other_absmax);
+  const float yunsc = (1.0f / ysc) * (1.0f / ysc);
+  const int g = lane >> 2, tq = lane & 3;
+  const int sg = ((g >> 2) & 1) << 2;          // swizzle bit of rows 8 m + g
+  const int o0 = tq ^ sg, o1 = o0 ^ 4;         // physical positions of panel columns tq and tq + 4 in such a row
+  const int oc = (2 * tq) ^ sg;                // ... of the accumulator columns 2 tq, 2 tq + 1
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(a.counter, 1u);
+    __syncthreads();
+    const unsigned int ticket = s_ticket;
+    if (static_cast<int64_t>(ticket) >= a.n_rows) break;
+    const int64_t row = a.row_order ? a.row_order[ticket] : static_cast<int64_t>(ticket);
+    const int64_t s = a.indptr[row];
+    const int64_t nnz64 = a.indptr[row + 1] - s;
+    if (nnz64 <= 0) continue;   // reference: rows with no observation keep their previous value (algo.py:316-317)
+    const int nnz = static_cast<int>(nnz64);
+    const int nchunk = (nnz + CH - 1) / CH;
+
+    // all threads: cp.async gather of chunk c into buffer `yb` (8 rows x 32 pieces of 16 bytes; short chunks zero-filled)
+    auto gather = [&](int c, float* yb) {
+      const int cnt = min(CH, nnz - c * CH);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int p = tid + 128 * q;
+        const int r = p >> 5, c4 = p & 31;
+        const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(yb + r * LDY + 4 * c4));
+        if (r < cnt) {
+          const int idx = a.indices[s + c * CH + r];
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(a.other + static_cast<int64_t>(idx) * KP + 4 * c4));
+        } else {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 0;\n" ::"r"(dst), "l"(a.other));
+        }
+      }
+      cp_async_commit();
+    };
+
+    // ---- gather + Gram: warp 0 -> A11, warp 1 -> A22 (lower triangles), warps 2 / 3 -> upper / lower half of A21 ------
+    float acc[20][4];
+    float bsum = 0.f;                            // right-hand side entry `tid` (fp32: the refinement residual is b-free)
+#pragma unroll
+    for (int t = 0; t < 20; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+    const int abase = (warp == 0) ? 0 : (warp == 3 ? 6 : 4);   // first 16-column group of the A side
+    for (int c = -1; c < nchunk; ++c) {
+      const int buf = c & 1;
+      if (c + 1 < nchunk) {
+        gather(c + 1, ybuf + (buf ^ 1) * CH * LDY);
+        if (c < 0) continue;
+        cp_async_wait<1>();
+      } else {
+        if (c < 0) continue;
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      const float* yb = ybuf + buf * CH * LDY;
+#pragma unroll
+      for (int r = 0; r < CH; ++r) bsum += yb[r * LDY + tid];
+      const float* y0 = yb + (2 * tq) * LDY + g;
+      const float* y1 = y0 + LDY;
+      if (warp < 2) {
+        uint32_t hi[4][2], lo[4][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+          k64_split_h2(y0[16 * (abase + mi)] * ysc, y1[16 * (abase + mi)] * ysc, hi[mi][0], lo[mi][0]);
+          k64_split_h2(y0[16 * (abase + mi) + 8] * ysc, y1[16 * (abase + mi) + 8] * ysc, hi[mi][1], lo[mi][1]);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], hi[mi][0], hi[mi][1], hi[nj >> 1][nj & 1]);
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], hi[mi][0], hi[mi][1], lo[nj >> 1][nj & 1]);
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], lo[mi][0], lo[mi][1], hi[nj >> 1][nj & 1]);
+      } else {
+        uint32_t ahi[2][2], alo[2][2], bhi[4][2], blo[4][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+          k64_split_h2(y0[16 * (abase + mi)] * ysc, y1[16 * (abase + mi)] * ysc, ahi[mi][0], alo[mi][0]);
+          k64_split_h2(y0[16 * (abase + mi) + 8] * ysc, y1[16 * (abase + mi) + 8] * ysc, ahi[mi][1], alo[mi][1]);
+        }
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+          k64_split_h2(y0[16 * mb] * ysc, y1[16 * mb] * ysc, bhi[mb][0], blo[mb][0]);
+          k64_split_h2(y0[16 * mb + 8] * ysc, y1[16 * mb + 8] * ysc, bhi[mb][1], blo[mb][1]);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int nj = 0; nj < 8; ++nj) mma_f16(acc[8 * mi + nj], ahi[mi][0], ahi[mi][1], bhi[nj >> 1][nj & 1]);
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int nj = 0; nj < 8; ++nj) mma_f16(acc[8 * mi + nj], ahi[mi][0], ahi[mi][1], blo[nj >> 1][nj & 1]);
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int nj = 0; nj < 8; ++nj) mma_f16(acc[8 * mi + nj], alo[mi][0], alo[mi][1], bhi[nj >> 1][nj & 1]);
+      }
+      __syncthreads();                           // the buffer may be overwritten by the gather after next
+    }
+
+    // ---- accumulator tiles -> shared memory (unscaled, + lambda I on the diagonal blocks) ---------------------------
+    if (warp < 2) {
+      float* P = warp == 0 ? P11 : P22;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int nj = 0; nj <= 2 * mi + 1; ++nj) {
+          float (&d)[4] = acc[k64_tile(mi, nj)];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int gi = 16 * mi + g + ((e & 2) ? 8 : 0), gj = 8 * nj + 2 * tq + (e & 1);
+            d[e] *= yunsc;
+            if (nj >= 2 * mi && gi == gj) d[e] += (64 * warp + gi < a.k) ? lam : 1.0f;
+          }
+          float* pn = P + k64_pb0(nj);
+          if (nj <= 2 * mi) *reinterpret_cast<float2*>(pn + 8 * (16 * mi + g) + oc) = make_float2(d[0], d[1]);
+          *reinterpret_cast<float2*>(pn + 8 * (16 * mi + 8 + g) + oc) = make_float2(d[2], d[3]);
+        }
+    } else {
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int nj = 0; nj < 8; ++nj) {
+          const float (&d)[4] = acc[8 * mi + nj];
+          float* pn = B21 + k128_f0(nj) + 8 * (16 * (2 * (warp - 2) + mi) + g) + oc;
+          *reinterpret_cast<float2*>(pn) = make_float2(d[0] * yunsc, d[1] * yunsc);
+          *reinterpret_cast<float2*>(pn + 64) = make_float2(d[2] * yunsc, d[3] * yunsc);
+        }
+    }
+    bs[tid] = bsum;
+    __syncthreads();
+
+    // ---- L11 = chol(A11), z1 = L11^-1 b1 ------------------------------------------------------------------------------
+    if (warp == 0) k64_chol(P11, invd, bs, lane);
+    __syncthreads();
+
+    // ---- L21 = A21 L11^-T (warp w: rows 16 w .. 16 w + 15 of the block), b2 -= L21 z1 -----------------------------------
+    {
+      const int rr = min(lane, 15);              // lanes 16..31 shadow row 15 (results dropped)
+      const int srow = k64_swz(rr);              // 16 w is a multiple of 16: swizzle bit of row 16 w + r is that of r
+      float bb = bs[64 + 16 * warp + rr];
+#pragma unroll 1
+      for (int J = 0; J < 8; ++J) {
+        float* fj = B21 + k128_f0(J) + 8 * (16 * warp);
+        if (J > 0) {
+          float d[4];
+          {
+            const float2 t0 = *reinterpret_cast<const float2*>(fj + 8 * g + oc);
+            const float2 t1 = *reinterpret_cast<const float2*>(fj + 8 * (8 + g) + oc);
+            d[0] = t0.x; d[1] = t0.y; d[2] = t1.x; d[3] = t1.y;
+          }
+#pragma unroll 1
+          for (int K = 0; K < J; ++K) {
+            const float* pk = P11 + k64_pb0(K);
+            const float* pa = B21 + k128_f0(K) + 8 * (16 * warp + g);
+            uint32_t bh[2], bl[2], ah[4], al[4];
+            k64_split(pk[8 * (8 * J + g) + o0], bh[0], bl[0]);
+            k64_split(pk[8 * (8 * J + g) + o1], bh[1], bl[1]);
+            k64_split_neg(pa[o0], ah[0], al[0]);
+            k64_split_neg(pa[64 + o0], ah[1], al[1]);
+            k64_split_neg(pa[o1], ah[2], al[2]);
+            k64_split_neg(pa[64 + o1], ah[3], al[3]);
+            mma_tf32(d, ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+            mma_tf32(d, ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+            mma_tf32(d, al[0], al[1], al[2], al[3], bh[0], bh[1]);
+          }
+          *reinterpret_cast<float2*>(fj + 8 * g + oc) = make_float2(d[0], d[1]);
+          *reinterpret_cast<float2*>(fj + 8 * (8 + g) + oc) = make_float2(d[2], d[3]);
+          __syncwarp();
+        }
+        // row-local solve against the 8 x 8 diagonal block J of L11 (broadcast loads)
+        float av[8];
+        {
+          const float4 lo = *reinterpret_cast<const float4*>(fj + 8 * rr + srow);
+          const float4 hi = *reinterpret_cast<const float4*>(fj + 8 * rr + (srow ^ 4));
+          av[0] = lo.x; av[1] = lo.y; av[2] = lo.z; av[3] = lo.w; av[4] = hi.x; av[5] = hi.y; av[6] = hi.z; av[7] = hi.w;
+        }
+        const float* dj = P11 + k64_pb0(J) + 64 * J;     // row c of the diagonal block at dj + 8 c
+        const float4 i0 = *reinterpret_cast<const float4*>(invd + 8 * J), i1 = *reinterpret_cast<const float4*>(invd + 8 * J + 4);
+        const float4 z0 = *reinterpret_cast<const float4*>(bs + 8 * J), z1v = *reinterpret_cast<const float4*>(bs + 8 * J + 4);
+        const float iv[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+        const float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1v.x, z1v.y, z1v.z, z1v.w};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float accv = av[c];
+          if (c > 0) {
+            const int sc = k64_swz(c);
+            const float4 dl = *reinterpret_cast<const float4*>(dj + 8 * c + sc);
+            const float4 dh = *reinterpret_cast<const float4*>(dj + 8 * c + (sc ^ 4));
+            const float dv[8] = {dl.x, dl.y, dl.z, dl.w, dh.x, dh.y, dh.z, dh.w};
+#pragma unroll
+            for (int cp = 0; cp < c; ++cp) accv = fmaf(-av[cp], dv[cp], accv);
+          }
+          av[c] = accv * iv[c];
+          bb = fmaf(-av[c], zv[c], bb);
+        }
+        if (lane < 16) {
+          *reinterpret_cast<float4*>(fj + 8 * rr + srow) = make_float4(av[0], av[1], av[2], av[3]);
+          *reinterpret_cast<float4*>(fj + 8 * rr + (srow ^ 4)) = make_float4(av[4], av[5], av[6], av[7]);
+        }
+        __syncwarp();
+      }
+      if (lane < 16) bs[64 + 16 * warp + rr] = bb;
+    }
+    __syncthreads();
+
+    // ---- S = A22 - L21 L21^T on the tensor cores: warp 0: tiles (3, 0..3), 1: (3, 4..7), 2: (2, 0..5), 3: (0, 0..1), (1, 0..3)
+    {
+      const int ntile = warp < 2 ? 4 : 6;
+#pragma unroll 1
+      for (int t = 0; t < ntile; ++t) {
+        int mi, nj;
+        if (warp == 0) { mi = 3; nj = t; }
+        else if (warp == 1) { mi = 3; nj = 4 + t; }
+        else if (warp == 2) { mi = 2; nj = t; }
+        else { mi = t < 2 ? 0 : 1; nj = t < 2 ? t : t - 2; }
+        float* pn = P22 + k64_pb0(nj);
+        const bool upper_ok = nj <= 2 * mi;      // rows 16 mi + g of the odd tile nj = 2 mi + 1 lie above the diagonal
+        float d[4];
+        {
+          const float2 t0 = *reinterpret_cast<const float2*>(pn + 8 * (16 * mi + g) + oc);
+          const float2 t1 = *reinterpret_cast<const float2*>(pn + 8 * (16 * mi + 8 + g) + oc);
+          d[0] = t0.x; d[1] = t0.y; d[2] = t1.x; d[3] = t1.y;
+        }
+#pragma unroll 2
+        for (int K = 0; K < 8; ++K) {
+          const float* pa = B21 + k128_f0(K) + 8 * (16 * mi + g);
+          const float* pb = B21 + k128_f0(K) + 8 * (8 * nj + g);
+          uint32_t bh[2], bl[2], ah[4], al[4];
+          k64_split(pb[o0], bh[0], bl[0]);
+          k64_split(pb[o1], bh[1], bl[1]);
+          k64_split_neg(pa[o0], ah[0], al[0]);
+          k64_split_neg(pa[64 + o0], ah[1], al[1]);
+          k64_split_neg(pa[o1], ah[2], al[2]);
+          k64_split_neg(pa[64 + o1], ah[3], al[3]);
+          mma_tf32(d, ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+          mma_tf32(d, ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+          mma_tf32(d, al[0], al[1], al[2], al[3], bh[0], bh[1]);
+        }
+        if (upper_ok) *reinterpret_cast<float2*>(pn + 8 * (16 * mi + g) + oc) = make_float2(d[0], d[1]);
+        *reinterpret_cast<float2*>(pn + 8 * (16 * mi + 8 + g) + oc) = make_float2(d[2], d[3]);
+      }
+    }
+    __syncthreads();
+
+    // ---- L22 = chol(S), z2 = L22^-1 (b2 - L21 z1); back substitution; refinement -----------------------------------------
+    if (warp == 0) k64_chol(P22, invd + 64, bs + 64, lane);
+    // x = L^-T z for z in bs[0..127]  (warp 0): x2 = L22^-T z2, x1 = L11^-T (z1 - L21^T x2)
+    auto backsolve = [&](float& x1a, float& x1b, float& x2a, float& x2b) {
+      x2a = bs[64 + lane]; x2b = bs[96 + lane];
+      x1a = bs[lane]; x1b = bs[32 + lane];
+      __syncwarp();
+      k64_backward(P22, invd + 64, x2a, x2b, lane);
+      const float* c0 = B21 + k128_f0(lane >> 3);          // L21[i][l]      = c0[8 i + ((l & 7) ^ swz(i))]
+      const float* c1 = B21 + k128_f0(4 + (lane >> 3));    // L21[i][l + 32]
+      const int q0 = lane & 7, q1 = q0 ^ 4;
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) {
+        const float xi = __shfl_sync(FULL_MASK, x2a, i);
+        const int q = (i & 4) ? q1 : q0;
+        x1a = fmaf(-c0[8 * i + q], xi, x1a);
+        x1b = fmaf(-c1[8 * i + q], xi, x1b);
+      }
+#pragma unroll 8
+      for (int i = 32; i < 64; ++i) {
+        const float xi = __shfl_sync(FULL_MASK, x2b, i - 32);
+        const int q = (i & 4) ? q1 : q0;
+        x1a = fmaf(-c0[8 * i + q], xi, x1a);
+        x1b = fmaf(-c1[8 * i + q], xi, x1b);
+      }
+      k64_backward(P11, invd, x1a, x1b, lane);
+    };
+    double xd[4] = {0.0, 0.0, 0.0, 0.0};          // warp 0: x entries lane, lane + 32, lane + 64, lane + 96
+    for (int it = 0;; ++it) {
+      if (warp == 0) {
+        float x1a, x1b, x2a, x2b;
+        backsolve(x1a, x1b, x2a, x2b);
+        xd[0] += static_cast<double>(x1a); xd[1] += static_cast<double>(x1b);
+        xd[2] += static_cast<double>(x2a); xd[3] += static_cast<double>(x2b);
+      }
+      if (it >= a.ir_steps) break;
+      if (warp == 0) {
+        xs[lane] = xd[0]; xs[32 + lane] = xd[1]; xs[64 + lane] = xd[2]; xs[96 + lane] = xd[3];
+      }
+      __syncthreads();
+      // r = b - A x = sum_i (1 - <y_i, x>) y_i - lambda x : thread `tid` owns entry `tid`
+      double r = -((tid < a.k) ? a.lambda : 1.0) * xs[tid];
+      for (int c = -1; c < nchunk; ++c) {
+        const int buf = c & 1;
+        if (c + 1 < nchunk) {
+          gather(c + 1, ybuf + (buf ^ 1) * CH * LDY);
+          if (c < 0) continue;
+          cp_async_wait<1>();
+        } else {
+          if (c < 0) continue;
+          cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float* yb = ybuf + buf * CH * LDY;
+        const int cnt = min(CH, nnz - c * CH);
+#pragma unroll
+        for (int rr2 = 0; rr2 < 2; ++rr2) {       // warp w: rows 2 w, 2 w + 1 of the chunk
+          const int i = 2 * warp + rr2;
+          const float* yr = yb + i * LDY;
+          double t = 0.0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) t = fma(static_cast<double>(yr[lane + 32 * q]), xs[lane + 32 * q], t);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL_MASK, t, o);
+          if (lane == 0) ts[i] = (i < cnt) ? 1.0 - t : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < CH; ++i) r = fma(ts[i], static_cast<double>(yb[i * LDY + tid]), r);
+        __syncthreads();
+      }
+      bs[tid] = static_cast<float>(r);            // xs is dead from here on: its bytes take the right-hand side
+      __syncthreads();
+      if (warp == 0) {
+        k64_forward(P11, invd, bs, lane);         // z1
+        {                                          // r2 -= L21 z1 : lane owns rows lane, lane + 32 of L21
+          float b2a = bs[64 + lane], b2b = bs[96 + lane];
+          const int s0 = k64_swz(lane);            // swz(lane + 32) is the same
+#pragma unroll 1
+          for (int K = 0; K < 8; ++K) {
+            const float4 z0 = *reinterpret_cast<const float4*>(bs + 8 * K), z1v = *reinterpret_cast<const float4*>(bs + 8 * K + 4);
+            const float* fa = B21 + k128_f0(K) + 8 * lane;
+            const float4 al0 = *reinterpret_cast<const float4*>(fa + s0), ah0 = *reinterpret_cast<const float4*>(fa + (s0 ^ 4));
+            const float4 al1 = *reinterpret_cast<const float4*>(fa + 256 + s0), ah1 = *reinterpret_cast<const float4*>(fa + 256 + (s0 ^ 4));
+            b2a -= al0.x * z0.x + al0.y * z0.y + al0.z * z0.z + al0.w * z0.w + ah0.x * z1v.x + ah0.y * z1v.y + ah0.z * z1v.z + ah0.w * z1v.w;
+            b2b -= al1.x * z0.x + al1.y * z0.y + al1.z * z0.z + al1.w * z0.w + ah1.x * z1v.x + ah1.y * z1v.y + ah1.z * z1v.z + ah1.w * z1v.w;
+          }
+          __syncwarp();
+          bs[64 + lane] = b2a;
+          bs[96 + lane] = b2b;
+          __syncwarp();
+        }
+        k64_forward(P22, invd + 64, bs + 64, lane);   // z2
+      }
+    }
+    if (warp == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float xo = (lane + 32 * q < a.k) ? static_cast<float>(xd[q]) : 0.0f;
+        a.mine[row * KP + lane + 32 * q] = xo;
+        for (int pr = 0; pr < a.n_peers; ++pr) a.peers[pr][row * KP + lane + 32 * q] = xo;
+      }
+    }
+  }
+}
+
+int launch_k128(rl_context* h, const AlsArgs& args) {
+  auto kern = als_k128_kernel;
+  const size_t smem = K128Smem::bytes;
+  RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  RL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+  if (per_sm < 1) return fail(h, RL_ERR_CUDA, "als_k128: kernel does not fit on an SM (smem %zu)", smem);
+  int64_t grid = static_cast<int64_t>(h->sm_count) * per_sm;
+  if (grid > args.n_rows) grid = args.n_rows;
+  if (grid < 1) grid = 1;
+  RL_CUDA(h, cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), h->stream));
+  kern<<<static_cast<unsigned>(grid), 128, smem, h->stream>>>(args);
+  RL_LAUNCH_CHECK(h, "als_k128_kernel");
+  return RL_OK;
+}

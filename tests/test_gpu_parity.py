@@ -599,7 +599,7 @@ def test_cold_start_under_one_second():
     )
     root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
     best = min(float(subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True,
-                                    check=True).stdout.strip()) for _ in range(2))
+                                    check=True).stdout.strip()) for _ in range(3))
     assert best < 1.0, best
 
 
