@@ -326,7 +326,7 @@ def run_b200(args, w):
             "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "ms_per_rank": per_rank,
         }
         if world == 1 and not args.no_cpu:
-            v, s, desc = cpu_reference_leg(w, inputs, 20_000, 20_000, 2_000)
+            v, s, desc = cpu_reference_leg(w, inputs, 60_000, 60_000, 6_000)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": blas_threads(), "kind": "port", "sample": desc,
                                     "seconds": s}
         _emit(line)

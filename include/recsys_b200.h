@@ -126,9 +126,16 @@ int rl_ipc_close(rl_handle h, void* dev_ptr);
 /* G = Y^T Y, float64 (kp x kp row-major), Y (n x kp) float32.  Used for the w0 term above. */
 int rl_gram_dev(rl_handle h, const float* y_dev, int64_t n, int k, double* gram_dev);
 
+/* CSR of the transposed observation pattern (rows = items; the reference scans dense columns instead, algo.py:325),
+ * built on the device by a stable sort of the (column, row) pairs.  indptr_t_dev: n_cols + 1 int64, indices_t_dev: nnz int32,
+ * ascending inside each row.  nnz = indptr[n_rows] is passed by the caller (no device -> host read). */
+int rl_csr_transpose_dev(rl_handle h, int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr_dev,
+                         const int32_t* indices_dev, int64_t* indptr_t_dev, int32_t* indices_t_dev);
+
 /* whole fit on HOST buffers: replaces RecommenderSystem._fit_als, algo.py:300-337 (minus the RNG draw, which
  * stays with the caller so that np.random semantics are kept).  user_f / item_f: (n x k) float64 (RL_F64) or
- * float32 (RL_F32) host arrays, in: initial factors, out: fitted factors.  *_t is the CSR of the transpose. */
+ * float32 (RL_F32) host arrays, in: initial factors, out: fitted factors.  *_t is the CSR of the transpose; pass
+ * indptr_t = indices_t = NULL to have it built on the device (rl_csr_transpose_dev) underneath the first user half-step. */
 int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k,
                     const int64_t* indptr, const int32_t* indices,
                     const int64_t* indptr_t, const int32_t* indices_t,

@@ -45,6 +45,7 @@ SIGNATURES = {
     "rl_ipc_open": (_i32, [_vp, _vp, _i64, C.POINTER(_vp)]),
     "rl_ipc_close": (_i32, [_vp, _vp]),
     "rl_gram_dev": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "rl_csr_transpose_dev": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "rl_als_fit_host": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _dbl, _i32, _i32, _vp, _vp, _i32]),
     "rl_score_topn_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _dbl, _vp, _vp, _i32, _vp, _vp, _i32]),
     "rl_score_dump_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32]),

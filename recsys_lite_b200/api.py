@@ -30,7 +30,7 @@ import numpy as np
 from scipy import sparse
 
 from . import _ffi
-from .csr import observed_pattern, transpose_pattern
+from .csr import observed_pattern
 
 MAX_FACTORS = 128   # rl_padded_k
 MAX_TOP_N = 128     # on-chip list capacity of the selection kernels
@@ -114,11 +114,11 @@ class RecommenderSystem:
             if user_f.shape != (n_users, factors) or item_f.shape != (n_items, factors):
                 raise ValueError("init factors must have shapes (n_users, factors) and (n_items, factors)")
         indptr, indices = observed_pattern(ratings)
-        indptr_t, indices_t = transpose_pattern(indptr, indices, n_items)
         if n_users and n_items and iterations > 0:
             h = _ffi.default_handle()
+            # the transposed pattern (users of every item) is built on the device, underneath the first user half-step
             h.call("rl_als_fit_host", n_users, n_items, factors, _ffi.ptr(indptr), _ffi.ptr(indices),
-                   _ffi.ptr(indptr_t), _ffi.ptr(indices_t), int(iterations), float(lambda_),
+                   None, None, int(iterations), float(lambda_),
                    _PRECISIONS[precision], int(ir_steps), _ffi.ptr(user_f), _ffi.ptr(item_f), _ffi.RL_F64)
         return {"user_factors": user_f, "item_factors": item_f, "factors": factors}
 

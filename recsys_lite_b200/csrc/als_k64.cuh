@@ -490,6 +490,8 @@ als_k64_kernel(const AlsArgs a) {
 
     // ---- + lambda I (+ w0 Y^T Y), accumulator tiles -> panel storage: element e of tile (mi, nj) is
     //      A[16 mi + g + 8 (e >> 1)][8 nj + 2 tq + (e & 1)]; the first 8 rows of the odd tiles nj = 2 mi + 1 lie above the diagonal
+    // (cooperative modes: the warps, then the CTAs of the cluster, add their parts one after the other -- a fixed
+    //  order, so that the result does not depend on timing)
     {
       const int oc = (2 * tq) ^ (((g >> 2) & 1) << 2);
 #pragma unroll
@@ -506,30 +508,43 @@ als_k64_kernel(const AlsArgs a) {
               if (nj >= 2 * mi && gi == gj) d[e] += (gi < a.k) ? lam : 1.0f;
             }
           }
-          float* pn = Lt + k64_pb0(nj);
-          if constexpr (!COOP) {
-            if (nj <= 2 * mi) *reinterpret_cast<float2*>(pn + 8 * (16 * mi + g) + oc) = make_float2(d[0], d[1]);
-            *reinterpret_cast<float2*>(pn + 8 * (16 * mi + 8 + g) + oc) = make_float2(d[2], d[3]);
-          } else {
-            if (nj <= 2 * mi) { atomicAdd(pn + 8 * (16 * mi + g) + oc, d[0]); atomicAdd(pn + 8 * (16 * mi + g) + oc + 1, d[1]); }
-            atomicAdd(pn + 8 * (16 * mi + 8 + g) + oc, d[2]);
-            atomicAdd(pn + 8 * (16 * mi + 8 + g) + oc + 1, d[3]);
-          }
         }
+#pragma unroll 1
+      for (int w = 0; w < NW; ++w) {
+        if (!COOP || warp == w) {
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int nj = 0; nj <= 2 * mi + 1; ++nj) {
+              const float (&d)[4] = acc[k64_tile(mi, nj)];
+              float2* p0 = reinterpret_cast<float2*>(Lt + k64_pb0(nj) + 8 * (16 * mi + g) + oc);
+              float2* p1 = reinterpret_cast<float2*>(Lt + k64_pb0(nj) + 8 * (16 * mi + 8 + g) + oc);
+              if constexpr (!COOP) {
+                if (nj <= 2 * mi) *p0 = make_float2(d[0], d[1]);
+                *p1 = make_float2(d[2], d[3]);
+              } else {
+                if (nj <= 2 * mi) { const float2 o = *p0; *p0 = make_float2(o.x + d[0], o.y + d[1]); }
+                const float2 o = *p1;
+                *p1 = make_float2(o.x + d[2], o.y + d[3]);
+              }
+            }
+          if constexpr (COOP) { bs[lane] += bf0; bs[32 + lane] += bf1; }
+        }
+        if constexpr (COOP) __syncthreads();
+      }
     }
     // ---- blocked Cholesky on the tensor cores, forward substitution fused ------------------------------------
     if constexpr (!COOP) {
       bs[lane] = bf0;
       bs[32 + lane] = bf1;
       __syncwarp();
-    } else {
-      atomicAdd(bs + lane, bf0);
-      atomicAdd(bs + 32 + lane, bf1);
-      __syncthreads();
-      if constexpr (CLUSTER) {                  // this CTA's totals -> the leader's (zeroed before the barrier above)
-        if (crank != 0) {
-          for (int p = threadIdx.x; p < K64_LSZ; p += NW * 32) atomicAdd(Lt0 + p, Lt[p]);
-          if (threadIdx.x < K64) atomicAdd(bs0 + threadIdx.x, bs[threadIdx.x]);
+    } else if constexpr (CLUSTER) {             // every CTA's totals -> the leader's, CTA after CTA (DSMEM)
+      cg::this_cluster().sync();                // the leader's own warps are done with its copy
+#pragma unroll 1
+      for (unsigned int cta = 1; cta < NCTA; ++cta) {
+        if (crank == cta) {
+          for (int p = threadIdx.x; p < K64_LSZ; p += NW * 32) Lt0[p] += Lt[p];
+          if (threadIdx.x < K64) bs0[threadIdx.x] += bs[threadIdx.x];
         }
         cg::this_cluster().sync();
       }
@@ -615,13 +630,19 @@ als_k64_kernel(const AlsArgs a) {
         }
         __syncwarp();
       }
-      if constexpr (COOP) {                     // partial residuals of the warps meet in shared memory
-        atomicAdd(rs + lane, r0);
-        atomicAdd(rs + 32 + lane, r1);
-        __syncthreads();
+      if constexpr (COOP) {                     // partial residuals: warp after warp, then CTA after CTA (fixed order)
+#pragma unroll 1
+        for (int w = 0; w < NW; ++w) {
+          if (warp == w) { rs[lane] += r0; rs[32 + lane] += r1; }
+          __syncthreads();
+        }
         if constexpr (CLUSTER) {
-          if (crank != 0 && threadIdx.x < K64) atomicAdd(rs0 + threadIdx.x, rs[threadIdx.x]);
           cg::this_cluster().sync();
+#pragma unroll 1
+          for (unsigned int cta = 1; cta < NCTA; ++cta) {
+            if (crank == cta && threadIdx.x < K64) rs0[threadIdx.x] += rs[threadIdx.x];
+            cg::this_cluster().sync();
+          }
         }
         r0 = rs[lane];
         r1 = rs[32 + lane];

@@ -443,6 +443,12 @@ int rl_ipc_close(rl_handle h, void* dev_ptr) {
   return fail(h, RL_ERR_INVALID, "rl_ipc_close: pointer was not returned by rl_ipc_open");
 }
 
+int rl_csr_transpose_dev(rl_handle h, int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr_dev,
+                         const int32_t* indices_dev, int64_t* indptr_t_dev, int32_t* indices_t_dev) {
+  RL_NEED(h);
+  return launch_csr_transpose(h, n_rows, n_cols, nnz, indptr_dev, indices_dev, indptr_t_dev, indices_t_dev);
+}
+
 int rl_gram_dev(rl_handle h, const float* y_dev, int64_t n, int k, double* gram_dev) {
   RL_NEED(h);
   return launch_gram(h, y_dev, n, k, gram_dev);
@@ -455,9 +461,13 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const 
   const int kp = rl::padded_k(k);
   if (kp == 0) return fail(h, RL_ERR_INVALID, "rl_als_fit_host: k=%d outside [1, 128]", k);
   if (n_users < 0 || n_items < 0 || iterations < 0) return fail(h, RL_ERR_INVALID, "rl_als_fit_host: negative size");
-  if (!indptr || !indptr_t || !user_f || !item_f) return fail(h, RL_ERR_INVALID, "rl_als_fit_host: null pointer");
+  if (!indptr || !user_f || !item_f) return fail(h, RL_ERR_INVALID, "rl_als_fit_host: null pointer");
+  if ((indptr_t == nullptr) != (indices_t == nullptr) && indptr[n_users] > 0)
+    return fail(h, RL_ERR_INVALID, "rl_als_fit_host: pass both transposed arrays or neither");
+  const bool device_transpose = indptr_t == nullptr;     // built on the device underneath the first user half-step
   const int64_t nnz = indptr[n_users];
-  if (nnz != indptr_t[n_items]) return fail(h, RL_ERR_INVALID, "rl_als_fit_host: CSR and transposed CSR disagree on nnz");
+  if (!device_transpose && nnz != indptr_t[n_items])
+    return fail(h, RL_ERR_INVALID, "rl_als_fit_host: CSR and transposed CSR disagree on nnz");
   // Host traffic runs on the copy stream, ordered against the kernels by events:
   //   copy:    V, user CSR | U (initial), item CSR ................... | U back (during the last item half-step)
   //   compute:              | user half-step, empty rows <- initial U | item half-step ... | V back
@@ -489,9 +499,17 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const 
     RL_TRY(ev_user_ready.record(h, cs));
     RL_TRY(factors_h2d(h, user_f, factor_dtype, n_users, k, u_upload, st_u));
     RL_TRY(ev_u0_ready.record(h, cs));
-    RL_CUDA(h, cudaMemcpyAsync(d_tp.p, indptr_t, sizeof(int64_t) * (n_items + 1), cudaMemcpyHostToDevice, cs));
-    if (nnz) RL_CUDA(h, cudaMemcpyAsync(d_tx.p, indices_t, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, cs));
-    RL_TRY(ev_item_ready.record(h, cs));
+    if (!device_transpose) {
+      RL_CUDA(h, cudaMemcpyAsync(d_tp.p, indptr_t, sizeof(int64_t) * (n_items + 1), cudaMemcpyHostToDevice, cs));
+      if (nnz) RL_CUDA(h, cudaMemcpyAsync(d_tx.p, indices_t, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, cs));
+      RL_TRY(ev_item_ready.record(h, cs));
+    }
+  }
+  if (device_transpose) {   // on the second compute stream, beside the first user half-step
+    RL_TRY(ev_user_ready.wait(h, h->aux_stream));
+    StreamScope on_aux(h, h->aux_stream);
+    RL_TRY(launch_csr_transpose(h, n_users, n_items, nnz, d_ip.as<int64_t>(), d_ix.as<int32_t>(), d_tp.as<int64_t>(), d_tx.as<int32_t>()));
+    RL_TRY(ev_item_ready.record(h, h->aux_stream));
   }
   RL_TRY(ev_user_ready.wait(h, ks));
   if (!lazy_u) RL_TRY(ev_u0_ready.wait(h, ks));

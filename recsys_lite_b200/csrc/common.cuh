@@ -82,6 +82,8 @@ int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, 
                          float* mine, double lambda, double w0, const double* gram0, int precision,
                          int ir_steps, const int32_t* row_order, int n_peers = 0, float* const* peers = nullptr);
 int launch_gram(rl_context* h, const float* y, int64_t n, int k, double* gram);
+int launch_csr_transpose(rl_context* h, int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                         int64_t* indptr_t, int32_t* indices_t);
 int launch_score_topn(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k,
                       const int64_t* seen_indptr, const int32_t* seen_indices, double gbias, const float* ubias,
                       const float* ibias, int n, int32_t* idx_out, double* score_out, int mode);

@@ -761,3 +761,30 @@ def test_full_size_config4_sampled_properties(h):
             tol = 4 * np.finfo(np.float32).eps * np.abs(sc[want]).max()
             bad += not np.allclose(np.sort(sc[idx[u]])[::-1], sc[want], rtol=0, atol=tol)
     assert bad == 0
+
+
+def test_csr_transpose_dev_and_fit_without_host_transpose(h):
+    """rl_csr_transpose_dev (stable device sort of the (item, user) pairs) equals the host transposition (scipy csr -> csc,
+    sorted), incl. empty rows / columns; rl_als_fit_host with NULL transposed arrays equals the call that gets them."""
+    from devbuf import Dev
+    from recsys_lite_b200 import _ffi
+    n_users, n_items, k = 5000, 1300, 64
+    indptr, indices = gen.synth_pattern(n_users, n_items, mean_deg=9, seed=21, skew=True)
+    deg = np.diff(indptr)
+    deg[[0, 77]] = 0
+    keep = np.repeat(deg > 0, np.diff(indptr))
+    indices = indices[keep]
+    indptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    ti, tx = o_als.transpose_pattern(indptr, indices, n_items)
+    d_ip, d_ix = Dev(h, indptr), Dev(h, indices)
+    d_tp, d_tx = Dev(h, shape=(n_items + 1,), dtype=np.int64), Dev(h, shape=(len(indices),), dtype=np.int32)
+    h.call("rl_csr_transpose_dev", n_users, n_items, len(indices), d_ip.ptr, d_ix.ptr, d_tp.ptr, d_tx.ptr)
+    assert np.array_equal(d_tp.get(), ti) and np.array_equal(d_tx.get(), tx)
+    rng = np.random.default_rng(2)
+    u0, v0 = rng.random((n_users, k)), rng.random((n_items, k))
+    ua, va, ub, vb = u0.copy(), v0.copy(), u0.copy(), v0.copy()
+    h.call("rl_als_fit_host", n_users, n_items, k, _ffi.ptr(indptr), _ffi.ptr(indices), _ffi.ptr(ti), _ffi.ptr(tx), 2, 0.01, 0, 1,
+           _ffi.ptr(ua), _ffi.ptr(va), _ffi.RL_F64)
+    h.call("rl_als_fit_host", n_users, n_items, k, _ffi.ptr(indptr), _ffi.ptr(indices), None, None, 2, 0.01, 0, 1,
+           _ffi.ptr(ub), _ffi.ptr(vb), _ffi.RL_F64)
+    assert np.array_equal(ua, ub) and np.array_equal(va, vb)
