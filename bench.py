@@ -347,10 +347,10 @@ def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
     steps = max(1, min(args.steps, 3))
     if world == 1:
         pin = lambda a: _pinned_copy(a)                    # noqa: E731
-        p_ip, p_ix, p_tp, p_tx = pin(indptr), pin(indices), pin(indptr_t), pin(indices_t)
+        p_ip, p_ix = pin(indptr), pin(indices)      # the item-side pattern is built on the device (as RecommenderSystem.fit does)
         p_u, p_v = pin(u0), pin(v0)
         idx = _ffi.pinned_empty((nu, n), np.int32)
-        h2d = p_ip.nbytes + p_ix.nbytes + p_tp.nbytes + p_tx.nbytes + 2 * (p_u.nbytes + p_v.nbytes) + p_ip.nbytes + p_ix.nbytes
+        h2d = p_ip.nbytes + p_ix.nbytes + 2 * (p_u.nbytes + p_v.nbytes) + p_ip.nbytes + p_ix.nbytes
         d2h = p_u.nbytes + p_v.nbytes + idx.nbytes
         times = []
         for i in range(1 + steps):
@@ -358,7 +358,7 @@ def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
             p_v[:] = v0
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            h.call("rl_als_fit_host", nu, ni, k, _ffi.ptr(p_ip), _ffi.ptr(p_ix), _ffi.ptr(p_tp), _ffi.ptr(p_tx), 1,
+            h.call("rl_als_fit_host", nu, ni, k, _ffi.ptr(p_ip), _ffi.ptr(p_ix), None, None, 1,
                    float(w["lam"]), prec, args.ir_steps, _ffi.ptr(p_u), _ffi.ptr(p_v), _ffi.RL_F32)
             h.call("rl_recommend_host", _ffi.ptr(p_u), _ffi.ptr(p_v), _ffi.RL_F32, nu, ni, k, _ffi.ptr(p_ip), _ffi.ptr(p_ix),
                    0.0, None, None, n, _ffi.ptr(idx), None, args.score_mode)

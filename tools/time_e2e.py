@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--items", type=int, default=100000)
     ap.add_argument("--k", type=int, default=64)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--device-transpose", action="store_true", help="pass NULL for the transposed pattern (built on the device)")
     args = ap.parse_args()
     h = _ffi.default_handle()
     nu, ni, k = args.users, args.items, args.k
@@ -39,8 +40,8 @@ def main():
         p_v[:] = v0
         h.synchronize()
         t0 = time.perf_counter()
-        h.call("rl_als_fit_host", nu, ni, k, _ffi.ptr(p_ip), _ffi.ptr(p_ix), _ffi.ptr(p_tp), _ffi.ptr(p_tx), 1, 0.01, 0, 1,
-               _ffi.ptr(p_u), _ffi.ptr(p_v), _ffi.RL_F32)
+        h.call("rl_als_fit_host", nu, ni, k, _ffi.ptr(p_ip), _ffi.ptr(p_ix), None if args.device_transpose else _ffi.ptr(p_tp),
+               None if args.device_transpose else _ffi.ptr(p_tx), 1, 0.01, 0, 1, _ffi.ptr(p_u), _ffi.ptr(p_v), _ffi.RL_F32)
         t1 = time.perf_counter()
         h.call("rl_recommend_host", _ffi.ptr(p_u), _ffi.ptr(p_v), _ffi.RL_F32, nu, ni, k, _ffi.ptr(p_ip), _ffi.ptr(p_ix), 0.0, None,
                None, 10, _ffi.ptr(idx), None, 0)
