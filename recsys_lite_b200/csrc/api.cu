@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of librecsys_b200.so (include/recsys_b200.h): handle, memory helpers, host-buffer wrappers.
 #include <cuda.h>
 #include <cstdarg>
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -488,6 +489,22 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const 
     RL_TRY(d_u0.alloc(h, sizeof(float) * n_users * kp));
     u_upload = d_u0.as<float>();
   }
+  // Row ranges of the first user half-step: 1/8, 1/8, 1/4, 1/2 of the observations (large problems only), so that it
+  // starts after an eighth of the index upload instead of all of it.
+  int n_parts = 1;
+  int64_t part_row[5] = {0, n_users, n_users, n_users, n_users};
+  if (iterations > 0 && nnz >= (int64_t(1) << 22) && n_users >= 4096) {
+    const double frac[3] = {0.125, 0.25, 0.5};
+    n_parts = 4;
+    for (int c = 0; c < 3; ++c) {
+      const int64_t target = static_cast<int64_t>(frac[c] * static_cast<double>(nnz));
+      part_row[c + 1] = std::lower_bound(indptr, indptr + n_users + 1, target) - indptr;
+      if (part_row[c + 1] > n_users) part_row[c + 1] = n_users;
+      if (part_row[c + 1] < part_row[c]) part_row[c + 1] = part_row[c];
+    }
+    part_row[4] = n_users;
+  }
+  Event ev_part[4];
   Event ev_alloc;
   RL_TRY(ev_alloc.record(h, ks));      // the buffers come from the stream-ordered pool on the compute stream
   RL_TRY(ev_alloc.wait(h, cs));
@@ -495,7 +512,11 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const 
     StreamScope on_copy(h, cs);
     RL_TRY(factors_h2d(h, item_f, factor_dtype, n_items, k, d_v.as<float>(), st_v));
     RL_CUDA(h, cudaMemcpyAsync(d_ip.p, indptr, sizeof(int64_t) * (n_users + 1), cudaMemcpyHostToDevice, cs));
-    if (nnz) RL_CUDA(h, cudaMemcpyAsync(d_ix.p, indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, cs));
+    for (int c = 0; c < n_parts; ++c) {       // the first user half-step starts on part 0 while the other parts travel
+      const int64_t o0 = indptr[part_row[c]], o1 = indptr[part_row[c + 1]];
+      if (o1 > o0) RL_CUDA(h, cudaMemcpyAsync(d_ix.as<int32_t>() + o0, indices + o0, sizeof(int32_t) * (o1 - o0), cudaMemcpyHostToDevice, cs));
+      RL_TRY(ev_part[c].record(h, cs));
+    }
     RL_TRY(ev_user_ready.record(h, cs));
     RL_TRY(factors_h2d(h, user_f, factor_dtype, n_users, k, u_upload, st_u));
     RL_TRY(ev_u0_ready.record(h, cs));
@@ -511,12 +532,22 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const 
     RL_TRY(launch_csr_transpose(h, n_users, n_items, nnz, d_ip.as<int64_t>(), d_ix.as<int32_t>(), d_tp.as<int64_t>(), d_tx.as<int32_t>()));
     RL_TRY(ev_item_ready.record(h, h->aux_stream));
   }
-  RL_TRY(ev_user_ready.wait(h, ks));
+  if (iterations == 0 || n_parts == 1) RL_TRY(ev_user_ready.wait(h, ks));
   if (!lazy_u) RL_TRY(ev_u0_ready.wait(h, ks));
   bool u_on_copy = false;
   for (int it = 0; it < iterations; ++it) {
-    RL_TRY(launch_als_half_step(h, n_users, n_items, k, d_ip.as<int64_t>(), d_ix.as<int32_t>(), nullptr, nullptr,
-                                d_v.as<float>(), d_u.as<float>(), lambda, 0.0, nullptr, precision, ir_steps, nullptr));
+    if (it == 0 && n_parts > 1) {
+      for (int c = 0; c < n_parts; ++c) {      // indptr holds absolute offsets: pass its window, keep the indices whole
+        RL_TRY(ev_part[c].wait(h, ks));
+        const int64_t r0 = part_row[c], r1 = part_row[c + 1];
+        if (r1 > r0)
+          RL_TRY(launch_als_half_step(h, r1 - r0, n_items, k, d_ip.as<int64_t>() + r0, d_ix.as<int32_t>(), nullptr, nullptr,
+                                      d_v.as<float>(), d_u.as<float>() + r0 * kp, lambda, 0.0, nullptr, precision, ir_steps, nullptr));
+      }
+    } else {
+      RL_TRY(launch_als_half_step(h, n_users, n_items, k, d_ip.as<int64_t>(), d_ix.as<int32_t>(), nullptr, nullptr,
+                                  d_v.as<float>(), d_u.as<float>(), lambda, 0.0, nullptr, precision, ir_steps, nullptr));
+    }
     if (it == 0) {
       RL_TRY(ev_u0_ready.wait(h, ks));
       int64_t g = (n_users * (kp / 4) + 255) / 256;
@@ -586,10 +617,24 @@ int rl_recommend_host(rl_handle h, const void* user_f, const void* item_f, int f
   if (user_bias) RL_TRY(upload(h, d_ub, user_bias, sizeof(float) * n_users));
   if (item_bias) RL_TRY(upload(h, d_ib, item_bias, sizeof(float) * n_items));
   cudaStream_t cs = h->copy_stream, ks = h->stream;
+  // chunk boundaries, never a fraction of a sweep; large calls start with two small chunks (2 and 6 sweeps) so that
+  // the first scoring kernel waits for a small upload only and each later upload hides behind the chunk before it
   const int64_t sweep = static_cast<int64_t>(128) * h->sm_count;
-  int64_t per = ((n_users / 4 + sweep - 1) / sweep) * sweep;            // about four chunks, never a fraction of a sweep
-  if (per <= 0 || n_users < 2 * sweep) per = n_users;
-  const int n_chunks = static_cast<int>((n_users + per - 1) / per);
+  const int64_t n_sweeps = (n_users + sweep - 1) / sweep;
+  std::vector<int64_t> bound{0};
+  if (n_sweeps >= 16) {
+    bound.push_back(2 * sweep);
+    bound.push_back(8 * sweep);
+    const int64_t rest = n_sweeps - 8, per3 = (rest + 2) / 3;
+    for (int c = 1; c <= 2; ++c) bound.push_back((8 + c * per3) * sweep);
+  } else if (n_sweeps >= 2) {
+    const int64_t per4 = (n_sweeps + 3) / 4;
+    for (int c = 1; c * per4 < n_sweeps; ++c) bound.push_back(c * per4 * sweep);
+  }
+  while (bound.back() >= n_users) bound.pop_back();
+  if (bound.empty()) bound.push_back(0);
+  bound.push_back(n_users);
+  const int n_chunks = static_cast<int>(bound.size()) - 1;
   std::vector<Event> ready(n_chunks), done(n_chunks);
   std::vector<DevBuf> stage(n_chunks);
   Event ev_alloc, ev_copy_done;
@@ -600,7 +645,7 @@ int rl_recommend_host(rl_handle h, const void* user_f, const void* item_f, int f
     RL_TRY(factors_h2d(h, item_f, factor_dtype, n_items, k, d_v.as<float>(), st_v));
     if (seen_indptr) RL_CUDA(h, cudaMemcpyAsync(d_sp.p, seen_indptr, sizeof(int64_t) * (n_users + 1), cudaMemcpyHostToDevice, cs));
     for (int c = 0; c < n_chunks; ++c) {
-      const int64_t r0 = c * per, r1 = (r0 + per < n_users) ? r0 + per : n_users;
+      const int64_t r0 = bound[c], r1 = bound[c + 1];
       const size_t es = factor_dtype == RL_F64 ? 8 : 4;
       RL_TRY(factors_h2d(h, static_cast<const char*>(user_f) + static_cast<size_t>(r0) * k * es, factor_dtype, r1 - r0, k,
                          d_u.as<float>() + r0 * kp, stage[c]));
@@ -612,7 +657,7 @@ int rl_recommend_host(rl_handle h, const void* user_f, const void* item_f, int f
   }
   unsigned int overflow_total = 0;
   for (int c = 0; c < n_chunks; ++c) {
-    const int64_t r0 = c * per, r1 = (r0 + per < n_users) ? r0 + per : n_users;
+    const int64_t r0 = bound[c], r1 = bound[c + 1];
     RL_TRY(ready[c].wait(h, ks));
     h->last_overflow = 0;
     // seen_indptr holds absolute offsets into the full seen_indices array: pass its window, keep the indices whole

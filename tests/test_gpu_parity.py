@@ -300,6 +300,35 @@ def test_host_entry_points_overlapped_chunks_equal_device_path(h, k, dtype, bias
     assert np.array_equal(idx, d_idx.get()) and np.array_equal(val, d_val.get())
 
 
+def test_host_entry_points_large_call_partitions_equal_device_path(h):
+    """Above 4 M observations rl_als_fit_host runs the first user half-step in four row ranges (1/8, 1/8, 1/4, 1/2 of
+    the observations) behind the index upload, and from 16 sweeps on rl_recommend_host starts with two small chunks:
+    same bits as one device call each."""
+    from devbuf import Dev, padded, unpadded
+    from recsys_lite_b200 import _ffi
+    n_users, n_items, k, n = 320_000, 2_000, 64, 10
+    indptr, indices = gen.synth_pattern(n_users, n_items, mean_deg=14, seed=5)
+    assert indptr[-1] >= 1 << 22 and n_users >= 16 * 128 * 148
+    rng = np.random.default_rng(5)
+    u0 = rng.random((n_users, k), dtype=np.float32)
+    v0 = rng.random((n_items, k), dtype=np.float32)
+    uh, vh = u0.copy(), v0.copy()
+    h.call("rl_als_fit_host", n_users, n_items, k, _ffi.ptr(indptr), _ffi.ptr(indices), None, None, 1, 0.01, 0, 1,
+           _ffi.ptr(uh), _ffi.ptr(vh), _ffi.RL_F32)
+    ti, tx = o_als.transpose_pattern(indptr, indices, n_items)
+    d_u, d_v = padded(h, u0, k), padded(h, v0, k)
+    d_ip, d_ix, d_tp, d_tx = Dev(h, indptr), Dev(h, indices), Dev(h, ti), Dev(h, tx)
+    h.call("rl_als_half_step_dev", n_users, n_items, k, d_ip.ptr, d_ix.ptr, None, None, d_v.ptr, d_u.ptr, 0.01, 0.0, None, 0, 1, None)
+    h.call("rl_als_half_step_dev", n_items, n_users, k, d_tp.ptr, d_tx.ptr, None, None, d_u.ptr, d_v.ptr, 0.01, 0.0, None, 0, 1, None)
+    assert np.array_equal(uh, unpadded(h, d_u, k, np.float32)) and np.array_equal(vh, unpadded(h, d_v, k, np.float32))
+    idx = np.empty((n_users, n), np.int32)
+    h.call("rl_recommend_host", _ffi.ptr(uh), _ffi.ptr(vh), _ffi.RL_F32, n_users, n_items, k, _ffi.ptr(indptr), _ffi.ptr(indices),
+           0.0, None, None, n, _ffi.ptr(idx), None, 0)
+    d_idx = Dev(h, shape=(n_users, n), dtype=np.int32)
+    h.call("rl_score_topn_dev", d_u.ptr, n_users, d_v.ptr, n_items, k, d_ip.ptr, d_ix.ptr, 0.0, None, None, n, d_idx.ptr, None, 0)
+    assert np.array_equal(idx, d_idx.get())
+
+
 @pytest.mark.parametrize("case", ["lit", "order", "ragged", "rand_f64", "rand_f32"])
 def test_top_n_api_matches_reference_golden(golden_dir, case):
     """top_n(est, known, n) vs the reference's output (algo.py:587-659): shape, dtype, indices up to ties."""
