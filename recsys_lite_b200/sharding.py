@@ -162,15 +162,23 @@ class ShardedProblem:
         self.V[:, : self.k].copy_(torch.from_numpy(np.ascontiguousarray(v_host, dtype=np.float32)))
 
     # -- one ALS half-step on this rank's rows, then the exchange -------------------------------------------
-    def user_half_step(self, lam, precision, ir_steps):
+    def user_half_step(self, lam, precision, ir_steps, rows=None):
+        """rows = (r0, r1): only that part of this rank's user range (callers that stream the pattern in, part by part)."""
         ulo, uhi = self.plan.users
+        r0, r1 = (0, uhi - ulo) if rows is None else rows
+        if r1 <= r0:
+            return
         if getattr(self, "peer_stores", False):
-            self.h.call("rl_als_half_step_peers_dev", uhi - ulo, self.n_items, self.k, self.up.data_ptr(), self.ux.data_ptr(),
-                        None, None, self.V.data_ptr(), self.U[ulo:].data_ptr(), float(lam), 0.0, None, precision,
-                        ir_steps, None, self.plan.world - 1, self._peers_u)
+            import ctypes as C
+            peers = self._peers_u
+            if r0:
+                peers = (C.c_void_p * (self.plan.world - 1))(*[p + r0 * 4 * self.kp for p in self._peers_u])
+            self.h.call("rl_als_half_step_peers_dev", r1 - r0, self.n_items, self.k, self.up[r0:].data_ptr(), self.ux.data_ptr(),
+                        None, None, self.V.data_ptr(), self.U[ulo + r0:].data_ptr(), float(lam), 0.0, None, precision,
+                        ir_steps, None, self.plan.world - 1, peers)
         else:
-            self.h.call("rl_als_half_step_dev", uhi - ulo, self.n_items, self.k, self.up.data_ptr(), self.ux.data_ptr(),
-                        None, None, self.V.data_ptr(), self.U[ulo:].data_ptr(), float(lam), 0.0, None, precision,
+            self.h.call("rl_als_half_step_dev", r1 - r0, self.n_items, self.k, self.up[r0:].data_ptr(), self.ux.data_ptr(),
+                        None, None, self.V.data_ptr(), self.U[ulo + r0:].data_ptr(), float(lam), 0.0, None, precision,
                         ir_steps, None)
 
     def item_half_step(self, lam, precision, ir_steps):
