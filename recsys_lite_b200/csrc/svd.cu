@@ -325,17 +325,48 @@ int launch_svd_topk(rl_context* h, const float* m_dev, int64_t m, int64_t n, int
   if (nn > 1) {
     const int np = (nn + 1) & ~1;
     const double tol = 1e-15;
-    for (int sweep = 0; sweep < 60; ++sweep) {
-      RL_CUDA(h, cudaMemsetAsync(rot, 0, sizeof(unsigned int), h->stream));
-      for (int round = 0; round < np - 1; ++round) {
+    // One sweep = np - 1 dependent launches of a few microseconds each: launch-bound.  The sweep is captured once into
+    // a CUDA graph (counter reset + all rounds) and replayed until a sweep rotates nothing; small problems and a
+    // failed capture take the plain launches.
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    if (np - 1 >= 32 && cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      bool ok = cudaMemsetAsync(rot, 0, sizeof(unsigned int), h->stream) == cudaSuccess;
+      for (int round = 0; ok && round < np - 1; ++round) {
         jacobi_round_kernel<<<np / 2, 256, 0, h->stream>>>(w, v, nn, np, round, tol, scal, rot);
-        RL_LAUNCH_CHECK(h, "jacobi_round_kernel");
+        ok = cudaGetLastError() == cudaSuccess;
+      }
+      if (cudaStreamEndCapture(h->stream, &graph) != cudaSuccess || !ok || !graph ||
+          cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        graph = nullptr;
+        exec = nullptr;
+        (void)cudaGetLastError();
+      }
+    }
+    int rc_sweeps = RL_OK;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+      cudaError_t e = cudaSuccess;
+      if (exec) {
+        e = cudaGraphLaunch(exec, h->stream);
+        if (e == cudaSuccess) h->launches += np - 1;
+      } else {
+        e = cudaMemsetAsync(rot, 0, sizeof(unsigned int), h->stream);
+        for (int round = 0; e == cudaSuccess && round < np - 1; ++round) {
+          jacobi_round_kernel<<<np / 2, 256, 0, h->stream>>>(w, v, nn, np, round, tol, scal, rot);
+          e = cudaGetLastError();
+          if (e == cudaSuccess) h->launches++;
+        }
       }
       unsigned int done = 0;
-      RL_CUDA(h, cudaMemcpyAsync(&done, rot, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
-      RL_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (e == cudaSuccess) e = cudaMemcpyAsync(&done, rot, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      if (e != cudaSuccess) { rc_sweeps = cuda_fail(h, e, "jacobi sweep"); break; }
       if (done == 0) break;
     }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc_sweeps != RL_OK) return rc_sweeps;
   }
   select_topk_kernel<<<2 * h->sm_count, 256, 0, h->stream>>>(w, v, nn, k, lam, nullptr, nullptr);
   RL_LAUNCH_CHECK(h, "select_topk_kernel");
