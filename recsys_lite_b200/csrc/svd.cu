@@ -116,7 +116,42 @@ __global__ void __launch_bounds__(256) jacobi_round_kernel(double* __restrict__ 
   if (p > q) { const int t = p; p = q; q = t; }
   double* wp = w + static_cast<int64_t>(p) * n;
   double* wq = w + static_cast<int64_t>(q) * n;
+  double* vp = v + static_cast<int64_t>(p) * n;
+  double* vq = v + static_cast<int64_t>(q) * n;
   double al = 0.0, be = 0.0, ga = 0.0;
+  if (n <= 1024) {
+    // Columns of up to 1024 entries live in registers for the whole round: all four columns are requested at once (one
+    // L2 round trip instead of two in a row around the reduction -- the round is a chain of latencies, not of work).
+    double x[4], y[4], c4[4], d4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = threadIdx.x + 256 * e;
+      const bool in = r < n;
+      x[e] = in ? wp[r] : 0.0; y[e] = in ? wq[r] : 0.0;
+      c4[e] = in ? vp[r] : 0.0; d4[e] = in ? vq[r] : 0.0;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { al = fma(x[e], x[e], al); be = fma(y[e], y[e], be); ga = fma(x[e], y[e], ga); }
+    block_sum3(al, be, ga, red);
+    const double floor2r = (1e-14 * scal[0]) * (1e-14 * scal[0]);
+    if (al <= floor2r || be <= floor2r) return;
+    if (fabs(ga) <= tol * sqrt(al * be)) return;
+    const double zeta = (be - al) / (2.0 * ga);
+    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = threadIdx.x + 256 * e;
+      if (r < n) {
+        wp[r] = c * x[e] - sn * y[e];
+        wq[r] = sn * x[e] + c * y[e];
+        vp[r] = c * c4[e] - sn * d4[e];
+        vq[r] = sn * c4[e] + c * d4[e];
+      }
+    }
+    if (threadIdx.x == 0) atomicAdd(rotations, 1u);
+    return;
+  }
   for (int r = threadIdx.x; r < n; r += 256) {
     const double x = wp[r], y = wq[r];
     al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
@@ -129,8 +164,6 @@ __global__ void __launch_bounds__(256) jacobi_round_kernel(double* __restrict__ 
   const double zeta = (be - al) / (2.0 * ga);
   const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
   const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-  double* vp = v + static_cast<int64_t>(p) * n;
-  double* vq = v + static_cast<int64_t>(q) * n;
   for (int r = threadIdx.x; r < n; r += 256) {
     const double x = wp[r], y = wq[r];
     wp[r] = c * x - s * y;
