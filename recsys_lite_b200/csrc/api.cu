@@ -655,16 +655,23 @@ int rl_recommend_host(rl_handle h, const void* user_f, const void* item_f, int f
       RL_TRY(ready[c].record(h, cs));
     }
   }
+  // rows the tensor-core pass cannot finish are collected over all chunks and scored exactly once at the end: no host
+  // round trip and no small launch per chunk
+  DevBuf d_over;
+  RL_TRY(d_over.alloc(h, 256 + sizeof(int32_t) * n_users));
+  RL_CUDA(h, cudaMemsetAsync(d_over.p, 0, 256, ks));
+  rl::ScoreDefer defer{reinterpret_cast<int32_t*>(static_cast<char*>(d_over.p) + 256), static_cast<unsigned int*>(d_over.p), 0};
   unsigned int overflow_total = 0;
   for (int c = 0; c < n_chunks; ++c) {
     const int64_t r0 = bound[c], r1 = bound[c + 1];
     RL_TRY(ready[c].wait(h, ks));
     h->last_overflow = 0;
+    defer.row_offset = r0;
     // seen_indptr holds absolute offsets into the full seen_indices array: pass its window, keep the indices whole
     RL_TRY(launch_score_topn(h, d_u.as<float>() + r0 * kp, r1 - r0, d_v.as<float>(), n_items, k,
                              seen_indptr ? d_sp.as<int64_t>() + r0 : nullptr, seen_indptr ? d_sx.as<int32_t>() : nullptr, global_bias,
                              user_bias ? d_ub.as<float>() + r0 : nullptr, item_bias ? d_ib.as<float>() : nullptr, n,
-                             d_idx.as<int32_t>() + r0 * n, score_out ? d_sc.as<double>() + r0 * n : nullptr, mode));
+                             d_idx.as<int32_t>() + r0 * n, score_out ? d_sc.as<double>() + r0 * n : nullptr, mode, &defer));
     overflow_total += h->last_overflow;
     RL_TRY(done[c].record(h, ks));
     RL_TRY(done[c].wait(h, cs));
@@ -672,7 +679,33 @@ int rl_recommend_host(rl_handle h, const void* user_f, const void* item_f, int f
     if (score_out)
       RL_CUDA(h, cudaMemcpyAsync(score_out + r0 * n, d_sc.as<double>() + r0 * n, sizeof(double) * (r1 - r0) * n, cudaMemcpyDeviceToHost, cs));
   }
-  h->last_overflow = overflow_total;
+  unsigned int n_over = 0;
+  RL_CUDA(h, cudaMemcpyAsync(&n_over, defer.count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ks));
+  RL_CUDA(h, cudaStreamSynchronize(ks));
+  if (n_over > 0) {
+    RL_TRY(launch_score_overflow(h, d_u.as<float>(), n_users, d_v.as<float>(), n_items, k, seen_indptr ? d_sp.as<int64_t>() : nullptr,
+                                 seen_indptr ? d_sx.as<int32_t>() : nullptr, n, d_idx.as<int32_t>(), score_out ? d_sc.as<double>() : nullptr,
+                                 defer.rows, n_over));
+    // their rows were copied home before they were final: send them again (a handful of rows, or everything)
+    std::vector<int32_t> rows(n_over <= 256 ? n_over : 0);
+    if (!rows.empty()) RL_CUDA(h, cudaMemcpyAsync(rows.data(), defer.rows, sizeof(int32_t) * n_over, cudaMemcpyDeviceToHost, ks));
+    RL_TRY(ev_copy_done.record(h, cs));          // the chunk downloads come first
+    RL_TRY(ev_copy_done.wait(h, ks));
+    RL_CUDA(h, cudaStreamSynchronize(ks));
+    if (!rows.empty()) {
+      for (int32_t r : rows) {
+        RL_CUDA(h, cudaMemcpyAsync(idx_out + static_cast<int64_t>(r) * n, d_idx.as<int32_t>() + static_cast<int64_t>(r) * n,
+                                   sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ks));
+        if (score_out)
+          RL_CUDA(h, cudaMemcpyAsync(score_out + static_cast<int64_t>(r) * n, d_sc.as<double>() + static_cast<int64_t>(r) * n,
+                                     sizeof(double) * n, cudaMemcpyDeviceToHost, ks));
+      }
+    } else {
+      RL_CUDA(h, cudaMemcpyAsync(idx_out, d_idx.p, sizeof(int32_t) * n_users * n, cudaMemcpyDeviceToHost, ks));
+      if (score_out) RL_CUDA(h, cudaMemcpyAsync(score_out, d_sc.p, sizeof(double) * n_users * n, cudaMemcpyDeviceToHost, ks));
+    }
+  }
+  h->last_overflow = overflow_total + n_over;
   RL_TRY(ev_copy_done.record(h, cs));
   RL_TRY(ev_copy_done.wait(h, ks));
   RL_CUDA(h, cudaStreamSynchronize(ks));

@@ -84,9 +84,22 @@ int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, 
 int launch_gram(rl_context* h, const float* y, int64_t n, int k, double* gram);
 int launch_csr_transpose(rl_context* h, int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr, const int32_t* indices,
                          int64_t* indptr_t, int32_t* indices_t);
+// Callers that score one problem in several row ranges (rl_recommend_host) collect the rows the tensor-core pass hands
+// to the exact kernel in ONE list of absolute row numbers and finish them with a single launch_score_overflow at the
+// end, instead of a host round trip and a small launch per range.
+struct ScoreDefer {
+  int32_t* rows;            // device, room for every row of the whole problem
+  unsigned int* count;      // device, zeroed by the caller
+  int64_t row_offset;       // absolute row number of row 0 of this call
+};
 int launch_score_topn(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k,
                       const int64_t* seen_indptr, const int32_t* seen_indices, double gbias, const float* ubias,
-                      const float* ibias, int n, int32_t* idx_out, double* score_out, int mode);
+                      const float* ibias, int n, int32_t* idx_out, double* score_out, int mode,
+                      const ScoreDefer* defer = nullptr);
+// the deferred rows: exact kernel over the whole problem's arrays (all pointers at row 0); n_rows from the counter
+int launch_score_overflow(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k,
+                          const int64_t* seen_indptr, const int32_t* seen_indices, int n, int32_t* idx_out, double* score_out,
+                          const int32_t* rows, unsigned int n_rows);
 int launch_score_dump(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k, float* out,
                       int64_t ld, int terms);
 int launch_topn_dense(rl_context* h, const void* est, int est_dtype, const void* known, int known_dtype,

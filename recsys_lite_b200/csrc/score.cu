@@ -153,7 +153,7 @@ int launch_dense_error(rl_context* h, const void* pred, int pdtype, const void* 
 }
 
 bool score_tc_supported(int kp, int n, int64_t n_users, int64_t n_items, const float* ubias, const float* ibias, double gbias);
-int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int64_t dump_ld, int terms);
+int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int64_t dump_ld, int terms, const ScoreDefer* defer = nullptr);
 
 int launch_score_dump(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k, float* out, int64_t ld,
                       int terms) {
@@ -166,7 +166,7 @@ int launch_score_dump(rl_context* h, const float* uf, int64_t n_users, const flo
 
 int launch_score_topn(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k,
                       const int64_t* seen_indptr, const int32_t* seen_indices, double gbias, const float* ubias,
-                      const float* ibias, int n, int32_t* idx_out, double* score_out, int mode) {
+                      const float* ibias, int n, int32_t* idx_out, double* score_out, int mode, const ScoreDefer* defer) {
   const int kp = padded_k(k);
   if (kp == 0) return fail(h, RL_ERR_INVALID, "score_topn: k=%d outside [1, 128]", k);
   if (n <= 0) return fail(h, RL_ERR_INVALID, "score_topn: n must be positive, got %d", n);
@@ -180,8 +180,17 @@ int launch_score_topn(rl_context* h, const float* uf, int64_t n_users, const flo
   if (mode < RL_SCORE_AUTO || mode > RL_SCORE_TENSOR_TF32X1) return fail(h, RL_ERR_INVALID, "score_topn: unknown mode %d", mode);
   if ((mode == RL_SCORE_TENSOR || mode == RL_SCORE_TENSOR_TF32X1) && !tc_ok)
     return fail(h, RL_ERR_INVALID, "score_topn: tensor-core path needs k <= 128, n <= 16, >= 1024 items and no bias terms");
-  if (mode != RL_SCORE_EXACT && tc_ok) return launch_score_tc(h, kp, a, nullptr, 0, mode == RL_SCORE_TENSOR_TF32X1 ? 1 : 3);
+  if (mode != RL_SCORE_EXACT && tc_ok) return launch_score_tc(h, kp, a, nullptr, 0, mode == RL_SCORE_TENSOR_TF32X1 ? 1 : 3, defer);
   return launch_score_exact(h, kp, a);
+}
+
+int launch_score_overflow(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k,
+                          const int64_t* seen_indptr, const int32_t* seen_indices, int n, int32_t* idx_out, double* score_out,
+                          const int32_t* rows, unsigned int n_rows) {
+  if (n_rows == 0) return RL_OK;
+  ScoreArgs a{uf, vf, n_users, n_items, seen_indptr, seen_indices, 0.0, nullptr, nullptr, n, idx_out, score_out, rows,
+              static_cast<int64_t>(n_rows), true};
+  return launch_score_exact(h, padded_k(k), a);
 }
 
 int launch_topn_dense(rl_context* h, const void* est, int est_dtype, const void* known, int known_dtype,

@@ -92,6 +92,7 @@ struct TcArgs {
   const float* vmax;        // max_i |v_i|_2
   float err;                // relative error bound of the approximate scores (TC_ERR1 / TC_ERR3)
   int32_t* overflow_rows;   // rows that need the exact kernel
+  int64_t row_offset;       // added to the row numbers written there (callers that score a problem in row ranges)
   unsigned int* overflow_count;
   float* dump;              // debug: raw tensor-core scores, (n_users_padded x dump_ld)
   int64_t dump_ld;
@@ -508,7 +509,7 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
       if (!valid) continue;
       if (overflow) {
         const unsigned slot = atomicAdd(a.overflow_count, 1u);
-        a.overflow_rows[slot] = static_cast<int32_t>(user);
+        a.overflow_rows[slot] = static_cast<int32_t>(user + a.row_offset);
         continue;
       }
       double ex[TC_SETS * TC_CAND];
@@ -816,7 +817,7 @@ bool score_tc_supported(int kp, int n, int64_t n_users, int64_t n_items, const f
 
 // tensor-core candidate pass + in-kernel exact re-scoring; overflow rows are finished by the exact kernel.
 // terms: 1 = single fp16 product, 3 = split operands (default).  kp: padded k of the caller's factor rows.
-int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int64_t dump_ld, int terms) {
+int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int64_t dump_ld, int terms, const ScoreDefer* defer) {
   if (terms != 1 && terms != 3) return fail(h, RL_ERR_INVALID, "score_tc: terms must be 1 or 3");
   const int kph = kp <= 64 ? 64 : 128;         // fp16 row width of the tensor-core operands (zero padded)
   // scratch: vmax (4 B) | overflow count (4 B) | debug counters | overflow rows (n_users x 4 B) | V_hi | V_lo
@@ -864,6 +865,7 @@ int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int
   a.seen_indptr = sa.seen_indptr; a.seen_indices = sa.seen_indices; a.n = sa.n; a.idx_out = sa.idx_out; a.score_out = sa.score_out;
   a.vmax = vmax; a.err = terms == 3 ? TC_ERR3 : TC_ERR1;
   a.overflow_rows = orows; a.overflow_count = ocount; a.dump = dump; a.dump_ld = dump_ld;
+  if (defer && !dump) { a.overflow_rows = defer->rows; a.overflow_count = defer->count; a.row_offset = defer->row_offset; }
   a.n_user_tiles = static_cast<int>((sa.n_users + TC_BM - 1) / TC_BM);
   a.n_item_tiles = static_cast<int>((sa.n_items + TC_BN - 1) / TC_BN);
   const bool want_dbg = getenv("RL_TC_DEBUG") != nullptr;
@@ -872,6 +874,7 @@ int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int
   if (kph == 64) rc = launch_tc_k<64>(h, terms, dump != nullptr, mv, mvlo, a);
   else rc = launch_tc_k<128>(h, terms, dump != nullptr, mv, mvlo, a);
   if (rc != RL_OK || dump) return rc;
+  if (defer && !want_dbg) return RL_OK;        // the caller finishes the listed rows (launch_score_overflow)
   // rows whose candidate buffer overflowed: exact kernel on the list (needs the count on the host)
   unsigned int n_over = 0;
   RL_CUDA(h, cudaMemcpyAsync(&n_over, ocount, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));

@@ -589,6 +589,31 @@ def test_tensor_core_topn_heavy_users_and_overflow(h):
     assert np.array_equal(d_idx.get(), ref)
 
 
+@pytest.mark.parametrize("n_users", [200, 700])
+def test_recommend_host_finishes_overflow_rows_once(h, n_users):
+    """rl_recommend_host collects the rows the tensor-core pass cannot finish (here: massive ties) over all chunks and
+    scores them exactly in one launch at the end; their rows travel home again (one by one up to 256 rows, else the
+    whole result): same indices and scores as the exact kernel."""
+    from devbuf import Dev, padded
+    from recsys_lite_b200 import _ffi
+    k, n, n_items = 64, 10, 2100
+    rng = np.random.default_rng(n_users)
+    uf = (rng.integers(0, 2, (n_users, k)) * 0.5).astype(np.float32)
+    vf = (rng.integers(0, 2, (n_items, k)) * 0.5).astype(np.float32)
+    uf[:, 6:] = 0                                       # scores in {0, .25, ..., 1.5}: hundreds of items tie at the top of every row
+    indptr, indices = gen.synth_pattern(n_users, n_items, mean_deg=30, seed=3)
+    idx = np.empty((n_users, n), np.int32)
+    val = np.empty((n_users, n), np.float64)
+    h.call("rl_recommend_host", _ffi.ptr(uf), _ffi.ptr(vf), _ffi.RL_F32, n_users, n_items, k, _ffi.ptr(indptr), _ffi.ptr(indices),
+           0.0, None, None, n, _ffi.ptr(idx), _ffi.ptr(val), 0)
+    over = h.lib.rl_last_overflow_rows(h.h)
+    assert over > (256 if n_users == 700 else 0) and (n_users == 700 or over <= 256)
+    d_u, d_v, d_ip, d_ix = padded(h, uf, k), padded(h, vf, k), Dev(h, indptr), Dev(h, indices)
+    d_idx, d_val = Dev(h, shape=(n_users, n), dtype=np.int32), Dev(h, shape=(n_users, n), dtype=np.float64)
+    h.call("rl_score_topn_dev", d_u.ptr, n_users, d_v.ptr, n_items, k, d_ip.ptr, d_ix.ptr, 0.0, None, None, n, d_idx.ptr, d_val.ptr, 1)
+    assert np.array_equal(idx, d_idx.get()) and np.array_equal(val, d_val.get())
+
+
 def test_benchmark_entry_points_and_cli(tmp_path, capsys):
     """benchmark_algorithm (algo.py:746-827), quick_benchmark (benchmark.py:524-555) and the benchmark command
     (cli.py:153-211) on a 60 x 30 matrix: result keys, error handling, the Time | RMSE | MAE line."""
