@@ -239,7 +239,7 @@ int launch_score_exact_kr(rl_context* h, const ScoreArgs& a_in) {
   if (grid * 2 <= h->sm_count && item_tiles >= 16) {
     int64_t slices = (2 * static_cast<int64_t>(h->sm_count) + grid - 1) / grid;
     if (slices > item_tiles / 4) slices = item_tiles / 4;
-    if (slices > 64) slices = 64;
+    if (slices > 512) slices = 512;
     const int64_t tiles_per = (item_tiles + slices - 1) / slices;
     a.slice_items = tiles_per * SE_IT;
     a.slices = static_cast<int>((item_tiles + tiles_per - 1) / tiles_per);
