@@ -363,7 +363,9 @@ int launch_svd_topk(rl_context* h, const float* m_dev, int64_t m, int64_t n, int
     // failed capture take the plain launches.
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    if (np - 1 >= 32 && cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+    const bool capturing = np - 1 >= 32 && cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (!capturing) (void)cudaGetLastError();   // e.g. the legacy default stream cannot be captured: plain launches
+    if (capturing) {
       bool ok = cudaMemsetAsync(rot, 0, sizeof(unsigned int), h->stream) == cudaSuccess;
       for (int round = 0; ok && round < np - 1; ++round) {
         jacobi_round_kernel<<<np / 2, 256, 0, h->stream>>>(w, v, nn, np, round, tol, scal, rot);

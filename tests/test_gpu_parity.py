@@ -614,6 +614,24 @@ def test_recommend_host_finishes_overflow_rows_once(h, n_users):
     assert np.array_equal(idx, d_idx.get()) and np.array_equal(val, d_val.get())
 
 
+def test_svd_reconstruct_on_default_stream_matches_own_stream(h):
+    """The Jacobi sweeps are replayed from a CUDA graph captured on the handle's stream; the legacy default stream cannot
+    be captured, so a handle switched to it takes plain launches: same bits either way."""
+    from recsys_lite_b200 import _ffi
+    m = gen.sample_ratings(300, 120, sparsity=0.7, random_state=2).astype(np.float32)
+    outs = []
+    for default_stream in (False, True):
+        h.set_stream(0 if default_stream else None)
+        out = np.empty_like(m)
+        try:
+            h.call("rl_svd_reconstruct_host", _ffi.ptr(m), m.shape[0], m.shape[1], 8, _ffi.ptr(out), None, None, None)
+        finally:
+            h.set_stream(None)
+        outs.append(out)
+    assert np.array_equal(outs[0], outs[1])
+    assert np.max(np.abs(outs[0].astype(np.float64) - o_svd.reconstruct_f64(m, 8))) < 1e-4
+
+
 def test_benchmark_entry_points_and_cli(tmp_path, capsys):
     """benchmark_algorithm (algo.py:746-827), quick_benchmark (benchmark.py:524-555) and the benchmark command
     (cli.py:153-211) on a 60 x 30 matrix: result keys, error handling, the Time | RMSE | MAE line."""
