@@ -87,14 +87,13 @@ __global__ void __launch_bounds__(SE_THREADS) score_topn_exact_kernel(const Scor
     j_begin = static_cast<int64_t>(blockIdx.y) * a.slice_items;     // a multiple of SE_IT
     j_end = min(a.n_items, j_begin + a.slice_items);
 #pragma unroll
-    for (int uu = 0; uu < SE_UPW; ++uu) {       // skip the seen items in front of this slice (ascending list)
-      for (;;) {
-        const int64_t p = cur[uu] + lane;
-        const int idx = (p < end[uu]) ? a.seen_indices[p] : INT_MAX;
-        const unsigned b = __ballot_sync(FULL_MASK, idx < j_begin);
-        cur[uu] += __popc(b);
-        if (b != FULL_MASK) break;
+    for (int uu = 0; uu < SE_UPW; ++uu) {       // skip the seen items in front of this slice (ascending list): bisection,
+      int64_t lo = cur[uu], hi = end[uu];        // heavy users have 10^4 .. 10^5 of them and there are hundreds of slices
+      while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if (a.seen_indices[mid] < j_begin) lo = mid + 1; else hi = mid;
       }
+      cur[uu] = lo;
     }
   }
 
