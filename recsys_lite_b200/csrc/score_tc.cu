@@ -356,7 +356,12 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
   const uint32_t bar0 = base + S::off_bar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   constexpr int TC_SLOTS = S::SLOTS;
-  constexpr int B_FULL = 0, B_EMPTY = TC_SLOTS, A_FULL = 2 * TC_SLOTS, A_EMPTY = A_FULL + 1, T_FULL = A_FULL + 2, T_EMPTY = T_FULL + TC_ACC;
+  constexpr int B_FULL = 0, B_EMPTY = TC_SLOTS, A_FULL = 2 * TC_SLOTS, A_EMPTY = A_FULL + 2, T_FULL = A_FULL + 4, T_EMPTY = T_FULL + TC_ACC;
+  // The user tile (A operand) takes KP of the 128 TMEM columns in front of the accumulators: with KP = 64 there are two
+  // buffers, and the loaders write the NEXT user tile while the MMAs of the current sweep still read this one.
+  constexpr int A_BUFS = KP <= 64 ? 2 : 1;
+  auto a_buf = [](uint32_t ut_local) { return A_BUFS == 2 ? (ut_local & 1u) : 0u; };
+  auto a_phase = [](uint32_t ut_local) { return A_BUFS == 2 ? ((ut_local >> 1) & 1u) : (ut_local & 1u); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + T_EMPTY + TC_ACC);
   int* claim = reinterpret_cast<int*>(bars + T_EMPTY + TC_ACC + 1);   // [2 parities][4 lane quarters] item-tile tickets
   constexpr uint32_t A_LO_COL = KP / 2;      // TMEM columns [0, KP/2): user rows, hi parts (two fp16 per column); [KP/2, KP): lo parts
@@ -366,8 +371,7 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_SLOTS; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
     for (int i = 0; i < TC_ACC; ++i) { mbar_init(BAR(T_FULL + i), 1); mbar_init(BAR(T_EMPTY + i), 4); }
-    mbar_init(BAR(A_FULL), 4);
-    mbar_init(BAR(A_EMPTY), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(A_FULL + i), 4); mbar_init(BAR(A_EMPTY + i), 1); }
     for (int i = 0; i < 8; ++i) claim[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -413,7 +417,8 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
       long long w_a = 0, w_t = 0, w_b = 0;
       const long long t_start = clock64();
       for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x, ++ut_local) {
-        mbar_wait_t(BAR(A_FULL), ut_local & 1, w_a);        // user tile written to TMEM by the loader warps
+        mbar_wait_t(BAR(A_FULL + a_buf(ut_local)), a_phase(ut_local), w_a);   // user tile written to TMEM by the loader warps
+        const uint32_t a_tmem = tmem_base + a_buf(ut_local) * KP;
         tc_fence_after();
         for (int it = 0; it < a.n_item_tiles; ++it, ++it_global) {
           const uint32_t acc = it_global % TC_ACC, aph = (it_global / TC_ACC) & 1;
@@ -432,23 +437,23 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
             if (part == 0) {                         // U_hi . V_hi  (+ U_lo . V_hi)
 #pragma unroll
               for (int kk = 0; kk < KP / 16; ++kk)
-                tc_mma_f16_ts(d_tmem, tmem_base + kk * 8, bd0 + RL_BOFF(kk), TC_IDESC, kk != 0 ? 1u : 0u);
+                tc_mma_f16_ts(d_tmem, a_tmem + kk * 8, bd0 + RL_BOFF(kk), TC_IDESC, kk != 0 ? 1u : 0u);
               if (TERMS == 3) {
 #pragma unroll
                 for (int kk = 0; kk < KP / 16; ++kk)
-                  tc_mma_f16_ts(d_tmem, tmem_base + A_LO_COL + kk * 8, bd0 + RL_BOFF(kk), TC_IDESC, 1u);
+                  tc_mma_f16_ts(d_tmem, a_tmem + A_LO_COL + kk * 8, bd0 + RL_BOFF(kk), TC_IDESC, 1u);
               }
             } else {                                 // U_hi . V_lo
 #pragma unroll
               for (int kk = 0; kk < KP / 16; ++kk)
-                tc_mma_f16_ts(d_tmem, tmem_base + kk * 8, bd0 + RL_BOFF(kk), TC_IDESC, 1u);
+                tc_mma_f16_ts(d_tmem, a_tmem + kk * 8, bd0 + RL_BOFF(kk), TC_IDESC, 1u);
             }
 #undef RL_BOFF
             tc_commit(BAR(B_EMPTY + slot));          // slot reusable once these MMAs retire
           }
           tc_commit(BAR(T_FULL + acc));              // accumulator ready for the epilogue
         }
-        tc_commit(BAR(A_EMPTY));                     // user tile in TMEM may be overwritten
+        tc_commit(BAR(A_EMPTY + a_buf(ut_local)));   // this user tile's TMEM columns may be overwritten
       }
       if (a.dbg && blockIdx.x == 0) { a.dbg[2] = clock64() - t_start; a.dbg[3] = w_a; a.dbg[4] = w_t; a.dbg[5] = w_b; }
     }
@@ -456,10 +461,11 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
     // =========================================== user-tile loaders =========================================
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t_row0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     auto load_tile = [&](int ut, uint32_t ut_local) {
       const int64_t user = static_cast<int64_t>(ut) * TC_BM + row;
-      mbar_wait_relaxed(BAR(A_EMPTY), (ut_local & 1) ^ 1, 200);
+      mbar_wait_relaxed(BAR(A_EMPTY + a_buf(ut_local)), a_phase(ut_local) ^ 1, 200);
+      const uint32_t t_row = t_row0 + a_buf(ut_local) * KP;
       tc_fence_after();
       const float4* up = reinterpret_cast<const float4*>(a.uf + user * a.ldf);
       float su = 1.0f;
@@ -480,7 +486,7 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(A_FULL));
+      if (lane == 0) mbar_arrive(BAR(A_FULL + a_buf(ut_local)));
     };
     uint32_t ut_local = 0;
     if (static_cast<int>(blockIdx.x) < a.n_user_tiles) load_tile(blockIdx.x, 0);
@@ -491,6 +497,9 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
       }
       const int64_t user = static_cast<int64_t>(ut) * TC_BM + row;
       const bool valid = user < a.n_users;
+      const bool has_next = ut + static_cast<int>(gridDim.x) < a.n_user_tiles;
+      // two user-tile buffers: the next tile goes into the other one while this sweep runs
+      if (A_BUFS == 2 && has_next) load_tile(ut + gridDim.x, ut_local + 1);
       // ---- take over the candidates of this user tile from the epilogue sets -----------------------------------
       named_bar_sync(1, 128 * (TC_SETS + 1));     // every set has finished its last tile of the sweep
       bool overflow = false;
@@ -504,7 +513,7 @@ score_topn_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
         for (int c = 0; c < c_e; ++c) ids[total++] = __float_as_int(om.c2[c * TC_BM + row].y);
       }
       named_bar_sync(2, 128 * (TC_SETS + 1));     // candidates copied: the sets may reset and start the next sweep
-      if (ut + static_cast<int>(gridDim.x) < a.n_user_tiles) load_tile(ut + gridDim.x, ut_local + 1);
+      if (A_BUFS == 1 && has_next) load_tile(ut + gridDim.x, ut_local + 1);
       // ---- exact float64 re-scoring, ranking by (score desc, index asc); overlaps the next sweep ----------------
       if (!valid) continue;
       if (overflow) {
