@@ -8,19 +8,22 @@
 //              K-major), mbarrier complete_tx signalling;
 //   warp 1     MMA issuer: tcgen05.mma.kind::f16 (M=128, N=128, K=16), A operand (the user tile) from TMEM, B from the
 //              fp16 tiles in shared memory, three 128-column fp32 accumulator stages in TMEM;
-//   warp 2     TMEM allocation (512 columns: up to 128 for the user tile hi|lo, 3 x 128 accumulators);
+//   warp 2     TMEM allocation (512 columns: 128 for the user tile hi|lo -- two buffers of 64 when k <= 64 --, 3 x 128
+//              accumulators);
 //   warps 4-7  user-tile loaders: each thread reads its user's factor row from global memory, scales it by a power of
 //              two, splits it into two fp16 numbers and writes both (packed two per column) into its TMEM lane with
-//              tcgen05.st -- no shared-memory copy of U; the same threads finish the PREVIOUS user tile (exact
-//              re-scoring of its candidates) while the next sweep runs;
-//   warps 8-19 three epilogue sets that take item tiles round robin: tcgen05.ld 32 columns at a time, 3-input max over
-//              groups of 8 scores and ONE compare against the row threshold per group (~0.6 instructions per score);
-//              scores above the threshold are pushed to a small per-row FIFO and drained at the end of the tile by
-//              all 32 rows of the warp in parallel: seen-item cursor check (CSR, ascending), top-n tracker, candidate
-//              buffer in shared memory.
+//              tcgen05.st -- no shared-memory copy of U; with two buffers the next tile is written while the sweep
+//              runs; the same threads finish the PREVIOUS user tile (exact re-scoring of its candidates) while the
+//              next sweep runs;
+//   warps 8-15 two epilogue sets (two warps per TMEM lane quarter) that take item tiles by ticket: tcgen05.ld 32 columns
+//              at a time, software pipelined, 3-input max over groups of 8 scores and ONE compare against the row
+//              threshold per group (~0.6 instructions per score); scores above the threshold are appended to a small
+//              per-row buffer and folded in by all 32 rows of the warp in a batch pass when one of them fills up:
+//              seen-item cursor check (CSR, ascending), top-n tracker, candidate buffer in shared memory.
 //
-// Precision (TERMS).  A single fp16 product is only good to 2^-10 |u||v|: with 10^5 items the top scores of ALS
-// factors are ~3e-5 apart, so the candidate window would hold hundreds of items.  TERMS = 3 is the split-operand
+// Precision (TERMS).  A single fp16 product is only good to 2^-10 |u||v| (4e-4 |u||v| with the window computed from
+// what the rounding really dropped): the top scores of converged ALS factors sit closer than that at 10^5 items -- a
+// quarter of the rows overflows the candidate buffer after 8 iterations.  TERMS = 3 is the split-operand
 // scheme: x s = x_hi + x_lo + r with s a power of two that puts max|x| at <= 2^14 (one s for all of V, one per
 // user row: a per-row scale multiplies that row's scores by a constant and changes no ranking), x_hi = fp16(x s),
 // x_lo = fp16(x s - x_hi), |r| <= 2^-22 |x s| (22 significant bits; entries more than 2^17 below the row maximum
