@@ -154,16 +154,23 @@ int rl_score_topn_dev(rl_handle h, const float* user_f_dev, int64_t n_users,
                       const int64_t* seen_indptr_dev, const int32_t* seen_indices_dev,
                       double global_bias, const float* user_bias_dev, const float* item_bias_dev,
                       int n, int32_t* idx_out_dev, double* score_out_dev, int mode);
-#define RL_SCORE_AUTO 0   /* tensor-core candidate pass + exact rescoring when shapes allow, else exact   */
+#define RL_SCORE_AUTO 0   /* best tensor-core candidate pass the shape allows (centred single product for k <= 64,
+                             split operands for k <= 128) + exact rescoring, else the exact kernel          */
 #define RL_SCORE_EXACT 1  /* CUDA-core float64 scoring of every pair                                       */
 #define RL_SCORE_TENSOR 2 /* force the tcgen05 candidate pass, split-operand 3 x fp16 (error if unsupported shape) */
 #define RL_SCORE_TENSOR_TF32X1 3 /* same with a single fp16 product: wider candidate window, more exact-kernel fallbacks */
+#define RL_SCORE_TENSOR_CENTRED 4 /* force the centred, norm-classed single-product pass (score_tc2.cu; k <= 64) */
 
 /* debug / validation of the tensor-core path: raw tensor-core scores U V^T (terms = 1: one tf32 product, 3: split
  * operands), out (n_users x ld) float32 with ld >= n_items rounded up to 128 (the padding columns receive the
  * zero-filled tail of the last tile). */
 int rl_score_dump_dev(rl_handle h, const float* user_f_dev, int64_t n_users, const float* item_f_dev, int64_t n_items,
                       int k, float* out_dev, int64_t ld, int terms);
+/* the same for the centred single-product pass: raw accumulators (n_users x ld; column = position in class order,
+ * ld >= (ceil(n_items / 128) + 8) * 128), the power-of-two row scales (n_users), the position -> item id map (ld int32,
+ * -1 = padding) and the 256-byte class table (see score_tc2.cu: ClassTable). */
+int rl_score_dump_centred_dev(rl_handle h, const float* user_f_dev, int64_t n_users, const float* item_f_dev, int64_t n_items,
+                              int k, float* out_dev, int64_t ld, float* row_scale_dev, int32_t* perm_dev, void* table_dev);
 /* number of user rows the last tensor-core rl_score_topn_dev call handed to the exact kernel (candidate overflow) */
 int64_t rl_last_overflow_rows(rl_handle h);
 

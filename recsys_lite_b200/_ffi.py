@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "librecsys_b200.so")
 
 RL_F32, RL_F64 = 0, 1
 RL_PREC_FP32_IR, RL_PREC_FP64 = 0, 1
-RL_SCORE_AUTO, RL_SCORE_EXACT, RL_SCORE_TENSOR, RL_SCORE_TENSOR_TF32X1 = 0, 1, 2, 3
+RL_SCORE_AUTO, RL_SCORE_EXACT, RL_SCORE_TENSOR, RL_SCORE_TENSOR_TF32X1, RL_SCORE_TENSOR_CENTRED = 0, 1, 2, 3, 4
 ABI_VERSION = 1
 
 _i64, _i32, _dbl, _vp = C.c_int64, C.c_int, C.c_double, C.c_void_p
@@ -49,6 +49,7 @@ SIGNATURES = {
     "rl_als_fit_host": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _dbl, _i32, _i32, _vp, _vp, _i32]),
     "rl_score_topn_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _dbl, _vp, _vp, _i32, _vp, _vp, _i32]),
     "rl_score_dump_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32]),
+    "rl_score_dump_centred_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp]),
     "rl_last_overflow_rows": (_i64, [_vp]),
     "rl_recommend_host": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i32, _vp, _vp, _dbl, _vp, _vp, _i32, _vp, _vp, _i32]),
     "rl_topn_dense_dev": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i32, _vp, _vp]),

@@ -589,6 +589,12 @@ int rl_score_dump_dev(rl_handle h, const float* user_f_dev, int64_t n_users, con
   return launch_score_dump(h, user_f_dev, n_users, item_f_dev, n_items, k, out_dev, ld, terms);
 }
 
+int rl_score_dump_centred_dev(rl_handle h, const float* user_f_dev, int64_t n_users, const float* item_f_dev, int64_t n_items, int k,
+                              float* out_dev, int64_t ld, float* row_scale_dev, int32_t* perm_dev, void* table_dev) {
+  RL_NEED(h);
+  return launch_score_dump_centred(h, user_f_dev, n_users, item_f_dev, n_items, k, out_dev, ld, row_scale_dev, perm_dev, table_dev);
+}
+
 int64_t rl_last_overflow_rows(rl_handle h) { return h ? static_cast<int64_t>(h->last_overflow) : -1; }
 
 int rl_recommend_host(rl_handle h, const void* user_f, const void* item_f, int factor_dtype, int64_t n_users,

@@ -102,6 +102,8 @@ int launch_score_overflow(rl_context* h, const float* uf, int64_t n_users, const
                           const int32_t* rows, unsigned int n_rows);
 int launch_score_dump(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k, float* out,
                       int64_t ld, int terms);
+int launch_score_dump_centred(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k, float* out,
+                              int64_t ld, float* row_scale, int32_t* perm, void* table);
 int launch_topn_dense(rl_context* h, const void* est, int est_dtype, const void* known, int known_dtype,
                       int64_t n_users, int64_t n_items, int n, int32_t* idx_out, int32_t* n_valid_out);
 int launch_svd_topk(rl_context* h, const float* m_dev, int64_t m, int64_t n, int k, double* s_out, double* left_out,

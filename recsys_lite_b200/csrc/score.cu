@@ -154,6 +154,18 @@ int launch_dense_error(rl_context* h, const void* pred, int pdtype, const void* 
 
 bool score_tc_supported(int kp, int n, int64_t n_users, int64_t n_items, const float* ubias, const float* ibias, double gbias);
 int launch_score_tc(rl_context* h, int kp, const ScoreArgs& sa, float* dump, int64_t dump_ld, int terms, const ScoreDefer* defer = nullptr);
+bool score_tc2_supported(int kp, int n, int64_t n_users, int64_t n_items, const float* ubias, const float* ibias, double gbias);
+int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefer* defer, float* dump, int64_t dump_ld, float* dump_su,
+                     int32_t* dump_perm, void* dump_tab);
+
+int launch_score_dump_centred(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k, float* out,
+                              int64_t ld, float* row_scale, int32_t* perm, void* table) {
+  const int kp = padded_k(k);
+  if (!score_tc2_supported(kp, 1, n_users, n_items, nullptr, nullptr, 0.0)) return fail(h, RL_ERR_INVALID, "score_dump_centred: unsupported shape");
+  if (!uf || !vf || !out || !row_scale || ld < ((n_items + 127) / 128 + 8) * 128) return fail(h, RL_ERR_INVALID, "score_dump_centred: bad argument");
+  ScoreArgs a{uf, vf, n_users, n_items, nullptr, nullptr, 0.0, nullptr, nullptr, 1, nullptr, nullptr, nullptr, 0, false};
+  return launch_score_tc2(h, kp, a, nullptr, out, ld, row_scale, perm, table);
+}
 
 int launch_score_dump(rl_context* h, const float* uf, int64_t n_users, const float* vf, int64_t n_items, int k, float* out, int64_t ld,
                       int terms) {
@@ -177,7 +189,12 @@ int launch_score_topn(rl_context* h, const float* uf, int64_t n_users, const flo
     return fail(h, RL_ERR_INVALID, "score_topn: seen_indices without seen_indptr");
   ScoreArgs a{uf, vf, n_users, n_items, seen_indptr, seen_indices, gbias, ubias, ibias, n, idx_out, score_out, nullptr, 0, false};
   const bool tc_ok = score_tc_supported(kp, n, n_users, n_items, ubias, ibias, gbias);
-  if (mode < RL_SCORE_AUTO || mode > RL_SCORE_TENSOR_TF32X1) return fail(h, RL_ERR_INVALID, "score_topn: unknown mode %d", mode);
+  if (mode < RL_SCORE_AUTO || mode > RL_SCORE_TENSOR_CENTRED) return fail(h, RL_ERR_INVALID, "score_topn: unknown mode %d", mode);
+  const bool tc2_ok = score_tc2_supported(kp, n, n_users, n_items, ubias, ibias, gbias);
+  if (mode == RL_SCORE_TENSOR_CENTRED && !tc2_ok)
+    return fail(h, RL_ERR_INVALID, "score_topn: centred tensor-core path needs k <= 64, n <= 16, >= 1024 items and no bias terms");
+  if ((mode == RL_SCORE_AUTO || mode == RL_SCORE_TENSOR_CENTRED) && tc2_ok)
+    return launch_score_tc2(h, kp, a, defer, nullptr, 0, nullptr, nullptr, nullptr);
   if ((mode == RL_SCORE_TENSOR || mode == RL_SCORE_TENSOR_TF32X1) && !tc_ok)
     return fail(h, RL_ERR_INVALID, "score_topn: tensor-core path needs k <= 128, n <= 16, >= 1024 items and no bias terms");
   if (mode != RL_SCORE_EXACT && tc_ok) return launch_score_tc(h, kp, a, nullptr, 0, mode == RL_SCORE_TENSOR_TF32X1 ? 1 : 3, defer);

@@ -1,0 +1,986 @@
+// score_tc2.cu -- single-product tensor-core scoring on CENTRED, norm-classed item factors, fused with seen-item
+// masking and exact top-n (tcgen05 / TMEM / TMA).  Default path of rl_score_topn_dev for k <= 64.
+//
+// Replaces predict + top_n of the reference (algo.py:143-147 `U @ V.T`, algo.py:533-659 as composed in
+// recommend, algo.py:172-201) for ALS factors without ever writing the n_users x n_items score matrix.
+//
+// Why centring.  The reference's ALS has no negative term, so its factors converge towards "every score = 1": after
+// 25 iterations at C4 the scores of one user are 0.9977 +- 9e-3 and the top ten sit 3e-5 apart, while |u||v| ~ 1.
+// An error bound relative to |u||v| (what the split-operand kernel of score_tc.cu uses) then lets hundreds of items
+// into the candidate window.  Ranking a user's items by u.v_i is ranking them by u.(v_i - vbar): the constant
+// u.vbar drops out.  With w_i = v_i - vbar the operand of the GEMM shrinks with the spread of the scores, and so
+// does the rounding error of ONE fp16 product:
+//     |fp16(u).fp16(w_i) - u.w_i|  <=  |u - u_h| |w_i| + |u_h| |w_i - w_h,i|  (+ fp32 accumulation)
+// -- computed from what the roundings actually dropped, per user row and per item class.  Items are binned by
+// |w_i| into factor-of-two classes (largest first; each class padded to whole 128-item tiles, ascending item id
+// inside a class), so that the 8 % of slow-converging items with |w_i| ~ 1 do not set the window of the 92 % with
+// |w_i| ~ 0.015.  One product instead of three (score_tc.cu) is a third of the tensor work, and the kernel is
+// power-bound on exactly that work.
+//
+// Exactness.  All quantities in "raw" units (scores times s_u s, both powers of two).  For item i of class c:
+// a_i = tensor-core value, T_i = s_u s u.(v_i - vbar) the true centred score, |a_i - T_i| <= eps_c (eps_c covers the
+// two operand roundings, the rounding of the fp32 subtraction v_i - vbar, fp32 accumulation, and the float64
+// summation error of the final re-scoring).  Each row tracks the n best LOWER bounds L_i = a_i - eps_c of unseen
+// items; Lth = the n-th best is a lower bound of the n-th best true score.  An item is a candidate iff its UPPER
+// bound H_i = a_i + eps_c reaches Lth: every member of the exact top-n is a candidate.  Candidates are re-scored in
+// float64 from the original u, v_i (same summation order as the exact kernel) and ranked by (score desc, index
+// asc): the result is identical to rl_score_topn_dev(mode = RL_SCORE_EXACT).
+//
+// One persistent CTA per SM owns TWO user tiles of 128 at a time ("halves": every V tile fetched from L2 feeds two
+// MMA groups) and sweeps the items in tiles of 128:
+//   warp 0       TMA producer: W_hi tiles (128 x 64 fp16, 128B swizzle, K-major) through a shared-memory ring;
+//   warp 1       MMA issuer: tcgen05.mma.kind::f16 (M=128, N=128, K=16), A (a user tile) from TMEM, B from shared
+//                memory, fp32 accumulators in three 128-column TMEM stages shared by the two halves; also issues the
+//                512-byte bulk copy of the tile's item ids (position -> item id) that completes on the same mbarrier;
+//   warp 2       TMEM allocation;
+//   warps 4-11   scan warps, one per (half, TMEM lane quarter): tcgen05.ld 32 columns at a time, software pipelined,
+//                3-input max over groups of 8 scores, ONE compare per group against the row threshold; scores above it
+//                are pushed as (score, item id) into the row's ring in shared memory;
+//   warps 12-19  selection warps, one thread per user row: drain the row's ring in order -- seen-item cursor
+//                (ascending CSR row, restarted at class boundaries), top-n tracker of lower bounds in registers,
+//                candidate list in shared memory, threshold published for the scan thread; at the end of a sweep
+//                they write the candidate ids to global memory and put the next-but-one user tile into TMEM
+//                (tcgen05.st of the fp16-rounded, power-of-two scaled row -- no shared-memory copy of U).
+// A second small kernel re-scores the candidates exactly and writes the top-n.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "score_exact.cuh"
+#include "tcgen05_ptx.cuh"
+
+namespace rl {
+
+namespace {
+
+using namespace tc;
+
+constexpr int T2_BM = 128;        // users per half (TMEM lanes)
+constexpr int T2_BN = 128;        // items per tile
+constexpr int T2_ACC = 3;         // TMEM accumulator stages
+constexpr int T2_NCLS = 8;        // item classes by |w_i| (factor of two each)
+constexpr int T2_THREADS = 32 * 20;
+constexpr int T2_RING = 16;       // ring slots per row
+constexpr int T2_CAND = 40;       // candidate slots per row
+constexpr int T2_IDS = 8;         // item-id slices in flight (one per half-tile, indexed by sequence number)
+constexpr int T2_EMPTY = INT_MIN; // ring slot free
+constexpr int T2_END = -100;      // ring marker: end of the sweep
+constexpr int T2_CLS0 = -2;       // ring marker: class c starts = T2_CLS0 - c   (item id -1 = padding position)
+
+// what the preprocessing kernels leave for the main kernel
+struct ClassTable {
+  int first_tile[T2_NCLS + 1];    // first item tile of class c; first_tile[T2_NCLS] = n_tiles
+  int n_tiles;
+  int pad0;
+  float wc[T2_NCLS];              // >= max over classes c' >= c of |w_i| s          (raw units, inflated)
+  float rc[T2_NCLS];              // >= max over classes c' >= c of |w_i s - fp16(w_i s)|
+  float scale;                    // s: power of two, max |w_ij| s <= 2^14
+  float vmax_raw;                 // >= max_i |v_i| s
+  unsigned wmax_bits, amax_bits, vmax_bits;   // reductions in progress (non-negative floats order as unsigned)
+  unsigned wc_bits[T2_NCLS], rc_bits[T2_NCLS];
+};
+
+template <int KP>
+struct T2Smem {
+  static constexpr int SLOTS = KP > 64 ? 2 : 4;
+  static constexpr uint32_t B_BYTES = T2_BN * KP * 2;
+  static constexpr uint32_t off_b = 0;
+  static constexpr uint32_t off_ring = off_b + SLOTS * B_BYTES;                    // [RING][256] (score, id)
+  static constexpr uint32_t off_cand = off_ring + T2_RING * 2 * T2_BM * 8;         // [CAND][256] (upper bound, id)
+  static constexpr uint32_t off_thr = off_cand + T2_CAND * 2 * T2_BM * 8;          // [256] (threshold, sweep tag)
+  static constexpr uint32_t off_ids = off_thr + 2 * T2_BM * 8;                     // [T2_IDS][128] item ids
+  static constexpr uint32_t off_tab = off_ids + T2_IDS * T2_BN * 4;                // ClassTable copy
+  static constexpr uint32_t off_bar = off_tab + 256;
+  static constexpr uint32_t total = off_bar + 256 + 1024;
+  static_assert(sizeof(ClassTable) <= 256, "class table");
+  static_assert(total <= 227 * 1024, "score_tc2 exceeds shared memory");
+};
+
+struct T2Args {
+  const float* uf;
+  int ldf;
+  int64_t n_users;
+  const int64_t* seen_indptr;
+  const int32_t* seen_indices;
+  int n;
+  const ClassTable* tab;
+  const int32_t* perm;          // position -> item id (-1: padding)
+  int32_t* cand_ids;            // [n_users][T2_CAND]
+  int32_t* cand_cnt;            // [n_users]: number of candidates, -1 = overflow (row goes to the exact kernel)
+  float acc_rel;                // allowance for the fp32 accumulation of the tensor core, relative to |u_h||w_h|
+  float* dump;                  // debug: raw accumulators (n_users x dump_ld), dump_su: the row scales
+  float* dump_su;
+  int64_t dump_ld;
+  int n_user_tiles;
+  long long* dbg;
+};
+
+__device__ __forceinline__ void ring_put(uint32_t addr, float score, int id) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(__float_as_int(score)), "r"(id) : "memory");
+}
+__device__ __forceinline__ void ring_get(uint32_t addr, float& score, int& id) {
+  int sb;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(sb), "=r"(id) : "r"(addr) : "memory");
+  score = __int_as_float(sb);
+}
+__device__ __forceinline__ int lds_volatile(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// instruction descriptor: D fp32, A/B fp16, both K-major, N = 128, M = 128
+constexpr uint32_t T2_IDESC = (1u << 4) | (static_cast<uint32_t>(T2_BN >> 3) << 17) | (static_cast<uint32_t>(T2_BM >> 4) << 24);
+
+template <int KP, int NT, bool DUMP>
+__global__ void __launch_bounds__(T2_THREADS, 1)
+score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
+  using S = T2Smem<KP>;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* sm = smem_raw + (base - raw);
+  constexpr int SLOTS = S::SLOTS;
+  constexpr int B_FULL = 0, B_EMPTY = SLOTS, A_FULL = 2 * SLOTS, A_EMPTY = A_FULL + 2, T_FULL = A_FULL + 4, T_EMPTY = T_FULL + T2_ACC;
+  const uint32_t bar0 = base + S::off_bar;
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::off_bar);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + T_EMPTY + T2_ACC);
+  ClassTable* tab = reinterpret_cast<ClassTable*>(sm + S::off_tab);
+  constexpr int A_BUFS = KP <= 64 ? 2 : 1;
+  constexpr uint32_t A_COLS = KP / 2;           // TMEM columns of one user tile (two fp16 per column)
+  constexpr uint32_t ACC_COL0 = 128;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // contiguous range of 128-user tiles of this CTA, taken two at a time
+  const int tile_begin = static_cast<int>(static_cast<int64_t>(a.n_user_tiles) * blockIdx.x / gridDim.x);
+  const int tile_end = static_cast<int>(static_cast<int64_t>(a.n_user_tiles) * (blockIdx.x + 1) / gridDim.x);
+  const int n_sweeps = (tile_end - tile_begin + 1) / 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SLOTS; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+    for (int i = 0; i < T2_ACC; ++i) { mbar_init(BAR(T_FULL + i), 2); mbar_init(BAR(T_EMPTY + i), 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(A_FULL + i), 8); mbar_init(BAR(A_EMPTY + i), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(ClassTable) / 4); i += T2_THREADS)
+    reinterpret_cast<int*>(tab)[i] = reinterpret_cast<const int*>(a.tab)[i];
+  for (int i = threadIdx.x; i < T2_RING * 2 * T2_BM; i += T2_THREADS) ring_put(base + S::off_ring + 8u * i, 0.f, T2_EMPTY);
+  for (int i = threadIdx.x; i < 2 * T2_BM; i += T2_THREADS) ring_put(base + S::off_thr + 8u * i, 0.f, -1);
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_tiles = tab->n_tiles;
+  auto a_buf = [](int sweep) { return A_BUFS == 2 ? static_cast<uint32_t>(sweep & 1) : 0u; };
+  auto a_phase = [](int sweep) { return A_BUFS == 2 ? static_cast<uint32_t>((sweep >> 1) & 1) : static_cast<uint32_t>(sweep & 1); };
+
+  if (warp == 0) {
+    // =========================================== TMA producer ==============================================
+    if (lane == 0) {
+      uint32_t slot_global = 0;
+      for (int j = 0; j < n_sweeps; ++j) {
+        for (int it = 0; it < n_tiles; ++it, ++slot_global) {
+          const uint32_t slot = slot_global % SLOTS, ph = (slot_global / SLOTS) & 1;
+          mbar_wait_relaxed(BAR(B_EMPTY + slot), ph ^ 1, 64);
+          mbar_expect_tx(BAR(B_FULL + slot), S::B_BYTES);
+#pragma unroll
+          for (int kh = 0; kh < KP / 64; ++kh)
+            tma_load_2d(base + S::off_b + slot * S::B_BYTES + kh * (T2_BN * 128), &map_w, BAR(B_FULL + slot), kh * 64, it * T2_BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================== MMA issuer ================================================
+    if (lane == 0) {
+      uint32_t slot_global = 0, seq = 0;
+      long long w_a = 0, w_t = 0, w_b = 0;
+      const long long t_start = clock64();
+      for (int j = 0; j < n_sweeps; ++j) {
+        const int halves = (tile_begin + 2 * j + 1 < tile_end) ? 2 : 1;
+        mbar_wait_t(BAR(A_FULL + a_buf(j)), a_phase(j), w_a);
+        tc_fence_after();
+        for (int it = 0; it < n_tiles; ++it, ++slot_global) {
+          const uint32_t slot = slot_global % SLOTS, ph = (slot_global / SLOTS) & 1;
+          mbar_wait_t(BAR(B_FULL + slot), ph, w_b);
+          tc_fence_after();
+          const uint64_t bd0 = make_desc(base + S::off_b + slot * S::B_BYTES);
+#define RL_BOFF(kk) (static_cast<uint64_t>((((kk) >> 2) * (T2_BN * 128) + ((kk) & 3) * 32) >> 4))
+          for (int hh = 0; hh < halves; ++hh, ++seq) {
+            const uint32_t acc = seq % T2_ACC, aph = (seq / T2_ACC) & 1;
+            mbar_wait_t(BAR(T_EMPTY + acc), aph ^ 1, w_t);
+            tc_fence_after();
+            // the item ids of this tile travel with the accumulator stage (the B slot is recycled before the scan)
+            mbar_expect_tx(BAR(T_FULL + acc), T2_BN * 4);
+            bulk_load(base + S::off_ids + (seq % T2_IDS) * (T2_BN * 4), a.perm + static_cast<int64_t>(it) * T2_BN, T2_BN * 4,
+                      BAR(T_FULL + acc));
+            const uint32_t d_tmem = tmem_base + ACC_COL0 + acc * T2_BN;
+            const uint32_t a_tmem = tmem_base + a_buf(j) * (2 * A_COLS) + hh * A_COLS;
+#pragma unroll
+            for (int kk = 0; kk < KP / 16; ++kk)
+              tc_mma_f16_ts(d_tmem, a_tmem + kk * 8, bd0 + RL_BOFF(kk), T2_IDESC, kk != 0 ? 1u : 0u);
+            tc_commit(BAR(T_FULL + acc));
+          }
+#undef RL_BOFF
+          tc_commit(BAR(B_EMPTY + slot));
+        }
+        tc_commit(BAR(A_EMPTY + a_buf(j)));
+      }
+      if (a.dbg && blockIdx.x == 0) { a.dbg[0] = clock64() - t_start; a.dbg[1] = w_a; a.dbg[2] = w_t; a.dbg[3] = w_b; }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // =========================================== scan warps ================================================
+    const int hh = (warp - 4) >> 2, q = warp & 3;
+    const int rowg = hh * T2_BM + q * 32 + lane;                 // row inside the CTA's pair of user tiles
+    const uint32_t ring_row = base + S::off_ring + 8u * rowg;     // slot r at + r * (256 * 8)
+    const uint32_t thr_addr = base + S::off_thr + 8u * rowg;
+    uint32_t seq_base = 0, tail = 0;
+    long long w_full = 0, w_ring = 0, n_push = 0;
+    const long long t_start = clock64();
+    auto push = [&](float sc, int id) {
+      const uint32_t addr = ring_row + (tail % T2_RING) * (2 * T2_BM * 8);
+      if (lds_volatile(addr + 4) != T2_EMPTY) {
+        const long long t0 = clock64();
+        uint32_t spin = 0;
+        while (lds_volatile(addr + 4) != T2_EMPTY) {
+          __nanosleep(40);
+          if (++spin > (1u << 24)) { printf("score_tc2: ring timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+        }
+        w_ring += clock64() - t0;
+      }
+      ring_put(addr, sc, id);
+      ++tail;
+      ++n_push;
+    };
+    for (int j = 0; j < n_sweeps; ++j) {
+      const int halves = (tile_begin + 2 * j + 1 < tile_end) ? 2 : 1;
+      if (hh >= halves) { seq_base += static_cast<uint32_t>(n_tiles) * halves; continue; }
+      const int64_t user = static_cast<int64_t>(tile_begin + 2 * j + hh) * T2_BM + q * 32 + lane;
+      const bool valid = user < a.n_users;
+      int cls = 0;
+      while (cls + 1 < T2_NCLS && tab->first_tile[cls + 1] == 0) ++cls;      // empty leading classes
+      int next_cls_tile = tab->first_tile[cls + 1];
+      if (!DUMP && valid) push(0.f, T2_CLS0 - cls);
+      for (int it = 0; it < n_tiles; ++it) {
+        const uint32_t seq = seq_base + (halves == 2 ? 2 * it + hh : it);
+        const uint32_t acc = seq % T2_ACC, aph = (seq / T2_ACC) & 1;
+        if (it == next_cls_tile) {
+          while (cls + 1 < T2_NCLS && tab->first_tile[cls + 1] <= it) ++cls;
+          next_cls_tile = cls + 1 <= T2_NCLS ? tab->first_tile[cls + 1] : n_tiles;
+          if (!DUMP && valid) push(0.f, T2_CLS0 - cls);
+        }
+        mbar_wait_t(BAR(T_FULL + acc), aph, w_full);
+        tc_fence_after();
+        float thr;
+        {
+          int tag;
+          ring_get(thr_addr, thr, tag);
+          if (tag != j) thr = -CUDART_INF_F;
+          if (!valid) thr = CUDART_INF_F;
+        }
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ACC_COL0 + acc * T2_BN;
+        const int* ids = reinterpret_cast<const int*>(sm + S::off_ids + (seq % T2_IDS) * (T2_BN * 4));
+        auto release_stage = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
+        };
+        float s0[32], s1[32];
+        auto scan32 = [&](const float (&sg)[32], const int col0) {
+          if (DUMP) {
+            if (valid) {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) a.dump[user * a.dump_ld + static_cast<int64_t>(it) * T2_BN + col0 + jj] = sg[jj];
+            }
+            return;
+          }
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const float m8 = max3(max3(sg[8 * b], sg[8 * b + 1], sg[8 * b + 2]), max3(sg[8 * b + 3], sg[8 * b + 4], sg[8 * b + 5]),
+                                  fmaxf(sg[8 * b + 6], sg[8 * b + 7]));
+            if (m8 > thr) {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                if (sg[8 * b + jj] > thr) {
+                  const int id = ids[col0 + 8 * b + jj];
+                  if (id >= 0) push(sg[8 * b + jj], id);
+                }
+              }
+            }
+          }
+          __syncwarp();     // the pushes diverge; tcgen05.ld / wait need the whole warp
+        };
+        tc_ld32(t_row, s0);
+#pragma unroll 1
+        for (int gp = 0; gp < T2_BN / 64; ++gp) {
+          tc_wait_ld_dep(s0);
+          tc_ld32(t_row + gp * 64 + 32, s1);
+          scan32(s0, gp * 64);
+          tc_wait_ld_dep(s1);
+          if (gp + 1 < T2_BN / 64) tc_ld32(t_row + gp * 64 + 64, s0);
+          else release_stage();
+          scan32(s1, gp * 64 + 32);
+        }
+      }
+      if (!DUMP && valid) push(0.f, T2_END);
+      seq_base += static_cast<uint32_t>(n_tiles) * halves;
+    }
+    if (a.dbg && blockIdx.x == 0 && lane == 0) {
+      long long* d = a.dbg + 8 + 4 * (warp - 4);
+      d[0] = clock64() - t_start; d[1] = w_full; d[2] = w_ring; d[3] = n_push;
+    }
+  } else if (warp >= 12) {
+    // ======================== selection warps: user-tile loaders + per-row selection ==========================
+    const int hh = (warp - 12) >> 2, q = warp & 3;
+    const int rowg = hh * T2_BM + q * 32 + lane;
+    const uint32_t ring_row = base + S::off_ring + 8u * rowg;
+    const uint32_t cand_row = base + S::off_cand + 8u * rowg;
+    const uint32_t thr_addr = base + S::off_thr + 8u * rowg;
+    const uint32_t t_row0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float scale = tab->scale;
+    // writes the user tile of sweep j (this thread: one row of half hh) into TMEM; returns (|u s_u - u_h|, |u_h|, |u s_u|)
+    auto load_tile = [&](int j) -> float3 {
+      const int tile = tile_begin + 2 * j + hh;
+      const int64_t user = static_cast<int64_t>(tile) * T2_BM + q * 32 + lane;
+      const bool valid = tile < tile_end && user < a.n_users;
+      mbar_wait_relaxed(BAR(A_EMPTY + a_buf(j)), a_phase(j) ^ 1, 100);
+      tc_fence_after();
+      const uint32_t t_row = t_row0 + a_buf(j) * (2 * A_COLS) + hh * A_COLS;
+      const float4* up = reinterpret_cast<const float4*>(a.uf + user * a.ldf);
+      float su = 1.0f;
+      if (valid) {
+        float mx = 0.f;
+        for (int c = 0; c < a.ldf / 4; ++c) {
+          const float4 x = up[c];
+          mx = fmaxf(fmaxf(mx, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
+        }
+        su = pow2_scale(mx);
+      }
+      float nn = 0.f, rr = 0.f, hn = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < KP; c0 += 64) {
+        uint32_t hi[32];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid && c0 + 4 * c < a.ldf) v = up[c0 / 4 + c];
+          v.x *= su; v.y *= su; v.z *= su; v.w *= su;
+          const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+          nn += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          hn += f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y;
+          const float r0 = v.x - f0.x, r1 = v.y - f0.y, r2 = v.z - f1.x, r3 = v.w - f1.y;   // exact in fp32
+          rr += r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
+          hi[2 * c] = *reinterpret_cast<const uint32_t*>(&h0);
+          hi[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+        }
+        tc_st32(t_row + c0 / 2, hi);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(A_FULL + a_buf(j)));
+      if (DUMP && valid) a.dump_su[user] = su;
+      return make_float3(sqrtf(rr) * 1.0001f, sqrtf(hn) * 1.0001f, sqrtf(nn) * 1.0001f);
+    };
+    float3 e_cur = load_tile(0), e_nxt = make_float3(0.f, 0.f, 0.f);
+    if (A_BUFS == 2 && n_sweeps > 1) e_nxt = load_tile(1);
+    if (DUMP) {
+      for (int j = A_BUFS; j < n_sweeps; ++j) load_tile(j);
+    } else {
+      uint32_t head = 0;
+      long long c_idle = 0, n_rec = 0, n_cmp = 0;
+      const long long t_start = clock64();
+      for (int j = 0; j < n_sweeps; ++j) {
+        const int halves = (tile_begin + 2 * j + 1 < tile_end) ? 2 : 1;
+        const int64_t user = static_cast<int64_t>(tile_begin + 2 * j + hh) * T2_BM + q * 32 + lane;
+        const bool valid = hh < halves && user < a.n_users;
+        if (valid) {
+          // ---- per-row state of this sweep (registers) ----
+          float tk[NT];
+#pragma unroll
+          for (int i = 0; i < NT; ++i) tk[i] = i < NT - a.n ? CUDART_INF_F : -CUDART_INF_F;
+          float lth = -CUDART_INF_F, eps = 0.f;
+          int cnt = 0;
+          bool over = false;
+          int64_t row_begin = 0, cur = 0, end = 0;
+          if (a.seen_indptr) { row_begin = a.seen_indptr[user]; end = a.seen_indptr[user + 1]; }
+          int w[8], wp = 0, nxt = INT_MAX;
+          auto refill = [&]() {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = (cur + i < end) ? a.seen_indices[cur + i] : INT_MAX;
+            wp = 0;
+            nxt = w[0];
+          };
+          auto publish = [&]() {
+            const float thr = over ? CUDART_INF_F : __fsub_rd(lth, eps);
+            ring_put(thr_addr, thr, j);
+          };
+          auto compact = [&]() {
+            int jw = 0;
+            for (int f = 0; f < cnt; ++f) {
+              float hb; int id;
+              ring_get(cand_row + f * (2 * T2_BM * 8), hb, id);
+              if (hb >= lth) { ring_put(cand_row + jw * (2 * T2_BM * 8), hb, id); ++jw; }
+            }
+            cnt = jw;
+            ++n_cmp;
+          };
+          for (;;) {
+            const uint32_t addr = ring_row + (head % T2_RING) * (2 * T2_BM * 8);
+            float sc; int id;
+            ring_get(addr, sc, id);
+            if (id == T2_EMPTY) {
+              const long long t0 = clock64();
+              __nanosleep(64);
+              c_idle += clock64() - t0;
+              continue;
+            }
+            ring_put(addr, 0.f, T2_EMPTY);
+            ++head;
+            if (id >= 0) {
+              ++n_rec;
+              if (over) continue;
+              while (nxt < id) {                      // seen cursor: ids ascend inside a class
+                ++cur;
+                if (++wp == 8) refill();
+                else {
+                  nxt = w[1];
+#pragma unroll
+                  for (int i = 2; i < 8; ++i)
+                    if (i == wp) nxt = w[i];
+                }
+              }
+              if (nxt == id) continue;                // already seen by this user
+              const float lb = __fsub_rd(sc, eps), hb = __fadd_ru(sc, eps);
+              if (lb > tk[NT - 1]) {
+#pragma unroll
+                for (int i = NT - 1; i > 0; --i) tk[i] = fmaxf(tk[i], fminf(tk[i - 1], lb));
+                tk[0] = fmaxf(tk[0], lb);
+                lth = tk[NT - 1];
+                publish();
+              }
+              if (hb >= lth) {
+                ring_put(cand_row + cnt * (2 * T2_BM * 8), hb, id);
+                if (++cnt == T2_CAND) {
+                  compact();
+                  if (cnt > T2_CAND - 4) { over = true; cnt = 0; publish(); }
+                }
+              }
+            } else if (id == T2_END) {
+              break;
+            } else {                                  // class marker
+              const int c = T2_CLS0 - id;
+              eps = (e_cur.x * tab->wc[c] + e_cur.y * tab->rc[c] + a.acc_rel * e_cur.y * (tab->wc[c] + tab->rc[c]) +
+                     e_cur.z * (6.1e-8f * tab->wc[c] + 6.0e-14f * tab->vmax_raw)) * 1.0001f + 1e-30f;
+              cur = row_begin;
+              refill();
+              publish();
+            }
+          }
+          // ---- end of the sweep: final candidates to global memory ----
+          if (!over) compact();
+          int32_t* out = a.cand_ids + user * T2_CAND;
+          for (int f = 0; f < cnt; ++f) {
+            float hb; int id;
+            ring_get(cand_row + f * (2 * T2_BM * 8), hb, id);
+            out[f] = id;
+          }
+          a.cand_cnt[user] = over ? -1 : cnt;
+        }
+        // the user tile of the sweep after next goes into the TMEM buffer this sweep has just finished with
+        __syncwarp();       // the rows of the warp finish their sweeps at different times; tcgen05.st needs all of them
+        e_cur = e_nxt;
+        if (j + A_BUFS < n_sweeps) {
+          const float3 e = load_tile(j + A_BUFS);
+          if (A_BUFS == 2) e_nxt = e; else e_cur = e;
+        }
+      }
+      if (a.dbg && blockIdx.x == 0 && lane == 0) {
+        long long* d = a.dbg + 40 + 4 * (warp - 12);
+        d[0] = clock64() - t_start; d[1] = c_idle; d[2] = n_rec; d[3] = n_cmp;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- exact re-scoring of the candidates: one warp per user, float64 dot products in the exact kernel's order -------
+template <int KP>
+__global__ void __launch_bounds__(256) rescore_kernel(const float* __restrict__ uf, const float* __restrict__ vf, int64_t n_users, int n,
+                                                      const int32_t* __restrict__ cand_ids, const int32_t* __restrict__ cand_cnt,
+                                                      int32_t* __restrict__ idx_out, double* __restrict__ score_out,
+                                                      int32_t* __restrict__ overflow_rows, unsigned int* __restrict__ overflow_count,
+                                                      int64_t row_offset) {
+  const int lane = threadIdx.x & 31;
+  const int64_t user = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (user >= n_users) return;
+  const int cnt = cand_cnt[user];
+  if (cnt < 0) {
+    if (lane == 0) overflow_rows[atomicAdd(overflow_count, 1u)] = static_cast<int32_t>(user + row_offset);
+    return;
+  }
+  constexpr int PER = (T2_CAND + 31) / 32;
+  int id[PER];
+  double sc[PER];
+  const float* up = uf + user * KP;
+#pragma unroll
+  for (int p = 0; p < PER; ++p) {
+    const int c = lane + 32 * p;
+    id[p] = c < cnt ? cand_ids[user * T2_CAND + c] : -1;
+    sc[p] = -CUDART_INF;
+    if (id[p] >= 0) {
+      const float* vp = vf + static_cast<int64_t>(id[p]) * KP;
+      double accd = 0.0;
+#pragma unroll 4
+      for (int k4 = 0; k4 < KP / 4; ++k4) {
+        const float4 x = *reinterpret_cast<const float4*>(up + 4 * k4);
+        const float4 y = *reinterpret_cast<const float4*>(vp + 4 * k4);
+        accd = fma(static_cast<double>(x.x), static_cast<double>(y.x), accd);
+        accd = fma(static_cast<double>(x.y), static_cast<double>(y.y), accd);
+        accd = fma(static_cast<double>(x.z), static_cast<double>(y.z), accd);
+        accd = fma(static_cast<double>(x.w), static_cast<double>(y.w), accd);
+      }
+      sc[p] = accd;
+    }
+  }
+  // rank of every candidate = number of candidates that beat it (score desc, index asc)
+  int rank[PER];
+#pragma unroll
+  for (int p = 0; p < PER; ++p) rank[p] = 0;
+  for (int c = 0; c < cnt; ++c) {
+    double os = 0.0;
+    int oi = 0;
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+      const double s_p = __shfl_sync(FULL_MASK, sc[p], c & 31);
+      const int i_p = __shfl_sync(FULL_MASK, id[p], c & 31);
+      if ((c >> 5) == p) { os = s_p; oi = i_p; }
+    }
+#pragma unroll
+    for (int p = 0; p < PER; ++p)
+      if (id[p] >= 0 && beats(os, oi, sc[p], id[p])) ++rank[p];
+  }
+#pragma unroll
+  for (int p = 0; p < PER; ++p) {
+    if (id[p] >= 0 && rank[p] < n) {
+      idx_out[user * n + rank[p]] = id[p];
+      if (score_out) score_out[user * n + rank[p]] = sc[p];
+    }
+  }
+  for (int r = cnt + lane; r < n; r += 32) {       // fewer than n unseen items
+    idx_out[user * n + r] = -1;
+    if (score_out) score_out[user * n + r] = -CUDART_INF;
+  }
+}
+
+// ---- preprocessing of the item factors ------------------------------------------------------------------------------
+constexpr int PP_ROWS = 1024;     // items per block of the placement kernels
+
+// column sums in float64: deterministic two-stage reduction (partial[block][kp], then one block)
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ v, int64_t n, int kp, double* __restrict__ partial) {
+  __shared__ double red[256 * 4];
+  const int c4n = kp / 4, c4 = threadIdx.x % c4n, rl = threadIdx.x / c4n, rstep = 256 / c4n;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = per * blockIdx.x, r1 = min(n, r0 + per);
+  for (int64_t r = r0 + rl; r < r1; r += rstep) {
+    const float4 x = *reinterpret_cast<const float4*>(v + r * kp + 4 * c4);
+    s0 += x.x; s1 += x.y; s2 += x.z; s3 += x.w;
+  }
+  red[threadIdx.x * 4 + 0] = s0; red[threadIdx.x * 4 + 1] = s1; red[threadIdx.x * 4 + 2] = s2; red[threadIdx.x * 4 + 3] = s3;
+  __syncthreads();
+  if (rl == 0) {
+    for (int o = 1; o < rstep; ++o) {
+      s0 += red[(o * c4n + c4) * 4 + 0]; s1 += red[(o * c4n + c4) * 4 + 1];
+      s2 += red[(o * c4n + c4) * 4 + 2]; s3 += red[(o * c4n + c4) * 4 + 3];
+    }
+    double* p = partial + static_cast<int64_t>(blockIdx.x) * kp + 4 * c4;
+    p[0] = s0; p[1] = s1; p[2] = s2; p[3] = s3;
+  }
+}
+__global__ void __launch_bounds__(128) colsum_final_kernel(const double* __restrict__ partial, int nblk, int kp, int64_t n, float* __restrict__ vbar,
+                                                           ClassTable* __restrict__ tab) {
+  const int c = threadIdx.x;
+  if (c < kp) {
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += partial[static_cast<int64_t>(b) * kp + c];
+    vbar[c] = static_cast<float>(s / static_cast<double>(n));
+  }
+  if (c == 0) {
+    tab->wmax_bits = tab->amax_bits = tab->vmax_bits = 0u;
+    for (int i = 0; i < T2_NCLS; ++i) tab->wc_bits[i] = tab->rc_bits[i] = 0u;
+  }
+}
+
+// w_i = fl32(v_i - vbar): norms, largest norm, largest entry, largest |v_i| (kp / 4 lanes per row)
+__global__ void __launch_bounds__(256) centre_norm_kernel(const float* __restrict__ v, int64_t n, int kp, const float* __restrict__ vbar,
+                                                          float* __restrict__ wnorm, ClassTable* __restrict__ tab) {
+  const int c4n = kp / 4;
+  const int64_t total = n * c4n;
+  float wmax = 0.f, amax = 0.f, vmax = 0.f;
+  for (int64_t p0 = static_cast<int64_t>(blockIdx.x) * blockDim.x; p0 < total; p0 += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t p = p0 + threadIdx.x;
+    float nn = 0.f, vv = 0.f, am = 0.f;
+    int64_t r = 0;
+    if (p < total) {
+      r = p / c4n;
+      const int c4 = static_cast<int>(p - r * c4n);
+      const float4 x = *reinterpret_cast<const float4*>(v + r * kp + 4 * c4);
+      const float4 m = *reinterpret_cast<const float4*>(vbar + 4 * c4);
+      const float w0 = x.x - m.x, w1 = x.y - m.y, w2 = x.z - m.z, w3 = x.w - m.w;
+      nn = w0 * w0 + w1 * w1 + w2 * w2 + w3 * w3;
+      vv = x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+      am = fmaxf(fmaxf(fabsf(w0), fabsf(w1)), fmaxf(fabsf(w2), fabsf(w3)));
+    }
+    for (int o = c4n >> 1; o > 0; o >>= 1) {      // c4n is a power of two <= 32 and rows do not straddle warps
+      nn += __shfl_xor_sync(FULL_MASK, nn, o);
+      vv += __shfl_xor_sync(FULL_MASK, vv, o);
+    }
+    if (p < total) {
+      const float wn = sqrtf(nn) * 1.00001f;
+      if ((threadIdx.x & (c4n - 1)) == 0) wnorm[r] = wn;
+      wmax = fmaxf(wmax, wn);
+      vmax = fmaxf(vmax, sqrtf(vv) * 1.00001f);
+      amax = fmaxf(amax, am);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wmax = fmaxf(wmax, __shfl_xor_sync(FULL_MASK, wmax, o));
+    amax = fmaxf(amax, __shfl_xor_sync(FULL_MASK, amax, o));
+    vmax = fmaxf(vmax, __shfl_xor_sync(FULL_MASK, vmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&tab->wmax_bits, __float_as_uint(wmax));
+    atomicMax(&tab->amax_bits, __float_as_uint(amax));
+    atomicMax(&tab->vmax_bits, __float_as_uint(vmax));
+  }
+}
+
+__device__ __forceinline__ int class_of(float wn, float wmax) {
+  if (!(wn > 0.f) || !(wmax > 0.f)) return T2_NCLS - 1;
+  const float ratio = wmax / wn;                     // >= 1 up to rounding
+  int c = ilogbf(ratio);
+  return c < 0 ? 0 : (c > T2_NCLS - 1 ? T2_NCLS - 1 : c);
+}
+
+// class of every item, per-block class counts
+__global__ void __launch_bounds__(PP_ROWS) classify_kernel(const float* __restrict__ wnorm, int64_t n, const ClassTable* __restrict__ tab,
+                                                           unsigned char* __restrict__ cls, int* __restrict__ block_counts) {
+  __shared__ int cnt[T2_NCLS];
+  if (threadIdx.x < T2_NCLS) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * PP_ROWS + threadIdx.x;
+  if (r < n) {
+    const int c = class_of(wnorm[r], __uint_as_float(tab->wmax_bits));
+    cls[r] = static_cast<unsigned char>(c);
+    atomicAdd(&cnt[c], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < T2_NCLS) block_counts[blockIdx.x * T2_NCLS + threadIdx.x] = cnt[threadIdx.x];
+}
+
+// class bases (whole tiles), per-block offsets inside the classes, the scale
+__global__ void __launch_bounds__(32) class_scan_kernel(int* __restrict__ block_counts, int nblk, ClassTable* __restrict__ tab) {
+  __shared__ int total[T2_NCLS];
+  const int c = threadIdx.x;
+  if (c < T2_NCLS) {
+    int run = 0;
+    for (int b = 0; b < nblk; ++b) {
+      const int x = block_counts[b * T2_NCLS + c];
+      block_counts[b * T2_NCLS + c] = run;
+      run += x;
+    }
+    total[c] = run;
+  }
+  __syncwarp();
+  if (c == 0) {
+    int tile = 0;
+    for (int i = 0; i < T2_NCLS; ++i) {
+      tab->first_tile[i] = tile;
+      tile += (total[i] + T2_BN - 1) / T2_BN;
+    }
+    tab->first_tile[T2_NCLS] = tile;
+    tab->n_tiles = tile;
+    tab->scale = pow2_scale(__uint_as_float(tab->amax_bits));
+  }
+}
+
+// stable placement: position of item r = class base + (number of items of its class with a smaller id); writes the
+// position -> id map and the fp16 row of the centred, scaled factors; per-class maxima of |w s| and |w s - fp16(w s)|
+template <int KPH>
+__global__ void __launch_bounds__(PP_ROWS) place_kernel(const float* __restrict__ v, int64_t n, int kp, const float* __restrict__ vbar,
+                                                        const float* __restrict__ wnorm, const unsigned char* __restrict__ cls,
+                                                        const int* __restrict__ block_offsets, ClassTable* __restrict__ tab,
+                                                        int32_t* __restrict__ perm, __half* __restrict__ whi) {
+  __shared__ int warp_cnt[32][T2_NCLS];
+  __shared__ int pos_s[PP_ROWS];
+  __shared__ float rmax_s[T2_NCLS], wmax_s[T2_NCLS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * PP_ROWS + tid;
+  const int c = r < n ? cls[r] : -1;
+  int my_rank = 0;
+#pragma unroll
+  for (int k = 0; k < T2_NCLS; ++k) {
+    const unsigned m = __ballot_sync(FULL_MASK, c == k);
+    if (c == k) my_rank = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) warp_cnt[warp][k] = __popc(m);
+  }
+  if (tid < T2_NCLS) { rmax_s[tid] = 0.f; wmax_s[tid] = 0.f; }
+  __syncthreads();
+  int pos = -1;
+  if (c >= 0) {
+    int before = 0;
+    for (int wv = 0; wv < warp; ++wv) before += warp_cnt[wv][c];
+    pos = tab->first_tile[c] * T2_BN + block_offsets[blockIdx.x * T2_NCLS + c] + before + my_rank;
+    perm[pos] = static_cast<int32_t>(r);
+  }
+  pos_s[tid] = pos;
+  __syncthreads();
+  // rows of this block, KPH / 4 lanes per row
+  const float s = tab->scale;
+  constexpr int C4N = KPH / 4;
+  for (int p = tid; p < PP_ROWS * C4N; p += PP_ROWS) {
+    const int rl = p / C4N, c4 = p % C4N;
+    const int64_t rr = static_cast<int64_t>(blockIdx.x) * PP_ROWS + rl;
+    float res = 0.f;
+    const int ps = pos_s[rl];
+    if (rr < n) {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f), m = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (4 * c4 < kp) {
+        x = *reinterpret_cast<const float4*>(v + rr * kp + 4 * c4);
+        m = *reinterpret_cast<const float4*>(vbar + 4 * c4);
+      }
+      const float w0 = (x.x - m.x) * s, w1 = (x.y - m.y) * s, w2 = (x.z - m.z) * s, w3 = (x.w - m.w) * s;
+      const __half2 h0 = __floats2half2_rn(w0, w1), h1 = __floats2half2_rn(w2, w3);
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      const float d0 = w0 - f0.x, d1 = w1 - f0.y, d2 = w2 - f1.x, d3 = w3 - f1.y;
+      res = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      uint2 packed;
+      packed.x = *reinterpret_cast<const uint32_t*>(&h0);
+      packed.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(whi + static_cast<int64_t>(ps) * KPH + 4 * c4) = packed;
+    }
+    for (int o = C4N >> 1; o > 0; o >>= 1) res += __shfl_xor_sync(FULL_MASK, res, o);
+    if (rr < n && c4 == 0) {
+      const int cc = cls[rr];
+      atomicMax(reinterpret_cast<unsigned*>(&rmax_s[cc]), __float_as_uint(sqrtf(res) * 1.0001f));
+      atomicMax(reinterpret_cast<unsigned*>(&wmax_s[cc]), __float_as_uint(wnorm[rr] * s * 1.0001f));
+    }
+  }
+  __syncthreads();
+  if (tid < T2_NCLS) {
+    atomicMax(&tab->rc_bits[tid], __float_as_uint(rmax_s[tid]));
+    atomicMax(&tab->wc_bits[tid], __float_as_uint(wmax_s[tid]));
+  }
+}
+
+// suffix maxima: the window of a class never is narrower than that of a later class (thresholds only move up)
+__global__ void class_finish_kernel(ClassTable* __restrict__ tab) {
+  if (threadIdx.x == 0) {
+    float w = 0.f, r = 0.f;
+    for (int c = T2_NCLS - 1; c >= 0; --c) {
+      w = fmaxf(w, __uint_as_float(tab->wc_bits[c]));
+      r = fmaxf(r, __uint_as_float(tab->rc_bits[c]));
+      tab->wc[c] = w;
+      tab->rc[c] = r;
+    }
+    tab->vmax_raw = __uint_as_float(tab->vmax_bits) * tab->scale * 1.0001f;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode2() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_map2(rl_context* h, CUtensorMap* map, const __half* ptr, int64_t rows, int kp) {
+  EncodeTiledFn enc = get_encode2();
+  if (!enc) return fail(h, RL_ERR_CUDA, "score_tc2: cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kp), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kp) * 2};
+  const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(T2_BN)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, RL_ERR_CUDA, "score_tc2: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return RL_OK;
+}
+
+template <int KP, bool DUMP>
+int launch_tc2_n(rl_context* h, const CUtensorMap& mw, const T2Args& a) {
+  const size_t smem = T2Smem<KP>::total;
+  int grid = a.n_user_tiles < 2 * h->sm_count ? (a.n_user_tiles + 1) / 2 : h->sm_count;
+  if (a.n <= 10) {
+    auto kern = score_tc2_kernel<KP, 10, DUMP>;
+    RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, T2_THREADS, smem, h->stream>>>(mw, a);
+  } else {
+    auto kern = score_tc2_kernel<KP, 16, DUMP>;
+    RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, T2_THREADS, smem, h->stream>>>(mw, a);
+  }
+  RL_LAUNCH_CHECK(h, "score_tc2_kernel");
+  return RL_OK;
+}
+
+}  // namespace
+
+bool score_tc2_supported(int kp, int n, int64_t n_users, int64_t n_items, const float* ubias, const float* ibias, double gbias) {
+  return (kp == 16 || kp == 32 || kp == 64) && n <= 16 && n_items >= 1024 && n_items < (INT64_C(1) << 30) && n_users >= 1 && !ubias &&
+         !ibias && gbias == 0.0;
+}
+
+// Centred single-product candidate pass + exact re-scoring.  Rows whose candidate list overflows are appended to the
+// overflow list (defer, or the call's own list which is then finished by the exact kernel).
+// dump != nullptr: debug mode, writes the raw accumulators (n_users x dump_ld, positions in class order), the row scales
+// (dump_su), the position -> id map (dump_perm, dump_ld entries) and the class table (dump_tab, 64 floats/ints).
+int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefer* defer, float* dump, int64_t dump_ld, float* dump_su,
+                     int32_t* dump_perm, void* dump_tab) {
+  const int kph = 64;
+  const int64_t n_items = sa.n_items;
+  const int64_t n_pos = ((n_items + T2_BN - 1) / T2_BN + T2_NCLS) * T2_BN;
+  const int nblk = static_cast<int>((n_items + PP_ROWS - 1) / PP_ROWS);
+  const int csum_blocks = 64;
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  // scratch layout
+  size_t off = 0;
+  const size_t o_tab = off; off += al(sizeof(ClassTable));
+  const size_t o_cnt = off; off += al(256);                                            // overflow count (+ debug counters)
+  const size_t o_dbg = off; off += al(128 * sizeof(long long));
+  const size_t o_vbar = off; off += al(sizeof(float) * 128);
+  const size_t o_part = off; off += al(sizeof(double) * csum_blocks * kp);
+  const size_t o_wn = off; off += al(sizeof(float) * n_items);
+  const size_t o_cls = off; off += al(n_items);
+  const size_t o_bc = off; off += al(sizeof(int) * nblk * T2_NCLS);
+  const size_t o_perm = off; off += al(sizeof(int32_t) * n_pos);
+  const size_t o_whi = off; off += al(sizeof(__half) * n_pos * kph);
+  const size_t o_orow = off; off += al(sizeof(int32_t) * sa.n_users);
+  const size_t o_ccnt = off; off += al(sizeof(int32_t) * sa.n_users);
+  const size_t o_cids = off; off += al(sizeof(int32_t) * sa.n_users * T2_CAND);
+  void* sc = nullptr;
+  int rc = scratch(h, off, &sc);
+  if (rc != RL_OK) return rc;
+  char* scb = static_cast<char*>(sc);
+  ClassTable* tab = reinterpret_cast<ClassTable*>(scb + o_tab);
+  unsigned int* ocount = reinterpret_cast<unsigned int*>(scb + o_cnt);
+  long long* dbg = reinterpret_cast<long long*>(scb + o_dbg);
+  float* vbar = reinterpret_cast<float*>(scb + o_vbar);
+  double* partial = reinterpret_cast<double*>(scb + o_part);
+  float* wnorm = reinterpret_cast<float*>(scb + o_wn);
+  unsigned char* cls = reinterpret_cast<unsigned char*>(scb + o_cls);
+  int* bc = reinterpret_cast<int*>(scb + o_bc);
+  int32_t* perm = reinterpret_cast<int32_t*>(scb + o_perm);
+  __half* whi = reinterpret_cast<__half*>(scb + o_whi);
+  int32_t* orows = reinterpret_cast<int32_t*>(scb + o_orow);
+  int32_t* ccnt = reinterpret_cast<int32_t*>(scb + o_ccnt);
+  int32_t* cids = reinterpret_cast<int32_t*>(scb + o_cids);
+
+  if (!dump && !(h->preloaded_exact & (1u << (kp >> 4)))) {
+    // first use of the fallback (module load, attribute set-up, pool growth) must not land inside a later, timed call
+    h->preloaded_exact |= 1u << (kp >> 4);
+    RL_CUDA(h, cudaMemsetAsync(orows, 0, sizeof(int32_t), h->stream));
+    ScoreArgs ea = sa;
+    ea.user_list = orows;
+    ea.n_list = 1;
+    ea.scatter = true;
+    if ((rc = launch_score_exact(h, kp, ea)) != RL_OK) return rc;
+  }
+  RL_CUDA(h, cudaMemsetAsync(scb + o_cnt, 0, 256 + al(128 * sizeof(long long)), h->stream));
+  RL_CUDA(h, cudaMemsetAsync(perm, 0xFF, sizeof(int32_t) * n_pos, h->stream));
+  RL_CUDA(h, cudaMemsetAsync(whi, 0, sizeof(__half) * n_pos * kph, h->stream));
+  colsum_partial_kernel<<<csum_blocks, 256, 0, h->stream>>>(sa.vf, n_items, kp, partial);
+  RL_LAUNCH_CHECK(h, "colsum_partial_kernel");
+  colsum_final_kernel<<<1, 128, 0, h->stream>>>(partial, csum_blocks, kp, n_items, vbar, tab);
+  RL_LAUNCH_CHECK(h, "colsum_final_kernel");
+  {
+    int64_t g = (n_items * (kp / 4) + 255) / 256;
+    if (g > 8 * h->sm_count) g = 8 * h->sm_count;
+    centre_norm_kernel<<<static_cast<unsigned>(g), 256, 0, h->stream>>>(sa.vf, n_items, kp, vbar, wnorm, tab);
+    RL_LAUNCH_CHECK(h, "centre_norm_kernel");
+  }
+  classify_kernel<<<nblk, PP_ROWS, 0, h->stream>>>(wnorm, n_items, tab, cls, bc);
+  RL_LAUNCH_CHECK(h, "classify_kernel");
+  class_scan_kernel<<<1, 32, 0, h->stream>>>(bc, nblk, tab);
+  RL_LAUNCH_CHECK(h, "class_scan_kernel");
+  place_kernel<64><<<nblk, PP_ROWS, 0, h->stream>>>(sa.vf, n_items, kp, vbar, wnorm, cls, bc, tab, perm, whi);
+  RL_LAUNCH_CHECK(h, "place_kernel");
+  class_finish_kernel<<<1, 32, 0, h->stream>>>(tab);
+  RL_LAUNCH_CHECK(h, "class_finish_kernel");
+
+  CUtensorMap mw;
+  if ((rc = make_map2(h, &mw, whi, n_pos, kph)) != RL_OK) return rc;
+  T2Args a{};
+  a.uf = sa.uf; a.ldf = kp; a.n_users = sa.n_users; a.seen_indptr = sa.seen_indptr; a.seen_indices = sa.seen_indices; a.n = sa.n;
+  a.tab = tab; a.perm = perm; a.cand_ids = cids; a.cand_cnt = ccnt;
+  a.acc_rel = static_cast<float>(kph) * 1.1920929e-7f;      // k * 2^-23
+  a.dump = dump; a.dump_su = dump_su; a.dump_ld = dump_ld;
+  a.n_user_tiles = static_cast<int>((sa.n_users + T2_BM - 1) / T2_BM);
+  const bool want_dbg = getenv("RL_TC_DEBUG") != nullptr;
+  a.dbg = want_dbg ? dbg : nullptr;
+  if (dump) {
+    if ((rc = launch_tc2_n<64, true>(h, mw, a)) != RL_OK) return rc;
+    if (dump_perm) RL_CUDA(h, cudaMemcpyAsync(dump_perm, perm, sizeof(int32_t) * (dump_ld < n_pos ? dump_ld : n_pos), cudaMemcpyDeviceToDevice, h->stream));
+    if (dump_tab) RL_CUDA(h, cudaMemcpyAsync(dump_tab, tab, 256, cudaMemcpyDeviceToDevice, h->stream));
+    return RL_OK;
+  }
+  if ((rc = launch_tc2_n<64, false>(h, mw, a)) != RL_OK) return rc;
+  int32_t* o_rows = defer ? defer->rows : orows;
+  unsigned int* o_count = defer ? defer->count : ocount;
+  const int64_t row_offset = defer ? defer->row_offset : 0;
+  {
+    const unsigned g = static_cast<unsigned>((sa.n_users + 7) / 8);
+    switch (kp) {
+      case 16: rescore_kernel<16><<<g, 256, 0, h->stream>>>(sa.uf, sa.vf, sa.n_users, sa.n, cids, ccnt, sa.idx_out, sa.score_out, o_rows, o_count, row_offset); break;
+      case 32: rescore_kernel<32><<<g, 256, 0, h->stream>>>(sa.uf, sa.vf, sa.n_users, sa.n, cids, ccnt, sa.idx_out, sa.score_out, o_rows, o_count, row_offset); break;
+      default: rescore_kernel<64><<<g, 256, 0, h->stream>>>(sa.uf, sa.vf, sa.n_users, sa.n, cids, ccnt, sa.idx_out, sa.score_out, o_rows, o_count, row_offset); break;
+    }
+    RL_LAUNCH_CHECK(h, "rescore_kernel");
+  }
+  if (want_dbg) {
+    long long d[128];
+    RL_CUDA(h, cudaMemcpyAsync(d, dbg, sizeof(d), cudaMemcpyDeviceToHost, h->stream));
+    RL_CUDA(h, cudaStreamSynchronize(h->stream));
+    fprintf(stderr, "score_tc2 dbg (block 0, cycles): mma total %lld wait_A %lld wait_Tempty %lld wait_Bfull %lld\n", d[0], d[1], d[2], d[3]);
+    for (int w = 0; w < 8; ++w)
+      fprintf(stderr, "  scan warp %d: total %lld wait_Tfull %lld wait_ring %lld pushes(lane0) %lld\n", w, d[8 + 4 * w], d[9 + 4 * w], d[10 + 4 * w], d[11 + 4 * w]);
+    for (int w = 0; w < 8; ++w)
+      fprintf(stderr, "  sel warp %d: total %lld idle %lld records(lane0) %lld compactions %lld\n", w, d[40 + 4 * w], d[41 + 4 * w], d[42 + 4 * w], d[43 + 4 * w]);
+  }
+  if (defer) return RL_OK;
+  unsigned int n_over = 0;
+  RL_CUDA(h, cudaMemcpyAsync(&n_over, ocount, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->last_overflow = n_over;
+  if (n_over > 0) {
+    ScoreArgs ea = sa;
+    ea.user_list = orows;
+    ea.n_list = n_over;
+    ea.scatter = true;
+    return launch_score_exact(h, kp, ea);
+  }
+  return RL_OK;
+}
+
+}  // namespace rl
