@@ -34,6 +34,9 @@ struct rl_context {
   // cooperative kernel?  Answered once per pattern by a reduction over indptr; a stale "no" only costs speed.
   struct LongRowsEntry { const void* indptr; int64_t n_rows; bool has_long; };
   std::vector<LongRowsEntry> long_rows_cache;
+  // scoring: number of entries of a seen-item pattern (keyed like long_rows_cache), read from the device once
+  struct SeenNnzEntry { const void* indptr; int64_t n_rows; int64_t nnz; };
+  std::vector<SeenNnzEntry> seen_nnz_cache;
   unsigned int preloaded_exact = 0;  // bit (kp >> 4): fallback kernels of the tensor-core scoring path are loaded
   unsigned int last_overflow = 0;  // rows the last tensor-core scoring call handed to the exact kernel
   std::vector<std::pair<void*, void*>> ipc_bases;  // (pointer handed out by rl_ipc_open, base of the mapping)

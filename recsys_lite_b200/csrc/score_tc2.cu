@@ -63,34 +63,36 @@ constexpr int T2_NCLS = 8;        // item classes by |w_i| (factor of two each)
 constexpr int T2_THREADS = 32 * 20;
 constexpr int T2_RING = 16;       // ring slots per row
 constexpr int T2_CAND = 40;       // candidate slots per row
-constexpr int T2_IDS = 8;         // item-id slices in flight (one per half-tile, indexed by sequence number)
+constexpr int T2_WIN = 32;        // seen positions of a row kept in shared memory at a time
 constexpr int T2_EMPTY = INT_MIN; // ring slot free
-constexpr int T2_END = -100;      // ring marker: end of the sweep
-constexpr int T2_CLS0 = -2;       // ring marker: class c starts = T2_CLS0 - c   (item id -1 = padding position)
+constexpr int T2_END = -100;      // ring marker: end of the sweep (records carry item POSITIONS >= 0)
+constexpr int T2_PERIOD = 3000;   // clocks between selection passes when no ring is filling up
 
 // what the preprocessing kernels leave for the main kernel
 struct ClassTable {
   int first_tile[T2_NCLS + 1];    // first item tile of class c; first_tile[T2_NCLS] = n_tiles
   int n_tiles;
   int pad0;
-  float wc[T2_NCLS];              // >= max over classes c' >= c of |w_i| s          (raw units, inflated)
-  float rc[T2_NCLS];              // >= max over classes c' >= c of |w_i s - fp16(w_i s)|
+  float wc[T2_NCLS];              // >= max over class c of |w_i| s                    (raw units, inflated)
+  float rc[T2_NCLS];              // >= max over class c of |w_i s - fp16(w_i s)|
   float scale;                    // s: power of two, max |w_ij| s <= 2^14
   float vmax_raw;                 // >= max_i |v_i| s
   unsigned wmax_bits, amax_bits, vmax_bits;   // reductions in progress (non-negative floats order as unsigned)
   unsigned wc_bits[T2_NCLS], rc_bits[T2_NCLS];
+  int count[T2_NCLS];             // items of class c (its last tile is padded with zero rows)
 };
 
 template <int KP>
 struct T2Smem {
-  static constexpr int SLOTS = KP > 64 ? 2 : 4;
+  static constexpr int SLOTS = KP > 64 ? 2 : 3;
   static constexpr uint32_t B_BYTES = T2_BN * KP * 2;
   static constexpr uint32_t off_b = 0;
   static constexpr uint32_t off_ring = off_b + SLOTS * B_BYTES;                    // [RING][256] (score, id)
   static constexpr uint32_t off_cand = off_ring + T2_RING * 2 * T2_BM * 8;         // [CAND][256] (upper bound, id)
   static constexpr uint32_t off_thr = off_cand + T2_CAND * 2 * T2_BM * 8;          // [256] (threshold, sweep tag)
-  static constexpr uint32_t off_ids = off_thr + 2 * T2_BM * 8;                     // [T2_IDS][128] item ids
-  static constexpr uint32_t off_tab = off_ids + T2_IDS * T2_BN * 4;                // ClassTable copy
+  static constexpr uint32_t off_win = off_thr + 2 * T2_BM * 8;                     // [T2_WIN][256] next seen positions of a row
+  static constexpr uint32_t off_eps = off_win + T2_WIN * 2 * T2_BM * 4;            // [2 sweep parities][NCLS][256] windows
+  static constexpr uint32_t off_tab = off_eps + 2 * T2_NCLS * 2 * T2_BM * 4;       // ClassTable copy
   static constexpr uint32_t off_bar = off_tab + 256;
   static constexpr uint32_t total = off_bar + 256 + 1024;
   static_assert(sizeof(ClassTable) <= 256, "class table");
@@ -102,11 +104,11 @@ struct T2Args {
   int ldf;
   int64_t n_users;
   const int64_t* seen_indptr;
-  const int32_t* seen_indices;
   int n;
   const ClassTable* tab;
-  const int32_t* perm;          // position -> item id (-1: padding)
-  int32_t* cand_ids;            // [n_users][T2_CAND]
+  const int32_t* seen_pos;      // the seen items of every row as POSITIONS, ascending per row (same indptr as seen_indices)
+  int64_t seen_cap;             // entries seen_pos has room for (rows beyond it go to the exact kernel)
+  int32_t* cand_ids;            // [n_users][T2_CAND] candidate positions
   int32_t* cand_cnt;            // [n_users]: number of candidates, -1 = overflow (row goes to the exact kernel)
   float acc_rel;                // allowance for the fp32 accumulation of the tensor core, relative to |u_h||w_h|
   float* dump;                  // debug: raw accumulators (n_users x dump_ld), dump_su: the row scales
@@ -114,6 +116,7 @@ struct T2Args {
   int64_t dump_ld;
   int n_user_tiles;
   long long* dbg;
+  int dbg_flags;                // RL_TC2_FLAGS: 1 = the scan pushes nothing, 2 = selection skips the seen cursor, 4 = stages released unread, 8 = loads only
 };
 
 __device__ __forceinline__ void ring_put(uint32_t addr, float score, int id) {
@@ -151,6 +154,8 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
   constexpr int A_BUFS = KP <= 64 ? 2 : 1;
   constexpr uint32_t A_COLS = KP / 2;           // TMEM columns of one user tile (two fp16 per column)
   constexpr uint32_t ACC_COL0 = 128;
+  constexpr uint32_t RS = 2 * T2_BM * 8;        // byte stride between ring / candidate slots of one row
+  constexpr uint32_t ES = 2 * T2_BM * 4;        // byte stride between classes of the window table / seen-window entries
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // contiguous range of 128-user tiles of this CTA, taken two at a time
@@ -160,7 +165,7 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < SLOTS; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
-    for (int i = 0; i < T2_ACC; ++i) { mbar_init(BAR(T_FULL + i), 2); mbar_init(BAR(T_EMPTY + i), 4); }
+    for (int i = 0; i < T2_ACC; ++i) { mbar_init(BAR(T_FULL + i), 1); mbar_init(BAR(T_EMPTY + i), 4); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(A_FULL + i), 8); mbar_init(BAR(A_EMPTY + i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -215,10 +220,6 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
             const uint32_t acc = seq % T2_ACC, aph = (seq / T2_ACC) & 1;
             mbar_wait_t(BAR(T_EMPTY + acc), aph ^ 1, w_t);
             tc_fence_after();
-            // the item ids of this tile travel with the accumulator stage (the B slot is recycled before the scan)
-            mbar_expect_tx(BAR(T_FULL + acc), T2_BN * 4);
-            bulk_load(base + S::off_ids + (seq % T2_IDS) * (T2_BN * 4), a.perm + static_cast<int64_t>(it) * T2_BN, T2_BN * 4,
-                      BAR(T_FULL + acc));
             const uint32_t d_tmem = tmem_base + ACC_COL0 + acc * T2_BN;
             const uint32_t a_tmem = tmem_base + a_buf(j) * (2 * A_COLS) + hh * A_COLS;
 #pragma unroll
@@ -237,82 +238,90 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
     // =========================================== scan warps ================================================
     const int hh = (warp - 4) >> 2, q = warp & 3;
     const int rowg = hh * T2_BM + q * 32 + lane;                 // row inside the CTA's pair of user tiles
-    const uint32_t ring_row = base + S::off_ring + 8u * rowg;     // slot r at + r * (256 * 8)
+    const uint32_t ring_row = base + S::off_ring + 8u * rowg;     // slot r at + r * RS
     const uint32_t thr_addr = base + S::off_thr + 8u * rowg;
     uint32_t seq_base = 0, tail = 0;
-    long long w_full = 0, w_ring = 0, n_push = 0;
+    long long w_full = 0, n_push = 0, n_slow = 0;
     const long long t_start = clock64();
-    auto push = [&](float sc, int id) {
-      const uint32_t addr = ring_row + (tail % T2_RING) * (2 * T2_BM * 8);
-      if (lds_volatile(addr + 4) != T2_EMPTY) {
-        const long long t0 = clock64();
-        uint32_t spin = 0;
-        while (lds_volatile(addr + 4) != T2_EMPTY) {
-          __nanosleep(40);
-          if (++spin > (1u << 24)) { printf("score_tc2: ring timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-        }
-        w_ring += clock64() - t0;
+    // room for `need` more records in this row's ring (the selection thread frees slots in order)
+    auto wait_room = [&](uint32_t need) {
+      const uint32_t addr = ring_row + ((tail + need - 1) % T2_RING) * RS + 4;
+      uint32_t spin = 0;
+      while (lds_volatile(addr) != T2_EMPTY) {
+        __nanosleep(32);
+        if (++spin > (1u << 24)) { printf("score_tc2: ring timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
       }
-      ring_put(addr, sc, id);
-      ++tail;
-      ++n_push;
     };
     for (int j = 0; j < n_sweeps; ++j) {
       const int halves = (tile_begin + 2 * j + 1 < tile_end) ? 2 : 1;
       if (hh >= halves) { seq_base += static_cast<uint32_t>(n_tiles) * halves; continue; }
       const int64_t user = static_cast<int64_t>(tile_begin + 2 * j + hh) * T2_BM + q * 32 + lane;
       const bool valid = user < a.n_users;
-      int cls = 0;
-      while (cls + 1 < T2_NCLS && tab->first_tile[cls + 1] == 0) ++cls;      // empty leading classes
-      int next_cls_tile = tab->first_tile[cls + 1];
-      if (!DUMP && valid) push(0.f, T2_CLS0 - cls);
+      const uint32_t eps_row = base + S::off_eps + (static_cast<uint32_t>(j & 1) * T2_NCLS * 2 * T2_BM + rowg) * 4u;
+      // the windows of this sweep were written by the selection warps before they released the user tile: they are read
+      // after an accumulator barrier of the sweep (which orders them), never before
+      int cls = -1, next_cls_tile = 0;
+      float eps_c = 0.f;
       for (int it = 0; it < n_tiles; ++it) {
         const uint32_t seq = seq_base + (halves == 2 ? 2 * it + hh : it);
         const uint32_t acc = seq % T2_ACC, aph = (seq / T2_ACC) & 1;
-        if (it == next_cls_tile) {
-          while (cls + 1 < T2_NCLS && tab->first_tile[cls + 1] <= it) ++cls;
-          next_cls_tile = cls + 1 <= T2_NCLS ? tab->first_tile[cls + 1] : n_tiles;
-          if (!DUMP && valid) push(0.f, T2_CLS0 - cls);
-        }
         mbar_wait_t(BAR(T_FULL + acc), aph, w_full);
         tc_fence_after();
+        if (it >= next_cls_tile) {
+          do { ++cls; next_cls_tile = tab->first_tile[cls + 1]; } while (it >= next_cls_tile);
+          eps_c = __int_as_float(lds_volatile(eps_row + cls * ES));
+        }
         float thr;
         {
+          // the selection thread publishes the n-th best LOWER bound of this sweep; an item of this class can only matter
+          // if its upper bound reaches it
+          float lth;
           int tag;
-          ring_get(thr_addr, thr, tag);
-          if (tag != j) thr = -CUDART_INF_F;
-          if (!valid) thr = CUDART_INF_F;
+          ring_get(thr_addr, lth, tag);
+          if (tag != j) lth = -CUDART_INF_F;
+          thr = valid ? __fsub_rd(lth, eps_c) : CUDART_INF_F;
+          if (a.dbg_flags & 1) thr = CUDART_INF_F;
         }
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ACC_COL0 + acc * T2_BN;
-        const int* ids = reinterpret_cast<const int*>(sm + S::off_ids + (seq % T2_IDS) * (T2_BN * 4));
         auto release_stage = [&]() {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
         };
+        if (a.dbg_flags & 4) { release_stage(); continue; }        // debug: MMA / TMA ceiling (stages released unread)
         float s0[32], s1[32];
-        auto scan32 = [&](const float (&sg)[32], const int col0) {
+        auto scan32 = [&](const float (&sg)[32], const int pos0) {
+          if (a.dbg_flags & 8) {                                    // debug: TMEM read ceiling (loads, no selection)
+            if (sg[0] == 1.2345e-30f) ++n_push;
+            return;
+          }
           if (DUMP) {
             if (valid) {
 #pragma unroll
-              for (int jj = 0; jj < 32; ++jj) a.dump[user * a.dump_ld + static_cast<int64_t>(it) * T2_BN + col0 + jj] = sg[jj];
+              for (int jj = 0; jj < 32; ++jj) a.dump[user * a.dump_ld + pos0 + jj] = sg[jj];
             }
             return;
           }
+          bool any = false;
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             const float m8 = max3(max3(sg[8 * b], sg[8 * b + 1], sg[8 * b + 2]), max3(sg[8 * b + 3], sg[8 * b + 4], sg[8 * b + 5]),
                                   fmaxf(sg[8 * b + 6], sg[8 * b + 7]));
             if (m8 > thr) {
+              // (score, position) records for the selection thread: straight-line predicated stores once 8 slots are free
+              wait_room(8);
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) {
                 if (sg[8 * b + jj] > thr) {
-                  const int id = ids[col0 + 8 * b + jj];
-                  if (id >= 0) push(sg[8 * b + jj], id);
+                  ring_put(ring_row + (tail % T2_RING) * RS, sg[8 * b + jj], pos0 + 8 * b + jj);
+                  ++tail;
+                  ++n_push;
                 }
               }
+              any = true;
             }
           }
+          if (any) ++n_slow;
           __syncwarp();     // the pushes diverge; tcgen05.ld / wait need the whole warp
         };
         tc_ld32(t_row, s0);
@@ -320,19 +329,24 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
         for (int gp = 0; gp < T2_BN / 64; ++gp) {
           tc_wait_ld_dep(s0);
           tc_ld32(t_row + gp * 64 + 32, s1);
-          scan32(s0, gp * 64);
+          scan32(s0, it * T2_BN + gp * 64);
           tc_wait_ld_dep(s1);
           if (gp + 1 < T2_BN / 64) tc_ld32(t_row + gp * 64 + 64, s0);
           else release_stage();
-          scan32(s1, gp * 64 + 32);
+          scan32(s1, it * T2_BN + gp * 64 + 32);
         }
       }
-      if (!DUMP && valid) push(0.f, T2_END);
+      if (!DUMP && valid) {
+        wait_room(1);
+        ring_put(ring_row + (tail % T2_RING) * RS, 0.f, T2_END);
+        ++tail;
+      }
+      __syncwarp();
       seq_base += static_cast<uint32_t>(n_tiles) * halves;
     }
     if (a.dbg && blockIdx.x == 0 && lane == 0) {
       long long* d = a.dbg + 8 + 4 * (warp - 4);
-      d[0] = clock64() - t_start; d[1] = w_full; d[2] = w_ring; d[3] = n_push;
+      d[0] = clock64() - t_start; d[1] = w_full; d[2] = n_slow; d[3] = n_push;
     }
   } else if (warp >= 12) {
     // ======================== selection warps: user-tile loaders + per-row selection ==========================
@@ -341,10 +355,10 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
     const uint32_t ring_row = base + S::off_ring + 8u * rowg;
     const uint32_t cand_row = base + S::off_cand + 8u * rowg;
     const uint32_t thr_addr = base + S::off_thr + 8u * rowg;
+    const uint32_t win_row = base + S::off_win + 4u * rowg;       // seen-position window: entry i at + i * ES
     const uint32_t t_row0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const float scale = tab->scale;
-    // writes the user tile of sweep j (this thread: one row of half hh) into TMEM; returns (|u s_u - u_h|, |u_h|, |u s_u|)
-    auto load_tile = [&](int j) -> float3 {
+    // writes the user tile of sweep j (this thread: one row of half hh) into TMEM and the row's windows into shared memory
+    auto load_tile = [&](int j) {
       const int tile = tile_begin + 2 * j + hh;
       const int64_t user = static_cast<int64_t>(tile) * T2_BM + q * 32 + lane;
       const bool valid = tile < tile_end && user < a.n_users;
@@ -381,129 +395,156 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
         }
         tc_st32(t_row + c0 / 2, hi);
       }
+      if (DUMP && valid) a.dump_su[user] = su;
+      // the windows of this row, one per item class, for the scan thread and the selection thread of sweep j
+      const float e1 = sqrtf(rr) * 1.0001f, e2 = sqrtf(hn) * 1.0001f, e3 = sqrtf(nn) * 1.0001f;
+      const uint32_t eps_row = base + S::off_eps + (static_cast<uint32_t>(j & 1) * T2_NCLS * 2 * T2_BM + rowg) * 4u;
+#pragma unroll
+      for (int c = 0; c < T2_NCLS; ++c) {
+        const float wcc = tab->wc[c], rcc = tab->rc[c];
+        const float eps = (e1 * wcc + e2 * rcc + a.acc_rel * e2 * (wcc + rcc) + e3 * (6.1e-8f * wcc + 6.0e-14f * tab->vmax_raw)) * 1.0001f + 1e-30f;
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(eps_row + c * ES), "r"(__float_as_int(eps)) : "memory");
+      }
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(A_FULL + a_buf(j)));
-      if (DUMP && valid) a.dump_su[user] = su;
-      return make_float3(sqrtf(rr) * 1.0001f, sqrtf(hn) * 1.0001f, sqrtf(nn) * 1.0001f);
     };
-    float3 e_cur = load_tile(0), e_nxt = make_float3(0.f, 0.f, 0.f);
-    if (A_BUFS == 2 && n_sweeps > 1) e_nxt = load_tile(1);
+    for (int j = 0; j < A_BUFS && j < n_sweeps; ++j) load_tile(j);
     if (DUMP) {
       for (int j = A_BUFS; j < n_sweeps; ++j) load_tile(j);
     } else {
       uint32_t head = 0;
-      long long c_idle = 0, n_rec = 0, n_cmp = 0;
+      long long c_idle = 0, n_rec = 0, n_cmp = 0, n_pass = 0, n_iter = 0, c_pass = 0, n_refill = 0;
       const long long t_start = clock64();
       for (int j = 0; j < n_sweeps; ++j) {
         const int halves = (tile_begin + 2 * j + 1 < tile_end) ? 2 : 1;
         const int64_t user = static_cast<int64_t>(tile_begin + 2 * j + hh) * T2_BM + q * 32 + lane;
         const bool valid = hh < halves && user < a.n_users;
-        if (valid) {
-          // ---- per-row state of this sweep (registers) ----
-          float tk[NT];
+        const uint32_t eps_row = base + S::off_eps + (static_cast<uint32_t>(j & 1) * T2_NCLS * 2 * T2_BM + rowg) * 4u;
+        // ---- per-row state of this sweep (registers) ----
+        float tk[NT];
 #pragma unroll
-          for (int i = 0; i < NT; ++i) tk[i] = i < NT - a.n ? CUDART_INF_F : -CUDART_INF_F;
-          float lth = -CUDART_INF_F, eps = 0.f;
-          int cnt = 0;
-          bool over = false;
-          int64_t row_begin = 0, cur = 0, end = 0;
-          if (a.seen_indptr) { row_begin = a.seen_indptr[user]; end = a.seen_indptr[user + 1]; }
-          int w[8], wp = 0, nxt = INT_MAX;
-          auto refill = [&]() {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = (cur + i < end) ? a.seen_indices[cur + i] : INT_MAX;
-            wp = 0;
-            nxt = w[0];
-          };
-          auto publish = [&]() {
-            const float thr = over ? CUDART_INF_F : __fsub_rd(lth, eps);
-            ring_put(thr_addr, thr, j);
-          };
-          auto compact = [&]() {
-            int jw = 0;
-            for (int f = 0; f < cnt; ++f) {
-              float hb; int id;
-              ring_get(cand_row + f * (2 * T2_BM * 8), hb, id);
-              if (hb >= lth) { ring_put(cand_row + jw * (2 * T2_BM * 8), hb, id); ++jw; }
-            }
-            cnt = jw;
-            ++n_cmp;
-          };
+        for (int i = 0; i < NT; ++i) tk[i] = i < NT - a.n ? CUDART_INF_F : -CUDART_INF_F;
+        float lth = -CUDART_INF_F, eps = 0.f;
+        int cnt = 0, cls = -1, cls_end_pos = 0, real_end_pos = 0;
+        bool over = false, done = !valid, dirty = false;
+        // cursor into the row's seen positions (ascending; a window of T2_WIN of them lives in shared memory)
+        int64_t cur = 0, end = 0;
+        if (valid && a.seen_indptr) {
+          cur = a.seen_indptr[user];
+          end = a.seen_indptr[user + 1];
+          if (end > a.seen_cap || cur > end) {      // stale capacity: the exact kernel takes the row
+            over = true; cur = end = 0; lth = CUDART_INF_F;
+            ring_put(thr_addr, lth, j);
+          }
+        }
+        int wp = 0, nxt = INT_MAX;
+        auto refill = [&]() {                                     // window <- seen_pos[cur .. cur + T2_WIN)
+#pragma unroll 8
+          for (int i = 0; i < T2_WIN; ++i) {
+            const int v = (cur + i < end) ? a.seen_pos[cur + i] : INT_MAX;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(win_row + i * ES), "r"(v) : "memory");
+          }
+          wp = 0;
+          nxt = lds_volatile(win_row);
+          ++n_refill;
+        };
+        if (valid) refill();
+        auto compact = [&]() {
+          int jw = 0;
+          for (int f = 0; f < cnt; ++f) {
+            float hb; int id;
+            ring_get(cand_row + f * RS, hb, id);
+            if (hb >= lth) { ring_put(cand_row + jw * RS, hb, id); ++jw; }
+          }
+          cnt = jw;
+          ++n_cmp;
+        };
+        long long last_pass = clock64();
+        // Passes are run in lock step by the 32 rows of the warp (a row's record costs the same few hundred clocks of the
+        // warp whether one lane or all of them have one): when a ring is half full, or every T2_PERIOD clocks.
+        while (!__all_sync(FULL_MASK, done)) {
+          bool pending = false, urgent = false;
+          if (!done) {
+            pending = lds_volatile(ring_row + (head % T2_RING) * RS + 4) != T2_EMPTY;
+            urgent = lds_volatile(ring_row + ((head + T2_RING / 2 - 1) % T2_RING) * RS + 4) != T2_EMPTY;
+          }
+          const bool go = __any_sync(FULL_MASK, urgent) || (__any_sync(FULL_MASK, pending) && clock64() - last_pass > T2_PERIOD);
+          if (!go) {
+            const long long t0 = clock64();
+            __nanosleep(256);
+            c_idle += clock64() - t0;
+            continue;
+          }
+          ++n_pass;
+          const long long t_pass0 = clock64();
           for (;;) {
-            const uint32_t addr = ring_row + (head % T2_RING) * (2 * T2_BM * 8);
-            float sc; int id;
-            ring_get(addr, sc, id);
-            if (id == T2_EMPTY) {
-              const long long t0 = clock64();
-              __nanosleep(64);
-              c_idle += clock64() - t0;
-              continue;
-            }
+            float sc = 0.f;
+            int pos = T2_EMPTY;
+            const uint32_t addr = ring_row + (head % T2_RING) * RS;
+            if (!done) ring_get(addr, sc, pos);
+            if (!__any_sync(FULL_MASK, pos != T2_EMPTY)) break;
+            ++n_iter;
+            if (pos == T2_EMPTY) continue;
             ring_put(addr, 0.f, T2_EMPTY);
             ++head;
-            if (id >= 0) {
-              ++n_rec;
-              if (over) continue;
-              while (nxt < id) {                      // seen cursor: ids ascend inside a class
-                ++cur;
-                if (++wp == 8) refill();
-                else {
-                  nxt = w[1];
-#pragma unroll
-                  for (int i = 2; i < 8; ++i)
-                    if (i == wp) nxt = w[i];
-                }
-              }
-              if (nxt == id) continue;                // already seen by this user
-              const float lb = __fsub_rd(sc, eps), hb = __fadd_ru(sc, eps);
-              if (lb > tk[NT - 1]) {
-#pragma unroll
-                for (int i = NT - 1; i > 0; --i) tk[i] = fmaxf(tk[i], fminf(tk[i - 1], lb));
-                tk[0] = fmaxf(tk[0], lb);
-                lth = tk[NT - 1];
-                publish();
-              }
-              if (hb >= lth) {
-                ring_put(cand_row + cnt * (2 * T2_BM * 8), hb, id);
-                if (++cnt == T2_CAND) {
-                  compact();
-                  if (cnt > T2_CAND - 4) { over = true; cnt = 0; publish(); }
-                }
-              }
-            } else if (id == T2_END) {
-              break;
-            } else {                                  // class marker
-              const int c = T2_CLS0 - id;
-              eps = (e_cur.x * tab->wc[c] + e_cur.y * tab->rc[c] + a.acc_rel * e_cur.y * (tab->wc[c] + tab->rc[c]) +
-                     e_cur.z * (6.1e-8f * tab->wc[c] + 6.0e-14f * tab->vmax_raw)) * 1.0001f + 1e-30f;
-              cur = row_begin;
-              refill();
-              publish();
+            if (pos == T2_END) { done = true; continue; }
+            ++n_rec;
+            if (over) continue;
+            if (pos >= cls_end_pos) {                 // first record of a new item class: its window, its extent
+              do { ++cls; cls_end_pos = tab->first_tile[cls + 1] * T2_BN; } while (pos >= cls_end_pos);
+              real_end_pos = tab->first_tile[cls] * T2_BN + tab->count[cls];
+              eps = __int_as_float(lds_volatile(eps_row + cls * ES));
             }
+            if (pos >= real_end_pos) continue;        // padding position at the end of a class
+            if (!(a.dbg_flags & 2)) {
+              while (nxt < pos) {                     // seen cursor: positions ascend over the whole sweep
+                ++cur;
+                if (++wp == T2_WIN) refill();
+                else nxt = lds_volatile(win_row + wp * ES);
+              }
+              if (nxt == pos) continue;               // already seen by this user
+            }
+            const float lb = __fsub_rd(sc, eps), hb = __fadd_ru(sc, eps);
+            if (lb > tk[NT - 1]) {
+#pragma unroll
+              for (int i = NT - 1; i > 0; --i) tk[i] = fmaxf(tk[i], fminf(tk[i - 1], lb));
+              tk[0] = fmaxf(tk[0], lb);
+              lth = tk[NT - 1];
+              dirty = true;
+            }
+            if (hb >= lth) {
+              ring_put(cand_row + cnt * RS, hb, pos);
+              if (++cnt == T2_CAND) {
+                compact();
+                if (cnt > T2_CAND - 4) { over = true; cnt = 0; lth = CUDART_INF_F; dirty = true; }
+              }
+            }
+            // published at once: while the threshold is low the scan thread feeds this pass faster than it drains
+            if (dirty) { ring_put(thr_addr, lth, j); dirty = false; }
           }
-          // ---- end of the sweep: final candidates to global memory ----
+          last_pass = clock64();
+          c_pass += last_pass - t_pass0;
+        }
+        if (valid) {
+          // ---- end of the sweep: final candidates (positions) to global memory ----
           if (!over) compact();
           int32_t* out = a.cand_ids + user * T2_CAND;
           for (int f = 0; f < cnt; ++f) {
-            float hb; int id;
-            ring_get(cand_row + f * (2 * T2_BM * 8), hb, id);
-            out[f] = id;
+            float hb; int pos;
+            ring_get(cand_row + f * RS, hb, pos);
+            out[f] = pos;
           }
           a.cand_cnt[user] = over ? -1 : cnt;
         }
         // the user tile of the sweep after next goes into the TMEM buffer this sweep has just finished with
-        __syncwarp();       // the rows of the warp finish their sweeps at different times; tcgen05.st needs all of them
-        e_cur = e_nxt;
-        if (j + A_BUFS < n_sweeps) {
-          const float3 e = load_tile(j + A_BUFS);
-          if (A_BUFS == 2) e_nxt = e; else e_cur = e;
-        }
+        __syncwarp();       // tcgen05.st needs the whole warp
+        if (j + A_BUFS < n_sweeps) load_tile(j + A_BUFS);
       }
       if (a.dbg && blockIdx.x == 0 && lane == 0) {
-        long long* d = a.dbg + 40 + 4 * (warp - 12);
-        d[0] = clock64() - t_start; d[1] = c_idle; d[2] = n_rec; d[3] = n_cmp;
+        long long* d = a.dbg + 40 + 8 * (warp - 12);
+        d[0] = clock64() - t_start; d[1] = c_idle; d[2] = n_rec; d[3] = n_cmp; d[4] = n_pass; d[5] = n_iter; d[6] = c_pass; d[7] = n_refill;
       }
     }
   }
@@ -518,7 +559,7 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
 template <int KP>
 __global__ void __launch_bounds__(256) rescore_kernel(const float* __restrict__ uf, const float* __restrict__ vf, int64_t n_users, int n,
                                                       const int32_t* __restrict__ cand_ids, const int32_t* __restrict__ cand_cnt,
-                                                      int32_t* __restrict__ idx_out, double* __restrict__ score_out,
+                                                      const int32_t* __restrict__ perm, int32_t* __restrict__ idx_out, double* __restrict__ score_out,
                                                       int32_t* __restrict__ overflow_rows, unsigned int* __restrict__ overflow_count,
                                                       int64_t row_offset) {
   const int lane = threadIdx.x & 31;
@@ -536,7 +577,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float* __restrict__ 
 #pragma unroll
   for (int p = 0; p < PER; ++p) {
     const int c = lane + 32 * p;
-    id[p] = c < cnt ? cand_ids[user * T2_CAND + c] : -1;
+    id[p] = c < cnt ? perm[cand_ids[user * T2_CAND + c]] : -1;     // candidate position -> item id
     sc[p] = -CUDART_INF;
     if (id[p] >= 0) {
       const float* vp = vf + static_cast<int64_t>(id[p]) * KP;
@@ -668,10 +709,11 @@ __global__ void __launch_bounds__(256) centre_norm_kernel(const float* __restric
 }
 
 __device__ __forceinline__ int class_of(float wn, float wmax) {
-  if (!(wn > 0.f) || !(wmax > 0.f)) return T2_NCLS - 1;
+  if (!(wn > 0.f) || !(wmax > 0.f)) return 0;
   const float ratio = wmax / wn;                     // >= 1 up to rounding
   int c = ilogbf(ratio);
-  return c < 0 ? 0 : (c > T2_NCLS - 1 ? T2_NCLS - 1 : c);
+  c = c < 0 ? 0 : (c > T2_NCLS - 1 ? T2_NCLS - 1 : c);
+  return T2_NCLS - 1 - c;                            // class 0 = smallest norms = narrowest window: scanned first
 }
 
 // class of every item, per-block class counts
@@ -708,6 +750,7 @@ __global__ void __launch_bounds__(32) class_scan_kernel(int* __restrict__ block_
     int tile = 0;
     for (int i = 0; i < T2_NCLS; ++i) {
       tab->first_tile[i] = tile;
+      tab->count[i] = total[i];
       tile += (total[i] + T2_BN - 1) / T2_BN;
     }
     tab->first_tile[T2_NCLS] = tile;
@@ -722,7 +765,7 @@ template <int KPH>
 __global__ void __launch_bounds__(PP_ROWS) place_kernel(const float* __restrict__ v, int64_t n, int kp, const float* __restrict__ vbar,
                                                         const float* __restrict__ wnorm, const unsigned char* __restrict__ cls,
                                                         const int* __restrict__ block_offsets, ClassTable* __restrict__ tab,
-                                                        int32_t* __restrict__ perm, __half* __restrict__ whi) {
+                                                        int32_t* __restrict__ perm, int32_t* __restrict__ inv, __half* __restrict__ whi) {
   __shared__ int warp_cnt[32][T2_NCLS];
   __shared__ int pos_s[PP_ROWS];
   __shared__ float rmax_s[T2_NCLS], wmax_s[T2_NCLS];
@@ -744,6 +787,7 @@ __global__ void __launch_bounds__(PP_ROWS) place_kernel(const float* __restrict_
     for (int wv = 0; wv < warp; ++wv) before += warp_cnt[wv][c];
     pos = tab->first_tile[c] * T2_BN + block_offsets[blockIdx.x * T2_NCLS + c] + before + my_rank;
     perm[pos] = static_cast<int32_t>(r);
+    inv[r] = pos;
   }
   pos_s[tid] = pos;
   __syncthreads();
@@ -785,15 +829,48 @@ __global__ void __launch_bounds__(PP_ROWS) place_kernel(const float* __restrict_
   }
 }
 
-// suffix maxima: the window of a class never is narrower than that of a later class (thresholds only move up)
+// The seen items of every row as positions, ascending: ids ascend inside a row and inside a class, so a stable
+// partition of the row by class IS the sort by position.  One warp per row, two passes (count, place).
+__global__ void __launch_bounds__(256) seen_positions_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                             int64_t n_rows, int64_t cap, const int32_t* __restrict__ inv,
+                                                             const unsigned char* __restrict__ cls, int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5); row < n_rows; row += static_cast<int64_t>(gridDim.x) * 8) {
+    const int64_t beg = indptr[row], end = indptr[row + 1];
+    if (end > cap || beg > end) continue;
+    int cnt[T2_NCLS];
+#pragma unroll
+    for (int k = 0; k < T2_NCLS; ++k) cnt[k] = 0;
+    for (int64_t p0 = beg; p0 < end; p0 += 32) {
+      const int64_t p = p0 + lane;
+      const int c = p < end ? cls[indices[p]] : -1;
+#pragma unroll
+      for (int k = 0; k < T2_NCLS; ++k) cnt[k] += __popc(__ballot_sync(FULL_MASK, c == k));
+    }
+    int run[T2_NCLS];
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < T2_NCLS; ++k) { run[k] = acc; acc += cnt[k]; }
+    for (int64_t p0 = beg; p0 < end; p0 += 32) {
+      const int64_t p = p0 + lane;
+      const int id = p < end ? indices[p] : 0;
+      const int c = p < end ? cls[id] : -1;
+#pragma unroll
+      for (int k = 0; k < T2_NCLS; ++k) {
+        const unsigned m = __ballot_sync(FULL_MASK, c == k);
+        if (c == k) out[beg + run[k] + __popc(m & lt)] = inv[id];
+        run[k] += __popc(m);
+      }
+    }
+  }
+}
+
 __global__ void class_finish_kernel(ClassTable* __restrict__ tab) {
   if (threadIdx.x == 0) {
-    float w = 0.f, r = 0.f;
-    for (int c = T2_NCLS - 1; c >= 0; --c) {
-      w = fmaxf(w, __uint_as_float(tab->wc_bits[c]));
-      r = fmaxf(r, __uint_as_float(tab->rc_bits[c]));
-      tab->wc[c] = w;
-      tab->rc[c] = r;
+    for (int c = 0; c < T2_NCLS; ++c) {
+      tab->wc[c] = __uint_as_float(tab->wc_bits[c]);
+      tab->rc[c] = __uint_as_float(tab->rc_bits[c]);
     }
     tab->vmax_raw = __uint_as_float(tab->vmax_bits) * tab->scale * 1.0001f;
   }
@@ -875,10 +952,25 @@ int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefe
   const size_t o_cls = off; off += al(n_items);
   const size_t o_bc = off; off += al(sizeof(int) * nblk * T2_NCLS);
   const size_t o_perm = off; off += al(sizeof(int32_t) * n_pos);
+  const size_t o_inv = off; off += al(sizeof(int32_t) * n_items);
   const size_t o_whi = off; off += al(sizeof(__half) * n_pos * kph);
   const size_t o_orow = off; off += al(sizeof(int32_t) * sa.n_users);
   const size_t o_ccnt = off; off += al(sizeof(int32_t) * sa.n_users);
   const size_t o_cids = off; off += al(sizeof(int32_t) * sa.n_users * T2_CAND);
+  // seen positions: as many entries as the pattern has (indptr[n_users]: read from the device once per pattern and handle)
+  int64_t seen_cap = 0;
+  if (sa.seen_indptr && !dump) {
+    bool hit = false;
+    for (const auto& e : h->seen_nnz_cache)
+      if (e.indptr == sa.seen_indptr && e.n_rows == sa.n_users) { seen_cap = e.nnz; hit = true; break; }
+    if (!hit) {
+      RL_CUDA(h, cudaMemcpyAsync(&seen_cap, sa.seen_indptr + sa.n_users, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+      RL_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (h->seen_nnz_cache.size() >= 64) h->seen_nnz_cache.clear();
+      h->seen_nnz_cache.push_back({sa.seen_indptr, sa.n_users, seen_cap});
+    }
+  }
+  const size_t o_spos = off; off += al(sizeof(int32_t) * static_cast<size_t>(seen_cap));
   void* sc = nullptr;
   int rc = scratch(h, off, &sc);
   if (rc != RL_OK) return rc;
@@ -892,6 +984,8 @@ int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefe
   unsigned char* cls = reinterpret_cast<unsigned char*>(scb + o_cls);
   int* bc = reinterpret_cast<int*>(scb + o_bc);
   int32_t* perm = reinterpret_cast<int32_t*>(scb + o_perm);
+  int32_t* inv = reinterpret_cast<int32_t*>(scb + o_inv);
+  int32_t* spos = reinterpret_cast<int32_t*>(scb + o_spos);
   __half* whi = reinterpret_cast<__half*>(scb + o_whi);
   int32_t* orows = reinterpret_cast<int32_t*>(scb + o_orow);
   int32_t* ccnt = reinterpret_cast<int32_t*>(scb + o_ccnt);
@@ -924,21 +1018,29 @@ int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefe
   RL_LAUNCH_CHECK(h, "classify_kernel");
   class_scan_kernel<<<1, 32, 0, h->stream>>>(bc, nblk, tab);
   RL_LAUNCH_CHECK(h, "class_scan_kernel");
-  place_kernel<64><<<nblk, PP_ROWS, 0, h->stream>>>(sa.vf, n_items, kp, vbar, wnorm, cls, bc, tab, perm, whi);
+  place_kernel<64><<<nblk, PP_ROWS, 0, h->stream>>>(sa.vf, n_items, kp, vbar, wnorm, cls, bc, tab, perm, inv, whi);
   RL_LAUNCH_CHECK(h, "place_kernel");
   class_finish_kernel<<<1, 32, 0, h->stream>>>(tab);
   RL_LAUNCH_CHECK(h, "class_finish_kernel");
+  if (sa.seen_indptr && !dump && seen_cap > 0) {
+    int64_t g = (sa.n_users + 7) / 8;
+    if (g > 16 * h->sm_count) g = 16 * h->sm_count;
+    seen_positions_kernel<<<static_cast<unsigned>(g), 256, 0, h->stream>>>(sa.seen_indptr, sa.seen_indices, sa.n_users, seen_cap, inv, cls, spos);
+    RL_LAUNCH_CHECK(h, "seen_positions_kernel");
+  }
 
   CUtensorMap mw;
   if ((rc = make_map2(h, &mw, whi, n_pos, kph)) != RL_OK) return rc;
   T2Args a{};
-  a.uf = sa.uf; a.ldf = kp; a.n_users = sa.n_users; a.seen_indptr = sa.seen_indptr; a.seen_indices = sa.seen_indices; a.n = sa.n;
-  a.tab = tab; a.perm = perm; a.cand_ids = cids; a.cand_cnt = ccnt;
+  a.uf = sa.uf; a.ldf = kp; a.n_users = sa.n_users; a.seen_indptr = dump ? nullptr : sa.seen_indptr; a.n = sa.n;
+  a.seen_pos = spos; a.seen_cap = seen_cap;
+  a.tab = tab; a.cand_ids = cids; a.cand_cnt = ccnt;
   a.acc_rel = static_cast<float>(kph) * 1.1920929e-7f;      // k * 2^-23
   a.dump = dump; a.dump_su = dump_su; a.dump_ld = dump_ld;
   a.n_user_tiles = static_cast<int>((sa.n_users + T2_BM - 1) / T2_BM);
   const bool want_dbg = getenv("RL_TC_DEBUG") != nullptr;
   a.dbg = want_dbg ? dbg : nullptr;
+  a.dbg_flags = getenv("RL_TC2_FLAGS") ? atoi(getenv("RL_TC2_FLAGS")) : 0;
   if (dump) {
     if ((rc = launch_tc2_n<64, true>(h, mw, a)) != RL_OK) return rc;
     if (dump_perm) RL_CUDA(h, cudaMemcpyAsync(dump_perm, perm, sizeof(int32_t) * (dump_ld < n_pos ? dump_ld : n_pos), cudaMemcpyDeviceToDevice, h->stream));
@@ -952,9 +1054,9 @@ int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefe
   {
     const unsigned g = static_cast<unsigned>((sa.n_users + 7) / 8);
     switch (kp) {
-      case 16: rescore_kernel<16><<<g, 256, 0, h->stream>>>(sa.uf, sa.vf, sa.n_users, sa.n, cids, ccnt, sa.idx_out, sa.score_out, o_rows, o_count, row_offset); break;
-      case 32: rescore_kernel<32><<<g, 256, 0, h->stream>>>(sa.uf, sa.vf, sa.n_users, sa.n, cids, ccnt, sa.idx_out, sa.score_out, o_rows, o_count, row_offset); break;
-      default: rescore_kernel<64><<<g, 256, 0, h->stream>>>(sa.uf, sa.vf, sa.n_users, sa.n, cids, ccnt, sa.idx_out, sa.score_out, o_rows, o_count, row_offset); break;
+      case 16: rescore_kernel<16><<<g, 256, 0, h->stream>>>(sa.uf, sa.vf, sa.n_users, sa.n, cids, ccnt, perm, sa.idx_out, sa.score_out, o_rows, o_count, row_offset); break;
+      case 32: rescore_kernel<32><<<g, 256, 0, h->stream>>>(sa.uf, sa.vf, sa.n_users, sa.n, cids, ccnt, perm, sa.idx_out, sa.score_out, o_rows, o_count, row_offset); break;
+      default: rescore_kernel<64><<<g, 256, 0, h->stream>>>(sa.uf, sa.vf, sa.n_users, sa.n, cids, ccnt, perm, sa.idx_out, sa.score_out, o_rows, o_count, row_offset); break;
     }
     RL_LAUNCH_CHECK(h, "rescore_kernel");
   }
@@ -964,9 +1066,11 @@ int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefe
     RL_CUDA(h, cudaStreamSynchronize(h->stream));
     fprintf(stderr, "score_tc2 dbg (block 0, cycles): mma total %lld wait_A %lld wait_Tempty %lld wait_Bfull %lld\n", d[0], d[1], d[2], d[3]);
     for (int w = 0; w < 8; ++w)
-      fprintf(stderr, "  scan warp %d: total %lld wait_Tfull %lld wait_ring %lld pushes(lane0) %lld\n", w, d[8 + 4 * w], d[9 + 4 * w], d[10 + 4 * w], d[11 + 4 * w]);
+      fprintf(stderr, "  scan warp %d: total %lld wait_Tfull %lld slow chunks(lane0) %lld pushes(lane0) %lld\n", w, d[8 + 4 * w], d[9 + 4 * w], d[10 + 4 * w],
+              d[11 + 4 * w]);
     for (int w = 0; w < 8; ++w)
-      fprintf(stderr, "  sel warp %d: total %lld idle %lld records(lane0) %lld compactions %lld\n", w, d[40 + 4 * w], d[41 + 4 * w], d[42 + 4 * w], d[43 + 4 * w]);
+      fprintf(stderr, "  sel warp %d: total %lld idle %lld records(lane0) %lld compactions %lld passes %lld iterations %lld in-pass %lld refills %lld\n", w,
+              d[40 + 8 * w], d[41 + 8 * w], d[42 + 8 * w], d[43 + 8 * w], d[44 + 8 * w], d[45 + 8 * w], d[46 + 8 * w], d[47 + 8 * w]);
   }
   if (defer) return RL_OK;
   unsigned int n_over = 0;

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--ir", type=int, default=2)
     ap.add_argument("--iters", type=int, default=1, help="ALS iterations run before the scoring pass")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--every", type=int, default=0, help="also time a scoring pass after every N-th ALS iteration")
     args = ap.parse_args()
     h = _ffi.default_handle()
     nu, ni, k = args.users, args.items, args.k
@@ -57,9 +58,16 @@ def main():
             h.synchronize()
             print(f"als iteration {r}: {(time.perf_counter() - t) * 1e3:.3f} ms")
         return
-    for _ in range(args.iters):
-        als_iter()
     d_idx = Dev(h, shape=(nu, 10), dtype=np.int32)
+    for it in range(args.iters):
+        als_iter()
+        if args.every and (it + 1) % args.every == 0 and it + 1 < args.iters:
+            h.synchronize()
+            t = time.perf_counter()
+            h.call("rl_score_topn_dev", d_u.ptr, nu, d_v.ptr, ni, k, d_ip.ptr, d_ix.ptr, 0.0, None, None, 10, d_idx.ptr, None, args.mode)
+            h.synchronize()
+            print(f"after {it + 1} iterations: score_topn mode {args.mode}: {(time.perf_counter() - t) * 1e3:.3f} ms, overflow rows "
+                  f"{h.lib.rl_last_overflow_rows(h.h)}")
     for r in range(args.reps):
         h.synchronize()
         t = time.perf_counter()
