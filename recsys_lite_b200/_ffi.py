@@ -9,7 +9,7 @@ import threading
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librecsys_b200.so")
+LIB_PATH = os.environ.get("RL_B200_LIB") or os.path.join(HERE, "librecsys_b200.so")   # RL_B200_LIB: kernel-variant experiments
 
 RL_F32, RL_F64 = 0, 1
 RL_PREC_FP32_IR, RL_PREC_FP64 = 0, 1

@@ -60,9 +60,31 @@ constexpr int T2_BM = 128;        // users per half (TMEM lanes)
 constexpr int T2_BN = 128;        // items per tile
 constexpr int T2_ACC = 3;         // TMEM accumulator stages
 constexpr int T2_NCLS = 8;        // item classes by |w_i| (factor of two each)
-constexpr int T2_THREADS = 32 * 20;
-constexpr int T2_RING = 16;       // ring slots per row
+#ifndef T2_SUBS
+#define T2_SUBS 2               // scan warps per (half, TMEM lane quarter): 1 = one warp reads all 128 columns of an item tile
+#endif                          // (32 columns per tcgen05.ld), 2 = two warps, 64 columns each (16 per tcgen05.ld, 72 registers)
+constexpr int T2_THREADS = 32 * (4 + 8 * T2_SUBS + 8);   // 4 control + scan + 8 selection warps
+constexpr int T2_RING = 16 / T2_SUBS;   // ring slots per row and producer
+constexpr int T2_CH = 32 / T2_SUBS;     // columns per tcgen05.ld
 constexpr int T2_CAND = 40;       // candidate slots per row
+#ifndef T2_THR_PER_CHUNK
+#define T2_THR_PER_CHUNK 1      // re-read the row threshold for every 16 columns (1) or once per item tile (0)
+#endif
+#ifndef T2_PUSH_COUNTED
+#define T2_PUSH_COUNTED 1       // slow path: count the hits of a group, wait once for that much room, straight predicated stores
+#endif
+#ifndef T2_JOINT
+#define T2_JOINT 1              // candidate compaction / seen-window refills run jointly for the 32 rows of a selection warp
+#endif
+#ifndef T2_POLL_NS
+#define T2_POLL_NS 1500         // sleep of an idle selection warp between two looks at its rings
+#endif
+#ifndef T2_PERIOD_MIN
+#define T2_PERIOD_MIN 1000      // interval at the start of a sweep (thresholds move fast); grows by 150 clocks per item tile
+#endif
+#ifndef T2_PERIOD_MAX
+#define T2_PERIOD_MAX 16000     // largest interval (clocks) between two selection passes of a warp
+#endif
 constexpr int T2_WIN = 32;        // seen positions of a row kept in shared memory at a time
 constexpr int T2_EMPTY = INT_MIN; // ring slot free
 constexpr int T2_END = -100;      // ring marker: end of the sweep (records carry item POSITIONS >= 0)
@@ -87,8 +109,8 @@ struct T2Smem {
   static constexpr int SLOTS = KP > 64 ? 2 : 3;
   static constexpr uint32_t B_BYTES = T2_BN * KP * 2;
   static constexpr uint32_t off_b = 0;
-  static constexpr uint32_t off_ring = off_b + SLOTS * B_BYTES;                    // [RING][256] (score, id)
-  static constexpr uint32_t off_cand = off_ring + T2_RING * 2 * T2_BM * 8;         // [CAND][256] (upper bound, id)
+  static constexpr uint32_t off_ring = off_b + SLOTS * B_BYTES;                    // [2 producers][RING][256] (score, position)
+  static constexpr uint32_t off_cand = off_ring + T2_SUBS * T2_RING * 2 * T2_BM * 8;     // [CAND][256] (upper bound, position)
   static constexpr uint32_t off_thr = off_cand + T2_CAND * 2 * T2_BM * 8;          // [256] (threshold, sweep tag)
   static constexpr uint32_t off_win = off_thr + 2 * T2_BM * 8;                     // [T2_WIN][256] next seen positions of a row
   static constexpr uint32_t off_eps = off_win + T2_WIN * 2 * T2_BM * 4;            // [2 sweep parities][NCLS][256] windows
@@ -136,7 +158,7 @@ __device__ __forceinline__ int lds_volatile(uint32_t addr) {
 // instruction descriptor: D fp32, A/B fp16, both K-major, N = 128, M = 128
 constexpr uint32_t T2_IDESC = (1u << 4) | (static_cast<uint32_t>(T2_BN >> 3) << 17) | (static_cast<uint32_t>(T2_BM >> 4) << 24);
 
-template <int KP, int NT, bool DUMP>
+template <int KP, int NT, bool DUMP, bool DBG>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
   using S = T2Smem<KP>;
@@ -145,11 +167,26 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* sm = smem_raw + (base - raw);
   constexpr int SLOTS = S::SLOTS;
-  constexpr int B_FULL = 0, B_EMPTY = SLOTS, A_FULL = 2 * SLOTS, A_EMPTY = A_FULL + 2, T_FULL = A_FULL + 4, T_EMPTY = T_FULL + T2_ACC;
+  // barriers: B slot full / empty, user tile full / empty (two TMEM buffers), then PER HALF: accumulator stage full / empty.
+  // A parity wait is only sound when its waiter sees every phase of the barrier in order; with one MMA issuer per half the
+  // accumulator barriers therefore belong to one half each (T_FULL[h][s]: committed by issuer h, awaited by the scan warps of
+  // half h; T_EMPTY[h][s]: released by those warps, awaited by whichever issuer uses stage s next -- the schedule is static,
+  // so every issuer knows who used a stage last and how often).
+  constexpr int B_FULL = 0, B_EMPTY = SLOTS, A_FULL = 2 * SLOTS, A_EMPTY = A_FULL + 2, T_FULL = A_FULL + 4, T_EMPTY = T_FULL + 2 * T2_ACC;
   const uint32_t bar0 = base + S::off_bar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
+  auto wait_bar = [&](uint32_t bar, uint32_t parity, long long& acc) {     // DBG: the time spent waiting is counted
+    if constexpr (DBG) {
+      const long long t0 = clock64();
+      mbar_wait_sleep(bar, parity);
+      acc += clock64() - t0;
+    } else {
+      mbar_wait_sleep(bar, parity);
+    }
+  };
+  auto dflag = [&](int bit) { return DBG && (a.dbg_flags & bit) != 0; };
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::off_bar);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + T_EMPTY + T2_ACC);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + T_EMPTY + 2 * T2_ACC);
   ClassTable* tab = reinterpret_cast<ClassTable*>(sm + S::off_tab);
   constexpr int A_BUFS = KP <= 64 ? 2 : 1;
   constexpr uint32_t A_COLS = KP / 2;           // TMEM columns of one user tile (two fp16 per column)
@@ -158,20 +195,20 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
   constexpr uint32_t ES = 2 * T2_BM * 4;        // byte stride between classes of the window table / seen-window entries
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // contiguous range of 128-user tiles of this CTA, taken two at a time
+  // contiguous range of 128-user tiles of this CTA, taken two at a time ("halves")
   const int tile_begin = static_cast<int>(static_cast<int64_t>(a.n_user_tiles) * blockIdx.x / gridDim.x);
   const int tile_end = static_cast<int>(static_cast<int64_t>(a.n_user_tiles) * (blockIdx.x + 1) / gridDim.x);
   const int n_sweeps = (tile_end - tile_begin + 1) / 2;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < SLOTS; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
-    for (int i = 0; i < T2_ACC; ++i) { mbar_init(BAR(T_FULL + i), 1); mbar_init(BAR(T_EMPTY + i), 4); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(A_FULL + i), 8); mbar_init(BAR(A_EMPTY + i), 1); }
+    for (int i = 0; i < SLOTS; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 2); }
+    for (int i = 0; i < 2 * T2_ACC; ++i) { mbar_init(BAR(T_FULL + i), 1); mbar_init(BAR(T_EMPTY + i), 4 * T2_SUBS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(A_FULL + i), 8); mbar_init(BAR(A_EMPTY + i), 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < static_cast<int>(sizeof(ClassTable) / 4); i += T2_THREADS)
     reinterpret_cast<int*>(tab)[i] = reinterpret_cast<const int*>(a.tab)[i];
-  for (int i = threadIdx.x; i < T2_RING * 2 * T2_BM; i += T2_THREADS) ring_put(base + S::off_ring + 8u * i, 0.f, T2_EMPTY);
+  for (int i = threadIdx.x; i < T2_SUBS * T2_RING * 2 * T2_BM; i += T2_THREADS) ring_put(base + S::off_ring + 8u * i, 0.f, T2_EMPTY);
   for (int i = threadIdx.x; i < 2 * T2_BM; i += T2_THREADS) ring_put(base + S::off_thr + 8u * i, 0.f, -1);
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
@@ -200,159 +237,186 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
         }
       }
     }
-  } else if (warp == 1) {
-    // =========================================== MMA issuer ================================================
+  } else if (warp == 1 || warp == 3) {
+    // ============================ MMA issuers: one thread per half (the bookkeeping and the commit of one group run while
+    //                              the tensor pipe works on the other half's group: one issuer alone reaches 80 % of the pipe)
     if (lane == 0) {
-      uint32_t slot_global = 0, seq = 0;
+      const int my = warp >> 1;
+      uint32_t slot_global = 0, acc = 0;
+      uint32_t upar = 0;          // bit (g * 3 + s): parity of the number of uses of stage s by half g so far
+      uint32_t last = 0;          // 2 bits per stage: 0 = never used, 1 + g = last used by half g
       long long w_a = 0, w_t = 0, w_b = 0;
-      const long long t_start = clock64();
+      const long long t_start = DBG ? clock64() : 0;
       for (int j = 0; j < n_sweeps; ++j) {
         const int halves = (tile_begin + 2 * j + 1 < tile_end) ? 2 : 1;
-        mbar_wait_t(BAR(A_FULL + a_buf(j)), a_phase(j), w_a);
+        wait_bar(BAR(A_FULL + a_buf(j)), a_phase(j), w_a);
         tc_fence_after();
+        const uint32_t a_tmem = tmem_base + a_buf(j) * (2 * A_COLS) + my * A_COLS;
         for (int it = 0; it < n_tiles; ++it, ++slot_global) {
           const uint32_t slot = slot_global % SLOTS, ph = (slot_global / SLOTS) & 1;
-          mbar_wait_t(BAR(B_FULL + slot), ph, w_b);
+          wait_bar(BAR(B_FULL + slot), ph, w_b);     // (also the idle issuer of a one-half sweep: it must not run ahead of the ring)
           tc_fence_after();
           const uint64_t bd0 = make_desc(base + S::off_b + slot * S::B_BYTES);
 #define RL_BOFF(kk) (static_cast<uint64_t>((((kk) >> 2) * (T2_BN * 128) + ((kk) & 3) * 32) >> 4))
-          for (int hh = 0; hh < halves; ++hh, ++seq) {
-            const uint32_t acc = seq % T2_ACC, aph = (seq / T2_ACC) & 1;
-            mbar_wait_t(BAR(T_EMPTY + acc), aph ^ 1, w_t);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + ACC_COL0 + acc * T2_BN;
-            const uint32_t a_tmem = tmem_base + a_buf(j) * (2 * A_COLS) + hh * A_COLS;
+          for (int hh = 0; hh < halves; ++hh) {
+            if (hh == my) {
+              const uint32_t prev = (last >> (2 * acc)) & 3u;
+              if (prev) {           // the stage has to be drained by the scan warps of the half that used it last
+                const uint32_t g = prev - 1;
+                wait_bar(BAR(T_EMPTY + g * T2_ACC + acc), ((upar >> (g * 3 + acc)) & 1u) ^ 1u, w_t);
+                tc_fence_after();
+              }
+              const uint32_t d_tmem = tmem_base + ACC_COL0 + acc * T2_BN;
 #pragma unroll
-            for (int kk = 0; kk < KP / 16; ++kk)
-              tc_mma_f16_ts(d_tmem, a_tmem + kk * 8, bd0 + RL_BOFF(kk), T2_IDESC, kk != 0 ? 1u : 0u);
-            tc_commit(BAR(T_FULL + acc));
+              for (int kk = 0; kk < KP / 16; ++kk)
+                tc_mma_f16_ts(d_tmem, a_tmem + kk * 8, bd0 + RL_BOFF(kk), T2_IDESC, kk != 0 ? 1u : 0u);
+              tc_commit(BAR(T_FULL + my * T2_ACC + acc));
+            }
+            upar ^= 1u << (hh * 3 + acc);
+            last = (last & ~(3u << (2 * acc))) | (static_cast<uint32_t>(hh + 1) << (2 * acc));
+            acc = acc == T2_ACC - 1 ? 0 : acc + 1;
           }
 #undef RL_BOFF
-          tc_commit(BAR(B_EMPTY + slot));
+          if (my < halves) tc_commit(BAR(B_EMPTY + slot));
+          else mbar_arrive(BAR(B_EMPTY + slot));        // (the other issuer's commit tells when the MMAs are done with the slot)
         }
-        tc_commit(BAR(A_EMPTY + a_buf(j)));
+        if (my < halves) tc_commit(BAR(A_EMPTY + a_buf(j)));
+        else mbar_arrive(BAR(A_EMPTY + a_buf(j)));
       }
-      if (a.dbg && blockIdx.x == 0) { a.dbg[0] = clock64() - t_start; a.dbg[1] = w_a; a.dbg[2] = w_t; a.dbg[3] = w_b; }
+      if (DBG && a.dbg && blockIdx.x == 0) { long long* d = a.dbg + 4 * my; d[0] = clock64() - t_start; d[1] = w_a; d[2] = w_t; d[3] = w_b; }
     }
-  } else if (warp >= 4 && warp < 12) {
-    // =========================================== scan warps ================================================
-    const int hh = (warp - 4) >> 2, q = warp & 3;
+  } else if (warp >= 4 && warp < 4 + 8 * T2_SUBS) {
+    // ==================== scan warps: (half, column part, TMEM lane quarter) ==================================
+    // The kernel is bound by the integer / compare pipe: everything in the tile and chunk loops is kept in registers and
+    // advanced incrementally (no divisions, no re-derived addresses), one copy of the chunk body.
+    const int idx = warp - 4, hh = idx / (4 * T2_SUBS), sub = (idx >> 2) % T2_SUBS, q = idx & 3;
     const int rowg = hh * T2_BM + q * 32 + lane;                 // row inside the CTA's pair of user tiles
-    const uint32_t ring_row = base + S::off_ring + 8u * rowg;     // slot r at + r * RS
+    const uint32_t ring_row = base + S::off_ring + sub * (T2_RING * RS) + 8u * rowg;   // this producer's ring of the row
     const uint32_t thr_addr = base + S::off_thr + 8u * rowg;
-    uint32_t seq_base = 0, tail = 0;
-    long long w_full = 0, n_push = 0, n_slow = 0;
-    const long long t_start = clock64();
-    // room for `need` more records in this row's ring (the selection thread frees slots in order)
-    auto wait_room = [&](uint32_t need) {
-      const uint32_t addr = ring_row + ((tail + need - 1) % T2_RING) * RS + 4;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ACC_COL0 + sub * (T2_BN / T2_SUBS);
+    const uint32_t bar_full = BAR(T_FULL + hh * T2_ACC), bar_empty = BAR(T_EMPTY + hh * T2_ACC);
+    uint32_t tail = 0;            // records pushed so far (ring slot = tail % T2_RING)
+    uint32_t acc = 0;             // accumulator stage of the next half-tile of this half
+    uint32_t fpar = 0;            // bit s: parity of this half's next use of accumulator stage s
+    long long w_full = 0, n_push = 0, n_slow = 0, c_ld = 0, c_scan = 0;
+    const long long t_start = DBG ? clock64() : 0;
+    auto wait_slot = [&](uint32_t addr) {          // ring full: the selection thread frees slots in order
       uint32_t spin = 0;
       while (lds_volatile(addr) != T2_EMPTY) {
-        __nanosleep(32);
+        __nanosleep(64);
         if (++spin > (1u << 24)) { printf("score_tc2: ring timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
       }
     };
     for (int j = 0; j < n_sweeps; ++j) {
       const int halves = (tile_begin + 2 * j + 1 < tile_end) ? 2 : 1;
-      if (hh >= halves) { seq_base += static_cast<uint32_t>(n_tiles) * halves; continue; }
+      if (hh >= halves) { acc = (acc + static_cast<uint32_t>(n_tiles)) % T2_ACC; continue; }     // (only the last sweep)
+      const uint32_t step = halves == 2 ? 2u : 1u;
+      if (halves == 2 && hh == 1) acc = acc == T2_ACC - 1 ? 0 : acc + 1;      // half 1 takes the stage after half 0's
       const int64_t user = static_cast<int64_t>(tile_begin + 2 * j + hh) * T2_BM + q * 32 + lane;
       const bool valid = user < a.n_users;
+      const float floor_thr = (valid && !dflag(1)) ? -CUDART_INF_F : CUDART_INF_F;    // rows past the end never push
       const uint32_t eps_row = base + S::off_eps + (static_cast<uint32_t>(j & 1) * T2_NCLS * 2 * T2_BM + rowg) * 4u;
       // the windows of this sweep were written by the selection warps before they released the user tile: they are read
       // after an accumulator barrier of the sweep (which orders them), never before
       int cls = -1, next_cls_tile = 0;
       float eps_c = 0.f;
+      int pos = sub * (T2_BN / T2_SUBS);             // position of the first column of the next chunk
       for (int it = 0; it < n_tiles; ++it) {
-        const uint32_t seq = seq_base + (halves == 2 ? 2 * it + hh : it);
-        const uint32_t acc = seq % T2_ACC, aph = (seq / T2_ACC) & 1;
-        mbar_wait_t(BAR(T_FULL + acc), aph, w_full);
+        const uint32_t aph = (fpar >> acc) & 1u;
+        fpar ^= 1u << acc;
+        wait_bar(bar_full + 8u * acc, aph, w_full);
         tc_fence_after();
         if (it >= next_cls_tile) {
           do { ++cls; next_cls_tile = tab->first_tile[cls + 1]; } while (it >= next_cls_tile);
           eps_c = __int_as_float(lds_volatile(eps_row + cls * ES));
         }
-        float thr;
-        {
-          // the selection thread publishes the n-th best LOWER bound of this sweep; an item of this class can only matter
-          // if its upper bound reaches it
-          float lth;
-          int tag;
-          ring_get(thr_addr, lth, tag);
-          if (tag != j) lth = -CUDART_INF_F;
-          thr = valid ? __fsub_rd(lth, eps_c) : CUDART_INF_F;
-          if (a.dbg_flags & 1) thr = CUDART_INF_F;
-        }
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ACC_COL0 + acc * T2_BN;
-        auto release_stage = [&]() {
+        uint32_t t_addr = t_lane + acc * T2_BN;
+        if (dflag(4)) {                              // debug: MMA / TMA ceiling (stages released unread)
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
-        };
-        if (a.dbg_flags & 4) { release_stage(); continue; }        // debug: MMA / TMA ceiling (stages released unread)
-        float s0[32], s1[32];
-        auto scan32 = [&](const float (&sg)[32], const int pos0) {
-          if (a.dbg_flags & 8) {                                    // debug: TMEM read ceiling (loads, no selection)
-            if (sg[0] == 1.2345e-30f) ++n_push;
-            return;
-          }
-          if (DUMP) {
-            if (valid) {
-#pragma unroll
-              for (int jj = 0; jj < 32; ++jj) a.dump[user * a.dump_ld + pos0 + jj] = sg[jj];
+          if (lane == 0) mbar_arrive(bar_empty + 8u * acc);
+        } else {
+          long long tq0 = 0;
+          if constexpr (DBG) tq0 = clock64();
+#pragma unroll 1
+          for (int ch = 0; ch < T2_BN / T2_SUBS / T2_CH; ++ch, t_addr += T2_CH, pos += T2_CH) {
+            float sg[T2_CH];
+            tc_ld(t_addr, sg);
+            // the selection thread publishes the n-th best LOWER bound of this sweep; an item of this class can only
+            // matter if its upper bound reaches it.  Re-read for every chunk: the bound moves fastest right after the
+            // sweep's start (while the load is in flight)
+            float lth;
+            int tag;
+            ring_get(thr_addr, lth, tag);
+            if (tag != j) lth = -CUDART_INF_F;
+            const float thr = fmaxf(__fsub_rd(lth, eps_c), floor_thr);
+            tc_wait_dep(sg);
+            if constexpr (DBG) { const long long t1 = clock64(); c_ld += t1 - tq0; tq0 = t1; }
+            if (ch == T2_BN / T2_SUBS / T2_CH - 1) {     // the last chunk sits in registers: the stage goes back to the MMA
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_empty + 8u * acc);
             }
-            return;
-          }
-          bool any = false;
+            if (DUMP) {
+              if (valid) {
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const float m8 = max3(max3(sg[8 * b], sg[8 * b + 1], sg[8 * b + 2]), max3(sg[8 * b + 3], sg[8 * b + 4], sg[8 * b + 5]),
-                                  fmaxf(sg[8 * b + 6], sg[8 * b + 7]));
-            if (m8 > thr) {
-              // (score, position) records for the selection thread: straight-line predicated stores once 8 slots are free
-              wait_room(8);
+                for (int jj = 0; jj < T2_CH; ++jj) a.dump[user * a.dump_ld + pos + jj] = sg[jj];
+              }
+            } else if (!dflag(8)) {
+              bool any = false;
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                if (sg[8 * b + jj] > thr) {
-                  ring_put(ring_row + (tail % T2_RING) * RS, sg[8 * b + jj], pos0 + 8 * b + jj);
-                  ++tail;
-                  ++n_push;
+              for (int b = 0; b < T2_CH / 8; ++b) {
+                const float m8 = max3(max3(sg[8 * b], sg[8 * b + 1], sg[8 * b + 2]), max3(sg[8 * b + 3], sg[8 * b + 4], sg[8 * b + 5]),
+                                      fmaxf(sg[8 * b + 6], sg[8 * b + 7]));
+                if (m8 > thr) {
+                  // (score, position) records for the selection thread: count the hits, wait once for that much room (a
+                  // slot is free again once its position reads EMPTY), straight predicated stores
+                  uint32_t c = 0;
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) c += sg[8 * b + jj] > thr ? 1u : 0u;
+                  {
+                    const uint32_t last = ring_row + ((tail + c - 1) % T2_RING) * RS + 4;
+                    if (lds_volatile(last) != T2_EMPTY) wait_slot(last);
+                  }
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) {
+                    if (sg[8 * b + jj] > thr) {
+                      ring_put(ring_row + (tail % T2_RING) * RS, sg[8 * b + jj], pos + 8 * b + jj);
+                      ++tail;
+                    }
+                  }
+                  if constexpr (DBG) n_push += c;
+                  any = true;
                 }
               }
-              any = true;
+              if constexpr (DBG) { if (any) ++n_slow; }
+              __syncwarp();     // the pushes diverge; tcgen05.ld / wait need the whole warp
             }
+            if constexpr (DBG) { const long long t1 = clock64(); c_scan += t1 - tq0; tq0 = t1; }
           }
-          if (any) ++n_slow;
-          __syncwarp();     // the pushes diverge; tcgen05.ld / wait need the whole warp
-        };
-        tc_ld32(t_row, s0);
-#pragma unroll 1
-        for (int gp = 0; gp < T2_BN / 64; ++gp) {
-          tc_wait_ld_dep(s0);
-          tc_ld32(t_row + gp * 64 + 32, s1);
-          scan32(s0, it * T2_BN + gp * 64);
-          tc_wait_ld_dep(s1);
-          if (gp + 1 < T2_BN / 64) tc_ld32(t_row + gp * 64 + 64, s0);
-          else release_stage();
-          scan32(s1, it * T2_BN + gp * 64 + 32);
         }
+        pos += T2_BN - T2_BN / T2_SUBS;              // to this warp's columns of the next item tile
+        acc += step;
+        if (acc >= T2_ACC) acc -= T2_ACC;
       }
+      if (halves == 2 && hh == 1) acc = acc == 0 ? T2_ACC - 1 : acc - 1;      // back to the common count of half-tiles
       if (!DUMP && valid) {
-        wait_room(1);
-        ring_put(ring_row + (tail % T2_RING) * RS, 0.f, T2_END);
+        const uint32_t addr = ring_row + (tail % T2_RING) * RS;
+        if (lds_volatile(addr + 4) != T2_EMPTY) wait_slot(addr + 4);
+        ring_put(addr, 0.f, T2_END);
         ++tail;
       }
       __syncwarp();
-      seq_base += static_cast<uint32_t>(n_tiles) * halves;
     }
-    if (a.dbg && blockIdx.x == 0 && lane == 0) {
-      long long* d = a.dbg + 8 + 4 * (warp - 4);
-      d[0] = clock64() - t_start; d[1] = w_full; d[2] = n_slow; d[3] = n_push;
+    if (DBG && a.dbg && blockIdx.x == 0 && lane == 0) {
+      long long* d = a.dbg + 8 + 4 * idx;
+      d[0] = clock64() - t_start; d[1] = w_full; d[2] = c_ld; d[3] = c_scan;
     }
-  } else if (warp >= 12) {
+  } else if (warp >= 4 + 8 * T2_SUBS) {
     // ======================== selection warps: user-tile loaders + per-row selection ==========================
-    const int hh = (warp - 12) >> 2, q = warp & 3;
+    const int hh = (warp - 4 - 8 * T2_SUBS) >> 2, q = warp & 3;
     const int rowg = hh * T2_BM + q * 32 + lane;
-    const uint32_t ring_row = base + S::off_ring + 8u * rowg;
+    const uint32_t ring_a = base + S::off_ring + 8u * rowg, ring_b = ring_a + T2_RING * RS;   // the two producers of the row
     const uint32_t cand_row = base + S::off_cand + 8u * rowg;
     const uint32_t thr_addr = base + S::off_thr + 8u * rowg;
     const uint32_t win_row = base + S::off_win + 4u * rowg;       // seen-position window: entry i at + i * ES
@@ -396,7 +460,7 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
         tc_st32(t_row + c0 / 2, hi);
       }
       if (DUMP && valid) a.dump_su[user] = su;
-      // the windows of this row, one per item class, for the scan thread and the selection thread of sweep j
+      // the windows of this row, one per item class, for the scan threads and the selection thread of sweep j
       const float e1 = sqrtf(rr) * 1.0001f, e2 = sqrtf(hn) * 1.0001f, e3 = sqrtf(nn) * 1.0001f;
       const uint32_t eps_row = base + S::off_eps + (static_cast<uint32_t>(j & 1) * T2_NCLS * 2 * T2_BM + rowg) * 4u;
 #pragma unroll
@@ -414,7 +478,7 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
     if (DUMP) {
       for (int j = A_BUFS; j < n_sweeps; ++j) load_tile(j);
     } else {
-      uint32_t head = 0;
+      uint32_t head_a = 0, head_b = 0;
       long long c_idle = 0, n_rec = 0, n_cmp = 0, n_pass = 0, n_iter = 0, c_pass = 0, n_refill = 0;
       const long long t_start = clock64();
       for (int j = 0; j < n_sweeps; ++j) {
@@ -427,28 +491,30 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
 #pragma unroll
         for (int i = 0; i < NT; ++i) tk[i] = i < NT - a.n ? CUDART_INF_F : -CUDART_INF_F;
         float lth = -CUDART_INF_F, eps = 0.f;
-        int cnt = 0, cls = -1, cls_end_pos = 0, real_end_pos = 0;
-        bool over = false, done = !valid, dirty = false;
-        // cursor into the row's seen positions (ascending; a window of T2_WIN of them lives in shared memory)
-        int64_t cur = 0, end = 0;
+        int cnt = 0, cls_lo_pos = 0, cls_hi_pos = 0, real_end_pos = 0;
+        bool over = false, done_a = !valid, done_b = T2_SUBS == 1 || !valid;
+        // the row's seen positions (ascending); T2_WIN of them, from offset woff, live in shared memory; entries before
+        // win[wp] are below every position that can still arrive
+        const int32_t* seen = a.seen_pos;
+        int seen_len = 0, woff = 0, wp = 0;
         if (valid && a.seen_indptr) {
-          cur = a.seen_indptr[user];
-          end = a.seen_indptr[user + 1];
-          if (end > a.seen_cap || cur > end) {      // stale capacity: the exact kernel takes the row
-            over = true; cur = end = 0; lth = CUDART_INF_F;
+          const int64_t b0 = a.seen_indptr[user], e0 = a.seen_indptr[user + 1];
+          if (e0 > a.seen_cap || b0 > e0 || e0 - b0 > INT_MAX / 2) {      // stale capacity: the exact kernel takes the row
+            over = true; lth = CUDART_INF_F;
             ring_put(thr_addr, lth, j);
+          } else {
+            seen += b0;
+            seen_len = static_cast<int>(e0 - b0);
           }
         }
-        int wp = 0, nxt = INT_MAX;
-        auto refill = [&]() {                                     // window <- seen_pos[cur .. cur + T2_WIN)
+        auto refill = [&]() {                                     // window <- seen[woff .. woff + T2_WIN)
 #pragma unroll 8
           for (int i = 0; i < T2_WIN; ++i) {
-            const int v = (cur + i < end) ? a.seen_pos[cur + i] : INT_MAX;
+            const int v = (woff + i < seen_len) ? seen[woff + i] : INT_MAX;
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(win_row + i * ES), "r"(v) : "memory");
           }
           wp = 0;
-          nxt = lds_volatile(win_row);
-          ++n_refill;
+          if constexpr (DBG) ++n_refill;
         };
         if (valid) refill();
         auto compact = [&]() {
@@ -459,52 +525,88 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
             if (hb >= lth) { ring_put(cand_row + jw * RS, hb, id); ++jw; }
           }
           cnt = jw;
-          ++n_cmp;
+          if constexpr (DBG) ++n_cmp;
         };
         long long last_pass = clock64();
-        // Passes are run in lock step by the 32 rows of the warp (a row's record costs the same few hundred clocks of the
-        // warp whether one lane or all of them have one): when a ring is half full, or every T2_PERIOD clocks.
-        while (!__all_sync(FULL_MASK, done)) {
+        int period = T2_PERIOD_MIN;                          // clocks between passes when no ring is filling up; grows with the sweep
+        // Passes are run in lock step by the 32 rows of the warp (a row's record costs the same few hundred instructions of
+        // the warp whether one lane or all of them have one, so records are left to accumulate): when a ring is half full, or
+        // every `period` clocks.  Refills of the seen window and compactions of the candidate list run for all rows at once.
+        while (!__all_sync(FULL_MASK, done_a && done_b)) {
           bool pending = false, urgent = false;
-          if (!done) {
-            pending = lds_volatile(ring_row + (head % T2_RING) * RS + 4) != T2_EMPTY;
-            urgent = lds_volatile(ring_row + ((head + T2_RING / 2 - 1) % T2_RING) * RS + 4) != T2_EMPTY;
+          if (!done_a) {
+            pending = lds_volatile(ring_a + (head_a % T2_RING) * RS + 4) != T2_EMPTY;
+            urgent = lds_volatile(ring_a + ((head_a + T2_RING / 2 - 1) % T2_RING) * RS + 4) != T2_EMPTY;
           }
-          const bool go = __any_sync(FULL_MASK, urgent) || (__any_sync(FULL_MASK, pending) && clock64() - last_pass > T2_PERIOD);
+          if (!done_b) {
+            pending |= lds_volatile(ring_b + (head_b % T2_RING) * RS + 4) != T2_EMPTY;
+            urgent |= lds_volatile(ring_b + ((head_b + T2_RING / 2 - 1) % T2_RING) * RS + 4) != T2_EMPTY;
+          }
+          const bool go = __any_sync(FULL_MASK, urgent) || (__any_sync(FULL_MASK, pending) && clock64() - last_pass > period);
           if (!go) {
-            const long long t0 = clock64();
-            __nanosleep(256);
-            c_idle += clock64() - t0;
+            const long long t0 = DBG ? clock64() : 0;
+            __nanosleep(T2_POLL_NS);
+            if constexpr (DBG) c_idle += clock64() - t0;
             continue;
           }
-          ++n_pass;
-          const long long t_pass0 = clock64();
+          if constexpr (DBG) ++n_pass;
+          const long long t_pass0 = DBG ? clock64() : 0;
+          if (T2_JOINT && __any_sync(FULL_MASK, wp >= 3 * T2_WIN / 4)) {     // seen windows running low: refilled together
+            if (wp >= T2_WIN / 4) { woff += wp; refill(); }
+          }
+          int last_pos = 0;
           for (;;) {
-            float sc = 0.f;
-            int pos = T2_EMPTY;
-            const uint32_t addr = ring_row + (head % T2_RING) * RS;
-            if (!done) ring_get(addr, sc, pos);
+            // the record with the smaller position of the two producers' next ones (they are at most two tiles apart)
+            float sc = 0.f, sc_b = 0.f;
+            int pos = T2_EMPTY, pos_b = T2_EMPTY;
+            const uint32_t addr_a = ring_a + (head_a % T2_RING) * RS, addr_b = ring_b + (head_b % T2_RING) * RS;
+            if (!done_a) ring_get(addr_a, sc, pos);
+            if (!done_b) ring_get(addr_b, sc_b, pos_b);
+            const bool take_b = pos_b != T2_EMPTY && (pos == T2_EMPTY || pos_b < pos);
+            if (take_b) { pos = pos_b; sc = sc_b; }
             if (!__any_sync(FULL_MASK, pos != T2_EMPTY)) break;
-            ++n_iter;
+            if constexpr (DBG) ++n_iter;
             if (pos == T2_EMPTY) continue;
-            ring_put(addr, 0.f, T2_EMPTY);
-            ++head;
-            if (pos == T2_END) { done = true; continue; }
-            ++n_rec;
+            if (take_b) { ring_put(addr_b, 0.f, T2_EMPTY); ++head_b; }
+            else { ring_put(addr_a, 0.f, T2_EMPTY); ++head_a; }
+            if (pos == T2_END) {
+              if (take_b) done_b = true; else done_a = true;
+              continue;
+            }
+            if constexpr (DBG) ++n_rec;
             if (over) continue;
-            if (pos >= cls_end_pos) {                 // first record of a new item class: its window, its extent
-              do { ++cls; cls_end_pos = tab->first_tile[cls + 1] * T2_BN; } while (pos >= cls_end_pos);
-              real_end_pos = tab->first_tile[cls] * T2_BN + tab->count[cls];
-              eps = __int_as_float(lds_volatile(eps_row + cls * ES));
+            last_pos = pos;
+            if (pos < cls_lo_pos || pos >= cls_hi_pos) {          // record of another item class: its window, its extent
+              int c = 0;
+              while (pos >= tab->first_tile[c + 1] * T2_BN) ++c;
+              cls_lo_pos = tab->first_tile[c] * T2_BN;
+              cls_hi_pos = tab->first_tile[c + 1] * T2_BN;
+              real_end_pos = cls_lo_pos + tab->count[c];
+              eps = __int_as_float(lds_volatile(eps_row + c * ES));
             }
             if (pos >= real_end_pos) continue;        // padding position at the end of a class
-            if (!(a.dbg_flags & 2)) {
-              while (nxt < pos) {                     // seen cursor: positions ascend over the whole sweep
-                ++cur;
-                if (++wp == T2_WIN) refill();
-                else nxt = lds_volatile(win_row + wp * ES);
+            if (!dflag(2)) {
+              // seen items: nothing below (tile - 2) can arrive any more; look ahead from there without committing
+              const int low = ((pos >> 7) - 2) << 7;
+              int nx = lds_volatile(win_row + wp * ES);
+              while (nx < low) {
+                if (++wp == T2_WIN) { woff += T2_WIN; refill(); }
+                nx = lds_volatile(win_row + wp * ES);
               }
-              if (nxt == pos) continue;               // already seen by this user
+              int i = wp;
+              while (nx < pos) {
+                if (++i == T2_WIN) {                  // window exhausted inside the look-ahead (heavy users): bisection
+                  int lo = woff + T2_WIN, hi = seen_len;
+                  while (lo < hi) {
+                    const int mid = lo + ((hi - lo) >> 1);
+                    if (seen[mid] < pos) lo = mid + 1; else hi = mid;
+                  }
+                  nx = lo < seen_len ? seen[lo] : INT_MAX;
+                  break;
+                }
+                nx = lds_volatile(win_row + i * ES);
+              }
+              if (nx == pos) continue;                // already seen by this user
             }
             const float lb = __fsub_rd(sc, eps), hb = __fadd_ru(sc, eps);
             if (lb > tk[NT - 1]) {
@@ -512,20 +614,28 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
               for (int i = NT - 1; i > 0; --i) tk[i] = fmaxf(tk[i], fminf(tk[i - 1], lb));
               tk[0] = fmaxf(tk[0], lb);
               lth = tk[NT - 1];
-              dirty = true;
+              // published at once: while the threshold is low the scan threads feed this pass faster than it drains
+              ring_put(thr_addr, lth, j);
             }
             if (hb >= lth) {
               ring_put(cand_row + cnt * RS, hb, pos);
-              if (++cnt == T2_CAND) {
+              if (++cnt == T2_CAND) {                 // emergency: normally the joint compaction below keeps the list short
                 compact();
-                if (cnt > T2_CAND - 4) { over = true; cnt = 0; lth = CUDART_INF_F; dirty = true; }
+                if (cnt > T2_CAND - 4) { over = true; cnt = 0; lth = CUDART_INF_F; ring_put(thr_addr, lth, j); }
               }
             }
-            // published at once: while the threshold is low the scan thread feeds this pass faster than it drains
-            if (dirty) { ring_put(thr_addr, lth, j); dirty = false; }
           }
+          if (T2_JOINT && __any_sync(FULL_MASK, cnt >= T2_CAND - 10)) {     // candidate lists filling up: compacted together
+            if (cnt > 0 && !over) {
+              compact();
+              if (cnt > T2_CAND - 4) { over = true; cnt = 0; lth = CUDART_INF_F; ring_put(thr_addr, lth, j); }
+            }
+          }
+          // thresholds settle as the sweep goes on: let more records accumulate per pass
+          const int t_now = __reduce_max_sync(FULL_MASK, last_pos) >> 7;
+          period = min(T2_PERIOD_MAX, max(period, T2_PERIOD_MIN + 150 * t_now));
           last_pass = clock64();
-          c_pass += last_pass - t_pass0;
+          if constexpr (DBG) c_pass += last_pass - t_pass0;
         }
         if (valid) {
           // ---- end of the sweep: final candidates (positions) to global memory ----
@@ -542,8 +652,8 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
         __syncwarp();       // tcgen05.st needs the whole warp
         if (j + A_BUFS < n_sweeps) load_tile(j + A_BUFS);
       }
-      if (a.dbg && blockIdx.x == 0 && lane == 0) {
-        long long* d = a.dbg + 40 + 8 * (warp - 12);
+      if (DBG && a.dbg && blockIdx.x == 0 && lane == 0) {
+        long long* d = a.dbg + 80 + 8 * (warp - 4 - 8 * T2_SUBS);
         d[0] = clock64() - t_start; d[1] = c_idle; d[2] = n_rec; d[3] = n_cmp; d[4] = n_pass; d[5] = n_iter; d[6] = c_pass; d[7] = n_refill;
       }
     }
@@ -905,21 +1015,22 @@ int make_map2(rl_context* h, CUtensorMap* map, const __half* ptr, int64_t rows, 
   return RL_OK;
 }
 
-template <int KP, bool DUMP>
-int launch_tc2_n(rl_context* h, const CUtensorMap& mw, const T2Args& a) {
+template <int KP, int NT, bool DUMP, bool DBG>
+int launch_tc2_k(rl_context* h, const CUtensorMap& mw, const T2Args& a) {
   const size_t smem = T2Smem<KP>::total;
-  int grid = a.n_user_tiles < 2 * h->sm_count ? (a.n_user_tiles + 1) / 2 : h->sm_count;
-  if (a.n <= 10) {
-    auto kern = score_tc2_kernel<KP, 10, DUMP>;
-    RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<grid, T2_THREADS, smem, h->stream>>>(mw, a);
-  } else {
-    auto kern = score_tc2_kernel<KP, 16, DUMP>;
-    RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<grid, T2_THREADS, smem, h->stream>>>(mw, a);
-  }
+  const int grid = a.n_user_tiles < 2 * h->sm_count ? (a.n_user_tiles + 1) / 2 : h->sm_count;
+  auto kern = score_tc2_kernel<KP, NT, DUMP, DBG>;
+  RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<grid, T2_THREADS, smem, h->stream>>>(mw, a);
   RL_LAUNCH_CHECK(h, "score_tc2_kernel");
   return RL_OK;
+}
+
+template <int KP, bool DUMP>
+int launch_tc2_n(rl_context* h, const CUtensorMap& mw, const T2Args& a) {
+  if (!DUMP && a.dbg && a.n <= 10) return launch_tc2_k<KP, 10, false, true>(h, mw, a);   // RL_TC_DEBUG: counters, RL_TC2_FLAGS
+  if (a.n <= 10) return launch_tc2_k<KP, 10, DUMP, false>(h, mw, a);
+  return launch_tc2_k<KP, 16, DUMP, false>(h, mw, a);
 }
 
 }  // namespace
@@ -945,7 +1056,7 @@ int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefe
   size_t off = 0;
   const size_t o_tab = off; off += al(sizeof(ClassTable));
   const size_t o_cnt = off; off += al(256);                                            // overflow count (+ debug counters)
-  const size_t o_dbg = off; off += al(128 * sizeof(long long));
+  const size_t o_dbg = off; off += al(160 * sizeof(long long));
   const size_t o_vbar = off; off += al(sizeof(float) * 128);
   const size_t o_part = off; off += al(sizeof(double) * csum_blocks * kp);
   const size_t o_wn = off; off += al(sizeof(float) * n_items);
@@ -1001,7 +1112,7 @@ int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefe
     ea.scatter = true;
     if ((rc = launch_score_exact(h, kp, ea)) != RL_OK) return rc;
   }
-  RL_CUDA(h, cudaMemsetAsync(scb + o_cnt, 0, 256 + al(128 * sizeof(long long)), h->stream));
+  RL_CUDA(h, cudaMemsetAsync(scb + o_cnt, 0, 256 + al(160 * sizeof(long long)), h->stream));
   RL_CUDA(h, cudaMemsetAsync(perm, 0xFF, sizeof(int32_t) * n_pos, h->stream));
   RL_CUDA(h, cudaMemsetAsync(whi, 0, sizeof(__half) * n_pos * kph, h->stream));
   colsum_partial_kernel<<<csum_blocks, 256, 0, h->stream>>>(sa.vf, n_items, kp, partial);
@@ -1061,16 +1172,18 @@ int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefe
     RL_LAUNCH_CHECK(h, "rescore_kernel");
   }
   if (want_dbg) {
-    long long d[128];
+    long long d[160];
     RL_CUDA(h, cudaMemcpyAsync(d, dbg, sizeof(d), cudaMemcpyDeviceToHost, h->stream));
     RL_CUDA(h, cudaStreamSynchronize(h->stream));
-    fprintf(stderr, "score_tc2 dbg (block 0, cycles): mma total %lld wait_A %lld wait_Tempty %lld wait_Bfull %lld\n", d[0], d[1], d[2], d[3]);
-    for (int w = 0; w < 8; ++w)
-      fprintf(stderr, "  scan warp %d: total %lld wait_Tfull %lld slow chunks(lane0) %lld pushes(lane0) %lld\n", w, d[8 + 4 * w], d[9 + 4 * w], d[10 + 4 * w],
+    for (int i = 0; i < 2; ++i)
+      fprintf(stderr, "score_tc2 dbg (block 0, cycles): mma issuer %d total %lld wait_A %lld wait_Tempty %lld wait_Bfull %lld\n", i, d[4 * i], d[4 * i + 1],
+              d[4 * i + 2], d[4 * i + 3]);
+    for (int w = 0; w < 16; w += 3)
+      fprintf(stderr, "  scan warp %d: total %lld wait_Tfull %lld wait_ld %lld scan %lld\n", w, d[8 + 4 * w], d[9 + 4 * w], d[10 + 4 * w],
               d[11 + 4 * w]);
-    for (int w = 0; w < 8; ++w)
+    for (int w = 0; w < 8; w += 2)
       fprintf(stderr, "  sel warp %d: total %lld idle %lld records(lane0) %lld compactions %lld passes %lld iterations %lld in-pass %lld refills %lld\n", w,
-              d[40 + 8 * w], d[41 + 8 * w], d[42 + 8 * w], d[43 + 8 * w], d[44 + 8 * w], d[45 + 8 * w], d[46 + 8 * w], d[47 + 8 * w]);
+              d[80 + 8 * w], d[81 + 8 * w], d[82 + 8 * w], d[83 + 8 * w], d[84 + 8 * w], d[85 + 8 * w], d[86 + 8 * w], d[87 + 8 * w]);
   }
   if (defer) return RL_OK;
   unsigned int n_over = 0;

@@ -56,6 +56,31 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity,
     }
   }
 }
+// the same with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead of
+// burning issue slots in a spin loop -- the roles of the scoring kernels share four schedulers
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+#ifndef RL_WAIT_BACKOFF_NS
+#define RL_WAIT_BACKOFF_NS 400
+#endif
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait_hint(bar, parity, 4000u); ++spin) {
+    __nanosleep(RL_WAIT_BACKOFF_NS);      // the hinted wait returns early and often: without this the retry loop is a third of all instructions
+    if (spin > (1u << 22)) {
+      printf("score_tc: mbarrier timeout (sleeping wait; block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
   const long long t0 = clock64();
   mbar_wait(bar, parity);
@@ -98,6 +123,28 @@ __device__ __forceinline__ void tc_wait_ld_dep(float (&v)[32]) {
                :
                : "memory");
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_wait_ld_dep16(float (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]),
+                 "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tc_ld(uint32_t taddr, float (&v)[32]) { tc_ld32(taddr, v); }
+__device__ __forceinline__ void tc_ld(uint32_t taddr, float (&v)[16]) { tc_ld16(taddr, v); }
+__device__ __forceinline__ void tc_wait_dep(float (&v)[32]) { tc_wait_ld_dep(v); }
+__device__ __forceinline__ void tc_wait_dep(float (&v)[16]) { tc_wait_ld_dep16(v); }
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
