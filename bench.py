@@ -54,9 +54,52 @@ def load_peaks():
 
 
 def load_traffic():
-    """dram bytes per launch from the committed ncu --set full capture (profiles/), or None per kernel."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    """dram bytes per launch / tensor-pipe activity from the COMMITTED ncu --set full capture (profiles/r2_traffic.json: taken at
+    the last step of `bench.py --steps 20 --warmup 5`, see profiles/README.md), or {}.  Static profile data, not a measurement of
+    the current run: the line says so next to every such number."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def sampled_parity(w, indptr, indices, indptr_t, indices_t, u, v, idx_rows, users, items, lam, n):
+    """Size-independent checks of the device results against float64 NumPy on sampled rows (no oracle import: this runs in the
+    timed arm).  (1) top-n of `users`: ranking of the exact float64 scores of the float32 factors, seen items excluded, ties
+    (|ds| <= 4 eps32 max(1,|s|)) accepted as in oracle/compare.py; (2) every sampled user / item row solves its normal equations
+    (Y^T Y + lam I) x = Y^T 1 (reference algo.py:318-322 / :328-332): relative residual.  The item rows are checked against the U
+    they were solved with (the current one); the user rows only bound the drift since their solve (V has moved on by one item
+    half-step), so (2) reports them separately."""
+    u64, v64 = u.astype(np.float64), v.astype(np.float64)
+    bad = tied = 0
+    tol_rel = 4 * float(np.finfo(np.float32).eps)
+    for r, got in zip(users, idx_rows):
+        sc = v64 @ u64[r]
+        seen = indices[indptr[r]:indptr[r + 1]]
+        sc_m = sc.copy()
+        sc_m[seen] = -np.inf
+        order = np.lexsort((np.arange(len(sc_m)), -sc_m))[:n]
+        order = order[np.isfinite(sc_m[order])]
+        got = got[got >= 0]
+        if np.array_equal(order, got):
+            continue
+        ok = len(got) == len(order) and len(set(got.tolist())) == len(got) and not np.isin(got, seen).any()
+        if ok:
+            ok = bool(np.all(np.abs(sc[got] - sc[order]) <= tol_rel * np.maximum(1.0, np.abs(sc[order]))))
+        tied += ok
+        bad += not ok
+    res_items = 0.0
+    for i in items:
+        rows = indices_t[indptr_t[i]:indptr_t[i + 1]]
+        if len(rows) == 0:
+            continue
+        y = u64[rows]
+        a = y.T @ y + lam * np.eye(y.shape[1])
+        b = y.sum(axis=0)
+        res_items = max(res_items, float(np.linalg.norm(a @ v64[i] - b) / max(np.linalg.norm(b), 1e-300)))
+    return {"topn_rows_checked": int(len(users)), "topn_rows_tied": int(tied), "topn_rows_bad": int(bad),
+            "als_item_rows_checked": int(len(items)), "als_item_max_rel_residual": res_items,
+            "what": "float64 NumPy on sampled rows of the final state: top-n ranking (seen items masked, ties within 4 eps32) and the "
+                    "normal equations (Y^T Y + lam I) v_i = Y^T 1 of the last item half-step"}
+
 
 
 def make_inputs(w):
@@ -158,37 +201,60 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+class all_host_threads:
+    """BLAS / OpenMP thread pools set to every host core for the CPU leg, whatever the launcher exported (torchrun sets
+    OMP_NUM_THREADS=1 for its workers, which would throttle the reference arm at N > 1)."""
+
+    def __enter__(self):
+        self.ctx = None
+        try:
+            from threadpoolctl import threadpool_limits
+            self.ctx = threadpool_limits(limits=os.cpu_count() or 1)
+            self.ctx.__enter__()
+        except Exception:
+            self.ctx = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     inputs = make_inputs(w)
-    budget = 150.0 / max(1, args.steps + args.warmup)      # seconds of CPU work per step
-    scale = min(1.0, budget / 12.0)                        # 12 s ~ the (20K, 20K, 2K) sample on a 2 GHz core
-    nu_s, ni_s, nt_s = max(512, int(20_000 * scale)), max(128, int(20_000 * scale)), max(64, int(2_000 * scale))
+    # SURVEY 8(d): >= 20 K users / 20 K items per half-step and >= 2 K users for top-N, whatever --steps says; the sample is
+    # repeated at most 3 times (+1 warm-up) so that the arm ends within a few minutes
+    nu_s, ni_s, nt_s = 20_000, 20_000, 2_000
+    reps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
     vals, secs, desc = [], [], ""
-    for i in range(args.warmup + args.steps):
-        v, s, desc = cpu_reference_leg(w, inputs, nu_s, ni_s, nt_s)
-        if i >= args.warmup:
-            vals.append(v)
-            secs.append(s)
+    with all_host_threads():
+        for i in range(warm + reps):
+            v, s, desc = cpu_reference_leg(w, inputs, nu_s, ni_s, nt_s)
+            if i >= warm:
+                vals.append(v)
+                secs.append(s)
+        cores = blas_threads()
     value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, w, "host CPU"),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": blas_threads(), "kind": "port", "sample": desc},
+        "config": workload_config(args, w), "where": "host CPU",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "sample_seconds_per_step": float(np.mean(secs)),
+        "sample_seconds_per_step": float(np.mean(secs)), "sample_repeats": reps,
     }
     _emit(line)
 
 
-def workload_config(args, w, where):
+def workload_config(args, w):
     return {"workload": f"{args.workload}: implicit ALS k={w['k']} one full iteration + top-{w['n']} for all users, "
                         f"{w['n_users']} users x {w['n_items']} items, ~{w['mean_deg']} nnz/user ({'skewed: Zipf item popularity, log-normal degrees' if w.get('skew') else 'uniform synthetic'}, seed {w['seed']})",
-            "lambda": w["lam"], "where": where,
+            "lambda": w["lam"],
             "l2": "inputs larger than L2 (indices 2x%d MB, U %d MB); no flush" % (
                 w["n_users"] * w["mean_deg"] * 4 // 2**20, w["n_users"] * w["k"] * 4 // 2**20)}
 
@@ -235,7 +301,7 @@ def run_b200(args, w):
         torch.cuda.synchronize()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)      # noqa: E731
-    marks = []
+    marks, overflow_rows = [], []
 
     def step(record):
         e = [ev() for _ in range(5)] if record else None
@@ -255,6 +321,7 @@ def run_b200(args, w):
         if record:
             e[4].record()
             marks.append(e)
+            overflow_rows.append(int(h.lib.rl_last_overflow_rows(h.h)))
 
     for _ in range(args.warmup):
         step(False)
@@ -288,6 +355,34 @@ def run_b200(args, w):
     ms_per_step = total_ms / args.steps
     value = 1000.0 / ms_per_step
 
+    # ---- correctness of what was just timed (sampled, float64 NumPy; replicas compared across ranks) --------------
+    parity = None
+    if not args.no_parity:
+        rs = np.random.default_rng(1234 + rank)
+        users = np.sort(rs.choice(np.arange(ulo, uhi), size=min(64, uhi - ulo), replace=False))
+        items = np.sort(rs.choice(np.arange(ilo, ihi), size=min(64, ihi - ilo), replace=False))
+        u_host = prob.U[:, :k].cpu().numpy()
+        v_host = prob.V[:, :k].cpu().numpy()
+        idx_rows = idx_out[torch.from_numpy(users - ulo).to(device)].cpu().numpy()
+        parity = sampled_parity(w, indptr, indices, indptr_t, indices_t, u_host, v_host, idx_rows, users, items, w["lam"], n)
+        if world > 1:
+            # every rank must hold the same replicas after the fused exchange (NVLink peer stores): compare checksums
+            cs_ = torch.stack([prob.U[:, :k].double().sum(), prob.V[:, :k].double().sum(), prob.U[:, :k].double().abs().sum()])
+            allc = [torch.empty_like(cs_) for _ in range(world)]
+            dist.all_gather(allc, cs_)
+            same = all(torch.equal(allc[0], c) for c in allc)
+            agg = torch.tensor([float(parity["topn_rows_bad"]), parity["als_item_max_rel_residual"], 0.0 if same else 1.0],
+                               dtype=torch.float64, device=device)
+            dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+            parity["topn_rows_bad"] = int(agg[0].item())
+            parity["als_item_max_rel_residual"] = float(agg[1].item())
+            parity["replicas_identical_across_ranks"] = agg[2].item() == 0.0
+            parity["topn_rows_checked"] *= world
+            parity["als_item_rows_checked"] *= world
+        parity["ok"] = bool(parity["topn_rows_bad"] == 0 and parity["als_item_max_rel_residual"] <= 1e-4
+                            and parity.get("replicas_identical_across_ranks", True))
+        del u_host, v_host
+
     # ---- end-to-end leg: host buffers, copies inside the timed region -------------------------------------
     e2e = run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier)
 
@@ -302,20 +397,24 @@ def run_b200(args, w):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 factors; ALS solve " + ("f64" if prec else f"f32 + {args.ir_steps} f64 refinement steps")
                      + "; scores f64",
-            "data": "synthetic", "config": dict(workload_config(args, w, f"{world} x B200"), exchange=(
-                "none (1 GPU)" if world == 1 else "fused: solve kernel stores rows into the peers' replicas over NVLink (CUDA IPC) + "
-                "one-element all-reduce as barrier" if fused else "NCCL broadcasts of the row ranges")),
+            "data": "synthetic", "config": workload_config(args, w), "where": f"{world} x B200",
+            "exchange": ("none (1 GPU)" if world == 1 else "fused: solve kernel stores rows into the peers' replicas over NVLink "
+                         "(CUDA IPC) + one-element all-reduce as barrier" if fused else "NCCL broadcasts of the row ranges"),
             "als_iterations_per_s": 1000.0 / (t_user + t_item_x + t_x2),
             "top10_users_per_s": nu / (t_score / 1000.0),
             "ms": {"user_half_step": t_user, "exchange_U_plus_item_half_step": t_item_x, "exchange_V": t_x2, "score_topn": t_score},
+            "per_step": {"score_topn_ms": [round(float(x), 3) for x in seg[:, 3]],
+                         "overflow_rows": overflow_rows,
+                         "what": "rank 0, every timed step (each step is one more ALS iteration on the same factors: the scoring "
+                                 "kernel sees more and more converged factors); overflow_rows = rows finished by the exact kernel"},
             "roofline": {"kernel": "score_topn (rank 0 shard)", "bound": "tensor",
                          "achieved": flops_score / (t_score * 1e-3) / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": flops_score / (t_score * 1e-3) / 1e12 / peaks["tflops"], "traffic": traffic.get("score_topn"),
-                         "tensor_pipe_active_pct_ncu": (traffic.get("tensor_pipe_active_pct") or {}).get("score_topn"),
-                         "issued": {"achieved": 3.0 * flops_score / (t_score * 1e-3) / 1e12, "unit": "TFLOP/s",
-                                    "frac": 3.0 * flops_score / (t_score * 1e-3) / 1e12 / peaks["tflops"],
-                                    "what": "MMA work the tensor pipe executes: 3 fp16 products per score (exactness needs ~2^-22 products)"},
-                         "note": "algorithmic flops 2*n_users*n_items*k; the kernel issues 3 fp16 MMAs per product (split operands), so the tensor pipe does 3x the algorithmic flops",
+                         "static_profile": {"source": traffic.get("source"), "tensor_pipe_active_pct": (traffic.get("tensor_pipe_active_pct") or {}).get("score_topn"),
+                                            "what": "traffic and tensor-pipe activity come from the committed ncu capture named in `source`, not from this run"},
+                         "note": "algorithmic flops 2*n_users*n_items*k over the whole scoring call (preprocessing of V, the candidate pass "
+                                 "score_tc2_kernel, exact re-scoring); one fp16 tcgen05 product per score on centred factors (score_tc2.cu), so "
+                                 "issued MMA flops = algorithmic flops; the kernel is bound by the integer/compare pipe of the selection, not by the tensor pipe",
                          "peak_source": peaks["source"] + " bf16 sustained"},
             "roofline_als": {
                 "bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_source": peaks["source"],
@@ -326,12 +425,13 @@ def run_b200(args, w):
                 "item_half_step_incl_exchange": {"bytes": b_item, "achieved": b_item / (t_item_x * 1e-3) / 1e9,
                                                  "frac": b_item / (t_item_x * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                                  "traffic": traffic.get("als_item_half_step")}},
-            "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "ms_per_rank": per_rank,
+            "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "parity": parity, "ms_per_rank": per_rank,
         }
         if world == 1 and not args.no_cpu:
-            v, s, desc = cpu_reference_leg(w, inputs, 60_000, 60_000, 6_000)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": blas_threads(), "kind": "port", "sample": desc,
-                                    "seconds": s}
+            with all_host_threads():
+                v, s, desc = cpu_reference_leg(w, inputs, 60_000, 60_000, 6_000)
+                cores = blas_threads()
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds": s}
         _emit(line)
     if world > 1:
         dist.barrier()
@@ -347,18 +447,22 @@ def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
     from recsys_lite_b200 import _ffi
     indptr, indices, indptr_t, indices_t, u0, v0 = inputs
     nu, ni, k, n = w["n_users"], w["n_items"], w["k"], w["n"]
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, args.steps)
+    # every end-to-end step starts from the factors the device-resident steps ended with (the converged state `value` was
+    # measured on), not from the random initialisation: the scoring pass sees the same kind of data in both numbers
+    u_now = prob.U[:, :k].cpu().numpy().copy()
+    v_now = prob.V[:, :k].cpu().numpy().copy()
     if world == 1:
         pin = lambda a: _pinned_copy(a)                    # noqa: E731
         p_ip, p_ix = pin(indptr), pin(indices)      # the item-side pattern is built on the device (as RecommenderSystem.fit does)
-        p_u, p_v = pin(u0), pin(v0)
+        p_u, p_v = pin(u_now), pin(v_now)
         idx = _ffi.pinned_empty((nu, n), np.int32)
         h2d = p_ip.nbytes + p_ix.nbytes + 2 * (p_u.nbytes + p_v.nbytes) + p_ip.nbytes + p_ix.nbytes
         d2h = p_u.nbytes + p_v.nbytes + idx.nbytes
         times = []
         for i in range(1 + steps):
-            p_u[:] = u0
-            p_v[:] = v0
+            p_u[:] = u_now
+            p_v[:] = v_now
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             h.call("rl_als_fit_host", nu, ni, k, _ffi.ptr(p_ip), _ffi.ptr(p_ix), None, None, 1,
@@ -371,12 +475,13 @@ def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
         sec = float(np.mean(times))
         return {"value": 1.0 / sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": sec * 1e3, "steps": steps,
+                "state": "every step starts from the factors of the last device-resident step",
                 "api": "rl_als_fit_host(iterations=1) + rl_recommend_host(n=10), pinned float32 host buffers"}
     import torch.distributed as dist
     ulo, uhi = plan.users
     ilo, ihi = plan.items
     hp = {kk: torch.from_numpy(v).pin_memory() for kk, v in prob.host.items()}
-    hu, hv = torch.from_numpy(u0).pin_memory(), torch.from_numpy(v0).pin_memory()
+    hu, hv = torch.from_numpy(u_now).pin_memory(), torch.from_numpy(v_now).pin_memory()
     out_u = torch.empty((uhi - ulo, k), dtype=torch.float32).pin_memory()
     out_v = torch.empty((ihi - ilo, k), dtype=torch.float32).pin_memory()
     out_idx = torch.empty((uhi - ulo, n), dtype=torch.int32).pin_memory()
@@ -456,6 +561,7 @@ def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     return {"value": 1.0 / sec, "unit": UNIT, "h2d_bytes_per_step": int(tot[0].item()), "d2h_bytes_per_step": int(tot[1].item()),
             "ms_per_step": sec * 1e3, "steps": steps, "checked": "equal to the single-stream step (U, V ranges and top-n rows, bitwise)",
+            "state": "every step starts from the factors of the last device-resident step",
             "api": "per-rank pinned H2D of its CSR/CSC ranges + factors on a copy stream (user half-step in 4 row ranges behind it), rl_als_half_step(_peers)_dev/rl_score_topn_dev + exchanges, D2H of its ranges"}
 
 
@@ -497,6 +603,7 @@ def main():
     ap.add_argument("--score-mode", type=int, default=0, help="0 auto, 1 exact CUDA-core, 2 tensor-core candidate pass")
     ap.add_argument("--no-peer-stores", action="store_true", help="N > 1: exchange with NCCL broadcasts instead of the fused NVLink stores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled float64 parity check of the final state")
     args = ap.parse_args()
     _quiet_stdout()
     if args.warmup < 3 and args.impl == "b200" and not os.environ.get("RL_BENCH_ALLOW_SHORT_WARMUP"):
