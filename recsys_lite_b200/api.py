@@ -20,7 +20,11 @@ Documented deviations from the reference:
   * factors are kept in float32 on the device and returned as float64 (reference: float64 throughout):
     relative factor error ~1e-6 against the reference, inside the stated 1e-4 tolerance;
   * equal scores are ordered by ascending item index (the reference's tie order is implementation defined);
-  * ``algorithm="knn"`` is accepted by the constructor but ``fit`` raises NotImplementedError (out of scope).
+  * ``algorithm="knn"`` is accepted by the constructor but ``fit`` raises NotImplementedError (out of scope);
+  * limits of the fused kernels: ALS fit 1..128 factors (NotImplementedError beyond); ``recommend`` with more than 128
+    factors (SVD models default to min(shape) // 4) or n > 128 takes the unfused device path (predict + top_n per row
+    chunk); ``svd_reconstruct`` / the SVD fit need min(n_users, n_items) <= 4096 (ValueError beyond: the device
+    eigen-solver is a one-CTA-per-column-pair Jacobi).
 """
 from __future__ import annotations
 
@@ -146,6 +150,7 @@ class RecommenderSystem:
         left = np.empty((n_users, k_eff), dtype=np.float64)
         right = np.empty((n_items, k_eff), dtype=np.float64)
         if np.isfinite(centred).all() and centred.any():
+            _check_svd_shape(centred.shape)
             h = _ffi.default_handle()
             h.call("rl_svd_reconstruct_host", _ffi.ptr(centred), n_users, n_items, k_eff, None,
                    _ffi.ptr(s), _ffi.ptr(left), _ffi.ptr(right))
@@ -215,13 +220,19 @@ class RecommenderSystem:
         if n_users == 0 or n_items == 0:
             return np.empty((0, 0), dtype=int)
         n_dev = min(int(n), n_items)
-        if n_dev > MAX_TOP_N:
-            raise NotImplementedError(f"n={n}: the selection kernels keep at most {MAX_TOP_N} items per user")
-        idx = np.empty((n_users, n_dev), dtype=np.int32)
         indptr = indices = None
         if exclude_rated:
             indptr, indices = observed_pattern(ratings)
         h = _ffi.default_handle()
+        if a.shape[1] > MAX_FACTORS or n_dev > MAX_TOP_N:
+            # outside the fused kernels (SVD models default to min(shape) // 4 factors; n > 128): score rows in chunks with
+            # rl_predict_host and select with rl_topn_dense_host, MAX_TOP_N items per pass (selected items join the mask)
+            idx = self._recommend_unfused(h, a, b, gb, rb, cb, indptr, indices, n_dev)
+            if not exclude_rated:
+                return idx.astype(np.int64)
+            n_valid = np.minimum(n_dev, n_items - np.diff(indptr)).astype(np.int32)
+            return _finish_topn(idx, n_valid)
+        idx = np.empty((n_users, n_dev), dtype=np.int32)
         h.call("rl_recommend_host", _ffi.ptr(np.ascontiguousarray(a)), _ffi.ptr(np.ascontiguousarray(b)), _ffi.RL_F64,
                n_users, n_items, a.shape[1], _ffi.ptr(indptr), _ffi.ptr(indices), gb, _ffi.ptr(rb), _ffi.ptr(cb),
                n_dev, _ffi.ptr(idx), None, _ffi.RL_SCORE_AUTO)
@@ -229,6 +240,37 @@ class RecommenderSystem:
             return idx.astype(np.int64)   # reference: argsort result, int64 (algo.py:207)
         n_valid = np.minimum(n_dev, n_items - np.diff(indptr)).astype(np.int32)
         return _finish_topn(idx, n_valid)
+
+    @staticmethod
+    def _recommend_unfused(h, a, b, gb, rb, cb, indptr, indices, n_dev, max_cells: int = 1 << 26) -> np.ndarray:
+        """predict + top_n as two device calls per row chunk (algo.py:172-201 literally); any factor count, any n."""
+        n_users, n_items, kk = a.shape[0], b.shape[0], a.shape[1]
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        idx = np.full((n_users, n_dev), -1, dtype=np.int32)
+        rows = max(1, min(n_users, max_cells // max(1, n_items)))
+        for r0 in range(0, n_users, rows):
+            r1 = min(n_users, r0 + rows)
+            est = np.empty((r1 - r0, n_items), dtype=np.float64)
+            h.call("rl_predict_host", _ffi.ptr(a[r0:r1]), _ffi.ptr(b), _ffi.RL_F64, r1 - r0, n_items, kk, gb,
+                   _ffi.ptr(None if rb is None else np.ascontiguousarray(rb[r0:r1])), _ffi.ptr(cb), _ffi.ptr(est), _ffi.RL_F64)
+            known = np.zeros((r1 - r0, n_items), dtype=np.float32)
+            if indptr is not None:
+                for r in range(r0, r1):
+                    known[r - r0, indices[indptr[r]:indptr[r + 1]]] = 1.0
+            done = 0
+            while done < n_dev:
+                take = min(MAX_TOP_N, n_dev - done)
+                part = np.empty((r1 - r0, take), dtype=np.int32)
+                nv = np.empty(r1 - r0, dtype=np.int32)
+                h.call("rl_topn_dense_host", _ffi.ptr(est), _ffi.RL_F64, _ffi.ptr(known), _ffi.RL_F32, r1 - r0, n_items, take,
+                       _ffi.ptr(part), _ffi.ptr(nv))
+                idx[r0:r1, done:done + take] = part
+                done += take
+                if done < n_dev:                      # the next pass must not return these again
+                    rr, cc = np.nonzero(part >= 0)
+                    known[rr, part[rr, cc]] = 1.0
+        return idx
 
     # ---------------------------------------------------------------------------------- persistence
     def save(self, path: str) -> None:
@@ -256,7 +298,16 @@ class RecommenderSystem:
         self._fitted = False
 
 
+MAX_SVD_SMALL_DIM = 4096   # rl_svd_topk_dev: Jacobi eigen-solver on the Gram matrix of the smaller dimension
+
+
+def _check_svd_shape(shape):
+    if min(shape) > MAX_SVD_SMALL_DIM:
+        raise ValueError(f"the device SVD needs min(n_users, n_items) <= {MAX_SVD_SMALL_DIM}, got shape {tuple(shape)}")
+
+
 def _reconstruct_device(mat32: np.ndarray, k: int) -> np.ndarray:
+    _check_svd_shape(mat32.shape)
     out = np.empty_like(mat32)
     h = _ffi.default_handle()
     h.call("rl_svd_reconstruct_host", _ffi.ptr(mat32), mat32.shape[0], mat32.shape[1], int(k), _ffi.ptr(out),

@@ -75,7 +75,18 @@ __global__ void __launch_bounds__(256) fill_empty_rows_kernel(const int64_t* __r
 struct DevBuf {
   void* p = nullptr;
   rl_context* ctx = nullptr;
-  ~DevBuf() { if (p) cudaFreeAsync(p, ctx->stream); }
+  // The free is ordered on the compute stream; transfers of the host wrappers run on the copy stream.  On the regular
+  // paths the compute stream has already waited for them; on an early error return it has not, so the free itself is made
+  // to wait for whatever the copy stream still has in flight.
+  ~DevBuf() {
+    if (!p) return;
+    if (ctx->copy_stream && ctx->copy_stream != ctx->stream) {
+      if (!ctx->free_guard) cudaEventCreateWithFlags(&ctx->free_guard, cudaEventDisableTiming);
+      if (ctx->free_guard && cudaEventRecord(ctx->free_guard, ctx->copy_stream) == cudaSuccess)
+        cudaStreamWaitEvent(ctx->stream, ctx->free_guard, 0);
+    }
+    cudaFreeAsync(p, ctx->stream);
+  }
   int alloc(rl_context* h, size_t bytes) {
     ctx = h;
     RL_CUDA(h, cudaMallocAsync(&p, bytes ? bytes : 16, h->stream));
@@ -262,6 +273,7 @@ int rl_destroy(rl_handle h) {
   if (h->long_list) cudaFree(h->long_list);
   if (h->aux_fork) cudaEventDestroy(h->aux_fork);
   if (h->aux_join) cudaEventDestroy(h->aux_join);
+  if (h->free_guard) cudaEventDestroy(h->free_guard);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return RL_OK;
@@ -552,8 +564,10 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const 
       RL_TRY(ev_u0_ready.wait(h, ks));
       int64_t g = (n_users * (kp / 4) + 255) / 256;
       if (g > 8 * h->sm_count) g = 8 * h->sm_count;
-      fill_empty_rows_kernel<<<static_cast<unsigned>(g), 256, 0, ks>>>(d_ip.as<int64_t>(), n_users, kp, d_u0.as<float>(), d_u.as<float>());
-      RL_LAUNCH_CHECK(h, "fill_empty_rows_kernel");
+      if (g > 0) {                     // (no users: nothing to restore, and a grid of 0 blocks is an invalid launch)
+        fill_empty_rows_kernel<<<static_cast<unsigned>(g), 256, 0, ks>>>(d_ip.as<int64_t>(), n_users, kp, d_u0.as<float>(), d_u.as<float>());
+        RL_LAUNCH_CHECK(h, "fill_empty_rows_kernel");
+      }
       RL_TRY(ev_item_ready.wait(h, ks));
     }
     if (it == iterations - 1) {        // U is final: send it home while the item half-step runs

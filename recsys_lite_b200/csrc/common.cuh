@@ -22,6 +22,7 @@ struct rl_context {
   cudaStream_t copy_stream = nullptr; // host <-> device traffic of the *_host entry points, overlapped with the kernels
   cudaStream_t aux_stream = nullptr;  // second compute stream: the cooperative long-row ALS kernel runs beside the warp-per-row one
   cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+  cudaEvent_t free_guard = nullptr;   // orders the release of staging buffers behind the copy stream (DevBuf)
   int32_t* long_list = nullptr;       // rows for the cooperative ALS kernel (device), capacity long_list_rows
   int64_t long_list_rows = 0;
   unsigned int* counter = nullptr;    // device work counters (row schedulers), 64 x u32

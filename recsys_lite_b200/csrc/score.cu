@@ -31,7 +31,9 @@ __global__ void __launch_bounds__(256) topn_dense_kernel(const TE* __restrict__ 
       open = !(static_cast<double>(kn[j]) > 0.0);
       if (open) sv = static_cast<double>(e[j]);
     }
-    unrated += __popc(__ballot_sync(FULL_MASK, open));
+    // n_valid counts what can be ranked: unrated items whose estimate is neither -inf nor NaN (the reference's result for
+    // such estimates is implementation defined; here they are never returned and never counted)
+    unrated += __popc(__ballot_sync(FULL_MASK, open && sv == sv && sv != -CUDART_INF));
     unsigned m = __ballot_sync(FULL_MASK, open && sv != -CUDART_INF && beats(sv, static_cast<int>(j), tv, tix));
     while (m) {
       const int l = __ffs(m) - 1;

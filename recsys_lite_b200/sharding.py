@@ -83,6 +83,21 @@ class ShardedProblem:
         self.up, self.ux, self.ip, self.ix = t(up), t(ux), t(ip), t(ix)
         self.U = torch.zeros((self.n_users, self.kp), dtype=torch.float32, device=device)
         self.V = torch.zeros((self.n_items, self.kp), dtype=torch.float32, device=device)
+        self._bound_stream = None
+        self._bind_stream()
+
+    def _bind_stream(self):
+        """The handle's kernels (and their NVLink peer stores), torch's copies and the NCCL barrier must be ordered on ONE
+        stream: the handle is (re)bound to torch's current stream before anything is enqueued.  (A default Handle owns a
+        private non-blocking stream: with it the one-element all-reduce would not wait for the solve kernel, and peers
+        would read half-written replicas.)"""
+        import torch
+        if getattr(self.device, "type", str(self.device)) != "cuda" and "cuda" not in str(self.device):
+            return
+        cur = torch.cuda.current_stream(self.device).cuda_stream
+        if cur != self._bound_stream:
+            self.h.set_stream(cur)
+            self._bound_stream = cur
 
     # -- fused exchange over peer memory ---------------------------------------------------------------------
     def enable_peer_stores(self, group=None):
@@ -147,6 +162,7 @@ class ShardedProblem:
         """Every rank's kernel (and with it its NVLink stores into this replica) has finished once this one-element
         all-reduce, enqueued behind the kernel on the same stream, completes."""
         import torch.distributed as dist
+        self._bind_stream()
         dist.all_reduce(self._barrier_buf, group=self._group)
 
     def close_peer_stores(self):
@@ -158,6 +174,7 @@ class ShardedProblem:
 
     def set_factors(self, u_host, v_host):
         import torch
+        self._bind_stream()
         self.U[:, : self.k].copy_(torch.from_numpy(np.ascontiguousarray(u_host, dtype=np.float32)))
         self.V[:, : self.k].copy_(torch.from_numpy(np.ascontiguousarray(v_host, dtype=np.float32)))
 
@@ -168,6 +185,7 @@ class ShardedProblem:
         r0, r1 = (0, uhi - ulo) if rows is None else rows
         if r1 <= r0:
             return
+        self._bind_stream()
         if getattr(self, "peer_stores", False):
             import ctypes as C
             peers = self._peers_u
@@ -183,6 +201,7 @@ class ShardedProblem:
 
     def item_half_step(self, lam, precision, ir_steps):
         ilo, ihi = self.plan.items
+        self._bind_stream()
         if getattr(self, "peer_stores", False):
             self.h.call("rl_als_half_step_peers_dev", ihi - ilo, self.n_users, self.k, self.ip.data_ptr(), self.ix.data_ptr(),
                         None, None, self.U.data_ptr(), self.V[ilo:].data_ptr(), float(lam), 0.0, None, precision,
@@ -214,5 +233,6 @@ class ShardedProblem:
     def recommend(self, n, idx_out, mode=0):
         """top-n for this rank's users (seen items = its CSR rows) into idx_out (users_local x n int32 tensor)."""
         ulo, uhi = self.plan.users
+        self._bind_stream()
         self.h.call("rl_score_topn_dev", self.U[ulo:].data_ptr(), uhi - ulo, self.V.data_ptr(), self.n_items, self.k,
                     self.up.data_ptr(), self.ux.data_ptr(), 0.0, None, None, int(n), idx_out.data_ptr(), None, mode)

@@ -864,3 +864,43 @@ def test_csr_transpose_dev_and_fit_without_host_transpose(h):
     h.call("rl_als_fit_host", n_users, n_items, k, _ffi.ptr(indptr), _ffi.ptr(indices), None, None, 2, 0.01, 0, 1,
            _ffi.ptr(ub), _ffi.ptr(vb), _ffi.RL_F64)
     assert np.array_equal(ua, ub) and np.array_equal(va, vb)
+
+
+# ------------------------------------------------------------------------------- r2: limits of the fused kernels
+def test_recommend_wide_models_and_large_n_take_the_unfused_path():
+    """SVD models default to min(shape) // 4 factors: beyond 128 (and for n > 128) `recommend` must still work -- predict +
+    top_n per row chunk on the device -- and agree with the reference composition predict -> top_n (algo.py:172-201)."""
+    from recsys_lite_b200 import RecommenderSystem, top_n
+    rng = np.random.default_rng(5)
+    r = (rng.random((620, 700)) < 0.05) * rng.integers(1, 6, (620, 700))
+    r = r.astype(np.float32)
+    m = RecommenderSystem(algorithm="svd", use_sparse=False).fit(r)          # k = 155 > 128
+    assert m._model["u"].shape[1] == 155
+    rec = m.recommend(r, n=10)
+    want = top_n(m.predict(r), r, n=10)
+    assert rec.shape == want.shape
+    pred = m.predict(r).astype(np.float64)
+    res = compare.topn_matches(rec, want, lambda row: pred[row], lambda row: np.nonzero(r[row] > 0)[0], rtol=1e-5)
+    assert not res["bad"], res
+    als = RecommenderSystem(algorithm="als").fit(r, k=8, iterations=2)
+    big = als.recommend(r, n=300)                                               # n > 128: several selection passes
+    uf, vf = als._model["user_factors"], als._model["item_factors"]
+    indptr, indices = o_als.pattern_to_csr(r)
+    ref, _ = o_topn.recommend_blocked(uf, vf, indptr, indices, n=300)
+    res = compare.topn_matches(big, ref[:, : big.shape[1]], lambda row: uf[row] @ vf.T, lambda row: indices[indptr[row]:indptr[row + 1]])
+    assert big.shape == (620, 300) and not res["bad"], res
+    with pytest.raises(ValueError, match="device SVD needs"):
+        from recsys_lite_b200 import svd_reconstruct
+        svd_reconstruct(np.ones((4100, 4100), dtype=np.float32), k=2)
+
+
+def test_top_n_ignores_nan_and_minus_inf_estimates_and_empty_fit(h):
+    """-inf / NaN estimates are never returned and never counted as valid (the reference's behaviour for them is
+    implementation defined); a fit without users is a no-op instead of an invalid launch."""
+    from recsys_lite_b200 import RecommenderSystem, top_n
+    est = np.array([[1.0, np.nan, 3.0, 2.0, -np.inf], [np.nan, np.nan, -np.inf, 0.5, 0.25]], dtype=np.float64)
+    known = np.array([[0, 0, 0, 1, 0], [0, 0, 0, 0, 0]], dtype=np.float32)
+    out = top_n(est, known, n=4)
+    assert out.tolist() == [[2, 0], [3, 4]]
+    m = RecommenderSystem(algorithm="als").fit(np.zeros((0, 7), dtype=np.float32), k=4, iterations=3)
+    assert m._model["user_factors"].shape == (0, 4) and m._model["item_factors"].shape == (7, 4)
