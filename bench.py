@@ -386,6 +386,8 @@ def run_b200(args, w):
     # ---- end-to-end leg: host buffers, copies inside the timed region -------------------------------------
     e2e = run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier)
 
+    api = run_api_leg(args, w, inputs, prob, k) if (world == 1 and not args.no_api) else None
+
     line = None
     if rank == 0:
         traffic = load_traffic() if (world == 1 and args.workload == "C4") else {}
@@ -425,7 +427,7 @@ def run_b200(args, w):
                 "item_half_step_incl_exchange": {"bytes": b_item, "achieved": b_item / (t_item_x * 1e-3) / 1e9,
                                                  "frac": b_item / (t_item_x * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                                  "traffic": traffic.get("als_item_half_step")}},
-            "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "parity": parity, "ms_per_rank": per_rank,
+            "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "e2e_api": api, "parity": parity, "ms_per_rank": per_rank,
         }
         if world == 1 and not args.no_cpu:
             with all_host_threads():
@@ -437,6 +439,38 @@ def run_b200(args, w):
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+def run_api_leg(args, w, inputs, prob, k):
+    """The same step through the drop-in Python surface (what a user of the reference calls): RecommenderSystem("als")
+    .fit(R_csr, k, iterations=1, init=...) + .recommend(R_csr, n) on pageable NumPy / SciPy inputs; the model stays in HBM between
+    the two calls (api.py: _ResidentALS), the top-n lists come back as the reference's int array."""
+    import torch
+    from scipy import sparse
+    from recsys_lite_b200 import RecommenderSystem
+    indptr, indices = inputs[0], inputs[1]
+    nu, ni, n = w["n_users"], w["n_items"], w["n"]
+    r = sparse.csr_matrix((np.ones(len(indices), np.float32), indices, indptr), shape=(nu, ni))
+    u_now = prob.U[:, :k].cpu().numpy().copy()
+    v_now = prob.V[:, :k].cpu().numpy().copy()
+    t_fit, t_rec = [], []
+    steps = max(1, min(args.steps, 5))
+    for i in range(1 + steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        m = RecommenderSystem("als").fit(r, k=k, iterations=1, lambda_=w["lam"], init=(u_now, v_now))
+        t1 = time.perf_counter()
+        rec = m.recommend(r, n=n)
+        t2 = time.perf_counter()
+        if i > 0:
+            t_fit.append(t1 - t0)
+            t_rec.append(t2 - t1)
+        del m
+    sec = float(np.mean(t_fit) + np.mean(t_rec))
+    return {"value": 1.0 / sec, "unit": UNIT, "ms_per_step": sec * 1e3, "ms_fit": float(np.mean(t_fit)) * 1e3,
+            "ms_recommend": float(np.mean(t_rec)) * 1e3, "steps": steps, "result_shape": list(rec.shape),
+            "api": "RecommenderSystem('als').fit(scipy CSR, k=64, iterations=1, init=float32 arrays) + .recommend(R, n=10); pageable "
+                   "host inputs, model resident in HBM between the calls, int top-n array back on the host"}
 
 
 def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
@@ -603,6 +637,7 @@ def main():
     ap.add_argument("--score-mode", type=int, default=0, help="0 auto, 1 exact CUDA-core, 2 tensor-core candidate pass")
     ap.add_argument("--no-peer-stores", action="store_true", help="N > 1: exchange with NCCL broadcasts instead of the fused NVLink stores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-api", action="store_true", help="skip the e2e_api leg (the step through RecommenderSystem.fit / .recommend)")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled float64 parity check of the final state")
     args = ap.parse_args()
     _quiet_stdout()

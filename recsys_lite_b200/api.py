@@ -65,6 +65,129 @@ def _finish_topn(idx, n_valid):
     return idx[:, :widest]
 
 
+class _DevBuf:
+    """One device allocation through the C ABI (rl_dev_alloc / rl_dev_free)."""
+
+    def __init__(self, h, nbytes: int):
+        import ctypes as C
+        self.h, self.nbytes = h, int(nbytes)
+        p = C.c_void_p()
+        h.call("rl_dev_alloc", max(self.nbytes, 16), C.byref(p))
+        self.ptr = p
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            try:
+                self.h.synchronize()
+                self.h.call("rl_dev_free", self.ptr)
+            except Exception:
+                pass
+            self.ptr = None
+
+    def __del__(self):
+        self.free()
+
+
+class _ResidentALS:
+    """ALS factors (float32, padded rows) and the training pattern kept in HBM between fit / recommend / predict, so that
+    the drop-in surface moves the model over PCIe only when the caller asks for the NumPy arrays."""
+
+    def __init__(self, h, n_users, n_items, k):
+        self.h, self.n_users, self.n_items, self.k = h, int(n_users), int(n_items), int(k)
+        self.kp = h.lib.rl_padded_k(self.k)
+        self.u = _DevBuf(h, 4 * self.n_users * self.kp)
+        self.v = _DevBuf(h, 4 * self.n_items * self.kp)
+        self.ip = self.ix = self.tp = self.tx = None
+        self.pattern_key = None
+
+    @staticmethod
+    def key_of(ratings, indptr, indices):
+        return (id(ratings), tuple(ratings.shape), int(indptr[-1]), int(indices[:64].sum()) if len(indices) else 0)
+
+    def upload_pattern(self, indptr, indices, key, transpose=True):
+        h = self.h
+        nnz = int(indptr[-1])
+        self.ip, self.ix = _DevBuf(h, indptr.nbytes), _DevBuf(h, max(indices.nbytes, 16))
+        h.call("rl_memcpy_h2d", self.ip.ptr, _ffi.ptr(indptr), indptr.nbytes)
+        if nnz:
+            h.call("rl_memcpy_h2d", self.ix.ptr, _ffi.ptr(indices), indices.nbytes)
+        if transpose:
+            self.tp, self.tx = _DevBuf(h, 8 * (self.n_items + 1)), _DevBuf(h, max(4 * nnz, 16))
+            h.call("rl_csr_transpose_dev", self.n_users, self.n_items, nnz, self.ip.ptr, self.ix.ptr, self.tp.ptr, self.tx.ptr)
+        self.pattern_key = key
+
+    def upload_factors(self, user_f, item_f):
+        self.h.call("rl_factors_upload", _ffi.ptr(user_f), _rl_dtype(user_f), self.n_users, self.k, self.u.ptr)
+        self.h.call("rl_factors_upload", _ffi.ptr(item_f), _rl_dtype(item_f), self.n_items, self.k, self.v.ptr)
+
+    def iterate(self, iterations, lam, precision, ir_steps):
+        h = self.h
+        for _ in range(int(iterations)):
+            h.call("rl_als_half_step_dev", self.n_users, self.n_items, self.k, self.ip.ptr, self.ix.ptr, None, None,
+                   self.v.ptr, self.u.ptr, float(lam), 0.0, None, precision, int(ir_steps), None)
+            h.call("rl_als_half_step_dev", self.n_items, self.n_users, self.k, self.tp.ptr, self.tx.ptr, None, None,
+                   self.u.ptr, self.v.ptr, float(lam), 0.0, None, precision, int(ir_steps), None)
+
+    def download(self):
+        uf = np.empty((self.n_users, self.k), dtype=np.float64)
+        vf = np.empty((self.n_items, self.k), dtype=np.float64)
+        self.h.call("rl_factors_download", self.u.ptr, self.n_users, self.k, _ffi.ptr(uf), _ffi.RL_F64)
+        self.h.call("rl_factors_download", self.v.ptr, self.n_items, self.k, _ffi.ptr(vf), _ffi.RL_F64)
+        return uf, vf
+
+    def free(self):
+        for b in (self.u, self.v, self.ip, self.ix, self.tp, self.tx):
+            if b is not None:
+                b.free()
+
+
+class _LazyALSModel(dict):
+    """The reference's ALS model dict ({"user_factors", "item_factors", "factors"}, algo.py:333-337) whose two arrays stay
+    in HBM until somebody reads them.  Reading any of them downloads both as float64 NumPy arrays and makes the HOST copy
+    authoritative from then on (the owner drops its device copy: callers may edit the arrays in place)."""
+
+    _LAZY = ("user_factors", "item_factors")
+
+    def __init__(self, owner, factors):
+        super().__init__(user_factors=None, item_factors=None, factors=factors)
+        self._owner = owner
+        self._pending = True
+
+    def _materialise(self):
+        if self._pending:
+            self._pending = False
+            uf, vf = self._owner._resident.download()
+            super().__setitem__("user_factors", uf)
+            super().__setitem__("item_factors", vf)
+            self._owner._drop_resident()
+
+    def __getitem__(self, key):
+        if key in self._LAZY:
+            self._materialise()
+        return super().__getitem__(key)
+
+    def get(self, key, default=None):
+        if key in self._LAZY:
+            self._materialise()
+        return super().get(key, default)
+
+    def items(self):
+        self._materialise()
+        return super().items()
+
+    def values(self):
+        self._materialise()
+        return super().values()
+
+    def copy(self):
+        self._materialise()
+        return dict(super().items())
+
+    def __reduce__(self):           # pickled (joblib save) as a plain dict of NumPy arrays
+        self._materialise()
+        return (dict, (dict(super().items()),))
+
+
 class RecommenderSystem:
     """B200 implementation of the reference's ``RecommenderSystem`` for ``algorithm="als" | "svd"``."""
 
@@ -74,6 +197,7 @@ class RecommenderSystem:
         self.use_sparse = use_sparse
         self._model: Optional[Dict[str, Any]] = None
         self._fitted = False
+        self._resident: Optional[_ResidentALS] = None
         if algorithm not in ("svd", "als", "knn"):
             raise ValueError(f"Unsupported algorithm: '{algorithm}'")
 
@@ -113,18 +237,42 @@ class RecommenderSystem:
             user_f = np.random.rand(n_users, factors)   # draw order of algo.py:309-310
             item_f = np.random.rand(n_items, factors)
         else:
-            user_f = np.array(init[0], dtype=np.float64, order="C", copy=True)
-            item_f = np.array(init[1], dtype=np.float64, order="C", copy=True)
+            # read only (uploaded as they are: float32 or float64); copied to float64 only if they become the model
+            user_f = np.ascontiguousarray(init[0], dtype=None if np.asarray(init[0]).dtype == np.float32 else np.float64)
+            item_f = np.ascontiguousarray(init[1], dtype=None if np.asarray(init[1]).dtype == np.float32 else np.float64)
             if user_f.shape != (n_users, factors) or item_f.shape != (n_items, factors):
                 raise ValueError("init factors must have shapes (n_users, factors) and (n_items, factors)")
         indptr, indices = observed_pattern(ratings)
+        self._drop_resident()
         if n_users and n_items and iterations > 0:
             h = _ffi.default_handle()
-            # the transposed pattern (users of every item) is built on the device, underneath the first user half-step
-            h.call("rl_als_fit_host", n_users, n_items, factors, _ffi.ptr(indptr), _ffi.ptr(indices),
-                   None, None, int(iterations), float(lambda_),
-                   _PRECISIONS[precision], int(ir_steps), _ffi.ptr(user_f), _ffi.ptr(item_f), _ffi.RL_F64)
-        return {"user_factors": user_f, "item_factors": item_f, "factors": factors}
+            # The model stays in HBM (float32, padded rows): pattern and initial factors go up once, the transposed pattern
+            # (users of every item) is built on the device, and nothing comes back until the caller reads the arrays.
+            res = _ResidentALS(h, n_users, n_items, factors)
+            try:
+                res.upload_pattern(indptr, indices, _ResidentALS.key_of(ratings, indptr, indices))
+                res.upload_factors(user_f, item_f)
+                res.iterate(iterations, lambda_, _PRECISIONS[precision], ir_steps)
+                h.synchronize()
+            except Exception:
+                res.free()
+                raise
+            self._resident = res
+            return _LazyALSModel(self, factors)
+        return {"user_factors": np.array(user_f, dtype=np.float64), "item_factors": np.array(item_f, dtype=np.float64),
+                "factors": factors}
+
+    def _drop_resident(self):
+        if getattr(self, "_resident", None) is not None:
+            self._resident.free()
+            self._resident = None
+
+    def __getstate__(self):          # joblib / pickle: host arrays only (the device copy cannot travel)
+        state = dict(self.__dict__)
+        if isinstance(state.get("_model"), _LazyALSModel):
+            state["_model"] = state["_model"].copy()
+        state["_resident"] = None
+        return state
 
     def _fit_svd(self, ratings, k: Optional[int]) -> Dict[str, Any]:
         """algo.py:210-248: biases over entries > 0, centre every cell, rank-k SVD of the centred matrix.
@@ -190,6 +338,15 @@ class RecommenderSystem:
         if self.algorithm == "knn":
             self._need_model()
             raise NotImplementedError("algorithm='knn' is outside the B200 hot path")
+        if self.algorithm == "als" and self._need_model() is not None and self._resident is not None:
+            res = self._resident                      # U @ V.T from the device copy (float64 out, as the reference)
+            out = np.empty((res.n_users, res.n_items), dtype=np.float64)
+            d_out = _DevBuf(res.h, out.nbytes)
+            res.h.call("rl_lowrank_dev", res.u.ptr, res.v.ptr, _ffi.RL_F32, res.n_users, res.n_items, res.k, 0.0, None, None,
+                       d_out.ptr, _ffi.RL_F64)
+            res.h.call("rl_memcpy_d2h", _ffi.ptr(out), d_out.ptr, out.nbytes)
+            d_out.free()
+            return out
         a, b, gb, rb, cb, out_t = self._factor_view()
         m, n = a.shape[0], b.shape[0]
         kk = a.shape[1]
@@ -210,6 +367,10 @@ class RecommenderSystem:
         if self.algorithm == "knn":
             self._need_model()
             raise NotImplementedError("algorithm='knn' is outside the B200 hot path")
+        if self.algorithm == "als" and self._need_model() is not None and self._resident is not None:
+            out = self._recommend_resident(ratings, int(n), exclude_rated)
+            if out is not None:
+                return out
         a, b, gb, rb, cb, _ = self._factor_view()
         n_users, n_items = a.shape[0], b.shape[0]
         if exclude_rated and tuple(ratings.shape) != (n_users, n_items):
@@ -238,6 +399,48 @@ class RecommenderSystem:
                n_dev, _ffi.ptr(idx), None, _ffi.RL_SCORE_AUTO)
         if not exclude_rated:
             return idx.astype(np.int64)   # reference: argsort result, int64 (algo.py:207)
+        n_valid = np.minimum(n_dev, n_items - np.diff(indptr)).astype(np.int32)
+        return _finish_topn(idx, n_valid)
+
+    def _recommend_resident(self, ratings, n, exclude_rated):
+        """Fused scoring straight from the device copy of the factors; the training pattern is reused when `ratings` is
+        the matrix the model was fitted on.  Returns None when the shape needs the general path."""
+        res = self._resident
+        n_users, n_items = res.n_users, res.n_items
+        if exclude_rated and tuple(ratings.shape) != (n_users, n_items):
+            raise ValueError(
+                "Estimated and known matrices must have the same shape. "
+                f"Got {(n_users, n_items)} and {tuple(ratings.shape)}."
+            )
+        n_dev = min(n, n_items)
+        if n_dev > MAX_TOP_N:
+            return None
+        h = res.h
+        ip = ix = None
+        indptr = None
+        tmp = []
+        if exclude_rated:
+            indptr, indices = observed_pattern(ratings)
+            if res.pattern_key == _ResidentALS.key_of(ratings, indptr, indices):
+                ip, ix = res.ip, res.ix
+            else:
+                ip, ix = _DevBuf(h, indptr.nbytes), _DevBuf(h, max(indices.nbytes, 16))
+                tmp = [ip, ix]
+                h.call("rl_memcpy_h2d", ip.ptr, _ffi.ptr(indptr), indptr.nbytes)
+                if len(indices):
+                    h.call("rl_memcpy_h2d", ix.ptr, _ffi.ptr(indices), indices.nbytes)
+        idx = np.empty((n_users, n_dev), dtype=np.int32)
+        d_idx = _DevBuf(h, idx.nbytes)
+        try:
+            h.call("rl_score_topn_dev", res.u.ptr, n_users, res.v.ptr, n_items, res.k, ip.ptr if ip else None,
+                   ix.ptr if ix else None, 0.0, None, None, n_dev, d_idx.ptr, None, _ffi.RL_SCORE_AUTO)
+            h.call("rl_memcpy_d2h", _ffi.ptr(idx), d_idx.ptr, idx.nbytes)
+        finally:
+            d_idx.free()
+            for b in tmp:
+                b.free()
+        if not exclude_rated:
+            return idx.astype(np.int64)
         n_valid = np.minimum(n_dev, n_items - np.diff(indptr)).astype(np.int32)
         return _finish_topn(idx, n_valid)
 
@@ -294,8 +497,15 @@ class RecommenderSystem:
         return RecommenderSystem(algorithm=self.algorithm, random_state=self.random_state, use_sparse=self.use_sparse)
 
     def reset(self) -> None:
+        self._drop_resident()
         self._model = None
         self._fitted = False
+
+    def __del__(self):
+        try:
+            self._drop_resident()
+        except Exception:
+            pass
 
 
 MAX_SVD_SMALL_DIM = 4096   # rl_svd_topk_dev: Jacobi eigen-solver on the Gram matrix of the smaller dimension

@@ -17,8 +17,8 @@ def observed_pattern(ratings):
         if not m.has_canonical_format:
             m = m.copy()
             m.sum_duplicates()
-        keep = m.data > 0
-        if not keep.all():
+        if m.nnz and not (m.data.min() > 0):          # one pass; the common case (all stored values positive) allocates nothing
+            keep = m.data > 0
             m = sparse.csr_matrix((m.data * keep, m.indices, m.indptr), shape=m.shape)
             m.eliminate_zeros()
         if not m.has_sorted_indices:

@@ -904,3 +904,33 @@ def test_top_n_ignores_nan_and_minus_inf_estimates_and_empty_fit(h):
     assert out.tolist() == [[2, 0], [3, 4]]
     m = RecommenderSystem(algorithm="als").fit(np.zeros((0, 7), dtype=np.float32), k=4, iterations=3)
     assert m._model["user_factors"].shape == (0, 4) and m._model["item_factors"].shape == (7, 4)
+
+
+def test_als_model_stays_on_the_device_until_read(tmp_path):
+    """fit leaves the factors in HBM: recommend / predict use that copy, reading the model dict downloads it
+    (float64 NumPy, reference keys algo.py:333-337) and makes the host arrays authoritative, save / load round-trips."""
+    from recsys_lite_b200 import RecommenderSystem
+    from recsys_lite_b200.api import _LazyALSModel
+    indptr, indices = gen.synth_pattern(1500, 1300, mean_deg=25, seed=9)
+    r = sparse.csr_matrix((np.ones(len(indices), np.float32), indices, indptr), shape=(1500, 1300))
+    u0, v0 = gen.seeded_factors(1500, 1300, 24, 3)
+    m = RecommenderSystem("als").fit(r, k=24, iterations=3, init=(u0, v0))
+    assert isinstance(m._model, _LazyALSModel) and m._resident is not None
+    rec_dev = m.recommend(r, n=10)                       # resident factors + the training pattern already in HBM
+    rec_other = m.recommend(sparse.csr_matrix(r.toarray()), n=10)      # another object with the same content: pattern uploaded
+    pred_dev = m.predict(r)
+    assert m._resident is not None
+    uf, vf = m._model["user_factors"], m._model["item_factors"]          # first read: download, device copy dropped
+    assert m._resident is None and uf.dtype == np.float64 and uf.shape == (1500, 24) and set(m._model.keys()) == {
+        "user_factors", "item_factors", "factors"}
+    rec_host = m.recommend(r, n=10)                       # host path (rl_recommend_host) on the downloaded arrays
+    assert np.array_equal(rec_dev, rec_host) and np.array_equal(rec_dev, rec_other)
+    assert np.allclose(pred_dev, uf @ vf.T, rtol=0, atol=1e-12)
+    ti, tx = o_als.transpose_pattern(indptr, indices, 1300)
+    ref = o_als.fit_csr(indptr, indices, ti, tx, 24, iterations=3, lam=0.01, init=(u0, v0))
+    assert max(compare.factor_error(uf, ref["user_factors"]) + compare.factor_error(vf, ref["item_factors"])) <= compare.FACTOR_RTOL
+    m2 = RecommenderSystem("als").fit(r, k=24, iterations=3, init=(u0.astype(np.float32), v0.astype(np.float32)))
+    path = str(tmp_path / "m.joblib")
+    m2.save(path)                                          # pickled from the device copy as plain NumPy
+    m3 = RecommenderSystem.load(path)
+    assert type(m3._model) is dict and np.array_equal(m3.recommend(r, n=10), m2.recommend(r, n=10))
