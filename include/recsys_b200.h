@@ -213,6 +213,25 @@ int rl_svd_reconstruct_host(rl_handle h, const float* mat, int64_t m, int64_t n,
                             double* s_out, double* left_out, double* right_out);
 
 /* ALS predict on HOST buffers (algo.py:143-147): out (n_users x n_items) float64 = U V^T from (n x k) host factors. */
+/* SVD class fit on HOST buffers: replaces RecommenderSystem._fit_svd_dense (algo.py:210-248) including its bias stage
+ * (algo.py:218-235: global / per-user / per-item means of the entries > 0, centring of EVERY cell) -- the ratings go to
+ * the device once.  ratings (m x n) float32; ratings_is_f32 != 0: the means are rounded to float32 as NumPy does for a
+ * float32 matrix.  bias_out[0] = global bias (NaN without a positive entry), user_bias_out (m), item_bias_out (n)
+ * float64; s / left / right as rl_svd_topk_dev (rank k of the CENTRED matrix; zeros when it is all zero or not finite:
+ * status_out[0] = 1 then). */
+int rl_svd_fit_host(rl_handle h, const float* ratings, int64_t m, int64_t n, int k, int ratings_is_f32,
+                    double* bias_out, double* user_bias_out, double* item_bias_out,
+                    double* s_out, double* left_out, double* right_out, int* status_out);
+/* the bias stage alone on device buffers: tot_dev[0] / tot_dev[1] = sum / count of the positive entries (the global
+ * mean), user_bias_dev (m), item_bias_dev (n) float64, centred_dev (m x n) float32 (may be NULL). */
+int rl_bias_centre_dev(rl_handle h, const float* ratings_dev, int64_t m, int64_t n, int ratings_is_f32,
+                       double* tot_dev, double* user_bias_dev, double* item_bias_dev, float* centred_dev);
+
+/* precision@k / recall@k / NDCG@k of top-n lists against held-out item sets (reference tools.py:50-110), on HOST buffers:
+ * recs (n_users x n int32, -1 padded), relevant items as CSR rows (ascending); out3 = the three user averages. */
+int rl_ranking_metrics_host(rl_handle h, const int32_t* recs, int64_t n_users, int n, int k,
+                            const int64_t* actual_indptr, const int32_t* actual_indices, double* out3);
+
 int rl_predict_host(rl_handle h, const void* user_f, const void* item_f, int factor_dtype,
                     int64_t n_users, int64_t n_items, int k,
                     double global_bias, const float* user_bias, const float* item_bias,

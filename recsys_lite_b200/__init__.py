@@ -7,8 +7,10 @@ include/recsys_b200.h) -- there is no CPU fallback.
 """
 from .api import RecommenderSystem, compute_mae, compute_rmse, svd_reconstruct, top_n
 from .benchmark import benchmark_algorithm, quick_benchmark
+from .metrics import ndcg_at_k, precision_at_k, ranking_metrics, recall_at_k
+from .pipeline import RecsysPipeline
 
 __version__ = "0.1.0"
 
 __all__ = ["RecommenderSystem", "svd_reconstruct", "top_n", "compute_rmse", "compute_mae", "benchmark_algorithm",
-           "quick_benchmark", "__version__"]
+           "quick_benchmark", "RecsysPipeline", "precision_at_k", "recall_at_k", "ndcg_at_k", "ranking_metrics", "__version__"]

@@ -57,6 +57,9 @@ SIGNATURES = {
     "rl_svd_topk_dev": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp]),
     "rl_lowrank_dev": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i32, _dbl, _vp, _vp, _vp, _i32]),
     "rl_svd_reconstruct_host": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "rl_svd_fit_host": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rl_bias_centre_dev": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "rl_ranking_metrics_host": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "rl_predict_host": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i32, _dbl, _vp, _vp, _vp, _i32]),
     "rl_dense_error_host": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _vp, _vp]),
     "rl_observed_error_dev": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),

@@ -277,33 +277,27 @@ class RecommenderSystem:
     def _fit_svd(self, ratings, k: Optional[int]) -> Dict[str, Any]:
         """algo.py:210-248: biases over entries > 0, centre every cell, rank-k SVD of the centred matrix.
 
-        The bias means are plain NumPy reductions on the host (stage N3 of SURVEY 8(f) moves them on device);
-        the factorisation runs on the device.  Model keys as pinned by tests/test_algo.py:659-684.
+        Bias means (masked row / column means), centring and the factorisation all run on the device
+        (rl_svd_fit_host: csrc/bias.cu + csrc/svd.cu).  Model keys as pinned by tests/test_algo.py:659-684.
         """
         r = np.asarray(_dense(ratings))
         n_users, n_items = r.shape
         if k is None:
             k = max(1, min(n_users, n_items) // 4)
         k_eff = max(1, min(int(k), n_users, n_items))  # slicing u[:, :k] tolerates k > rank (algo.py:240-243)
-        pos = r > 0
-        cnt = pos.sum()
+        # bias means, centring and the factorisation in ONE device call: the ratings cross PCIe once (algo.py:218-243)
         ftype = np.float32 if r.dtype == np.float32 else np.float64
-        rs = np.where(pos, r, 0).astype(np.float64)
-        gb = ftype(rs.sum() / cnt) if cnt else ftype(np.nan)
-        cu, ci = pos.sum(axis=1), pos.sum(axis=0)
-        ub = np.where(cu > 0, rs.sum(axis=1) / np.maximum(cu, 1) - float(gb), 0.0).astype(ftype)
-        ib = np.where(ci > 0, rs.sum(axis=0) / np.maximum(ci, 1) - float(gb), 0.0).astype(ftype)
-        centred = np.ascontiguousarray((r - gb - ub[:, None] - ib[None, :]).astype(np.float32))
+        r32 = np.ascontiguousarray(r, dtype=np.float32)
+        bias, status = np.empty(1, dtype=np.float64), np.zeros(1, dtype=np.int32)
+        ub64, ib64 = np.empty(n_users, dtype=np.float64), np.empty(n_items, dtype=np.float64)
         s = np.empty(k_eff, dtype=np.float64)
         left = np.empty((n_users, k_eff), dtype=np.float64)
         right = np.empty((n_items, k_eff), dtype=np.float64)
-        if np.isfinite(centred).all() and centred.any():
-            _check_svd_shape(centred.shape)
-            h = _ffi.default_handle()
-            h.call("rl_svd_reconstruct_host", _ffi.ptr(centred), n_users, n_items, k_eff, None,
-                   _ffi.ptr(s), _ffi.ptr(left), _ffi.ptr(right))
-        else:
-            s[:], left[:], right[:] = 0.0, 0.0, 0.0
+        _check_svd_shape(r32.shape)
+        h = _ffi.default_handle()
+        h.call("rl_svd_fit_host", _ffi.ptr(r32), n_users, n_items, k_eff, 1 if ftype is np.float32 else 0, _ffi.ptr(bias),
+               _ffi.ptr(ub64), _ffi.ptr(ib64), _ffi.ptr(s), _ffi.ptr(left), _ffi.ptr(right), _ffi.ptr(status))
+        gb, ub, ib = ftype(bias[0]), ub64.astype(ftype), ib64.astype(ftype)
         safe = np.where(s > 0, s, 1.0)
         if n_users >= n_items:   # left = U S, right = V
             u, vt = left / safe, right.T

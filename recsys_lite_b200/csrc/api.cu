@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <cmath>
+
 #include "common.cuh"
 
 namespace rl {
@@ -791,6 +793,98 @@ int rl_svd_reconstruct_host(rl_handle h, const float* mat, int64_t m, int64_t n,
   if (s_out) RL_CUDA(h, cudaMemcpyAsync(s_out, d_s.p, sizeof(double) * k, cudaMemcpyDeviceToHost, h->stream));
   if (left_out) RL_CUDA(h, cudaMemcpyAsync(left_out, d_l.p, sizeof(double) * m * k, cudaMemcpyDeviceToHost, h->stream));
   if (right_out) RL_CUDA(h, cudaMemcpyAsync(right_out, d_rt.p, sizeof(double) * n * k, cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RL_OK;
+}
+
+// finite and not all zero?  flags[0] bit 0: non-finite seen, bit 1: non-zero seen
+__global__ void __launch_bounds__(256) finite_any_kernel(const float* __restrict__ x, int64_t n, int* __restrict__ flags) {
+  int f = 0;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < n; p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = x[p];
+    if (!isfinite(v)) f |= 1;
+    if (v != 0.f) f |= 2;
+  }
+  f |= __shfl_xor_sync(0xffffffffu, f, 16); f |= __shfl_xor_sync(0xffffffffu, f, 8); f |= __shfl_xor_sync(0xffffffffu, f, 4);
+  f |= __shfl_xor_sync(0xffffffffu, f, 2); f |= __shfl_xor_sync(0xffffffffu, f, 1);
+  if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+}
+
+int rl_ranking_metrics_host(rl_handle h, const int32_t* recs, int64_t n_users, int n, int k, const int64_t* actual_indptr,
+                            const int32_t* actual_indices, double* out3) {
+  RL_NEED(h);
+  if (n_users < 0 || n <= 0 || k <= 0 || !out3) return fail(h, RL_ERR_INVALID, "rl_ranking_metrics_host: bad argument");
+  out3[0] = out3[1] = out3[2] = 0.0;
+  if (n_users == 0) return RL_OK;
+  if (!recs || !actual_indptr) return fail(h, RL_ERR_INVALID, "rl_ranking_metrics_host: null pointer");
+  const int64_t nnz = actual_indptr[n_users];
+  DevBuf d_r, d_p, d_x, d_o;
+  RL_TRY(upload(h, d_r, recs, sizeof(int32_t) * n_users * n));
+  RL_TRY(upload(h, d_p, actual_indptr, sizeof(int64_t) * (n_users + 1)));
+  RL_TRY(upload(h, d_x, actual_indices, sizeof(int32_t) * nnz));
+  RL_TRY(d_o.alloc(h, 4 * sizeof(double)));
+  RL_TRY(launch_ranking_metrics(h, d_r.as<int32_t>(), n_users, n, k, d_p.as<int64_t>(), d_x.as<int32_t>(), d_o.as<double>()));
+  double o[4];
+  RL_CUDA(h, cudaMemcpyAsync(o, d_o.p, sizeof(o), cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < 3; ++i) out3[i] = o[i] / static_cast<double>(n_users);
+  return RL_OK;
+}
+
+int rl_bias_centre_dev(rl_handle h, const float* ratings_dev, int64_t m, int64_t n, int ratings_is_f32, double* tot_dev,
+                       double* user_bias_dev, double* item_bias_dev, float* centred_dev) {
+  RL_NEED(h);
+  return launch_bias_centre(h, ratings_dev, m, n, ratings_is_f32, tot_dev, user_bias_dev, item_bias_dev, centred_dev);
+}
+
+int rl_svd_fit_host(rl_handle h, const float* ratings, int64_t m, int64_t n, int k, int ratings_is_f32, double* bias_out,
+                    double* user_bias_out, double* item_bias_out, double* s_out, double* left_out, double* right_out, int* status_out) {
+  RL_NEED(h);
+  if (m <= 0 || n <= 0) return fail(h, RL_ERR_INVALID, "rl_svd_fit_host: zero dimension");
+  if (k < 1 || k > (m < n ? m : n)) return fail(h, RL_ERR_INVALID, "rl_svd_fit_host: k=%d out of range", k);
+  if (!ratings || !bias_out || !user_bias_out || !item_bias_out || !s_out || !left_out || !right_out || !status_out)
+    return fail(h, RL_ERR_INVALID, "rl_svd_fit_host: null pointer");
+  DevBuf d_r, d_c, d_tot, d_ub, d_ib, d_s, d_l, d_rt, d_fl;
+  const size_t cells = static_cast<size_t>(m) * n;
+  RL_TRY(upload(h, d_r, ratings, cells * sizeof(float)));
+  RL_TRY(d_c.alloc(h, cells * sizeof(float)));
+  RL_TRY(d_tot.alloc(h, 2 * sizeof(double)));
+  RL_TRY(d_ub.alloc(h, sizeof(double) * m));
+  RL_TRY(d_ib.alloc(h, sizeof(double) * n));
+  RL_TRY(d_fl.alloc(h, sizeof(int)));
+  RL_TRY(launch_bias_centre(h, d_r.as<float>(), m, n, ratings_is_f32, d_tot.as<double>(), d_ub.as<double>(), d_ib.as<double>(), d_c.as<float>()));
+  RL_CUDA(h, cudaMemsetAsync(d_fl.p, 0, sizeof(int), h->stream));
+  {
+    int64_t g = (static_cast<int64_t>(cells) + 255) / 256;
+    if (g > 8 * h->sm_count) g = 8 * h->sm_count;
+    finite_any_kernel<<<static_cast<unsigned>(g), 256, 0, h->stream>>>(d_c.as<float>(), static_cast<int64_t>(cells), d_fl.as<int>());
+    RL_LAUNCH_CHECK(h, "finite_any_kernel");
+  }
+  int flags = 0;
+  double tot[2] = {0.0, 0.0};
+  RL_CUDA(h, cudaMemcpyAsync(&flags, d_fl.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaMemcpyAsync(tot, d_tot.p, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaMemcpyAsync(user_bias_out, d_ub.p, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaMemcpyAsync(item_bias_out, d_ib.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  double gb = tot[1] > 0.0 ? tot[0] / tot[1] : std::nan("");
+  if (ratings_is_f32) gb = static_cast<double>(static_cast<float>(gb));
+  bias_out[0] = gb;
+  const bool degenerate = (flags & 1) || !(flags & 2);
+  status_out[0] = degenerate ? 1 : 0;
+  if (degenerate) {
+    for (int i = 0; i < k; ++i) s_out[i] = 0.0;
+    for (int64_t i = 0; i < m * k; ++i) left_out[i] = 0.0;
+    for (int64_t i = 0; i < n * k; ++i) right_out[i] = 0.0;
+    return RL_OK;
+  }
+  RL_TRY(d_s.alloc(h, sizeof(double) * k));
+  RL_TRY(d_l.alloc(h, sizeof(double) * m * k));
+  RL_TRY(d_rt.alloc(h, sizeof(double) * n * k));
+  RL_TRY(launch_svd_topk(h, d_c.as<float>(), m, n, k, d_s.as<double>(), d_l.as<double>(), d_rt.as<double>()));
+  RL_CUDA(h, cudaMemcpyAsync(s_out, d_s.p, sizeof(double) * k, cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaMemcpyAsync(left_out, d_l.p, sizeof(double) * m * k, cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaMemcpyAsync(right_out, d_rt.p, sizeof(double) * n * k, cudaMemcpyDeviceToHost, h->stream));
   RL_CUDA(h, cudaStreamSynchronize(h->stream));
   return RL_OK;
 }

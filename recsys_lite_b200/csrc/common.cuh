@@ -118,6 +118,10 @@ int launch_observed_error(rl_context* h, const float* uf, const float* vf, int k
                           const int64_t* indptr, const int32_t* indices, const float* values, double* out2);
 int launch_dense_error(rl_context* h, const void* pred, int pdtype, const void* actual, int adtype, int64_t n, double* out4,
                        int* flags);
+int launch_ranking_metrics(rl_context* h, const int32_t* recs, int64_t n_users, int n, int k, const int64_t* a_indptr,
+                           const int32_t* a_indices, double* out4);
+int launch_bias_centre(rl_context* h, const float* r, int64_t m, int64_t n, int as_float32, double* tot, double* ub, double* ib,
+                       float* centred);
 int launch_factors_convert(rl_context* h, const void* src, int src_dtype, int64_t rows, int k, int src_ld,
                            void* dst, int dst_dtype, int dst_ld);
 

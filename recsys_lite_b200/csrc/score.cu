@@ -135,7 +135,62 @@ __global__ void __launch_bounds__(256) dense_error_kernel(const TP* __restrict__
   }
 }
 
+// ---- ranking metrics of top-n lists against held-out item sets (reference tools.py:50-110): one thread per user,
+// recs (n_users x n, -1 padded), relevant items as CSR rows (ascending).  out4: sum over users of precision@k, recall@k
+// (capped at 1), dcg@k / idcg, and the number of users counted (users without recommendations or without relevant items
+// contribute 0, as in the reference).
+__global__ void __launch_bounds__(256) ranking_metrics_kernel(const int32_t* __restrict__ recs, int64_t n_users, int n, int k,
+                                                              const int64_t* __restrict__ a_indptr, const int32_t* __restrict__ a_indices,
+                                                              double* __restrict__ out4) {
+  double sp = 0.0, sr = 0.0, sn = 0.0;
+  for (int64_t u = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; u < n_users; u += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t a0 = a_indptr[u], a1 = a_indptr[u + 1];
+    int len = 0;
+    while (len < n && recs[u * n + len] >= 0) ++len;
+    if (len == 0 || a1 == a0) continue;
+    const int kk = k < len ? k : len;
+    int hits = 0;
+    double dcg = 0.0, idcg = 0.0;
+    for (int i = 0; i < kk; ++i) {
+      const int item = recs[u * n + i];
+      int64_t lo = a0, hi = a1;
+      while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if (a_indices[mid] < item) lo = mid + 1; else hi = mid;
+      }
+      const double w = 1.0 / log2(static_cast<double>(i) + 2.0);
+      if (lo < a1 && a_indices[lo] == item) { ++hits; dcg += w; }
+      idcg += w;       // the reference's ideal list counts every position once it has two or more entries (tools.py:100-103)
+    }
+    if (kk == 1)      // one-entry ideal list of the reference: counted iff NO item id below len(recs) is relevant (tools.py:100-103)
+      idcg = a_indices[a0] < len ? 0.0 : 1.0;
+    sp += static_cast<double>(hits) / static_cast<double>(k);
+    const double rec = static_cast<double>(hits) / static_cast<double>(a1 - a0);
+    sr += rec < 1.0 ? rec : 1.0;
+    if (idcg > 0.0) sn += dcg / idcg;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sp += __shfl_xor_sync(FULL_MASK, sp, o);
+    sr += __shfl_xor_sync(FULL_MASK, sr, o);
+    sn += __shfl_xor_sync(FULL_MASK, sn, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out4, sp); atomicAdd(out4 + 1, sr); atomicAdd(out4 + 2, sn); }
+}
+
 }  // namespace
+
+int launch_ranking_metrics(rl_context* h, const int32_t* recs, int64_t n_users, int n, int k, const int64_t* a_indptr,
+                           const int32_t* a_indices, double* out4) {
+  if (!recs || !a_indptr || !out4 || n <= 0 || k <= 0 || n_users < 0) return fail(h, RL_ERR_INVALID, "ranking_metrics: bad argument");
+  RL_CUDA(h, cudaMemsetAsync(out4, 0, 4 * sizeof(double), h->stream));
+  if (n_users == 0) return RL_OK;
+  int64_t grid = (n_users + 255) / 256;
+  if (grid > 16 * h->sm_count) grid = 16 * h->sm_count;
+  ranking_metrics_kernel<<<static_cast<unsigned>(grid), 256, 0, h->stream>>>(recs, n_users, n, k, a_indptr, a_indices, out4);
+  RL_LAUNCH_CHECK(h, "ranking_metrics_kernel");
+  return RL_OK;
+}
 
 int launch_dense_error(rl_context* h, const void* pred, int pdtype, const void* actual, int adtype, int64_t n, double* out4, int* flags) {
   if (!pred || !actual || !out4 || !flags || n < 0) return fail(h, RL_ERR_INVALID, "dense_error: bad argument");

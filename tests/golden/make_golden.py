@@ -116,6 +116,31 @@ def main():
     np.savez_compressed(os.path.join(OUT, "metrics.npz"), pred=p, actual=a,
                         rmse=ref.compute_rmse(p, a), mae=ref.compute_mae(p, a))
 
+    # ---- ranking metrics (tools.py:50-110) and the pipeline's recommend (tools.py:264-266) -------------------------
+    from recsys_lite import tools as ref_tools
+    rr = np.random.RandomState(11)
+    recs = [list(rr.choice(60, size=int(rr.randint(0, 9)), replace=False)) for _ in range(200)]
+    actual = [set(rr.choice(60, size=int(rr.randint(0, 12)), replace=False).tolist()) for _ in range(200)]
+    recs[3], actual[3] = [5], {0, 5}                       # one-entry lists: the reference's ideal-list quirk
+    recs[4], actual[4] = [5], {5, 40}
+    width = max(len(x) for x in recs)
+    rm = np.full((200, width), -1, dtype=np.int32)
+    for i, x in enumerate(recs):
+        rm[i, : len(x)] = x
+    am = np.zeros((200, 60), dtype=np.int8)
+    for i, a_set in enumerate(actual):
+        am[i, list(a_set)] = 1
+    vals = {k: (ref_tools.precision_at_k(recs, actual, k), ref_tools.recall_at_k(recs, actual, k), ref_tools.ndcg_at_k(recs, actual, k))
+            for k in (1, 3, 5, 10)}
+    np.savez_compressed(os.path.join(OUT, "ranking_metrics.npz"), recs=rm, actual=am,
+                        ks=np.array(sorted(vals)), values=np.array([vals[k] for k in sorted(vals)]))
+    print("ranking metrics", vals)
+    m = gen.sample_ratings(90, 25, sparsity=0.7, random_state=8)
+    model = ref.RecommenderSystem(algorithm="svd", use_sparse=False)
+    pipe = ref_tools.RecsysPipeline([("model", model)]).fit(m, k=5)
+    np.savez_compressed(os.path.join(OUT, "pipeline.npz"), ratings=m, k=5, recommend=np.array(pipe.recommend(m, n=4)),
+                        predict=pipe.predict(m))
+
 
 if __name__ == "__main__":
     main()

@@ -934,3 +934,74 @@ def test_als_model_stays_on_the_device_until_read(tmp_path):
     m2.save(path)                                          # pickled from the device copy as plain NumPy
     m3 = RecommenderSystem.load(path)
     assert type(m3._model) is dict and np.array_equal(m3.recommend(r, n=10), m2.recommend(r, n=10))
+
+
+# ------------------------------------------------------------------------- r2: "next" rows N1 / N3 / N4 of SURVEY 8(f)
+def test_bias_centre_dev_vs_numpy(h):
+    """rl_bias_centre_dev (algo.py:218-235): masked global / row / column means of the entries > 0 and the centring of
+    every cell, float32 semantics of the reference (means rounded to float32, left-to-right subtraction)."""
+    from devbuf import Dev
+    rng = np.random.default_rng(2)
+    r = (rng.random((300, 170)) < 0.2) * rng.uniform(0.5, 5.0, (300, 170))
+    r[7, :] = 0
+    r[:, 11] = 0
+    r[5, 5] = -2.0                                  # negatives are "unobserved" for the means but are centred like any cell
+    r = r.astype(np.float32)
+    d_r = Dev(h, r)
+    d_tot, d_ub, d_ib = Dev(h, shape=(2,), dtype=np.float64), Dev(h, shape=(300,), dtype=np.float64), Dev(h, shape=(170,), dtype=np.float64)
+    d_c = Dev(h, shape=r.shape, dtype=np.float32)
+    h.call("rl_bias_centre_dev", d_r.ptr, 300, 170, 1, d_tot.ptr, d_ub.ptr, d_ib.ptr, d_c.ptr)
+    tot, ub, ib, c = d_tot.get(), d_ub.get(), d_ib.get(), d_c.get()
+    gb = np.mean(r[r > 0])                          # float32, as the reference computes it
+    ub_ref = np.array([np.mean(x[x > 0]) - gb if (x > 0).any() else 0 for x in r], dtype=np.float32)
+    ib_ref = np.array([np.mean(r[:, j][r[:, j] > 0]) - gb if (r[:, j] > 0).any() else 0 for j in range(170)], dtype=np.float32)
+    # (NumPy's float32 means carry ~1e-7 relative summation noise; the device sums in float64 and rounds once)
+    assert abs(np.float32(tot[0] / tot[1]) - gb) <= 1e-6 * abs(gb) and tot[1] == (r > 0).sum()
+    assert np.allclose(ub, ub_ref, rtol=0, atol=2e-6) and np.allclose(ib, ib_ref, rtol=0, atol=2e-6)
+    assert ub[7] == 0 and ib[11] == 0
+    want = r - np.float32(tot[0] / tot[1]) - ub.astype(np.float32)[:, None] - ib.astype(np.float32)
+    assert np.array_equal(c, want.astype(np.float32))
+
+
+def test_ranking_metrics_match_reference_golden(golden_dir):
+    """precision@k / recall@k / NDCG@k (tools.py:50-110), list and array inputs, incl. the one-entry-list quirk."""
+    from recsys_lite_b200 import ndcg_at_k, precision_at_k, ranking_metrics, recall_at_k
+    g = _load(golden_dir, "ranking_metrics")
+    recs, actual = g["recs"], sparse.csr_matrix(g["actual"])
+    lists = [[int(x) for x in row if x >= 0] for row in recs]
+    sets = [set(np.nonzero(row)[0].tolist()) for row in g["actual"]]
+    for k, want in zip(g["ks"], g["values"]):
+        got = ranking_metrics(recs, actual, int(k))
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-15), (k, got, want)
+        assert np.allclose((precision_at_k(lists, sets, int(k)), recall_at_k(lists, sets, int(k)), ndcg_at_k(lists, sets, int(k))),
+                           want, rtol=1e-12, atol=1e-15)
+    assert ranking_metrics([], [], 5) == (0.0, 0.0, 0.0) and precision_at_k(lists, sets, 0) == 0.0
+
+
+def test_cli_predict_and_pipeline_route_to_the_fused_path(golden_dir, tmp_path, capsys):
+    """CLI `predict` (cli.py:34-150) on a scipy .npz pattern with --algorithm als never densifies and equals the API; the
+    reference's RecsysPipeline.recommend (tools.py:264-266) result is reproduced, through the fused recommend."""
+    from recsys_lite_b200 import RecommenderSystem, RecsysPipeline
+    from recsys_lite_b200 import cli
+    g = _load(golden_dir, "pipeline")
+    m = g["ratings"]
+    model = RecommenderSystem(algorithm="svd", use_sparse=False)
+    pipe = RecsysPipeline([("model", model)]).fit(m, k=int(g["k"]))
+    assert np.allclose(pipe.predict(m), g["predict"], rtol=0, atol=2e-5)
+    got = np.array(pipe.recommend(m, n=4))
+    pred = g["predict"].astype(np.float64)
+    res = compare.topn_matches(got, g["recommend"], lambda row: pred[row], lambda row: np.nonzero(m[row] > 0)[0], rtol=1e-5)
+    assert not res["bad"], res
+    with pytest.raises(RuntimeError, match="Error in pipeline step 'model'"):
+        RecsysPipeline([("model", RecommenderSystem("svd"))]).predict(m)
+    indptr, indices = gen.synth_pattern(400, 1100, mean_deg=20, seed=5)
+    r = sparse.csr_matrix((np.ones(len(indices), np.float32), indices, indptr), shape=(400, 1100))
+    path, out = str(tmp_path / "r.npz"), str(tmp_path / "recs.csv")
+    sparse.save_npz(path, r)
+    np.random.seed(7)
+    assert cli.main(["predict", path, "--algorithm", "als", "--rank", "16", "--top-n", "5", "--iterations", "2", "--output", out]) == 0
+    assert "Generated recommendations for 400 users" in capsys.readouterr().out
+    np.random.seed(7)
+    want = RecommenderSystem("als").fit(r, k=16, iterations=2).recommend(r, n=5)
+    assert np.array_equal(np.loadtxt(out, delimiter=",").astype(np.int32), want)
+    assert cli.main(["predict", str(tmp_path / "missing.csv")]) == 1
