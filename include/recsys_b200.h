@@ -227,6 +227,18 @@ int rl_svd_fit_host(rl_handle h, const float* ratings, int64_t m, int64_t n, int
 int rl_bias_centre_dev(rl_handle h, const float* ratings_dev, int64_t m, int64_t n, int ratings_is_f32,
                        double* tot_dev, double* user_bias_dev, double* item_bias_dev, float* centred_dev);
 
+/* G (p x q float64, row stride ldg) = op_x(X)^T op_y(Y) on the tensor cores (tcgen05, csrc/gram_tc.cu): X (n x p, row stride
+ * ldx), Y (n x q, row stride ldy) float32 device matrices, contraction over the long dimension n.  op: 0 = x, 1 = x^2 of the
+ * entries > 0, 2 = [x > 0], 3 = x [x > 0]; op | 8: the operand is handed over transposed ((p x n) row-major).  terms: 3 =
+ * split fp16 operands (fp32-accurate), 1 = one fp16 product (exact for small integers). */
+int rl_gram_tc_dev(rl_handle h, const float* x_dev, int ldx, int op_x, const float* y_dev, int ldy, int op_y, int64_t n, int p,
+                   int q, double* g_dev, int ldg, int terms);
+/* KNN item-item cosine over co-raters (replaces RecommenderSystem._fit_knn, algo.py:339-350) as three masked Gram products,
+ * and the neighbour-weighted prediction (algo.py:148-169) as two products with the k-sparse weight matrix.  HOST buffers:
+ * ratings (m x n) float32, sim (n x n) float64, pred (m x n) float64. */
+int rl_knn_item_sim_host(rl_handle h, const float* ratings, int64_t m, int n, double* sim_out);
+int rl_knn_predict_host(rl_handle h, const float* ratings, int64_t m, int n, const double* sim, int neighbors, double* pred_out);
+
 /* precision@k / recall@k / NDCG@k of top-n lists against held-out item sets (reference tools.py:50-110), on HOST buffers:
  * recs (n_users x n int32, -1 padded), relevant items as CSR rows (ascending); out3 = the three user averages. */
 int rl_ranking_metrics_host(rl_handle h, const int32_t* recs, int64_t n_users, int n, int k,

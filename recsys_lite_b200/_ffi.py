@@ -59,6 +59,9 @@ SIGNATURES = {
     "rl_svd_reconstruct_host": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
     "rl_svd_fit_host": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rl_bias_centre_dev": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "rl_gram_tc_dev": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _vp, _i32, _i32]),
+    "rl_knn_item_sim_host": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "rl_knn_predict_host": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp]),
     "rl_ranking_metrics_host": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "rl_predict_host": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i32, _dbl, _vp, _vp, _vp, _i32]),
     "rl_dense_error_host": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _vp, _vp]),

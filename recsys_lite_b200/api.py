@@ -20,7 +20,9 @@ Documented deviations from the reference:
   * factors are kept in float32 on the device and returned as float64 (reference: float64 throughout):
     relative factor error ~1e-6 against the reference, inside the stated 1e-4 tolerance;
   * equal scores are ordered by ascending item index (the reference's tie order is implementation defined);
-  * ``algorithm="knn"`` is accepted by the constructor but ``fit`` raises NotImplementedError (out of scope);
+  * ``algorithm="knn"`` (outside the north-star path): item similarities and predictions are computed as
+    masked Gram products on the tensor cores; neighbours with exactly equal similarity at the cut are chosen by ascending
+    item index (the reference's argsort order is implementation defined);
   * limits of the fused kernels: ALS fit 1..128 factors (NotImplementedError beyond); ``recommend`` with more than 128
     factors (SVD models default to min(shape) // 4) or n > 128 takes the unfused device path (predict + top_n per row
     chunk); ``svd_reconstruct`` / the SVD fit need min(n_users, n_items) <= 4096 (ValueError beyond: the device
@@ -216,7 +218,7 @@ class RecommenderSystem:
         elif self.algorithm == "svd":
             self._model = self._fit_svd(ratings, k)
         elif self.algorithm == "knn":
-            raise NotImplementedError("algorithm='knn' is outside the B200 hot path (SURVEY.md section 2 row 10)")
+            self._model = self._fit_knn(ratings, kwargs.get("neighbors", k or 10))
         else:
             raise ValueError(f"Unsupported algorithm: {self.algorithm}")
         self._fitted = True
@@ -274,6 +276,33 @@ class RecommenderSystem:
         state["_resident"] = None
         return state
 
+    def _fit_knn(self, ratings, neighbors: int) -> Dict[str, Any]:
+        """algo.py:339-350: item-item cosine over the users who rated both items -- on the device three masked Gram products
+        on the tensor cores (csrc/gram_tc.cu) instead of the reference's O(n_items^2) Python loop."""
+        r = np.ascontiguousarray(np.asarray(_dense(ratings)), dtype=np.float32)
+        if r.ndim != 2:
+            raise ValueError(f"Input matrix must be 2D (users x items), got {r.ndim}D.")
+        n_users, n_items = r.shape
+        sim = np.zeros((n_items, n_items), dtype=np.float64)
+        if n_users and n_items:
+            h = _ffi.default_handle()
+            h.call("rl_knn_item_sim_host", _ffi.ptr(r), n_users, n_items, _ffi.ptr(sim))
+        return {"item_sim": sim, "neighbors": neighbors, "ratings": ratings}
+
+    def _predict_knn(self, ratings) -> np.ndarray:
+        """algo.py:148-169: neighbour-weighted mean of the user's ratings of the `neighbors` most similar items, for the
+        cells the user has not rated (rated cells stay 0)."""
+        m = self._need_model()
+        r = np.ascontiguousarray(np.asarray(_dense(ratings)), dtype=np.float32)
+        sim = np.ascontiguousarray(m["item_sim"], dtype=np.float64)
+        if r.ndim != 2 or r.shape[1] != sim.shape[0]:
+            raise ValueError(f"ratings must have {sim.shape[0]} item columns, got shape {r.shape}")
+        out = np.zeros(r.shape, dtype=np.float64)
+        if r.size:
+            h = _ffi.default_handle()
+            h.call("rl_knn_predict_host", _ffi.ptr(r), r.shape[0], r.shape[1], _ffi.ptr(sim), int(m["neighbors"]), _ffi.ptr(out))
+        return out
+
     def _fit_svd(self, ratings, k: Optional[int]) -> Dict[str, Any]:
         """algo.py:210-248: biases over entries > 0, centre every cell, rank-k SVD of the centred matrix.
 
@@ -330,8 +359,7 @@ class RecommenderSystem:
     def predict(self, ratings):
         """als: U @ V.T float64, argument ignored (algo.py:143-147); svd: u@(s*vt)+biases (algo.py:363-368)."""
         if self.algorithm == "knn":
-            self._need_model()
-            raise NotImplementedError("algorithm='knn' is outside the B200 hot path")
+            return self._predict_knn(ratings)
         if self.algorithm == "als" and self._need_model() is not None and self._resident is not None:
             res = self._resident                      # U @ V.T from the device copy (float64 out, as the reference)
             out = np.empty((res.n_users, res.n_items), dtype=np.float64)
@@ -358,9 +386,11 @@ class RecommenderSystem:
         """predict + top_n fused on the device: the score matrix is never formed (algo.py:172-208)."""
         if n <= 0:
             raise ValueError(f"n must be positive. Got n={n}.")
-        if self.algorithm == "knn":
-            self._need_model()
-            raise NotImplementedError("algorithm='knn' is outside the B200 hot path")
+        if self.algorithm == "knn":            # the reference composes predict -> top_n (algo.py:172-201)
+            pred = self._predict_knn(ratings)
+            if not exclude_rated:
+                return np.argsort(-pred, axis=1, kind="stable")[:, :n].astype(np.int64)
+            return top_n(pred, np.asarray(_dense(ratings)), n=n)
         if self.algorithm == "als" and self._need_model() is not None and self._resident is not None:
             out = self._recommend_resident(ratings, int(n), exclude_rated)
             if out is not None:

@@ -709,6 +709,8 @@ int launch_gram(rl_context* h, const float* y, int64_t n, int k, double* gram) {
   const int kp = padded_k(k);
   if (kp == 0) return fail(h, RL_ERR_INVALID, "gram: k=%d outside [1, 128]", k);
   if (!y || !gram) return fail(h, RL_ERR_INVALID, "gram: null pointer");
+  // tall inputs: tcgen05 split-fp16 GEMM (gram_tc.cu); short ones are latency bound either way and keep the float64 FMA kernel
+  if (n >= 8192) return launch_gram_tc(h, y, kp, 0, y, kp, 0, n, kp, kp, gram, kp, 3);
   RL_CUDA(h, cudaMemsetAsync(gram, 0, sizeof(double) * kp * kp, h->stream));
   if (n == 0) return RL_OK;
   int64_t grid = (n + 31) / 32;

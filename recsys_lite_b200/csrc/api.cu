@@ -810,6 +810,37 @@ __global__ void __launch_bounds__(256) finite_any_kernel(const float* __restrict
   if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
 }
 
+int rl_gram_tc_dev(rl_handle h, const float* x_dev, int ldx, int op_x, const float* y_dev, int ldy, int op_y, int64_t n, int p, int q,
+                   double* g_dev, int ldg, int terms) {
+  RL_NEED(h);
+  return launch_gram_tc(h, x_dev, ldx, op_x, y_dev, ldy, op_y, n, p, q, g_dev, ldg, terms);
+}
+
+int rl_knn_item_sim_host(rl_handle h, const float* ratings, int64_t m, int n, double* sim_out) {
+  RL_NEED(h);
+  if (!ratings || !sim_out || m <= 0 || n <= 0) return fail(h, RL_ERR_INVALID, "rl_knn_item_sim_host: bad argument");
+  DevBuf d_r, d_s;
+  RL_TRY(upload(h, d_r, ratings, sizeof(float) * m * n));
+  RL_TRY(d_s.alloc(h, sizeof(double) * n * n));
+  RL_TRY(launch_knn_item_sim(h, d_r.as<float>(), m, n, d_s.as<double>()));
+  RL_CUDA(h, cudaMemcpyAsync(sim_out, d_s.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RL_OK;
+}
+
+int rl_knn_predict_host(rl_handle h, const float* ratings, int64_t m, int n, const double* sim, int neighbors, double* pred_out) {
+  RL_NEED(h);
+  if (!ratings || !sim || !pred_out || m <= 0 || n <= 0 || neighbors <= 0) return fail(h, RL_ERR_INVALID, "rl_knn_predict_host: bad argument");
+  DevBuf d_r, d_s, d_p;
+  RL_TRY(upload(h, d_r, ratings, sizeof(float) * m * n));
+  RL_TRY(upload(h, d_s, sim, sizeof(double) * n * n));
+  RL_TRY(d_p.alloc(h, sizeof(double) * m * n));
+  RL_TRY(launch_knn_predict(h, d_r.as<float>(), m, n, d_s.as<double>(), neighbors, d_p.as<double>()));
+  RL_CUDA(h, cudaMemcpyAsync(pred_out, d_p.p, sizeof(double) * m * n, cudaMemcpyDeviceToHost, h->stream));
+  RL_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RL_OK;
+}
+
 int rl_ranking_metrics_host(rl_handle h, const int32_t* recs, int64_t n_users, int n, int k, const int64_t* actual_indptr,
                             const int32_t* actual_indices, double* out3) {
   RL_NEED(h);

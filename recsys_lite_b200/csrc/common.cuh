@@ -86,6 +86,8 @@ int launch_als_half_step(rl_context* h, int64_t n_rows, int64_t n_other, int k, 
                          float* mine, double lambda, double w0, const double* gram0, int precision,
                          int ir_steps, const int32_t* row_order, int n_peers = 0, float* const* peers = nullptr);
 int launch_gram(rl_context* h, const float* y, int64_t n, int k, double* gram);
+int launch_gram_tc(rl_context* h, const float* x, int ldx, int op_x, const float* y, int ldy, int op_y, int64_t n, int p, int q,
+                   double* g, int ldg, int terms);
 int launch_csr_transpose(rl_context* h, int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr, const int32_t* indices,
                          int64_t* indptr_t, int32_t* indices_t);
 // Callers that score one problem in several row ranges (rl_recommend_host) collect the rows the tensor-core pass hands
@@ -118,6 +120,8 @@ int launch_observed_error(rl_context* h, const float* uf, const float* vf, int k
                           const int64_t* indptr, const int32_t* indices, const float* values, double* out2);
 int launch_dense_error(rl_context* h, const void* pred, int pdtype, const void* actual, int adtype, int64_t n, double* out4,
                        int* flags);
+int launch_knn_item_sim(rl_context* h, const float* r, int64_t m, int n, double* sim);
+int launch_knn_predict(rl_context* h, const float* r, int64_t m, int n, const double* sim, int k, double* pred);
 int launch_ranking_metrics(rl_context* h, const int32_t* recs, int64_t n_users, int n, int k, const int64_t* a_indptr,
                            const int32_t* a_indices, double* out4);
 int launch_bias_centre(rl_context* h, const float* r, int64_t m, int64_t n, int as_float32, double* tot, double* ub, double* ib,

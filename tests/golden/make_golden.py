@@ -141,6 +141,14 @@ def main():
     np.savez_compressed(os.path.join(OUT, "pipeline.npz"), ratings=m, k=5, recommend=np.array(pipe.recommend(m, n=4)),
                         predict=pipe.predict(m))
 
+    # ---- KNN item-item cosine + neighbour-weighted prediction (algo.py:339-350, :148-169) ------------------------------
+    rr = np.random.RandomState(21)
+    m = (rr.random_sample((60, 35)) < 0.35) * rr.uniform(1.0, 5.0, (60, 35))
+    m = m.astype(np.float32)
+    model = ref.RecommenderSystem(algorithm="knn").fit(m, k=6)
+    np.savez_compressed(os.path.join(OUT, "knn.npz"), ratings=m, neighbors=6, item_sim=model._model["item_sim"], pred=model.predict(m))
+    print("knn", model._model["item_sim"].shape)
+
 
 if __name__ == "__main__":
     main()

@@ -1005,3 +1005,45 @@ def test_cli_predict_and_pipeline_route_to_the_fused_path(golden_dir, tmp_path, 
     want = RecommenderSystem("als").fit(r, k=16, iterations=2).recommend(r, n=5)
     assert np.array_equal(np.loadtxt(out, delimiter=",").astype(np.int32), want)
     assert cli.main(["predict", str(tmp_path / "missing.csv")]) == 1
+
+
+@pytest.mark.parametrize("n,p,q,terms", [(5000, 64, 64, 3), (20000, 128, 64, 3), (777, 40, 200, 3), (4096, 130, 130, 1)])
+def test_gram_tc_matches_float64(h, n, p, q, terms):
+    """rl_gram_tc_dev: G = X^T Y on the tensor cores (tcgen05 SS-mode MMAs, split fp16 operands, split-K in float64) against
+    float64 NumPy; terms = 1 is exact on small integers (ratings, masks)."""
+    from devbuf import Dev
+    rng = np.random.default_rng(n + p)
+    if terms == 1:
+        x = rng.integers(0, 6, (n, p)).astype(np.float32)
+        y = rng.integers(0, 2, (n, q)).astype(np.float32)
+    else:
+        x = (rng.standard_normal((n, p)) * np.exp(rng.uniform(-2, 2, (1, p)))).astype(np.float32)
+        y = (rng.random((n, q)) - 0.3).astype(np.float32)
+    d_x, d_y, d_g = Dev(h, x), Dev(h, y), Dev(h, shape=(p, q), dtype=np.float64)
+    h.call("rl_gram_tc_dev", d_x.ptr, p, 0, d_y.ptr, q, 0, n, p, q, d_g.ptr, q, terms)
+    got = d_g.get()
+    want = x.astype(np.float64).T @ y.astype(np.float64)
+    scale = np.abs(x.astype(np.float64)).T @ np.abs(y.astype(np.float64))
+    err = float(np.max(np.abs(got - want) / np.maximum(scale, 1e-300)))
+    print(f"gram_tc n={n} p={p} q={q} terms={terms}: max |err| / sum|x||y| = {err:.2e}")
+    assert err == 0.0 if terms == 1 else err <= 2e-6
+    if p == q == 64:                                # the ABI's Gram of a factor matrix takes the same kernel for tall inputs
+        d_gg = Dev(h, shape=(64, 64), dtype=np.float64)
+        h.call("rl_gram_dev", d_x.ptr, n, 64, d_gg.ptr)
+        xx = x.astype(np.float64)
+        assert np.max(np.abs(d_gg.get() - xx.T @ xx) / (np.abs(xx).T @ np.abs(xx))) <= 2e-6
+
+
+def test_knn_matches_reference_golden(golden_dir):
+    """RecommenderSystem("knn"): item-item cosine over co-raters (algo.py:339-350) and the neighbour-weighted prediction
+    (algo.py:148-169) against the reference's own output."""
+    from recsys_lite_b200 import RecommenderSystem
+    g = _load(golden_dir, "knn")
+    m = g["ratings"]
+    model = RecommenderSystem(algorithm="knn").fit(m, k=int(g["neighbors"]))
+    assert set(model._model.keys()) == {"item_sim", "neighbors", "ratings"}
+    assert np.allclose(model._model["item_sim"], g["item_sim"], rtol=0, atol=2e-6)
+    pred = model.predict(m)
+    assert pred.shape == m.shape and np.allclose(pred, g["pred"], rtol=0, atol=2e-5)
+    rec = model.recommend(m, n=3)
+    assert rec.shape[0] == m.shape[0] and not np.any(m[np.arange(len(rec))[:, None].repeat(rec.shape[1], 1)[rec >= 0], rec[rec >= 0]] > 0)
