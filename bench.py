@@ -42,6 +42,10 @@ WORKLOADS = {
     "C4s": dict(n_users=1_000_000, n_items=100_000, mean_deg=50, k=64, seed=14, init_seed=4, n=10, lam=0.01, skew=True),
     "C3s": dict(n_users=100_000, n_items=20_000, mean_deg=50, k=64, seed=13, init_seed=3, n=10, lam=0.01, skew=True),
     "tiny": dict(n_users=20_000, n_items=4_000, mean_deg=30, k=64, seed=1, init_seed=1, n=10, lam=0.01),
+    # BASELINE.json configs[4]: ALS only, k = 128, meant for 8 GPUs; every rank builds only its own shards (run_sharded_als).
+    # `--gpus 1 --emulate-world 8` runs ONE rank's share of the 8-GPU problem on one GPU (no exchange).
+    "C5": dict(n_users=10_000_000, n_items=1_000_000, mean_deg=50, k=128, seed=5, init_seed=5, n=0, lam=0.01, sharded=True),
+    "C5tiny": dict(n_users=80_000, n_items=16_000, mean_deg=30, k=128, seed=5, init_seed=5, n=0, lam=0.01, sharded=True),
 }
 
 
@@ -170,12 +174,13 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU leg
-def cpu_reference_leg(w, inputs, n_user_rows, n_item_rows, n_topn_users):
+def cpu_reference_leg(w, inputs, n_user_rows, n_item_rows, n_topn_users, target=None):
     """The oracle's CSR restatement of algo.py:314-332 + blocked predict/top_n (algo.py:143-147, :533-659) on a
     bounded contiguous sample, extrapolated linearly in rows.  Returns (iterations/s, seconds, description)."""
     from oracle import als as o_als, topn as o_topn       # the CPU legs are the only place bench.py touches oracle/
     indptr, indices, indptr_t, indices_t, u0, v0 = inputs
     nu, ni = w["n_users"], w["n_items"]
+    tu, ti = target if target else (nu, ni)      # sizes the per-row costs are extrapolated to
     n_user_rows, n_item_rows, n_topn_users = min(n_user_rows, nu), min(n_item_rows, ni), min(n_topn_users, nu)
     u = u0.astype(np.float64)
     v = v0.astype(np.float64)
@@ -184,12 +189,13 @@ def cpu_reference_leg(w, inputs, n_user_rows, n_item_rows, n_topn_users):
     t1 = time.perf_counter()
     o_als.half_step_csr(indptr_t, indices_t, u, v, w["lam"], rows=range(n_item_rows))
     t2 = time.perf_counter()
-    o_topn.recommend_blocked(u, v, indptr, indices, n=w["n"], users=np.arange(n_topn_users), block=256)
+    if w["n"] > 0:
+        o_topn.recommend_blocked(u, v, indptr, indices, n=w["n"], users=np.arange(n_topn_users), block=256)
     t3 = time.perf_counter()
-    t_iter = (t1 - t0) * nu / n_user_rows + (t2 - t1) * ni / n_item_rows + (t3 - t2) * nu / n_topn_users
+    t_iter = (t1 - t0) * tu / n_user_rows + (t2 - t1) * ti / n_item_rows + (t3 - t2) * tu / n_topn_users
     desc = (f"oracle CSR restatement of algo.py:314-332 on the first {n_user_rows} users ({t1 - t0:.2f}s) and "
             f"{n_item_rows} items ({t2 - t1:.2f}s) + blocked U@V.T/top-{w['n']} for {n_topn_users} users ({t3 - t2:.2f}s), "
-            f"extrapolated linearly in rows to {nu} x {ni}; single Python process, BLAS threads as configured")
+            f"extrapolated linearly in rows to {tu} x {ti}; single Python process, BLAS threads as configured")
     return 1.0 / t_iter, t3 - t0, desc
 
 
@@ -225,6 +231,12 @@ def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    target = None
+    if w.get("sharded"):
+        # problems that are never built whole: the per-row costs are timed on a 1 / 50 scale model with the SAME row lengths
+        # (users x items scaled together keep ~50 nnz per user and ~500 per item) and extrapolated to the full row counts
+        target = (w["n_users"], w["n_items"])
+        w = dict(w, n_users=w["n_users"] // 50, n_items=w["n_items"] // 50)
     inputs = make_inputs(w)
     # >= 20 K users / 20 K items per half-step and >= 2 K users for top-N, whatever --steps says; the sample is
     # repeated at most 3 times (+1 warm-up) so that the arm ends within a few minutes
@@ -233,7 +245,7 @@ def run_reference(args, w):
     vals, secs, desc = [], [], ""
     with all_host_threads():
         for i in range(warm + reps):
-            v, s, desc = cpu_reference_leg(w, inputs, nu_s, ni_s, nt_s)
+            v, s, desc = cpu_reference_leg(w, inputs, nu_s, ni_s, nt_s, target=target)
             if i >= warm:
                 vals.append(v)
                 secs.append(s)
@@ -441,6 +453,141 @@ def run_b200(args, w):
     return line
 
 
+def run_sharded_als(args, w):
+    """ALS-only workloads whose pattern is never built whole (C5): one ALS iteration per step on this rank's shards, the factor
+    exchange fused into the solve kernels (NVLink peer stores) when there is more than one rank."""
+    import torch
+    import torch.distributed as dist
+    from recsys_lite_b200 import _ffi, synth
+    from recsys_lite_b200.sharding import ShardedProblem, ShardPlan
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    emu = args.emulate_world if (world == 1 and args.emulate_world > 1) else world
+    rank_e = args.emulate_rank if emu != world else rank
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    h = _ffi.Handle(local)
+    stream = torch.cuda.Stream(device=device)
+    torch.cuda.set_stream(stream)
+    h.set_stream(stream.cuda_stream)
+    peaks = load_peaks()
+    nu, ni, k = w["n_users"], w["n_items"], w["k"]
+    t_gen = time.perf_counter()
+    ub, ib, up, ux, ip, ix = synth.sharded_problem(nu, ni, w["mean_deg"], w["seed"], rank_e, emu)
+    t_gen = time.perf_counter() - t_gen
+    plan = ShardPlan(rank_e, emu, ub, ib)
+    prob = ShardedProblem(h, plan, None, None, None, None, k, device, shards=(up, ux, ip, ix), n_users=nu, n_items=ni)
+    ulo, uhi = plan.users
+    ilo, ihi = plan.items
+    v0 = np.random.default_rng([w["init_seed"], 999]).random((ni, k), dtype=np.float32)
+    u_rows = np.random.default_rng([w["init_seed"], 1000 + rank_e]).random((uhi - ulo, k), dtype=np.float32)
+    if emu != world:       # one rank of a larger job on its own: the other ranks' user rows are random stand-ins (never exchanged)
+        gen = torch.Generator(device=device)
+        gen.manual_seed(1234)
+        prob.U[:, :k].uniform_(0.0, 1.0, generator=gen)
+    prob.set_factor_rows(u_rows, v0)
+    fused = prob.enable_peer_stores() if (world > 1 and not args.no_peer_stores) else False
+    real_exchange = world > 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)      # noqa: E731
+    marks = []
+
+    def step(record):
+        e = [ev() for _ in range(3)] if record else None
+        if record:
+            e[0].record()
+        prob.user_half_step(w["lam"], 0, args.ir_steps)
+        if real_exchange:
+            prob.exchange_users()
+        if record:
+            e[1].record()
+        prob.item_half_step(w["lam"], 0, args.ir_steps)
+        if real_exchange:
+            prob.exchange_items()
+        if record:
+            e[2].record()
+            marks.append(e)
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = h.launches
+    t_begin, t_end = ev(), ev()
+    barrier()
+    t_begin.record()
+    for _ in range(args.steps):
+        step(True)
+    t_end.record()
+    barrier()
+    clk = clocks.stop()
+    launches = h.launches - launches0
+    total_ms = t_begin.elapsed_time(t_end)
+    seg = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(2)] for e in marks])
+    t_user, t_item = seg.mean(axis=0)
+    # sampled parity: the item rows of this rank solve their normal equations against the U they were computed from
+    rs = np.random.default_rng(77 + rank_e)
+    items = np.sort(rs.choice(ihi - ilo, size=min(32, ihi - ilo), replace=False))
+    res = 0.0
+    v_rows = prob.V[ilo:ihi, :k][torch.from_numpy(items).to(device)].double().cpu().numpy()
+    for j, i in enumerate(items):
+        rows = ix[ip[i]:ip[i + 1]]
+        if len(rows) == 0:
+            continue
+        y = prob.U[:, :k][torch.from_numpy(rows.astype(np.int64)).to(device)].double().cpu().numpy()
+        a = y.T @ y + w["lam"] * np.eye(k)
+        b = y.sum(axis=0)
+        res = max(res, float(np.linalg.norm(a @ v_rows[j] - b) / max(np.linalg.norm(b), 1e-300)))
+    stats = torch.tensor([total_ms, t_user, t_item, res], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    total_ms, t_user, t_item, res = stats.tolist()
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        b_user = als_bytes(uhi - ulo, len(ux), k)
+        b_item = als_bytes(ihi - ilo, len(ix), k)
+        line = {
+            "metric": METRIC, "value": 1000.0 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": f"f32 factors; ALS solve f32 + {args.ir_steps} f64 refinement steps", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: implicit ALS k={k}, one full iteration per step (no top-N: BASELINE.json configs[4]), "
+                                   f"{nu} users x {ni} items, ~{w['mean_deg']} nnz/user (uniform synthetic, seed {w['seed']}, generated shard-wise "
+                                   f"on every rank)", "lambda": w["lam"],
+                       "l2": "every rank's pattern shard and its factor replicas are far larger than L2; no flush"},
+            "where": f"{world} x B200" + (f" (one GPU playing rank {rank_e} of {emu}: its shards of the {emu}-GPU job, no exchange)" if emu != world else ""),
+            "exchange": ("none" if not real_exchange else "fused: solve kernel stores rows into the peers' replicas over NVLink (CUDA IPC)"
+                         if fused else "NCCL broadcasts of the row ranges"),
+            "ms": {"user_half_step_incl_exchange": t_user, "item_half_step_incl_exchange": t_item},
+            "roofline": {"kernel": "als_k128_kernel, user half-step (this rank's shard)", "bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                         "achieved": b_user / (t_user * 1e-3) / 1e9, "frac": b_user / (t_user * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                         "bytes": b_user, "peak_source": peaks["source"]},
+            "roofline_als": {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                             "item_half_step": {"bytes": b_item, "achieved": b_item / (t_item * 1e-3) / 1e9,
+                                                "frac": b_item / (t_item * 1e-3) / 1e9 / peaks["hbm_gbs"]}},
+            "parity": {"als_item_rows_checked": int(len(items)) * world, "als_item_max_rel_residual": res, "ok": bool(res <= 1e-4),
+                       "what": "float64 NumPy on sampled item rows: (Y^T Y + lam I) v_i = Y^T 1 against the U of the last user half-step"},
+            "shard": {"users": [ulo, uhi], "items": [ilo, ihi], "nnz_user_side": int(len(ux)), "nnz_item_side": int(len(ix)),
+                      "host_generation_s": round(t_gen, 1)},
+            "clocks": clk, "gpu_launches": int(launches),
+            "e2e": None, "cpu_baseline": None,
+        }
+        _emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_api_leg(args, w, inputs, prob, k):
     """The same step through the drop-in Python surface (what a user of the reference calls): RecommenderSystem("als")
     .fit(R_csr, k, iterations=1, init=...) + .recommend(R_csr, n) on pageable NumPy / SciPy inputs; the model stays in HBM between
@@ -637,6 +784,8 @@ def main():
     ap.add_argument("--score-mode", type=int, default=0, help="0 auto, 1 exact CUDA-core, 2 tensor-core candidate pass")
     ap.add_argument("--no-peer-stores", action="store_true", help="N > 1: exchange with NCCL broadcasts instead of the fused NVLink stores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--emulate-world", type=int, default=0, help="sharded workloads on one GPU: play one rank of a job of this size")
+    ap.add_argument("--emulate-rank", type=int, default=0)
     ap.add_argument("--no-api", action="store_true", help="skip the e2e_api leg (the step through RecommenderSystem.fit / .recommend)")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled float64 parity check of the final state")
     args = ap.parse_args()
@@ -646,6 +795,8 @@ def main():
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, w)
+    elif w.get("sharded"):
+        run_sharded_als(args, w)
     else:
         run_b200(args, w)
 

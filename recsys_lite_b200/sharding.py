@@ -67,16 +67,25 @@ def exchange_rows(full, bounds, rank: int, world: int, group=None):
 class ShardedProblem:
     """Device-resident ALS problem of one rank: its CSR / CSC row ranges and full factor replicas."""
 
-    def __init__(self, handle, plan: ShardPlan, indptr_u, indices_u, indptr_i, indices_i, k: int, device):
+    def __init__(self, handle, plan: ShardPlan, indptr_u, indices_u, indptr_i, indices_i, k: int, device, *, shards=None,
+                 n_users=None, n_items=None):
+        """indptr_* / indices_*: the GLOBAL CSR and transposed CSR (each rank cuts its ranges out), or -- problems too large to
+        build whole on every rank -- shards=(up, ux, ip, ix): this rank's rows of both patterns with local indptr (indices stay
+        global ids), together with n_users / n_items."""
         import torch
         self.h, self.plan, self.k = handle, plan, int(k)
         self.kp = handle.lib.rl_padded_k(self.k)
-        self.n_users, self.n_items = len(indptr_u) - 1, len(indptr_i) - 1
         self.device = device
         ulo, uhi = plan.users
         ilo, ihi = plan.items
-        up, ux = shard_rows(indptr_u, indices_u, ulo, uhi)
-        ip, ix = shard_rows(indptr_i, indices_i, ilo, ihi)
+        if shards is not None:
+            up, ux, ip, ix = shards
+            self.n_users, self.n_items = int(n_users), int(n_items)
+            assert len(up) == uhi - ulo + 1 and len(ip) == ihi - ilo + 1
+        else:
+            self.n_users, self.n_items = len(indptr_u) - 1, len(indptr_i) - 1
+            up, ux = shard_rows(indptr_u, indices_u, ulo, uhi)
+            ip, ix = shard_rows(indptr_i, indices_i, ilo, ihi)
         self.host = {"up": up, "ux": ux, "ip": ip, "ix": ix}   # kept for the end-to-end (H2D inside) leg
         self.nnz_users, self.nnz_items = len(ux), len(ix)
         t = lambda a: torch.from_numpy(a).to(device)           # noqa: E731
@@ -171,6 +180,15 @@ class ShardedProblem:
             for ptr in self._peer_ptrs:
                 self.h.call("rl_ipc_close", ptr)
             self.peer_stores = False
+
+    def set_factor_rows(self, u_rows, v_host):
+        """Initial factors of a sharded start: this rank's user rows and all of V (every other user row is written by its
+        owner's first half-step and arrives through the exchange before anybody reads it)."""
+        import torch
+        self._bind_stream()
+        ulo, uhi = self.plan.users
+        self.U[ulo:uhi, : self.k].copy_(torch.from_numpy(np.ascontiguousarray(u_rows, dtype=np.float32)))
+        self.V[:, : self.k].copy_(torch.from_numpy(np.ascontiguousarray(v_host, dtype=np.float32)))
 
     def set_factors(self, u_host, v_host):
         import torch

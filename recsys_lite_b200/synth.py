@@ -97,3 +97,40 @@ def pattern_to_dense(indptr, indices, n_items):
     rows = np.repeat(np.arange(n_users), np.diff(indptr))
     r[rows, indices] = 1.0
     return r
+
+
+def sharded_problem(n_users, n_items, mean_deg, seed, rank, world, n_blocks=None):
+    """Rank `rank`'s share of a problem too large to build whole on every rank (C5: 10 M x 1 M, 500 M nnz): the user rows are
+    generated in `n_blocks` (default `world`) independent blocks (`synth_pattern(..., row_offset=block)`), every rank walks all
+    blocks, keeps its own as the user-side shard and, of the others, only the entries whose item falls into its item range --
+    those become its rows of the transposed pattern.  Returns (user_bounds, item_bounds, up, ux, ip, ix): row boundaries of all
+    ranks and this rank's two CSR shards with local indptr (ux: global item ids, ix: global user ids, ascending)."""
+    from scipy import sparse
+    n_blocks = world if n_blocks is None else n_blocks
+    assert n_blocks % world == 0
+    ub = (np.arange(n_blocks + 1, dtype=np.int64) * n_users) // n_blocks          # block boundaries (users)
+    user_bounds = ub[:: n_blocks // world].copy()
+    item_bounds = (np.arange(world + 1, dtype=np.int64) * n_items) // world
+    ilo, ihi = int(item_bounds[rank]), int(item_bounds[rank + 1])
+    mine_ptr, mine_idx, t_rows, t_cols = [], [], [], []
+    for b in range(n_blocks):
+        nb = int(ub[b + 1] - ub[b])
+        ptr, idx = synth_pattern(nb, n_items, mean_deg, seed, row_offset=b)
+        if user_bounds[rank] <= ub[b] < user_bounds[rank + 1]:
+            mine_ptr.append(ptr)
+            mine_idx.append(idx)
+        keep = (idx >= ilo) & (idx < ihi)
+        rows = np.repeat(np.arange(nb, dtype=np.int64), np.diff(ptr))[keep] + ub[b]
+        t_rows.append(rows.astype(np.int32))
+        t_cols.append((idx[keep] - ilo).astype(np.int32))
+        del ptr, idx, keep, rows
+    up = np.zeros(1, dtype=np.int64)
+    for ptr in mine_ptr:
+        up = np.concatenate([up, ptr[1:] + up[-1]])
+    ux = np.concatenate(mine_idx)
+    rows, cols = np.concatenate(t_rows), np.concatenate(t_cols)
+    # transposed shard: rows = this rank's items, indices = global user ids ascending (users were walked in ascending order)
+    t = sparse.csr_matrix((np.ones(len(rows), dtype=np.int8), (cols, rows)), shape=(ihi - ilo, n_users))
+    t.sort_indices()
+    return (user_bounds, item_bounds, np.ascontiguousarray(up), np.ascontiguousarray(ux, dtype=np.int32),
+            np.ascontiguousarray(t.indptr, dtype=np.int64), np.ascontiguousarray(t.indices, dtype=np.int32))
