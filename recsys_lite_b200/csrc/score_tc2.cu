@@ -65,7 +65,10 @@ constexpr int T2_NCLS = 8;        // item classes by |w_i| (factor of two each)
 #endif                          // (32 columns per tcgen05.ld), 2 = two warps, 64 columns each (16 per tcgen05.ld, 72 registers)
 constexpr int T2_THREADS = 32 * (4 + 8 * T2_SUBS + 8);   // 4 control + scan + 8 selection warps
 constexpr int T2_RING = 16 / T2_SUBS;   // ring slots per row and producer
-constexpr int T2_CH = 32 / T2_SUBS;     // columns per tcgen05.ld
+#ifndef T2_CHUNK
+#define T2_CHUNK 32              // columns per tcgen05.ld of a scan warp (one chunk of the compare loop)
+#endif
+constexpr int T2_CH = T2_CHUNK;         // columns per tcgen05.ld (16 or 32)
 constexpr int T2_CAND = 40;       // candidate slots per row
 #ifndef T2_THR_PER_CHUNK
 #define T2_THR_PER_CHUNK 1      // re-read the row threshold for every 16 columns (1) or once per item tile (0)
@@ -80,7 +83,7 @@ constexpr int T2_CAND = 40;       // candidate slots per row
 #define T2_POLL_NS 1500         // sleep of an idle selection warp between two looks at its rings
 #endif
 #ifndef T2_PERIOD_MIN
-#define T2_PERIOD_MIN 1000      // interval at the start of a sweep (thresholds move fast); grows by 150 clocks per item tile
+#define T2_PERIOD_MIN 3000      // interval at the start of a sweep (thresholds move fast); grows by 150 clocks per item tile
 #endif
 #ifndef T2_PERIOD_MAX
 #define T2_PERIOD_MAX 16000     // largest interval (clocks) between two selection passes of a warp
