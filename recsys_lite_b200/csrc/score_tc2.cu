@@ -12,7 +12,7 @@
 // does the rounding error of ONE fp16 product:
 //     |fp16(u).fp16(w_i) - u.w_i|  <=  |u - u_h| |w_i| + |u_h| |w_i - w_h,i|  (+ fp32 accumulation)
 // -- computed from what the roundings actually dropped, per user row and per item class.  Items are binned by
-// |w_i| into factor-of-two classes (largest first; each class padded to whole 128-item tiles, ascending item id
+// |w_i| into factor-of-two classes (scan order: see class_scan_kernel; each class padded to whole 128-item tiles, ascending item id
 // inside a class), so that the 8 % of slow-converging items with |w_i| ~ 1 do not set the window of the 92 % with
 // |w_i| ~ 0.015.  One product instead of three (score_tc.cu) is a third of the tensor work, and the kernel is
 // power-bound on exactly that work.
@@ -105,6 +105,7 @@ struct ClassTable {
   unsigned wmax_bits, amax_bits, vmax_bits;   // reductions in progress (non-negative floats order as unsigned)
   unsigned wc_bits[T2_NCLS], rc_bits[T2_NCLS];
   int count[T2_NCLS];             // items of class c (its last tile is padded with zero rows)
+  int label_of[T2_NCLS];          // norm bin (class_of) -> class label = place in the scan order
 };
 
 template <int KP>
@@ -826,7 +827,7 @@ __device__ __forceinline__ int class_of(float wn, float wmax) {
   const float ratio = wmax / wn;                     // >= 1 up to rounding
   int c = ilogbf(ratio);
   c = c < 0 ? 0 : (c > T2_NCLS - 1 ? T2_NCLS - 1 : c);
-  return T2_NCLS - 1 - c;                            // class 0 = smallest norms = narrowest window: scanned first
+  return T2_NCLS - 1 - c;                            // bin 0 = smallest norms = narrowest window
 }
 
 // class of every item, per-block class counts
@@ -845,9 +846,22 @@ __global__ void __launch_bounds__(PP_ROWS) classify_kernel(const float* __restri
   if (threadIdx.x < T2_NCLS) block_counts[blockIdx.x * T2_NCLS + threadIdx.x] = cnt[threadIdx.x];
 }
 
-// class bases (whole tiles), per-block offsets inside the classes, the scale
-__global__ void __launch_bounds__(32) class_scan_kernel(int* __restrict__ block_counts, int nblk, ClassTable* __restrict__ tab) {
+// The scan order of the classes.  A row's candidate records are the items that beat its running n-th best: scanned in
+// an order in which the scores tend to RISE (after 20 ALS iterations the far-out items of the widest norm bins score
+// lowest, the members of the final top-n sit in the middle bins) every class restarts the harmonic sum n ln(size / n) of
+// records.  The exact top-n of T2_SAMPLE evenly spaced users says where the winners come from: classes are scanned by
+// falling density (sampled members / class size); bins nobody's top-n touched follow by rising norm.  Any order is exact.
+constexpr int T2_SAMPLE = 64;
+__global__ void __launch_bounds__(T2_SAMPLE) sample_users_kernel(int64_t n_users, int n_sample, int32_t* __restrict__ list) {
+  if (static_cast<int>(threadIdx.x) < n_sample) list[threadIdx.x] = static_cast<int32_t>((n_users * threadIdx.x) / n_sample);
+}
+
+// class bases (whole tiles) in scan order, per-block offsets inside the classes, the scale
+__global__ void __launch_bounds__(32) class_scan_kernel(int* __restrict__ block_counts, int nblk, ClassTable* __restrict__ tab,
+                                                        const int32_t* __restrict__ sample_idx, int n_sample_entries,
+                                                        const float* __restrict__ wnorm, int64_t n_items) {
   __shared__ int total[T2_NCLS];
+  __shared__ int hist[T2_NCLS];
   const int c = threadIdx.x;
   if (c < T2_NCLS) {
     int run = 0;
@@ -857,14 +871,35 @@ __global__ void __launch_bounds__(32) class_scan_kernel(int* __restrict__ block_
       run += x;
     }
     total[c] = run;
+    hist[c] = 0;
+  }
+  __syncwarp();
+  const float wmax = __uint_as_float(tab->wmax_bits);
+  for (int e = c; e < n_sample_entries; e += 32) {
+    const int id = sample_idx[e];
+    if (id >= 0 && id < n_items) atomicAdd(&hist[class_of(wnorm[id], wmax)], 1);
   }
   __syncwarp();
   if (c == 0) {
+    int order[T2_NCLS];
+    for (int i = 0; i < T2_NCLS; ++i) order[i] = i;
+    for (int i = 1; i < T2_NCLS; ++i) {            // stable insertion sort by falling hist / total
+      const int x = order[i];
+      int j = i;
+      while (j > 0) {
+        const int y = order[j - 1];
+        if (static_cast<long long>(hist[x]) * total[y] > static_cast<long long>(hist[y]) * total[x]) { order[j] = y; --j; }
+        else break;
+      }
+      order[j] = x;
+    }
     int tile = 0;
-    for (int i = 0; i < T2_NCLS; ++i) {
-      tab->first_tile[i] = tile;
-      tab->count[i] = total[i];
-      tile += (total[i] + T2_BN - 1) / T2_BN;
+    for (int l = 0; l < T2_NCLS; ++l) {
+      const int nc = order[l];
+      tab->label_of[nc] = l;
+      tab->first_tile[l] = tile;
+      tab->count[l] = total[nc];
+      tile += (total[nc] + T2_BN - 1) / T2_BN;
     }
     tab->first_tile[T2_NCLS] = tile;
     tab->n_tiles = tile;
@@ -873,10 +908,11 @@ __global__ void __launch_bounds__(32) class_scan_kernel(int* __restrict__ block_
 }
 
 // stable placement: position of item r = class base + (number of items of its class with a smaller id); writes the
-// position -> id map and the fp16 row of the centred, scaled factors; per-class maxima of |w s| and |w s - fp16(w s)|
+// position -> id map and the fp16 row of the centred, scaled factors; per-class maxima of |w s| and |w s - fp16(w s)|.
+// cls[] holds norm bins on entry and class labels (scan order) on exit.
 template <int KPH>
 __global__ void __launch_bounds__(PP_ROWS) place_kernel(const float* __restrict__ v, int64_t n, int kp, const float* __restrict__ vbar,
-                                                        const float* __restrict__ wnorm, const unsigned char* __restrict__ cls,
+                                                        const float* __restrict__ wnorm, unsigned char* __restrict__ cls,
                                                         const int* __restrict__ block_offsets, ClassTable* __restrict__ tab,
                                                         int32_t* __restrict__ perm, int32_t* __restrict__ inv, __half* __restrict__ whi) {
   __shared__ int warp_cnt[32][T2_NCLS];
@@ -898,7 +934,7 @@ __global__ void __launch_bounds__(PP_ROWS) place_kernel(const float* __restrict_
   if (c >= 0) {
     int before = 0;
     for (int wv = 0; wv < warp; ++wv) before += warp_cnt[wv][c];
-    pos = tab->first_tile[c] * T2_BN + block_offsets[blockIdx.x * T2_NCLS + c] + before + my_rank;
+    pos = tab->first_tile[tab->label_of[c]] * T2_BN + block_offsets[blockIdx.x * T2_NCLS + c] + before + my_rank;
     perm[pos] = static_cast<int32_t>(r);
     inv[r] = pos;
   }
@@ -930,12 +966,13 @@ __global__ void __launch_bounds__(PP_ROWS) place_kernel(const float* __restrict_
     }
     for (int o = C4N >> 1; o > 0; o >>= 1) res += __shfl_xor_sync(FULL_MASK, res, o);
     if (rr < n && c4 == 0) {
-      const int cc = cls[rr];
+      const int cc = tab->label_of[cls[rr]];
       atomicMax(reinterpret_cast<unsigned*>(&rmax_s[cc]), __float_as_uint(sqrtf(res) * 1.0001f));
       atomicMax(reinterpret_cast<unsigned*>(&wmax_s[cc]), __float_as_uint(wnorm[rr] * s * 1.0001f));
     }
   }
   __syncthreads();
+  if (c >= 0) cls[r] = static_cast<unsigned char>(tab->label_of[c]);
   if (tid < T2_NCLS) {
     atomicMax(&tab->rc_bits[tid], __float_as_uint(rmax_s[tid]));
     atomicMax(&tab->wc_bits[tid], __float_as_uint(wmax_s[tid]));
@@ -1085,6 +1122,8 @@ int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefe
     }
   }
   const size_t o_spos = off; off += al(sizeof(int32_t) * static_cast<size_t>(seen_cap));
+  const size_t o_slist = off; off += al(sizeof(int32_t) * T2_SAMPLE);
+  const size_t o_sidx = off; off += al(sizeof(int32_t) * T2_SAMPLE * 16);
   void* sc = nullptr;
   int rc = scratch(h, off, &sc);
   if (rc != RL_OK) return rc;
@@ -1130,7 +1169,22 @@ int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefe
   }
   classify_kernel<<<nblk, PP_ROWS, 0, h->stream>>>(wnorm, n_items, tab, cls, bc);
   RL_LAUNCH_CHECK(h, "classify_kernel");
-  class_scan_kernel<<<1, 32, 0, h->stream>>>(bc, nblk, tab);
+  // exact top-n of a few evenly spaced users: where the winners come from decides the scan order of the classes
+  const int n_sample = static_cast<int>(sa.n_users < T2_SAMPLE ? sa.n_users : T2_SAMPLE);
+  int32_t* slist = reinterpret_cast<int32_t*>(scb + o_slist);
+  int32_t* sidx = reinterpret_cast<int32_t*>(scb + o_sidx);
+  {
+    sample_users_kernel<<<1, T2_SAMPLE, 0, h->stream>>>(sa.n_users, n_sample, slist);
+    RL_LAUNCH_CHECK(h, "sample_users_kernel");
+    ScoreArgs ea = sa;
+    ea.user_list = slist;
+    ea.n_list = n_sample;
+    ea.scatter = false;
+    ea.idx_out = sidx;
+    ea.score_out = nullptr;
+    if ((rc = launch_score_exact(h, kp, ea)) != RL_OK) return rc;
+  }
+  class_scan_kernel<<<1, 32, 0, h->stream>>>(bc, nblk, tab, sidx, n_sample * sa.n, wnorm, n_items);
   RL_LAUNCH_CHECK(h, "class_scan_kernel");
   place_kernel<64><<<nblk, PP_ROWS, 0, h->stream>>>(sa.vf, n_items, kp, vbar, wnorm, cls, bc, tab, perm, inv, whi);
   RL_LAUNCH_CHECK(h, "place_kernel");
