@@ -30,6 +30,9 @@ Documented deviations from the reference:
 """
 from __future__ import annotations
 
+import os
+import sys
+import time
 from typing import Any, Dict, Optional
 
 import numpy as np
@@ -57,6 +60,26 @@ def _as_float_matrix(x, allow=(np.float32, np.float64), default=np.float64):
 
 def _rl_dtype(a):
     return _ffi.RL_F64 if a.dtype == np.float64 else _ffi.RL_F32
+
+
+_TIMING = bool(os.environ.get("RL_API_TIMING"))
+
+
+class _Tick:
+    """RL_API_TIMING=1: host-side phase times of fit / recommend on stderr (where the adapter's time goes)."""
+
+    def __init__(self, what):
+        self.what, self.t, self.parts = what, time.perf_counter(), []
+
+    def __call__(self, name):
+        if _TIMING:
+            t = time.perf_counter()
+            self.parts.append(f"{name} {1e3 * (t - self.t):.1f}")
+            self.t = t
+
+    def done(self):
+        if _TIMING:
+            sys.stderr.write(f"[rl api] {self.what}: " + ", ".join(self.parts) + " ms\n")
 
 
 def _finish_topn(idx, n_valid):
@@ -244,18 +267,26 @@ class RecommenderSystem:
             item_f = np.ascontiguousarray(init[1], dtype=None if np.asarray(init[1]).dtype == np.float32 else np.float64)
             if user_f.shape != (n_users, factors) or item_f.shape != (n_items, factors):
                 raise ValueError("init factors must have shapes (n_users, factors) and (n_items, factors)")
+        tick = _Tick("fit_als")
         indptr, indices = observed_pattern(ratings)
+        tick("pattern")
         self._drop_resident()
+        tick("drop")
         if n_users and n_items and iterations > 0:
             h = _ffi.default_handle()
             # The model stays in HBM (float32, padded rows): pattern and initial factors go up once, the transposed pattern
             # (users of every item) is built on the device, and nothing comes back until the caller reads the arrays.
             res = _ResidentALS(h, n_users, n_items, factors)
             try:
+                tick("alloc")
                 res.upload_pattern(indptr, indices, _ResidentALS.key_of(ratings, indptr, indices))
+                tick("pattern up")
                 res.upload_factors(user_f, item_f)
+                tick("factors up")
                 res.iterate(iterations, lambda_, _PRECISIONS[precision], ir_steps)
                 h.synchronize()
+                tick("iterate")
+                tick.done()
             except Exception:
                 res.free()
                 raise
@@ -443,8 +474,10 @@ class RecommenderSystem:
         ip = ix = None
         indptr = None
         tmp = []
+        tick = _Tick("recommend")
         if exclude_rated:
             indptr, indices = observed_pattern(ratings)
+            tick("pattern")
             if res.pattern_key == _ResidentALS.key_of(ratings, indptr, indices):
                 ip, ix = res.ip, res.ix
             else:
@@ -455,18 +488,27 @@ class RecommenderSystem:
                     h.call("rl_memcpy_h2d", ix.ptr, _ffi.ptr(indices), indices.nbytes)
         idx = np.empty((n_users, n_dev), dtype=np.int32)
         d_idx = _DevBuf(h, idx.nbytes)
+        tick("alloc")
         try:
             h.call("rl_score_topn_dev", res.u.ptr, n_users, res.v.ptr, n_items, res.k, ip.ptr if ip else None,
                    ix.ptr if ix else None, 0.0, None, None, n_dev, d_idx.ptr, None, _ffi.RL_SCORE_AUTO)
+            if _TIMING:
+                h.synchronize()
+            tick("score")
             h.call("rl_memcpy_d2h", _ffi.ptr(idx), d_idx.ptr, idx.nbytes)
+            tick("d2h")
         finally:
             d_idx.free()
             for b in tmp:
                 b.free()
+        tick("free")
         if not exclude_rated:
             return idx.astype(np.int64)
         n_valid = np.minimum(n_dev, n_items - np.diff(indptr)).astype(np.int32)
-        return _finish_topn(idx, n_valid)
+        out = _finish_topn(idx, n_valid)
+        tick("finish")
+        tick.done()
+        return out
 
     @staticmethod
     def _recommend_unfused(h, a, b, gb, rb, cb, indptr, indices, n_dev, max_cells: int = 1 << 26) -> np.ndarray:

@@ -69,7 +69,11 @@ constexpr int T2_RING = 16 / T2_SUBS;   // ring slots per row and producer
 #define T2_CHUNK 32              // columns per tcgen05.ld of a scan warp (one chunk of the compare loop)
 #endif
 constexpr int T2_CH = T2_CHUNK;         // columns per tcgen05.ld (16 or 32)
-constexpr int T2_CAND = 40;       // candidate slots per row
+constexpr int T2_CAND = 40;       // candidate slots per row (shared memory)
+#ifndef T2_SPILL_BLOCKS
+#define T2_SPILL_BLOCKS 6
+#endif
+constexpr int T2_SPILL_MAX = T2_SPILL_BLOCKS;   // ... plus up to this many pool blocks of T2_CAND positions in global memory when the list runs over
 #ifndef T2_THR_PER_CHUNK
 #define T2_THR_PER_CHUNK 1      // re-read the row threshold for every 16 columns (1) or once per item tile (0)
 #endif
@@ -134,8 +138,11 @@ struct T2Args {
   const ClassTable* tab;
   const int32_t* seen_pos;      // the seen items of every row as POSITIONS, ascending per row (same indptr as seen_indices)
   int64_t seen_cap;             // entries seen_pos has room for (rows beyond it go to the exact kernel)
-  int32_t* cand_ids;            // [n_users][T2_CAND] candidate positions
-  int32_t* cand_cnt;            // [n_users]: number of candidates, -1 = overflow (row goes to the exact kernel)
+  int32_t* cand_ids;            // [n_users][T2_CAND] candidate positions; spilled rows: [n blocks | block ids | block counts]
+  int32_t* cand_cnt;            // [n_users]: number of candidates, -1 = overflow (row goes to the exact kernel), -2 = spilled
+  int32_t* pool;                // [pool_blocks][T2_CAND] spilled candidate positions
+  unsigned int* pool_next;      // next free pool block
+  unsigned int pool_blocks;
   float acc_rel;                // allowance for the fp32 accumulation of the tensor core, relative to |u_h||w_h|
   float* dump;                  // debug: raw accumulators (n_users x dump_ld), dump_su: the row scales
   float* dump_su;
@@ -157,6 +164,52 @@ __device__ __forceinline__ int lds_volatile(uint32_t addr) {
   int v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
+}
+
+// The kernel is instruction-fetch sensitive (28 warps in six different roles per SM): the cold paths of the selection and
+// scan loops are real function calls.
+// seen-position window of a row <- seen[woff .. woff + T2_WIN)
+__device__ __noinline__ void t2_refill_window(const int32_t* __restrict__ seen, int seen_len, int woff, uint32_t win_row, uint32_t es) {
+#pragma unroll 8
+  for (int i = 0; i < T2_WIN; ++i) {
+    const int v = (woff + i < seen_len) ? seen[woff + i] : INT_MAX;
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(win_row + i * es), "r"(v) : "memory");
+  }
+}
+// drops the candidates whose upper bound fell below the row's threshold; returns the new length of the list
+__device__ __noinline__ int t2_compact_list(uint32_t cand_row, uint32_t rs, int cnt, float lth) {
+  int jw = 0;
+  for (int f = 0; f < cnt; ++f) {
+    float hb; int id;
+    ring_get(cand_row + f * rs, hb, id);
+    if (hb >= lth) { ring_put(cand_row + jw * rs, hb, id); ++jw; }
+  }
+  return jw;
+}
+// a scan thread waits for the selection thread to free ring slots (in order)
+__device__ __noinline__ void t2_wait_slot(uint32_t addr) {
+  uint32_t spin = 0;
+  while (lds_volatile(addr) != T2_EMPTY) {
+    __nanosleep(64);
+    if (++spin > (1u << 24)) { printf("score_tc2: ring timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+
+// rare path of the selection threads, kept out of line: the row's candidate list (cnt positions in shared memory, entry f at
+// cand_row + f * rs) moves to a fresh pool block; the row's header in cand_ids takes the block id and the count
+__device__ __noinline__ bool t2_spill_block(int32_t* pool, unsigned int* pool_next, unsigned int pool_blocks, int32_t* hdr, uint32_t cand_row,
+                                            uint32_t rs, int cnt, int n_blk) {
+  const unsigned int b = atomicAdd(pool_next, 1u);
+  if (b >= pool_blocks) return false;
+  int32_t* dst = pool + static_cast<size_t>(b) * T2_CAND;
+  for (int f = 0; f < cnt; ++f) {
+    float hb; int p;
+    ring_get(cand_row + f * rs, hb, p);
+    dst[f] = p;
+  }
+  hdr[1 + n_blk] = static_cast<int32_t>(b);
+  hdr[1 + T2_SPILL_MAX + n_blk] = cnt;
+  return true;
 }
 
 // instruction descriptor: D fp32, A/B fp16, both K-major, N = 128, M = 128
@@ -304,13 +357,7 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
     uint32_t fpar = 0;            // bit s: parity of this half's next use of accumulator stage s
     long long w_full = 0, n_push = 0, n_slow = 0, c_ld = 0, c_scan = 0;
     const long long t_start = DBG ? clock64() : 0;
-    auto wait_slot = [&](uint32_t addr) {          // ring full: the selection thread frees slots in order
-      uint32_t spin = 0;
-      while (lds_volatile(addr) != T2_EMPTY) {
-        __nanosleep(64);
-        if (++spin > (1u << 24)) { printf("score_tc2: ring timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-      }
-    };
+    auto wait_slot = [&](uint32_t addr) { t2_wait_slot(addr); };   // ring full: the selection thread frees slots in order
     for (int j = 0; j < n_sweeps; ++j) {
       const int halves = (tile_begin + 2 * j + 1 < tile_end) ? 2 : 1;
       if (hh >= halves) { acc = (acc + static_cast<uint32_t>(n_tiles)) % T2_ACC; continue; }     // (only the last sweep)
@@ -512,24 +559,28 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
           }
         }
         auto refill = [&]() {                                     // window <- seen[woff .. woff + T2_WIN)
-#pragma unroll 8
-          for (int i = 0; i < T2_WIN; ++i) {
-            const int v = (woff + i < seen_len) ? seen[woff + i] : INT_MAX;
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(win_row + i * ES), "r"(v) : "memory");
-          }
+          t2_refill_window(seen, seen_len, woff, win_row, ES);
           wp = 0;
           if constexpr (DBG) ++n_refill;
         };
         if (valid) refill();
         auto compact = [&]() {
-          int jw = 0;
-          for (int f = 0; f < cnt; ++f) {
-            float hb; int id;
-            ring_get(cand_row + f * RS, hb, id);
-            if (hb >= lth) { ring_put(cand_row + jw * RS, hb, id); ++jw; }
-          }
-          cnt = jw;
+          cnt = t2_compact_list(cand_row, RS, cnt, lth);
           if constexpr (DBG) ++n_cmp;
+        };
+        // The list is still full after a compaction (thresholds rise slowly while the densest classes go by): its positions
+        // move to a pool block in global memory and the list starts again; they are re-scored with the rest at the end.
+        // No block left: the exact kernel takes the row.
+        int n_blk = 0;
+        auto spill = [&]() -> bool {
+          if (n_blk == T2_SPILL_MAX) return false;
+          if (!t2_spill_block(a.pool, a.pool_next, a.pool_blocks, a.cand_ids + user * T2_CAND, cand_row, RS, cnt, n_blk)) return false;
+          ++n_blk;
+          cnt = 0;
+          return true;
+        };
+        auto full_list = [&]() {
+          if (!spill()) { over = true; cnt = 0; lth = CUDART_INF_F; ring_put(thr_addr, lth, j); }
         };
         long long last_pass = clock64();
         int period = T2_PERIOD_MIN;                          // clocks between passes when no ring is filling up; grows with the sweep
@@ -625,14 +676,14 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
               ring_put(cand_row + cnt * RS, hb, pos);
               if (++cnt == T2_CAND) {                 // emergency: normally the joint compaction below keeps the list short
                 compact();
-                if (cnt > T2_CAND - 4) { over = true; cnt = 0; lth = CUDART_INF_F; ring_put(thr_addr, lth, j); }
+                if (cnt > T2_CAND - 4) full_list();
               }
             }
           }
           if (T2_JOINT && __any_sync(FULL_MASK, cnt >= T2_CAND - 10)) {     // candidate lists filling up: compacted together
             if (cnt > 0 && !over) {
               compact();
-              if (cnt > T2_CAND - 4) { over = true; cnt = 0; lth = CUDART_INF_F; ring_put(thr_addr, lth, j); }
+              if (cnt > T2_CAND - 4) full_list();
             }
           }
           // thresholds settle as the sweep goes on: let more records accumulate per pass
@@ -644,13 +695,19 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
         if (valid) {
           // ---- end of the sweep: final candidates (positions) to global memory ----
           if (!over) compact();
+          if (!over && n_blk > 0 && cnt > 0 && !spill()) over = true;
           int32_t* out = a.cand_ids + user * T2_CAND;
-          for (int f = 0; f < cnt; ++f) {
-            float hb; int pos;
-            ring_get(cand_row + f * RS, hb, pos);
-            out[f] = pos;
+          if (!over && n_blk > 0) {
+            out[0] = n_blk;
+            a.cand_cnt[user] = -2;
+          } else {
+            for (int f = 0; f < cnt; ++f) {
+              float hb; int pos;
+              ring_get(cand_row + f * RS, hb, pos);
+              out[f] = pos;
+            }
+            a.cand_cnt[user] = over ? -1 : cnt;
           }
-          a.cand_cnt[user] = over ? -1 : cnt;
         }
         // the user tile of the sweep after next goes into the TMEM buffer this sweep has just finished with
         __syncwarp();       // tcgen05.st needs the whole warp
@@ -670,28 +727,17 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const T2Args a) {
 }
 
 // ---- exact re-scoring of the candidates: one warp per user, float64 dot products in the exact kernel's order -------
-template <int KP>
-__global__ void __launch_bounds__(256) rescore_kernel(const float* __restrict__ uf, const float* __restrict__ vf, int64_t n_users, int n,
-                                                      const int32_t* __restrict__ cand_ids, const int32_t* __restrict__ cand_cnt,
-                                                      const int32_t* __restrict__ perm, int32_t* __restrict__ idx_out, double* __restrict__ score_out,
-                                                      int32_t* __restrict__ overflow_rows, unsigned int* __restrict__ overflow_count,
-                                                      int64_t row_offset) {
-  const int lane = threadIdx.x & 31;
-  const int64_t user = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (user >= n_users) return;
-  const int cnt = cand_cnt[user];
-  if (cnt < 0) {
-    if (lane == 0) overflow_rows[atomicAdd(overflow_count, 1u)] = static_cast<int32_t>(user + row_offset);
-    return;
-  }
-  constexpr int PER = (T2_CAND + 31) / 32;
+// candidate c of the row has item id fetch(c); PER = candidates per lane
+template <int KP, int PER, typename Fetch>
+__device__ __forceinline__ void rescore_row(const float* __restrict__ uf, const float* __restrict__ vf, int64_t user, int n, int cnt, Fetch fetch,
+                                            int32_t* __restrict__ idx_out, double* __restrict__ score_out, int lane) {
   int id[PER];
   double sc[PER];
   const float* up = uf + user * KP;
 #pragma unroll
   for (int p = 0; p < PER; ++p) {
     const int c = lane + 32 * p;
-    id[p] = c < cnt ? perm[cand_ids[user * T2_CAND + c]] : -1;     // candidate position -> item id
+    id[p] = c < cnt ? fetch(c) : -1;
     sc[p] = -CUDART_INF;
     if (id[p] >= 0) {
       const float* vp = vf + static_cast<int64_t>(id[p]) * KP;
@@ -735,6 +781,52 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float* __restrict__ 
   for (int r = cnt + lane; r < n; r += 32) {       // fewer than n unseen items
     idx_out[user * n + r] = -1;
     if (score_out) score_out[user * n + r] = -CUDART_INF;
+  }
+}
+
+template <int KP>
+__global__ void __launch_bounds__(256) rescore_kernel(const float* __restrict__ uf, const float* __restrict__ vf, int64_t n_users, int n,
+                                                      const int32_t* __restrict__ cand_ids, const int32_t* __restrict__ cand_cnt,
+                                                      const int32_t* __restrict__ perm, int32_t* __restrict__ idx_out, double* __restrict__ score_out,
+                                                      int32_t* __restrict__ overflow_rows, unsigned int* __restrict__ overflow_count,
+                                                      int64_t row_offset, int32_t* __restrict__ spill_rows, unsigned int* __restrict__ spill_count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t user = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (user >= n_users) return;
+  const int cnt = cand_cnt[user];
+  if (cnt == -2) {            // spilled list: re-scored by rescore_spill_kernel
+    if (lane == 0) spill_rows[atomicAdd(spill_count, 1u)] = static_cast<int32_t>(user);
+    return;
+  }
+  if (cnt < 0) {
+    if (lane == 0) overflow_rows[atomicAdd(overflow_count, 1u)] = static_cast<int32_t>(user + row_offset);
+    return;
+  }
+  const int32_t* cp = cand_ids + user * T2_CAND;
+  rescore_row<KP, (T2_CAND + 31) / 32>(uf, vf, user, n, cnt, [&](int c) { return perm[cp[c]]; }, idx_out, score_out, lane);
+}
+
+// rows whose candidates went to pool blocks: the concatenation of the blocks, up to T2_SPILL_MAX * T2_CAND candidates
+template <int KP>
+__global__ void __launch_bounds__(256) rescore_spill_kernel(const float* __restrict__ uf, const float* __restrict__ vf, int n,
+                                                            const int32_t* __restrict__ cand_ids, const int32_t* __restrict__ pool,
+                                                            const int32_t* __restrict__ perm, int32_t* __restrict__ idx_out,
+                                                            double* __restrict__ score_out, const int32_t* __restrict__ spill_rows,
+                                                            const unsigned int* __restrict__ spill_count) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int total = *spill_count;
+  for (unsigned int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < total; i += gridDim.x * 8) {
+    const int64_t user = spill_rows[i];
+    const int32_t* hdr = cand_ids + user * T2_CAND;
+    const int nb = hdr[0];
+    int cnt = 0;
+    for (int b = 0; b < nb; ++b) cnt += hdr[1 + T2_SPILL_MAX + b];
+    auto fetch = [&](int c) {
+      int b = 0;
+      while (c >= hdr[1 + T2_SPILL_MAX + b]) { c -= hdr[1 + T2_SPILL_MAX + b]; ++b; }
+      return perm[pool[static_cast<size_t>(hdr[1 + b]) * T2_CAND + c]];
+    };
+    rescore_row<KP, (T2_CAND * (T2_SPILL_MAX > 0 ? T2_SPILL_MAX : 1) + 31) / 32>(uf, vf, user, n, cnt, fetch, idx_out, score_out, lane);
   }
 }
 
@@ -1122,6 +1214,9 @@ int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefe
     }
   }
   const size_t o_spos = off; off += al(sizeof(int32_t) * static_cast<size_t>(seen_cap));
+  const unsigned int pool_blocks = static_cast<unsigned int>(sa.n_users / 8 + 4096);
+  const size_t o_pool = off; off += al(sizeof(int32_t) * static_cast<size_t>(pool_blocks) * T2_CAND);
+  const size_t o_srow = off; off += al(sizeof(int32_t) * sa.n_users);
   const size_t o_slist = off; off += al(sizeof(int32_t) * T2_SAMPLE);
   const size_t o_sidx = off; off += al(sizeof(int32_t) * T2_SAMPLE * 16);
   void* sc = nullptr;
@@ -1203,6 +1298,11 @@ int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefe
   a.uf = sa.uf; a.ldf = kp; a.n_users = sa.n_users; a.seen_indptr = dump ? nullptr : sa.seen_indptr; a.n = sa.n;
   a.seen_pos = spos; a.seen_cap = seen_cap;
   a.tab = tab; a.cand_ids = cids; a.cand_cnt = ccnt;
+  unsigned int* pool_next = ocount + 4;
+  unsigned int* spill_count = ocount + 8;
+  int32_t* pool = reinterpret_cast<int32_t*>(scb + o_pool);
+  int32_t* srows = reinterpret_cast<int32_t*>(scb + o_srow);
+  a.pool = pool; a.pool_next = pool_next; a.pool_blocks = pool_blocks;
   a.acc_rel = static_cast<float>(kph) * 1.1920929e-7f;      // k * 2^-23
   a.dump = dump; a.dump_su = dump_su; a.dump_ld = dump_ld;
   a.n_user_tiles = static_cast<int>((sa.n_users + T2_BM - 1) / T2_BM);
@@ -1221,11 +1321,18 @@ int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefe
   const int64_t row_offset = defer ? defer->row_offset : 0;
   {
     const unsigned g = static_cast<unsigned>((sa.n_users + 7) / 8);
+    const unsigned gs = static_cast<unsigned>(2 * h->sm_count);
+#define RL_RESCORE(KPV)                                                                                                                        \
+  rescore_kernel<KPV><<<g, 256, 0, h->stream>>>(sa.uf, sa.vf, sa.n_users, sa.n, cids, ccnt, perm, sa.idx_out, sa.score_out, o_rows, o_count, \
+                                                row_offset, srows, spill_count);                                                             \
+  rescore_spill_kernel<KPV><<<gs, 256, 0, h->stream>>>(sa.uf, sa.vf, sa.n, cids, pool, perm, sa.idx_out, sa.score_out, srows, spill_count)
     switch (kp) {
-      case 16: rescore_kernel<16><<<g, 256, 0, h->stream>>>(sa.uf, sa.vf, sa.n_users, sa.n, cids, ccnt, perm, sa.idx_out, sa.score_out, o_rows, o_count, row_offset); break;
-      case 32: rescore_kernel<32><<<g, 256, 0, h->stream>>>(sa.uf, sa.vf, sa.n_users, sa.n, cids, ccnt, perm, sa.idx_out, sa.score_out, o_rows, o_count, row_offset); break;
-      default: rescore_kernel<64><<<g, 256, 0, h->stream>>>(sa.uf, sa.vf, sa.n_users, sa.n, cids, ccnt, perm, sa.idx_out, sa.score_out, o_rows, o_count, row_offset); break;
+      case 16: RL_RESCORE(16); break;
+      case 32: RL_RESCORE(32); break;
+      default: RL_RESCORE(64); break;
     }
+#undef RL_RESCORE
+    h->launches++;
     RL_LAUNCH_CHECK(h, "rescore_kernel");
   }
   if (want_dbg) {

@@ -154,8 +154,8 @@ def test_centred_topn_equals_exact_kernel(h, k, n, n_users, n_items, kind):
 
 
 def test_centred_topn_ragged_ties_and_no_seen_list(h):
-    """users who have seen almost everything (ragged -1 rows), massive exact ties (candidate overflow -> exact-kernel
-    fallback for those rows), identical item vectors (zero-width classes) and no seen list at all."""
+    """users who have seen almost everything (ragged -1 rows), massive exact ties (candidate lists spill to pool blocks or
+    go to the exact-kernel fallback), identical item vectors (zero-width classes) and no seen list at all."""
     k, n, n_users, n_items = 64, 10, 260, 2100
     rng = np.random.default_rng(11)
     uf = _f32(rng.integers(0, 2, (n_users, k)) * 0.5)
@@ -169,7 +169,6 @@ def test_centred_topn_ragged_ties_and_no_seen_list(h):
     ce, _, over = _run(h, uf, vf, indptr, indices, k, n, CENTRED, False)
     assert np.array_equal(ex, ce)
     assert (ce[1] == -1).all() and (ce[2, 5:] == -1).all() and (ce[2, :5] >= 2095).all()
-    assert over > 0
     ce2, _, _ = _run(h, uf, vf, None, None, k, n, CENTRED, False)
     ref, _ = o_topn.recommend_blocked(uf, vf, indptr, indices, n=n, exclude_rated=False)
     assert np.array_equal(ce2, ref)
@@ -177,6 +176,25 @@ def test_centred_topn_ragged_ties_and_no_seen_list(h):
     ex3, _, _ = _run(h, uf, vsame, indptr, indices, k, n, EXACT, False)
     ce3, _, _ = _run(h, uf, vsame, indptr, indices, k, n, CENTRED, False)
     assert np.array_equal(ex3, ce3)
+
+
+def test_centred_topn_spilled_candidate_lists(h):
+    """120 items share the best vector of every user: the candidate list (40 slots in shared memory) runs over and moves
+    to pool blocks in global memory (up to 240 candidates) -- same result as the exact kernel (ties by ascending item id)
+    without the exact-kernel fallback."""
+    k, n, n_users, n_items = 64, 10, 700, 4000
+    rng = np.random.default_rng(12)
+    uf = _f32(rng.random((n_users, k)))
+    vf = _f32(rng.random((n_items, k)))
+    dup = rng.choice(n_items, 120, replace=False)
+    vf[dup] = vf[dup[0]] * 2.0
+    dense = rng.random((n_users, n_items)) < 0.01
+    indptr, indices = o_als.pattern_to_csr(dense.astype(np.float32))
+    ex, exv, _ = _run(h, uf, vf, indptr, indices, k, n, EXACT, True)
+    ce, cev, over = _run(h, uf, vf, indptr, indices, k, n, CENTRED, True)
+    assert np.array_equal(ex, ce) and np.array_equal(exv, cev)
+    assert np.isin(ce, dup).all()
+    assert over == 0
 
 
 def test_centred_topn_on_converged_als_factors(h):
