@@ -80,6 +80,11 @@ int rl_pinned_free(void* p);
 /* plain device memory helpers so a ctypes-only caller needs no other CUDA binding */
 int rl_dev_alloc(rl_handle h, int64_t bytes, void** out);
 int rl_dev_free(rl_handle h, void* p);
+/* the same from the device's stream-ordered pool (cudaMallocAsync / cudaFreeAsync on the handle's stream: no device
+ * synchronisation, freed blocks stay cached until rl_trim).  Buffers handed out by rl_als_fit_resident_host are of this
+ * kind.  Not for rl_ipc_export. */
+int rl_dev_alloc_async(rl_handle h, int64_t bytes, void** out);
+int rl_dev_free_async(rl_handle h, void* p);
 int rl_memcpy_h2d(rl_handle h, void* dst_dev, const void* src_host, int64_t bytes);
 int rl_memcpy_d2h(rl_handle h, void* dst_host, const void* src_dev, int64_t bytes);
 /* (rows x k) host float64/float32 -> (rows x rl_padded_k(k)) device float32 with zero padding, and back */
@@ -141,6 +146,26 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k,
                     const int64_t* indptr_t, const int32_t* indices_t,
                     int iterations, double lambda, int precision, int ir_steps,
                     void* user_f, void* item_f, int factor_dtype);
+/* The same fit with the model LEFT ON THE DEVICE (what RecommenderSystem.fit of the drop-in surface calls: the reference
+ * keeps its model in the object, algo.py:333-337, here it stays in HBM until somebody reads it).  user_f / item_f are
+ * only read.  dev_out[0..5] receive device pointers owned by the caller (release with rl_dev_free_async): U (n_users x
+ * padded k float32), V, indptr, indices, indptr_t, indices_t of the pattern.  The call returns when the uploads have
+ * left the host buffers; the kernels may still be running on the handle's stream. */
+int rl_als_fit_resident_host(rl_handle h, int64_t n_users, int64_t n_items, int k,
+                             const int64_t* indptr, const int32_t* indices,
+                             const int64_t* indptr_t, const int32_t* indices_t,
+                             int iterations, double lambda, int precision, int ir_steps,
+                             const void* user_f, const void* item_f, int factor_dtype, void** dev_out);
+
+/* Host-side validation of a CSR pattern before it is handed to the kernels (what scipy's has_canonical_format /
+ * data.min() checks cost 60 ms for at 50 M entries, single-threaded): bit 0 of *flags_out = every row strictly
+ * ascending with column indices in [0, n_cols) and indptr non-decreasing from 0; bit 1 = every stored value > 0
+ * (algo.py:311: only positive cells count as observed).  indptr_dtype / data_dtype: RL_I32, RL_I64, RL_F32, RL_F64;
+ * data may be NULL (bit 1 set).  Multi-threaded over row ranges (threads <= 0: all cores, at most 32). */
+#define RL_I32 2
+#define RL_I64 3
+int rl_csr_check_host(const void* indptr, int indptr_dtype, const int32_t* indices, const void* data, int data_dtype,
+                      int64_t n_rows, int64_t n_cols, int threads, int* flags_out);
 
 /* ---- fused scoring + masking + top-n: replaces predict (algo.py:143-147 `U @ V.T`, or _predict_svd
  *      algo.py:363-368 with the bias terms) followed by top_n (algo.py:533-659) inside recommend
@@ -179,6 +204,11 @@ int rl_recommend_host(rl_handle h, const void* user_f, const void* item_f, int f
                       const int64_t* seen_indptr, const int32_t* seen_indices,
                       double global_bias, const float* user_bias, const float* item_bias,
                       int n, int32_t* idx_out, double* score_out, int mode);
+/* recommend from a model that already sits in HBM (rl_als_fit_resident_host): users are scored in chunks and the top-n
+ * rows of chunk c travel to idx_out (host, pageable or pinned) while chunk c + 1 is scored. */
+int rl_recommend_resident_host(rl_handle h, const float* user_f_dev, int64_t n_users, const float* item_f_dev, int64_t n_items,
+                               int k, const int64_t* seen_indptr_dev, const int32_t* seen_indices_dev, int n, int32_t* idx_out,
+                               int mode);
 
 /* ---- standalone masked row top-n: replaces _top_n_numba / top_n, algo.py:533-659, on dense est / known.
  *      idx_out (n_users x n) int32 padded with -1; n_valid_out[u] = min(n, #items with known <= 0). */

@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RL_B200_LIB") or os.path.join(HERE, "librecsys_b200.so")   # RL_B200_LIB: kernel-variant experiments
 
-RL_F32, RL_F64 = 0, 1
+RL_F32, RL_F64, RL_I32, RL_I64 = 0, 1, 2, 3
 RL_PREC_FP32_IR, RL_PREC_FP64 = 0, 1
 RL_SCORE_AUTO, RL_SCORE_EXACT, RL_SCORE_TENSOR, RL_SCORE_TENSOR_TF32X1, RL_SCORE_TENSOR_CENTRED = 0, 1, 2, 3, 4
 ABI_VERSION = 1
@@ -34,6 +34,8 @@ SIGNATURES = {
     "rl_pinned_free": (_i32, [_vp]),
     "rl_dev_alloc": (_i32, [_vp, _i64, C.POINTER(_vp)]),
     "rl_dev_free": (_i32, [_vp, _vp]),
+    "rl_dev_alloc_async": (_i32, [_vp, _i64, C.POINTER(_vp)]),
+    "rl_dev_free_async": (_i32, [_vp, _vp]),
     "rl_memcpy_h2d": (_i32, [_vp, _vp, _vp, _i64]),
     "rl_memcpy_d2h": (_i32, [_vp, _vp, _vp, _i64]),
     "rl_factors_upload": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp]),
@@ -47,6 +49,9 @@ SIGNATURES = {
     "rl_gram_dev": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "rl_csr_transpose_dev": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "rl_als_fit_host": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _dbl, _i32, _i32, _vp, _vp, _i32]),
+    "rl_als_fit_resident_host": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _dbl, _i32, _i32, _vp, _vp, _i32, C.POINTER(_vp)]),
+    "rl_csr_check_host": (_i32, [_vp, _i32, _vp, _vp, _i32, _i64, _i64, _i32, C.POINTER(_i32)]),
+    "rl_recommend_resident_host": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _i32]),
     "rl_score_topn_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _dbl, _vp, _vp, _i32, _vp, _vp, _i32]),
     "rl_score_dump_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32]),
     "rl_score_dump_centred_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp]),

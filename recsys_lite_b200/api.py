@@ -91,20 +91,23 @@ def _finish_topn(idx, n_valid):
 
 
 class _DevBuf:
-    """One device allocation through the C ABI (rl_dev_alloc / rl_dev_free)."""
+    """One device allocation through the C ABI, from the stream-ordered pool (rl_dev_alloc_async / rl_dev_free_async:
+    no cudaMalloc / cudaFree and no device synchronisation per call); `adopt` takes over a pointer the library handed out."""
 
-    def __init__(self, h, nbytes: int):
+    def __init__(self, h, nbytes: int = 0, adopt=None):
         import ctypes as C
         self.h, self.nbytes = h, int(nbytes)
+        if adopt is not None:
+            self.ptr = C.c_void_p(adopt)
+            return
         p = C.c_void_p()
-        h.call("rl_dev_alloc", max(self.nbytes, 16), C.byref(p))
+        h.call("rl_dev_alloc_async", max(self.nbytes, 16), C.byref(p))
         self.ptr = p
 
     def free(self):
         if getattr(self, "ptr", None):
             try:
-                self.h.synchronize()
-                self.h.call("rl_dev_free", self.ptr)
+                self.h.call("rl_dev_free_async", self.ptr)
             except Exception:
                 pass
             self.ptr = None
@@ -117,13 +120,17 @@ class _ResidentALS:
     """ALS factors (float32, padded rows) and the training pattern kept in HBM between fit / recommend / predict, so that
     the drop-in surface moves the model over PCIe only when the caller asks for the NumPy arrays."""
 
-    def __init__(self, h, n_users, n_items, k):
+    def __init__(self, h, n_users, n_items, k, adopt=None):
         self.h, self.n_users, self.n_items, self.k = h, int(n_users), int(n_items), int(k)
         self.kp = h.lib.rl_padded_k(self.k)
-        self.u = _DevBuf(h, 4 * self.n_users * self.kp)
-        self.v = _DevBuf(h, 4 * self.n_items * self.kp)
         self.ip = self.ix = self.tp = self.tx = None
         self.pattern_key = None
+        self.min_row_nnz = None
+        if adopt is not None:       # the six buffers of rl_als_fit_resident_host
+            self.u, self.v, self.ip, self.ix, self.tp, self.tx = (_DevBuf(h, adopt=p) if p else None for p in adopt)
+            return
+        self.u = _DevBuf(h, 4 * self.n_users * self.kp)
+        self.v = _DevBuf(h, 4 * self.n_items * self.kp)
 
     @staticmethod
     def key_of(ratings, indptr, indices):
@@ -267,6 +274,8 @@ class RecommenderSystem:
             item_f = np.ascontiguousarray(init[1], dtype=None if np.asarray(init[1]).dtype == np.float32 else np.float64)
             if user_f.shape != (n_users, factors) or item_f.shape != (n_items, factors):
                 raise ValueError("init factors must have shapes (n_users, factors) and (n_items, factors)")
+        if item_f.dtype != user_f.dtype:           # one dtype for both in the C call
+            item_f = np.ascontiguousarray(item_f, dtype=user_f.dtype)
         tick = _Tick("fit_als")
         indptr, indices = observed_pattern(ratings)
         tick("pattern")
@@ -276,20 +285,22 @@ class RecommenderSystem:
             h = _ffi.default_handle()
             # The model stays in HBM (float32, padded rows): pattern and initial factors go up once, the transposed pattern
             # (users of every item) is built on the device, and nothing comes back until the caller reads the arrays.
-            res = _ResidentALS(h, n_users, n_items, factors)
+            # One call (rl_als_fit_resident_host): uploads on the copy stream underneath the first half-steps, the item-side
+            # pattern built on the device; it hands back the six device buffers of the model and its pattern.
+            import ctypes as C
+            dev = (C.c_void_p * 6)()
+            h.call("rl_als_fit_resident_host", n_users, n_items, factors, _ffi.ptr(indptr), _ffi.ptr(indices), None, None,
+                   int(iterations), float(lambda_), _PRECISIONS[precision], int(ir_steps), _ffi.ptr(user_f), _ffi.ptr(item_f),
+                   _rl_dtype(user_f), dev)
+            res = _ResidentALS(h, n_users, n_items, factors, adopt=[dev[i] for i in range(6)])
+            res.pattern_key = _ResidentALS.key_of(ratings, indptr, indices)
             try:
-                tick("alloc")
-                res.upload_pattern(indptr, indices, _ResidentALS.key_of(ratings, indptr, indices))
-                tick("pattern up")
-                res.upload_factors(user_f, item_f)
-                tick("factors up")
-                res.iterate(iterations, lambda_, _PRECISIONS[precision], ir_steps)
                 h.synchronize()
-                tick("iterate")
-                tick.done()
             except Exception:
                 res.free()
                 raise
+            tick("fit")
+            tick.done()
             self._resident = res
             return _LazyALSModel(self, factors)
         return {"user_factors": np.array(user_f, dtype=np.float64), "item_factors": np.array(item_f, dtype=np.float64),
@@ -474,11 +485,13 @@ class RecommenderSystem:
         ip = ix = None
         indptr = None
         tmp = []
+        reuse = False
         tick = _Tick("recommend")
         if exclude_rated:
             indptr, indices = observed_pattern(ratings)
             tick("pattern")
-            if res.pattern_key == _ResidentALS.key_of(ratings, indptr, indices):
+            reuse = res.pattern_key == _ResidentALS.key_of(ratings, indptr, indices)
+            if reuse:
                 ip, ix = res.ip, res.ix
             else:
                 ip, ix = _DevBuf(h, indptr.nbytes), _DevBuf(h, max(indices.nbytes, 16))
@@ -487,25 +500,25 @@ class RecommenderSystem:
                 if len(indices):
                     h.call("rl_memcpy_h2d", ix.ptr, _ffi.ptr(indices), indices.nbytes)
         idx = np.empty((n_users, n_dev), dtype=np.int32)
-        d_idx = _DevBuf(h, idx.nbytes)
-        tick("alloc")
         try:
-            h.call("rl_score_topn_dev", res.u.ptr, n_users, res.v.ptr, n_items, res.k, ip.ptr if ip else None,
-                   ix.ptr if ix else None, 0.0, None, None, n_dev, d_idx.ptr, None, _ffi.RL_SCORE_AUTO)
-            if _TIMING:
-                h.synchronize()
-            tick("score")
-            h.call("rl_memcpy_d2h", _ffi.ptr(idx), d_idx.ptr, idx.nbytes)
-            tick("d2h")
+            # scored in chunks, the rows of a chunk travel home underneath the next one
+            h.call("rl_recommend_resident_host", res.u.ptr, n_users, res.v.ptr, n_items, res.k, ip.ptr if ip else None,
+                   ix.ptr if ix else None, n_dev, _ffi.ptr(idx), _ffi.RL_SCORE_AUTO)
+            tick("score + d2h")
         finally:
-            d_idx.free()
             for b in tmp:
                 b.free()
-        tick("free")
         if not exclude_rated:
             return idx.astype(np.int64)
-        n_valid = np.minimum(n_dev, n_items - np.diff(indptr)).astype(np.int32)
-        out = _finish_topn(idx, n_valid)
+        # trimmed as the reference trims (algo.py:629-639): width = the most unseen items any row has, capped at n
+        if reuse and res.min_row_nnz is not None:
+            least = res.min_row_nnz
+        else:
+            least = int(np.diff(indptr).min()) if n_users else 0
+            if reuse:
+                res.min_row_nnz = least
+        widest = max(0, min(n_dev, n_items - least))
+        out = idx[:, :widest] if widest else np.empty((n_users, 0), dtype=int)
         tick("finish")
         tick.done()
         return out

@@ -2,6 +2,7 @@
 #include <cuda.h>
 #include <cstdarg>
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include <cmath>
@@ -95,6 +96,7 @@ struct DevBuf {
     return RL_OK;
   }
   template <typename T> T* as() { return static_cast<T*>(p); }
+  void* release() { void* q = p; p = nullptr; return q; }      // the caller of the C ABI owns it from here on
 };
 
 #define RL_TRY(expr)            \
@@ -469,10 +471,12 @@ int rl_gram_dev(rl_handle h, const float* y_dev, int64_t n, int k, double* gram_
   return launch_gram(h, y_dev, n, k, gram_dev);
 }
 
-int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const int64_t* indptr, const int32_t* indices,
-                    const int64_t* indptr_t, const int32_t* indices_t, int iterations, double lambda, int precision,
-                    int ir_steps, void* user_f, void* item_f, int factor_dtype) {
-  RL_NEED(h);
+namespace {
+// keep == nullptr: fitted factors go back to user_f / item_f.  keep != nullptr: nothing is downloaded, the six device
+// buffers of the model and its pattern are handed to the caller.
+int als_fit_host_impl(rl_handle h, int64_t n_users, int64_t n_items, int k, const int64_t* indptr, const int32_t* indices,
+                      const int64_t* indptr_t, const int32_t* indices_t, int iterations, double lambda, int precision,
+                      int ir_steps, void* user_f, void* item_f, int factor_dtype, void** keep) {
   const int kp = rl::padded_k(k);
   if (kp == 0) return fail(h, RL_ERR_INVALID, "rl_als_fit_host: k=%d outside [1, 128]", k);
   if (n_users < 0 || n_items < 0 || iterations < 0) return fail(h, RL_ERR_INVALID, "rl_als_fit_host: negative size");
@@ -497,28 +501,38 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const 
   RL_TRY(d_tx.alloc(h, sizeof(int32_t) * (nnz ? nnz : 1)));
   RL_TRY(d_u.alloc(h, sizeof(float) * (n_users ? n_users : 1) * kp));
   RL_TRY(d_v.alloc(h, sizeof(float) * (n_items ? n_items : 1) * kp));
+  // The first user half-step overwrites every row that has observations: when every row has some, the initial U is
+  // never read and its upload (the largest transfer of the call) is skipped.
+  bool any_empty = iterations == 0;
+  for (int64_t r = 0; r < n_users && !any_empty; ++r) any_empty = indptr[r + 1] == indptr[r];
   const bool lazy_u = iterations > 0 && n_users > 0;
   float* u_upload = d_u.as<float>();
-  if (lazy_u) {
+  if (lazy_u && any_empty) {
     RL_TRY(d_u0.alloc(h, sizeof(float) * n_users * kp));
     u_upload = d_u0.as<float>();
   }
   // Row ranges of the first user half-step: 1/8, 1/8, 1/4, 1/2 of the observations (large problems only), so that it
   // starts after an eighth of the index upload instead of all of it.
+  // ... from PAGEABLE host memory (what the Python surface passes) the upload is slower than the half-step and holds the
+  // host thread: eight equal parts, each launched as soon as it has gone up.
   int n_parts = 1;
-  int64_t part_row[5] = {0, n_users, n_users, n_users, n_users};
+  int64_t part_row[9] = {0, n_users, n_users, n_users, n_users, n_users, n_users, n_users, n_users};
   if (iterations > 0 && nnz >= (int64_t(1) << 22) && n_users >= 4096) {
-    const double frac[3] = {0.125, 0.25, 0.5};
-    n_parts = 4;
-    for (int c = 0; c < 3; ++c) {
-      const int64_t target = static_cast<int64_t>(frac[c] * static_cast<double>(nnz));
+    cudaPointerAttributes pa{};
+    const bool pinned = cudaPointerGetAttributes(&pa, indices) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const double frac4[3] = {0.125, 0.25, 0.5};
+    n_parts = pinned ? 4 : 8;
+    for (int c = 0; c + 1 < n_parts; ++c) {
+      const double f = pinned ? frac4[c] : (c + 1) / 8.0;
+      const int64_t target = static_cast<int64_t>(f * static_cast<double>(nnz));
       part_row[c + 1] = std::lower_bound(indptr, indptr + n_users + 1, target) - indptr;
       if (part_row[c + 1] > n_users) part_row[c + 1] = n_users;
       if (part_row[c + 1] < part_row[c]) part_row[c + 1] = part_row[c];
     }
-    part_row[4] = n_users;
+    part_row[n_parts] = n_users;
   }
-  Event ev_part[4];
+  Event ev_part[8];
   Event ev_alloc;
   RL_TRY(ev_alloc.record(h, ks));      // the buffers come from the stream-ordered pool on the compute stream
   RL_TRY(ev_alloc.wait(h, cs));
@@ -530,9 +544,20 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const 
       const int64_t o0 = indptr[part_row[c]], o1 = indptr[part_row[c + 1]];
       if (o1 > o0) RL_CUDA(h, cudaMemcpyAsync(d_ix.as<int32_t>() + o0, indices + o0, sizeof(int32_t) * (o1 - o0), cudaMemcpyHostToDevice, cs));
       RL_TRY(ev_part[c].record(h, cs));
+      if (iterations > 0 && n_parts > 1) {
+        // launched here, between the copies: a copy from PAGEABLE memory holds the host thread until its data has left, so
+        // kernels enqueued after the whole loop would start only when every part has gone up
+        RL_TRY(ev_part[c].wait(h, ks));
+        const int64_t r0 = part_row[c], r1 = part_row[c + 1];
+        if (r1 > r0) {
+          StreamScope on_compute(h, ks);
+          RL_TRY(launch_als_half_step(h, r1 - r0, n_items, k, d_ip.as<int64_t>() + r0, d_ix.as<int32_t>(), nullptr, nullptr,
+                                      d_v.as<float>(), d_u.as<float>() + r0 * kp, lambda, 0.0, nullptr, precision, ir_steps, nullptr));
+        }
+      }
     }
     RL_TRY(ev_user_ready.record(h, cs));
-    RL_TRY(factors_h2d(h, user_f, factor_dtype, n_users, k, u_upload, st_u));
+    if (any_empty) RL_TRY(factors_h2d(h, user_f, factor_dtype, n_users, k, u_upload, st_u));
     RL_TRY(ev_u0_ready.record(h, cs));
     if (!device_transpose) {
       RL_CUDA(h, cudaMemcpyAsync(d_tp.p, indptr_t, sizeof(int64_t) * (n_items + 1), cudaMemcpyHostToDevice, cs));
@@ -551,13 +576,7 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const 
   bool u_on_copy = false;
   for (int it = 0; it < iterations; ++it) {
     if (it == 0 && n_parts > 1) {
-      for (int c = 0; c < n_parts; ++c) {      // indptr holds absolute offsets: pass its window, keep the indices whole
-        RL_TRY(ev_part[c].wait(h, ks));
-        const int64_t r0 = part_row[c], r1 = part_row[c + 1];
-        if (r1 > r0)
-          RL_TRY(launch_als_half_step(h, r1 - r0, n_items, k, d_ip.as<int64_t>() + r0, d_ix.as<int32_t>(), nullptr, nullptr,
-                                      d_v.as<float>(), d_u.as<float>() + r0 * kp, lambda, 0.0, nullptr, precision, ir_steps, nullptr));
-      }
+      // (the row ranges of the first user half-step were launched between the uploads of their index parts, above)
     } else {
       RL_TRY(launch_als_half_step(h, n_users, n_items, k, d_ip.as<int64_t>(), d_ix.as<int32_t>(), nullptr, nullptr,
                                   d_v.as<float>(), d_u.as<float>(), lambda, 0.0, nullptr, precision, ir_steps, nullptr));
@@ -566,13 +585,13 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const 
       RL_TRY(ev_u0_ready.wait(h, ks));
       int64_t g = (n_users * (kp / 4) + 255) / 256;
       if (g > 8 * h->sm_count) g = 8 * h->sm_count;
-      if (g > 0) {                     // (no users: nothing to restore, and a grid of 0 blocks is an invalid launch)
+      if (g > 0 && any_empty) {        // (no users: nothing to restore, and a grid of 0 blocks is an invalid launch)
         fill_empty_rows_kernel<<<static_cast<unsigned>(g), 256, 0, ks>>>(d_ip.as<int64_t>(), n_users, kp, d_u0.as<float>(), d_u.as<float>());
         RL_LAUNCH_CHECK(h, "fill_empty_rows_kernel");
       }
       RL_TRY(ev_item_ready.wait(h, ks));
     }
-    if (it == iterations - 1) {        // U is final: send it home while the item half-step runs
+    if (it == iterations - 1 && !keep) {        // U is final: send it home while the item half-step runs
       RL_TRY(ev_u_done.record(h, ks));
       RL_TRY(ev_u_done.wait(h, cs));
       StreamScope on_copy(h, cs);
@@ -582,11 +601,52 @@ int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const 
     RL_TRY(launch_als_half_step(h, n_items, n_users, k, d_tp.as<int64_t>(), d_tx.as<int32_t>(), nullptr, nullptr,
                                 d_u.as<float>(), d_v.as<float>(), lambda, 0.0, nullptr, precision, ir_steps, nullptr));
   }
+  if (keep) {
+    // the host buffers have been read once the copy stream is idle; the kernels go on running on the compute stream
+    RL_CUDA(h, cudaStreamSynchronize(cs));
+    RL_TRY(ev_copy_done.record(h, h->aux_stream));       // the device-side transposition
+    RL_TRY(ev_copy_done.wait(h, ks));
+    keep[0] = d_u.release(); keep[1] = d_v.release(); keep[2] = d_ip.release();
+    keep[3] = d_ix.release(); keep[4] = d_tp.release(); keep[5] = d_tx.release();
+    return RL_OK;
+  }
   if (!u_on_copy) RL_TRY(factors_d2h(h, d_u.as<float>(), n_users, k, user_f, factor_dtype, st_ud));
   RL_TRY(factors_d2h(h, d_v.as<float>(), n_items, k, item_f, factor_dtype, st_vd));
   RL_TRY(ev_copy_done.record(h, cs));  // the buffers are freed on the compute stream: it has to see the copy stream's work
   RL_TRY(ev_copy_done.wait(h, ks));
   RL_CUDA(h, cudaStreamSynchronize(ks));
+  return RL_OK;
+}
+}  // namespace
+
+int rl_als_fit_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const int64_t* indptr, const int32_t* indices,
+                    const int64_t* indptr_t, const int32_t* indices_t, int iterations, double lambda, int precision,
+                    int ir_steps, void* user_f, void* item_f, int factor_dtype) {
+  RL_NEED(h);
+  return als_fit_host_impl(h, n_users, n_items, k, indptr, indices, indptr_t, indices_t, iterations, lambda, precision, ir_steps,
+                           user_f, item_f, factor_dtype, nullptr);
+}
+
+int rl_als_fit_resident_host(rl_handle h, int64_t n_users, int64_t n_items, int k, const int64_t* indptr, const int32_t* indices,
+                             const int64_t* indptr_t, const int32_t* indices_t, int iterations, double lambda, int precision,
+                             int ir_steps, const void* user_f, const void* item_f, int factor_dtype, void** dev_out) {
+  RL_NEED(h);
+  if (!dev_out) return fail(h, RL_ERR_INVALID, "rl_als_fit_resident_host: null dev_out");
+  for (int i = 0; i < 6; ++i) dev_out[i] = nullptr;
+  return als_fit_host_impl(h, n_users, n_items, k, indptr, indices, indptr_t, indices_t, iterations, lambda, precision, ir_steps,
+                           const_cast<void*>(user_f), const_cast<void*>(item_f), factor_dtype, dev_out);
+}
+
+int rl_dev_alloc_async(rl_handle h, int64_t bytes, void** out) {
+  RL_NEED(h);
+  if (!out || bytes < 0) return fail(h, RL_ERR_INVALID, "rl_dev_alloc_async: bad argument");
+  RL_CUDA(h, cudaMallocAsync(out, static_cast<size_t>(bytes ? bytes : 16), h->stream));
+  return RL_OK;
+}
+
+int rl_dev_free_async(rl_handle h, void* p) {
+  RL_NEED(h);
+  if (p) RL_CUDA(h, cudaFreeAsync(p, h->stream));
   return RL_OK;
 }
 
@@ -731,6 +791,145 @@ int rl_recommend_host(rl_handle h, const void* user_f, const void* item_f, int f
   RL_TRY(ev_copy_done.record(h, cs));
   RL_TRY(ev_copy_done.wait(h, ks));
   RL_CUDA(h, cudaStreamSynchronize(ks));
+  return RL_OK;
+}
+
+int rl_recommend_resident_host(rl_handle h, const float* user_f_dev, int64_t n_users, const float* item_f_dev, int64_t n_items, int k,
+                               const int64_t* seen_indptr_dev, const int32_t* seen_indices_dev, int n, int32_t* idx_out, int mode) {
+  RL_NEED(h);
+  const int kp = rl::padded_k(k);
+  if (kp == 0) return fail(h, RL_ERR_INVALID, "rl_recommend_resident_host: k=%d outside [1, 128]", k);
+  if (n <= 0) return fail(h, RL_ERR_INVALID, "rl_recommend_resident_host: n must be positive, got %d", n);
+  if (n_users < 0 || n_items < 0) return fail(h, RL_ERR_INVALID, "rl_recommend_resident_host: negative size");
+  if (n_users == 0) return RL_OK;
+  if (!user_f_dev || !item_f_dev || !idx_out) return fail(h, RL_ERR_INVALID, "rl_recommend_resident_host: null pointer");
+  if ((seen_indptr_dev == nullptr) != (seen_indices_dev == nullptr))
+    return fail(h, RL_ERR_INVALID, "rl_recommend_resident_host: pass both seen arrays or neither");
+  // chunks of whole kernel sweeps; the rows of chunk c go home on the copy stream while chunk c + 1 is scored
+  cudaStream_t cs = h->copy_stream, ks = h->stream;
+  const int64_t sweep = static_cast<int64_t>(128) * h->sm_count;
+  const int64_t n_sweeps = (n_users + sweep - 1) / sweep;
+  const int64_t per = n_sweeps >= 8 ? (n_sweeps + 3) / 4 : n_sweeps;
+  std::vector<int64_t> bound{0};
+  for (int64_t b = per * sweep; b < n_users; b += per * sweep) bound.push_back(b);
+  bound.push_back(n_users);
+  const int n_chunks = static_cast<int>(bound.size()) - 1;
+  std::vector<Event> done(n_chunks);
+  Event ev_copy_done;
+  DevBuf d_idx, d_over;
+  RL_TRY(d_idx.alloc(h, sizeof(int32_t) * n_users * n));
+  RL_TRY(d_over.alloc(h, 256 + sizeof(int32_t) * n_users));
+  RL_CUDA(h, cudaMemsetAsync(d_over.p, 0, 256, ks));
+  rl::ScoreDefer defer{reinterpret_cast<int32_t*>(static_cast<char*>(d_over.p) + 256), static_cast<unsigned int*>(d_over.p), 0};
+  unsigned int overflow_total = 0;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int64_t r0 = bound[c], r1 = bound[c + 1];
+    h->last_overflow = 0;
+    defer.row_offset = r0;
+    RL_TRY(launch_score_topn(h, user_f_dev + r0 * kp, r1 - r0, item_f_dev, n_items, k, seen_indptr_dev ? seen_indptr_dev + r0 : nullptr,
+                             seen_indices_dev, 0.0, nullptr, nullptr, n, d_idx.as<int32_t>() + r0 * n, nullptr, mode, &defer));
+    overflow_total += h->last_overflow;
+    RL_TRY(done[c].record(h, ks));
+    RL_TRY(done[c].wait(h, cs));
+    RL_CUDA(h, cudaMemcpyAsync(idx_out + r0 * n, d_idx.as<int32_t>() + r0 * n, sizeof(int32_t) * (r1 - r0) * n, cudaMemcpyDeviceToHost, cs));
+  }
+  unsigned int n_over = 0;
+  RL_CUDA(h, cudaMemcpyAsync(&n_over, defer.count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ks));
+  RL_CUDA(h, cudaStreamSynchronize(ks));
+  if (n_over > 0) {      // rows the tensor-core pass could not finish: one exact launch, then they travel again
+    RL_TRY(launch_score_overflow(h, user_f_dev, n_users, item_f_dev, n_items, k, seen_indptr_dev, seen_indices_dev, n, d_idx.as<int32_t>(),
+                                 nullptr, defer.rows, n_over));
+    std::vector<int32_t> rows(n_over <= 256 ? n_over : 0);
+    if (!rows.empty()) RL_CUDA(h, cudaMemcpyAsync(rows.data(), defer.rows, sizeof(int32_t) * n_over, cudaMemcpyDeviceToHost, ks));
+    RL_TRY(ev_copy_done.record(h, cs));
+    RL_TRY(ev_copy_done.wait(h, ks));
+    RL_CUDA(h, cudaStreamSynchronize(ks));
+    if (!rows.empty()) {
+      for (int32_t r : rows)
+        RL_CUDA(h, cudaMemcpyAsync(idx_out + static_cast<int64_t>(r) * n, d_idx.as<int32_t>() + static_cast<int64_t>(r) * n,
+                                   sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ks));
+    } else {
+      RL_CUDA(h, cudaMemcpyAsync(idx_out, d_idx.p, sizeof(int32_t) * n_users * n, cudaMemcpyDeviceToHost, ks));
+    }
+  }
+  h->last_overflow = overflow_total + n_over;
+  RL_TRY(ev_copy_done.record(h, cs));
+  RL_TRY(ev_copy_done.wait(h, ks));
+  RL_CUDA(h, cudaStreamSynchronize(ks));
+  return RL_OK;
+}
+
+// ---- host-side CSR validation (no device work) -------------------------------------------------------------------------
+extern "C++" {
+namespace {
+template <typename TP, typename TD>
+int csr_check_rows(const TP* indptr, const int32_t* indices, const TD* data, int64_t r0, int64_t r1, int64_t n_cols) {
+  int ok = 3;
+  for (int64_t r = r0; r < r1; ++r) {
+    const int64_t s = static_cast<int64_t>(indptr[r]), e = static_cast<int64_t>(indptr[r + 1]);
+    if (e < s) return 0;
+    int64_t prev = -1;
+    bool sorted = true, pos = true;
+    for (int64_t p = s; p < e; ++p) {
+      const int64_t c = indices[p];
+      sorted &= c > prev;
+      prev = c;
+      if (data) pos &= data[p] > TD(0);
+    }
+    if (!sorted || prev >= n_cols) ok &= ~1;
+    if (!pos) ok &= ~2;
+    if (ok == 0) return 0;
+  }
+  return ok;
+}
+template <typename TP>
+int csr_check_dispatch(const TP* indptr, const int32_t* indices, const void* data, int data_dtype, int64_t r0, int64_t r1, int64_t n_cols) {
+  switch (data_dtype) {
+    case RL_F32: return csr_check_rows(indptr, indices, static_cast<const float*>(data), r0, r1, n_cols);
+    case RL_F64: return csr_check_rows(indptr, indices, static_cast<const double*>(data), r0, r1, n_cols);
+    case RL_I32: return csr_check_rows(indptr, indices, static_cast<const int32_t*>(data), r0, r1, n_cols);
+    default: return csr_check_rows(indptr, indices, static_cast<const int64_t*>(data), r0, r1, n_cols);
+  }
+}
+}  // namespace
+}  // extern "C++"
+
+int rl_csr_check_host(const void* indptr, int indptr_dtype, const int32_t* indices, const void* data, int data_dtype, int64_t n_rows,
+                      int64_t n_cols, int threads, int* flags_out) {
+  if (!indptr || !flags_out || n_rows < 0 || n_cols < 0) return fail(nullptr, RL_ERR_INVALID, "rl_csr_check_host: bad argument");
+  if ((indptr_dtype != RL_I32 && indptr_dtype != RL_I64) || (data && (data_dtype < RL_F32 || data_dtype > RL_I64)))
+    return fail(nullptr, RL_ERR_INVALID, "rl_csr_check_host: bad dtype");
+  const auto at = [&](int64_t r) -> int64_t {
+    return indptr_dtype == RL_I32 ? static_cast<const int32_t*>(indptr)[r] : static_cast<const int64_t*>(indptr)[r];
+  };
+  *flags_out = 0;
+  if (at(0) != 0) return RL_OK;
+  const int64_t nnz = at(n_rows);
+  if (nnz > 0 && !indices) return fail(nullptr, RL_ERR_INVALID, "rl_csr_check_host: null indices");
+  int nt = threads > 0 ? threads : static_cast<int>(std::thread::hardware_concurrency());
+  nt = std::max(1, std::min(nt, 32));
+  if (nnz < (int64_t(1) << 20)) nt = 1;
+  std::vector<int> part(nt, 3);
+  std::vector<int64_t> cut(nt + 1, n_rows);
+  cut[0] = 0;
+  for (int t = 1; t < nt; ++t) {       // row ranges with about the same number of entries
+    const int64_t target = nnz / nt * t;
+    int64_t lo = cut[t - 1], hi = n_rows;
+    while (lo < hi) { const int64_t mid = lo + (hi - lo) / 2; if (at(mid) < target) lo = mid + 1; else hi = mid; }
+    cut[t] = lo;
+  }
+  const auto work = [&](int t) {
+    part[t] = indptr_dtype == RL_I32
+                  ? csr_check_dispatch(static_cast<const int32_t*>(indptr), indices, data, data_dtype, cut[t], cut[t + 1], n_cols)
+                  : csr_check_dispatch(static_cast<const int64_t*>(indptr), indices, data, data_dtype, cut[t], cut[t + 1], n_cols);
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+  int ok = 3;
+  for (int t = 0; t < nt; ++t) ok &= part[t];
+  *flags_out = ok;
   return RL_OK;
 }
 

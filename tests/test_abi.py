@@ -139,3 +139,50 @@ def test_csr_helpers():
     lo, hi = int(bounds[1]), int(bounds[2])
     sp, sx = csr.shard_rows(a[0], a[1], lo, hi)
     assert sp[0] == 0 and sp[-1] == len(sx) and np.array_equal(sx, a[1][a[0][lo]:a[0][hi]])
+
+
+def test_csr_check_host_and_fast_pattern_path(lib):
+    """rl_csr_check_host (multi-threaded host validation, no device): bit 0 = canonical rows (strictly ascending, in range),
+    bit 1 = all stored values > 0; observed_pattern takes scipy's arrays as they are only when both hold and returns what
+    the scipy route returns otherwise (algo.py:311 semantics)."""
+    import ctypes as C
+    from scipy import sparse
+    from recsys_lite_b200 import csr, _ffi
+    from oracle import generators as gen
+
+    def flags(m, threads=0):
+        f = C.c_int(-1)
+        rc = lib.rl_csr_check_host(_ffi.ptr(m.indptr), csr._DT[m.indptr.dtype], _ffi.ptr(m.indices), _ffi.ptr(m.data),
+                                   csr._DT[m.data.dtype], m.shape[0], m.shape[1], threads, C.byref(f))
+        assert rc == 0
+        return f.value
+
+    indptr, indices = gen.synth_pattern(40000, 3000, mean_deg=40, seed=3)      # > 2^20 entries: the threaded path
+    for dt in (np.float32, np.float64, np.int32, np.int64):
+        m = sparse.csr_matrix((np.ones(len(indices), dt), indices, indptr), shape=(40000, 3000))
+        assert flags(m) == 3 and flags(m, 1) == 3 and flags(m, 5) == 3
+    m = sparse.csr_matrix((np.ones(len(indices), np.float32), indices.copy(), indptr), shape=(40000, 3000))
+    fast = csr.observed_pattern(m)
+    assert fast[1] is m.indices or np.shares_memory(fast[1], m.indices)     # no copy of the 4 nnz bytes
+    assert np.array_equal(fast[0], indptr) and fast[0].dtype == np.int64
+    row = 31234
+    s, e = indptr[row], indptr[row + 1]
+    m.data[s + 1] = -1.0                                                     # a negative value: bit 1 drops
+    assert flags(m) == 1
+    got = csr.observed_pattern(m)
+    keep = np.ones(len(indices), bool); keep[s + 1] = False
+    assert np.array_equal(got[1], indices[keep]) and got[0][-1] == len(indices) - 1
+    m.data[s + 1] = 1.0
+    m.indices[s], m.indices[s + 1] = m.indices[s + 1], m.indices[s]         # unsorted row: bit 0 drops
+    assert flags(m) == 2
+    m.has_sorted_indices = False
+    got = csr.observed_pattern(m)
+    assert np.array_equal(got[0], indptr) and np.array_equal(got[1], indices)
+    m2 = sparse.csr_matrix((np.ones(len(indices), np.float32), indices, indptr), shape=(40000, 3000))
+    m2.indices = m2.indices.copy()
+    m2.indices[e - 1] = 3000                                                # column out of range
+    assert flags(m2) == 2
+    m2.indices[e - 1] = m2.indices[e - 2]                                   # duplicate column
+    assert flags(m2) == 2
+    empty = sparse.csr_matrix((5, 7), dtype=np.float32)
+    assert flags(empty) == 3
