@@ -6,7 +6,7 @@ masked top-N, observed-entry RMSE).  It exists so the CUDA path can be checked
 bit-for-bit / within the stated fp tolerance on machines where ``/root/reference``
 is not present (the GPU box).
 
-Rules (enforced by tests/test_layout.py):
+Rules (enforced by tests/test_abi.py::test_product_never_imports_oracle):
   * only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
     ``--impl reference`` legs may import this package;
   * nothing under ``recsys_lite_b200/`` imports it -- the product path has no CPU

@@ -264,30 +264,43 @@ __device__ __forceinline__ void k64_forward(float* __restrict__ Lt, float* __res
   for (int J = 4; J < 8; ++J) k64_panel<false, false>(Lt, invd, bs, J, lane);
 }
 
-// v <- L^-T v   (v0: entry l, v1: entry l + 32), row i of the factor read across the lanes
+// v <- L^-T v   (v0: entry l, v1: entry l + 32), row i of the factor read across the lanes.
+// Step i: x_i = w_i / L_ii, then w_j -= L_ij x_i for j < i.  Lane i's entry is final (as w_i) from step i on, so the
+// division is left to the end (one multiply per lane instead of a select per step) and the updates are predicated on
+// j < i (the storage above the diagonal holds junk).  Blocks of eight rows: the swizzle bit of row i is a constant of the
+// unrolled body.
 __device__ __forceinline__ void k64_backward(const float* __restrict__ Lt, const float* __restrict__ invd, float& v0, float& v1, int lane) {
   const float* c0 = Lt + k64_pb0(lane >> 3);            // L[i][l]      = c0[8 i + ((l & 7) ^ swz(i))]
   const float* c1 = Lt + k64_pb0(4 + (lane >> 3));      // L[i][l + 32] = c1[8 i + ((l & 7) ^ swz(i))]
   const int q0 = lane & 7, q1 = q0 ^ 4;
-  const float* c0a = c0 + q0; const float* c0b = c0 + q1;   // rows with swizzle bit 0 / 1
-  const float* c1a = c1 + q0; const float* c1b = c1 + q1;
   const float inv0 = invd[lane], inv1 = invd[32 + lane];
-#pragma unroll 8
-  for (int i = 63; i >= 32; --i) {
-    const float xi = __shfl_sync(FULL_MASK, v1 * inv1, i - 32);     // the owner lane's product is the one that counts
-    const float l1 = (i & 4) ? c1b[8 * i] : c1a[8 * i];
-    const float l0 = (i & 4) ? c0b[8 * i] : c0a[8 * i];
-    const float upd = fmaf(-l1, xi, v1);
-    v1 = (lane < i - 32) ? upd : ((lane == i - 32) ? xi : v1);
-    v0 = fmaf(-l0, xi, v0);
+#pragma unroll 1
+  for (int b = 7; b >= 4; --b) {
+    const float* r1 = c1 + 64 * b;
+    const float* r0 = c0 + 64 * b;
+#pragma unroll
+    for (int r = 7; r >= 0; --r) {
+      const int i = 8 * b + r;
+      const float xi = __shfl_sync(FULL_MASK, v1 * inv1, i - 32);     // the owner lane's product is the one that counts
+      const float l1 = r1[8 * r + ((r & 4) ? q1 : q0)];
+      const float l0 = r0[8 * r + ((r & 4) ? q1 : q0)];
+      if (lane < i - 32) v1 = fmaf(-l1, xi, v1);
+      v0 = fmaf(-l0, xi, v0);
+    }
   }
-#pragma unroll 8
-  for (int i = 31; i >= 0; --i) {
-    const float xi = __shfl_sync(FULL_MASK, v0 * inv0, i);
-    const float l0 = (i & 4) ? c0b[8 * i] : c0a[8 * i];             // lanes >= i read below their panel: finite junk, not used
-    const float upd = fmaf(-l0, xi, v0);
-    v0 = (lane < i) ? upd : ((lane == i) ? xi : v0);
+#pragma unroll 1
+  for (int b = 3; b >= 0; --b) {
+    const float* r0 = c0 + 64 * b;
+#pragma unroll
+    for (int r = 7; r >= 0; --r) {
+      const int i = 8 * b + r;
+      const float xi = __shfl_sync(FULL_MASK, v0 * inv0, i);
+      const float l0 = r0[8 * r + ((r & 4) ? q1 : q0)];               // lanes >= i read below their panel: finite junk, not used
+      if (lane < i) v0 = fmaf(-l0, xi, v0);
+    }
   }
+  v0 *= inv0;
+  v1 *= inv1;
 }
 
 // rows longer than this are solved by a whole CTA (als_k64_kernel<.., K64_COOP_WARPS>) instead of one warp: on power-law
