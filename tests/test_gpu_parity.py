@@ -329,6 +329,64 @@ def test_host_entry_points_large_call_partitions_equal_device_path(h):
     assert np.array_equal(idx, d_idx.get())
 
 
+@pytest.mark.parametrize("empty_rows", [False, True])
+def test_resident_fit_and_recommend_equal_device_path(h, empty_rows):
+    """rl_als_fit_resident_host (pageable inputs: eight index parts, each range of the first user half-step launched
+    between the uploads; the initial U only travels when some row has no observation) leaves the same bits in HBM as the
+    plain device calls, hands out the six buffers, and rl_recommend_resident_host (chunked, results travelling underneath
+    the next chunk) returns what rl_score_topn_dev returns."""
+    import ctypes as C
+    from devbuf import Dev, padded, unpadded
+    from recsys_lite_b200 import _ffi
+    n_users, n_items, k, n = 320_000, 2_000, 64, 10
+    indptr, indices = gen.synth_pattern(n_users, n_items, mean_deg=14, seed=6)
+    if empty_rows:                                   # users 7 and 300000 lose their observations
+        keep = np.ones(len(indices), bool)
+        for r in (7, 300_000):
+            keep[indptr[r]:indptr[r + 1]] = False
+        cnt = np.diff(indptr)
+        cnt[[7, 300_000]] = 0
+        indices = np.ascontiguousarray(indices[keep])
+        indptr = np.concatenate(([0], np.cumsum(cnt))).astype(np.int64)
+    assert indptr[-1] >= 1 << 22
+    rng = np.random.default_rng(6)
+    u0 = rng.random((n_users, k), dtype=np.float32)
+    v0 = rng.random((n_items, k), dtype=np.float32)
+    dev = (C.c_void_p * 6)()
+    h.call("rl_als_fit_resident_host", n_users, n_items, k, _ffi.ptr(indptr), _ffi.ptr(indices), None, None, 2, 0.01, 0, 1,
+           _ffi.ptr(u0), _ffi.ptr(v0), _ffi.RL_F32, dev)
+    h.synchronize()
+    assert all(dev[i] for i in range(6))
+    ti, tx = o_als.transpose_pattern(indptr, indices, n_items)
+    d_u, d_v = padded(h, u0, k), padded(h, v0, k)
+    d_ip, d_ix, d_tp, d_tx = Dev(h, indptr), Dev(h, indices), Dev(h, ti), Dev(h, tx)
+    for _ in range(2):
+        h.call("rl_als_half_step_dev", n_users, n_items, k, d_ip.ptr, d_ix.ptr, None, None, d_v.ptr, d_u.ptr, 0.01, 0.0, None, 0, 1, None)
+        h.call("rl_als_half_step_dev", n_items, n_users, k, d_tp.ptr, d_tx.ptr, None, None, d_u.ptr, d_v.ptr, 0.01, 0.0, None, 0, 1, None)
+    want_u, want_v = unpadded(h, d_u, k, np.float32), unpadded(h, d_v, k, np.float32)
+    got_u = np.empty((n_users, k), np.float32)
+    got_v = np.empty((n_items, k), np.float32)
+    h.call("rl_factors_download", C.c_void_p(dev[0]), n_users, k, _ffi.ptr(got_u), _ffi.RL_F32)
+    h.call("rl_factors_download", C.c_void_p(dev[1]), n_items, k, _ffi.ptr(got_v), _ffi.RL_F32)
+    assert np.array_equal(got_u, want_u) and np.array_equal(got_v, want_v)
+    if empty_rows:
+        assert np.array_equal(got_u[7], u0[7]) and np.array_equal(got_u[300_000], u0[300_000])   # algo.py:316-317
+    got_tp = np.empty(n_items + 1, np.int64)
+    got_tx = np.empty(len(indices), np.int32)
+    h.call("rl_memcpy_d2h", _ffi.ptr(got_tp), C.c_void_p(dev[4]), got_tp.nbytes)
+    h.call("rl_memcpy_d2h", _ffi.ptr(got_tx), C.c_void_p(dev[5]), got_tx.nbytes)
+    assert np.array_equal(got_tp, ti) and np.array_equal(got_tx, tx)
+    idx = np.empty((n_users, n), np.int32)
+    h.call("rl_recommend_resident_host", C.c_void_p(dev[0]), n_users, C.c_void_p(dev[1]), n_items, k, C.c_void_p(dev[2]),
+           C.c_void_p(dev[3]), n, _ffi.ptr(idx), 0)
+    d_idx = Dev(h, shape=(n_users, n), dtype=np.int32)
+    h.call("rl_score_topn_dev", d_u.ptr, n_users, d_v.ptr, n_items, k, d_ip.ptr, d_ix.ptr, 0.0, None, None, n, d_idx.ptr, None, 0)
+    assert np.array_equal(idx, d_idx.get())
+    for i in range(6):
+        h.call("rl_dev_free_async", C.c_void_p(dev[i]))
+    h.synchronize()
+
+
 @pytest.mark.parametrize("case", ["lit", "order", "ragged", "rand_f64", "rand_f32"])
 def test_top_n_api_matches_reference_golden(golden_dir, case):
     """top_n(est, known, n) vs the reference's output (algo.py:587-659): shape, dtype, indices up to ties."""
