@@ -88,6 +88,37 @@ def test_half_step_dev_vs_oracle(h, k, precision):
     assert not raw[:, k:].any()
 
 
+@pytest.mark.parametrize("k", [72, 128])
+def test_half_step_k128_dual_and_primal_rows(h, k):
+    """64 < k <= 128: rows with at most 64 observations are solved in the dual form x = Y^T (Y Y^T + lambda I)^-1 1
+    (als_k128_dual_kernel), longer rows by the 128 x 128 normal equations (als_k128_kernel); both against the oracle
+    (algo.py:314-322) on one pattern that mixes 1 .. 300 observations per row, rows of exactly 64 / 65 and empty rows."""
+    from devbuf import Dev, padded, unpadded
+    n_rows, n_other = 900, 400
+    rng = np.random.default_rng(100 + k)
+    deg = rng.integers(1, 301, n_rows)
+    deg[:6] = [0, 1, 64, 65, 63, 0]
+    deg[rng.choice(np.arange(6, n_rows), 500, replace=False)] = rng.integers(1, 65, 500)   # most rows short, as on the C5 user side
+    rows = [np.sort(rng.choice(n_other, d, replace=False)).astype(np.int32) for d in deg]
+    indptr = np.concatenate(([0], np.cumsum(deg))).astype(np.int64)
+    indices = np.concatenate(rows).astype(np.int32)
+    other = rng.random((n_other, k))
+    mine0 = rng.random((n_rows, k))
+    ref = o_als.half_step_csr(indptr, indices, _f32(other), _f32(mine0).copy(), 0.01)
+    d_other, d_mine = padded(h, other, k), padded(h, mine0, k)
+    d_ip, d_ix = Dev(h, indptr), Dev(h, indices)
+    for ir in (1, 2):
+        h.call("rl_als_half_step_dev", n_rows, n_other, k, d_ip.ptr, d_ix.ptr, None, None, d_other.ptr, d_mine.ptr,
+               0.01, 0.0, None, 0, ir, None)
+        got = unpadded(h, d_mine, k)
+        short = (deg > 0) & (deg <= 64)
+        for name, sel in (("dual", short), ("primal", deg > 64)):
+            fro, mx = compare.factor_error(got[sel], ref[sel])
+            assert fro <= (2e-6 if ir == 2 else 5e-5) and mx <= (2e-5 if ir == 2 else 5e-4), (name, ir, fro, mx)
+        assert np.array_equal(got[[0, 5]], _f32(mine0)[[0, 5]])
+        assert not d_mine.get()[:, k:].any()
+
+
 def test_half_step_long_and_skewed_rows(h, monkeypatch):
     """item-side shape: few rows with hundreds..thousands of observations (chunked gather, many chunks)."""
     from devbuf import Dev, padded, unpadded
