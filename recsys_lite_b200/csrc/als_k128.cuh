@@ -85,6 +85,9 @@ __device__ __forceinline__ void k128_dual_row(const AlsArgs& a, int64_t row, int
   cp_async_wait<0>();
   __syncthreads();
   // ---- G = Y Y^T: A(m = observation, k = factor) and B = A^T, so the B fragment of n-tile nj is an A register ----
+  // only the leading 8 nblk rows / columns carry observations: the rest of G is an identity block that is neither
+  // accumulated (16-row tile groups) nor factored (8-column panels)
+  const int nblk = (nnz + 7) >> 3, mtiles = (nnz + 15) >> 4;
   float acc[20][4];
 #pragma unroll
   for (int t = 0; t < 20; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
@@ -94,6 +97,7 @@ __device__ __forceinline__ void k128_dual_row(const AlsArgs& a, int64_t row, int
     uint32_t hi[4][2], lo[4][2];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
+      if (mi >= mtiles) { hi[mi][0] = hi[mi][1] = lo[mi][0] = lo[mi][1] = 0u; continue; }
       const float2 y0 = *reinterpret_cast<const float2*>(yk + (16 * mi + g) * LDD);
       const float2 y1 = *reinterpret_cast<const float2*>(yk + (16 * mi + 8 + g) * LDD);
       k64_split_h2(y0.x * ysc, y0.y * ysc, hi[mi][0], lo[mi][0]);
@@ -101,16 +105,22 @@ __device__ __forceinline__ void k128_dual_row(const AlsArgs& a, int64_t row, int
     }
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
+      if (mi < mtiles) {
 #pragma unroll
-      for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], hi[mi][0], hi[mi][1], hi[nj >> 1][nj & 1]);
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-      for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], hi[mi][0], hi[mi][1], lo[nj >> 1][nj & 1]);
+        for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], hi[mi][0], hi[mi][1], hi[nj >> 1][nj & 1]);
+      }
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
+      if (mi < mtiles) {
 #pragma unroll
-      for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], lo[mi][0], lo[mi][1], hi[nj >> 1][nj & 1]);
+        for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], hi[mi][0], hi[mi][1], lo[nj >> 1][nj & 1]);
+      }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+      if (mi < mtiles) {
+#pragma unroll
+        for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], lo[mi][0], lo[mi][1], hi[nj >> 1][nj & 1]);
+      }
   }
   // ---- partial tiles -> panel storage, warp after warp (fixed order); warp 0 brings the diagonal ----
   {
@@ -139,14 +149,14 @@ __device__ __forceinline__ void k128_dual_row(const AlsArgs& a, int64_t row, int
       __syncthreads();
     }
   }
-  if (warp == 0) k64_chol(Lt, invd, bs, lane);
+  if (warp == 0) k64_chol(Lt, invd, bs, lane, nblk);
   // ---- z = L^-T L^-1 rhs, refinement, x = Y^T z ----
   double zd0 = 0.0, zd1 = 0.0;
   for (int it = 0;; ++it) {
     if (warp == 0) {
       float v0 = bs[lane], v1 = bs[32 + lane];
       __syncwarp();
-      k64_backward(Lt, invd, v0, v1, lane);
+      k64_backward(Lt, invd, v0, v1, lane, nblk);
       zd0 += static_cast<double>(v0);
       zd1 += static_cast<double>(v1);
       zs[lane] = zd0;
@@ -180,7 +190,7 @@ __device__ __forceinline__ void k128_dual_row(const AlsArgs& a, int64_t row, int
       }
     }
     __syncthreads();
-    if (warp == 0) k64_forward(Lt, invd, bs, lane);
+    if (warp == 0) k64_forward(Lt, invd, bs, lane, nblk);
   }
 }
 

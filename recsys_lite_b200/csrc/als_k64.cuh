@@ -219,13 +219,14 @@ __device__ __forceinline__ void k64_update(float (&d)[4][4], const float* __rest
 // Blocked left-looking Cholesky, in place in the panel storage (which holds A on entry, written there from the Gram
 // accumulators); L -> Lt, 1 / L_jj -> invd, and bs <- L^-1 bs on the way.  One copy of the code for all block columns
 // (the kernel is instruction-cache bound otherwise: every warp of an SM is in a different phase).
-__device__ __forceinline__ void k64_chol(float* __restrict__ Lt, float* __restrict__ invd, float* __restrict__ bs, int lane) {
+// nblk < 8: only the leading 8 nblk columns are factored (callers whose trailing rows / columns are an identity block).
+__device__ __forceinline__ void k64_chol(float* __restrict__ Lt, float* __restrict__ invd, float* __restrict__ bs, int lane, int nblk = 8) {
   const int g = lane >> 2, tq = lane & 3;
   const int sg = ((g >> 2) & 1) << 2;          // swizzle bit of rows 8 m + g
   const int o0 = tq ^ sg, o1 = o0 ^ 4;         // physical positions of panel columns tq and tq + 4 in such a row
   const int oc = (2 * tq) ^ sg;                // ... of the accumulator columns 2 tq, 2 tq + 1
 #pragma unroll 1
-  for (int J = 0; J < 8; ++J) {
+  for (int J = 0; J < nblk; ++J) {
     float* pj = Lt + k64_pb0(J);
     const int m0 = J >> 1;
     float d[4][4];
@@ -257,11 +258,11 @@ __device__ __forceinline__ void k64_chol(float* __restrict__ Lt, float* __restri
 }
 
 // bs <- L^-1 bs with the stored factor (the sweep of k64_panel with the rows loaded instead of computed)
-__device__ __forceinline__ void k64_forward(float* __restrict__ Lt, float* __restrict__ invd, float* __restrict__ bs, int lane) {
+__device__ __forceinline__ void k64_forward(float* __restrict__ Lt, float* __restrict__ invd, float* __restrict__ bs, int lane, int nblk = 8) {
 #pragma unroll 1
-  for (int J = 0; J < 4; ++J) k64_panel<true, false>(Lt, invd, bs, J, lane);
+  for (int J = 0; J < 4 && J < nblk; ++J) k64_panel<true, false>(Lt, invd, bs, J, lane);
 #pragma unroll 1
-  for (int J = 4; J < 8; ++J) k64_panel<false, false>(Lt, invd, bs, J, lane);
+  for (int J = 4; J < nblk; ++J) k64_panel<false, false>(Lt, invd, bs, J, lane);
 }
 
 // v <- L^-T v   (v0: entry l, v1: entry l + 32), row i of the factor read across the lanes.
@@ -269,13 +270,15 @@ __device__ __forceinline__ void k64_forward(float* __restrict__ Lt, float* __res
 // division is left to the end (one multiply per lane instead of a select per step) and the updates are predicated on
 // j < i (the storage above the diagonal holds junk).  Blocks of eight rows: the swizzle bit of row i is a constant of the
 // unrolled body.
-__device__ __forceinline__ void k64_backward(const float* __restrict__ Lt, const float* __restrict__ invd, float& v0, float& v1, int lane) {
+// nblk < 8: entries from 8 nblk on are taken as zero (not read) and returned as zero.
+__device__ __forceinline__ void k64_backward(const float* __restrict__ Lt, const float* __restrict__ invd, float& v0, float& v1, int lane,
+                                             int nblk = 8) {
   const float* c0 = Lt + k64_pb0(lane >> 3);            // L[i][l]      = c0[8 i + ((l & 7) ^ swz(i))]
   const float* c1 = Lt + k64_pb0(4 + (lane >> 3));      // L[i][l + 32] = c1[8 i + ((l & 7) ^ swz(i))]
   const int q0 = lane & 7, q1 = q0 ^ 4;
-  const float inv0 = invd[lane], inv1 = invd[32 + lane];
+  const float inv0 = lane < 8 * nblk ? invd[lane] : 0.f, inv1 = 32 + lane < 8 * nblk ? invd[32 + lane] : 0.f;
 #pragma unroll 1
-  for (int b = 7; b >= 4; --b) {
+  for (int b = nblk - 1; b >= 4; --b) {
     const float* r1 = c1 + 64 * b;
     const float* r0 = c0 + 64 * b;
 #pragma unroll
@@ -289,7 +292,7 @@ __device__ __forceinline__ void k64_backward(const float* __restrict__ Lt, const
     }
   }
 #pragma unroll 1
-  for (int b = 3; b >= 0; --b) {
+  for (int b = min(nblk - 1, 3); b >= 0; --b) {
     const float* r0 = c0 + 64 * b;
 #pragma unroll
     for (int r = 7; r >= 0; --r) {
