@@ -119,6 +119,13 @@ struct StreamScope {
   ~StreamScope() { h->stream = saved; }
 };
 
+// the chunks of one host-wrapper call score against the same V: its preprocessing (score_tc2.cu) is done once
+struct PrepScope {
+  rl_context* h;
+  explicit PrepScope(rl_context* ctx) : h(ctx) { h->tc2_prep_state = 1; }
+  ~PrepScope() { h->tc2_prep_state = 0; }
+};
+
 struct Event {  // ordering between the handle's compute and copy streams
   cudaEvent_t e = nullptr;
   ~Event() { if (e) cudaEventDestroy(e); }
@@ -707,7 +714,7 @@ int rl_recommend_host(rl_handle h, const void* user_f, const void* item_f, int f
   if (n_sweeps >= 16) {
     bound.push_back(2 * sweep);
     bound.push_back(8 * sweep);
-    const int64_t rest = n_sweeps - 8, per3 = (rest + 2) / 3;
+    const int64_t rest = n_sweeps - 8, per3 = ((rest + 5) / 6) * 2;      // even: the centred kernel takes user tiles in pairs
     for (int c = 1; c <= 2; ++c) bound.push_back((8 + c * per3) * sweep);
   } else if (n_sweeps >= 2) {
     const int64_t per4 = (n_sweeps + 3) / 4;
@@ -744,6 +751,7 @@ int rl_recommend_host(rl_handle h, const void* user_f, const void* item_f, int f
   RL_CUDA(h, cudaMemsetAsync(d_over.p, 0, 256, ks));
   rl::ScoreDefer defer{reinterpret_cast<int32_t*>(static_cast<char*>(d_over.p) + 256), static_cast<unsigned int*>(d_over.p), 0};
   unsigned int overflow_total = 0;
+  PrepScope prep(h);
   for (int c = 0; c < n_chunks; ++c) {
     const int64_t r0 = bound[c], r1 = bound[c + 1];
     RL_TRY(ready[c].wait(h, ks));
@@ -809,7 +817,7 @@ int rl_recommend_resident_host(rl_handle h, const float* user_f_dev, int64_t n_u
   cudaStream_t cs = h->copy_stream, ks = h->stream;
   const int64_t sweep = static_cast<int64_t>(128) * h->sm_count;
   const int64_t n_sweeps = (n_users + sweep - 1) / sweep;
-  const int64_t per = n_sweeps >= 8 ? (n_sweeps + 3) / 4 : n_sweeps;
+  const int64_t per = n_sweeps >= 8 ? ((n_sweeps + 7) / 8) * 2 : n_sweeps;      // even: the centred kernel takes user tiles in pairs
   std::vector<int64_t> bound{0};
   for (int64_t b = per * sweep; b < n_users; b += per * sweep) bound.push_back(b);
   bound.push_back(n_users);
@@ -822,6 +830,7 @@ int rl_recommend_resident_host(rl_handle h, const float* user_f_dev, int64_t n_u
   RL_CUDA(h, cudaMemsetAsync(d_over.p, 0, 256, ks));
   rl::ScoreDefer defer{reinterpret_cast<int32_t*>(static_cast<char*>(d_over.p) + 256), static_cast<unsigned int*>(d_over.p), 0};
   unsigned int overflow_total = 0;
+  PrepScope prep(h);
   for (int c = 0; c < n_chunks; ++c) {
     const int64_t r0 = bound[c], r1 = bound[c + 1];
     h->last_overflow = 0;

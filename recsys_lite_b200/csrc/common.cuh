@@ -40,6 +40,15 @@ struct rl_context {
   std::vector<SeenNnzEntry> seen_nnz_cache;
   unsigned int preloaded_exact = 0;  // bit (kp >> 4): fallback kernels of the tensor-core scoring path are loaded
   unsigned int last_overflow = 0;  // rows the last tensor-core scoring call handed to the exact kernel
+  // Centred scoring (score_tc2.cu): the preprocessing of the item factors depends on V alone.  The chunked host wrappers score
+  // several user ranges against the same V: 1 = armed (the next call prepares V and goes to 2), 2 = the prepared V in the scratch
+  // buffer may be reused (same scratch allocation, V pointer, shape), 0 = every call prepares (plain device calls: V may have changed)
+  int tc2_prep_state = 0;
+  const void* tc2_prep_v = nullptr;
+  const void* tc2_prep_scratch = nullptr;
+  size_t tc2_prep_scratch_bytes = 0;
+  int64_t tc2_prep_items = 0;
+  int tc2_prep_kp = 0;
   std::vector<std::pair<void*, void*>> ipc_bases;  // (pointer handed out by rl_ipc_open, base of the mapping)
 };
 

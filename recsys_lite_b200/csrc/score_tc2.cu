@@ -1250,41 +1250,51 @@ int launch_score_tc2(rl_context* h, int kp, const ScoreArgs& sa, const ScoreDefe
     if ((rc = launch_score_exact(h, kp, ea)) != RL_OK) return rc;
   }
   RL_CUDA(h, cudaMemsetAsync(scb + o_cnt, 0, 256 + al(160 * sizeof(long long)), h->stream));
-  RL_CUDA(h, cudaMemsetAsync(perm, 0xFF, sizeof(int32_t) * n_pos, h->stream));
-  RL_CUDA(h, cudaMemsetAsync(whi, 0, sizeof(__half) * n_pos * kph, h->stream));
-  colsum_partial_kernel<<<csum_blocks, 256, 0, h->stream>>>(sa.vf, n_items, kp, partial);
-  RL_LAUNCH_CHECK(h, "colsum_partial_kernel");
-  colsum_final_kernel<<<1, 128, 0, h->stream>>>(partial, csum_blocks, kp, n_items, vbar, tab);
-  RL_LAUNCH_CHECK(h, "colsum_final_kernel");
-  {
-    int64_t g = (n_items * (kp / 4) + 255) / 256;
-    if (g > 8 * h->sm_count) g = 8 * h->sm_count;
-    centre_norm_kernel<<<static_cast<unsigned>(g), 256, 0, h->stream>>>(sa.vf, n_items, kp, vbar, wnorm, tab);
-    RL_LAUNCH_CHECK(h, "centre_norm_kernel");
+  // the V-dependent part (everything up to the class table) is reused between the chunks of one host-wrapper call
+  const bool reuse = !dump && h->tc2_prep_state == 2 && h->tc2_prep_v == sa.vf && h->tc2_prep_scratch == sc &&
+                     h->tc2_prep_scratch_bytes == h->scratch_bytes && h->tc2_prep_items == n_items && h->tc2_prep_kp == kp;
+  if (!reuse) {
+    RL_CUDA(h, cudaMemsetAsync(perm, 0xFF, sizeof(int32_t) * n_pos, h->stream));
+    RL_CUDA(h, cudaMemsetAsync(whi, 0, sizeof(__half) * n_pos * kph, h->stream));
+    colsum_partial_kernel<<<csum_blocks, 256, 0, h->stream>>>(sa.vf, n_items, kp, partial);
+    RL_LAUNCH_CHECK(h, "colsum_partial_kernel");
+    colsum_final_kernel<<<1, 128, 0, h->stream>>>(partial, csum_blocks, kp, n_items, vbar, tab);
+    RL_LAUNCH_CHECK(h, "colsum_final_kernel");
+    {
+      int64_t g = (n_items * (kp / 4) + 255) / 256;
+      if (g > 8 * h->sm_count) g = 8 * h->sm_count;
+      centre_norm_kernel<<<static_cast<unsigned>(g), 256, 0, h->stream>>>(sa.vf, n_items, kp, vbar, wnorm, tab);
+      RL_LAUNCH_CHECK(h, "centre_norm_kernel");
+    }
+    classify_kernel<<<nblk, PP_ROWS, 0, h->stream>>>(wnorm, n_items, tab, cls, bc);
+    RL_LAUNCH_CHECK(h, "classify_kernel");
+    // exact top-n of a few evenly spaced users: where the winners come from decides the scan order of the classes
+    const int n_sample = static_cast<int>(sa.n_users < T2_SAMPLE ? sa.n_users : T2_SAMPLE);
+    int32_t* slist = reinterpret_cast<int32_t*>(scb + o_slist);
+    int32_t* sidx = reinterpret_cast<int32_t*>(scb + o_sidx);
+    {
+      sample_users_kernel<<<1, T2_SAMPLE, 0, h->stream>>>(sa.n_users, n_sample, slist);
+      RL_LAUNCH_CHECK(h, "sample_users_kernel");
+      ScoreArgs ea = sa;
+      ea.user_list = slist;
+      ea.n_list = n_sample;
+      ea.scatter = false;
+      ea.idx_out = sidx;
+      ea.score_out = nullptr;
+      if ((rc = launch_score_exact(h, kp, ea)) != RL_OK) return rc;
+    }
+    class_scan_kernel<<<1, 32, 0, h->stream>>>(bc, nblk, tab, sidx, n_sample * sa.n, wnorm, n_items);
+    RL_LAUNCH_CHECK(h, "class_scan_kernel");
+    place_kernel<64><<<nblk, PP_ROWS, 0, h->stream>>>(sa.vf, n_items, kp, vbar, wnorm, cls, bc, tab, perm, inv, whi);
+    RL_LAUNCH_CHECK(h, "place_kernel");
+    class_finish_kernel<<<1, 32, 0, h->stream>>>(tab);
+    RL_LAUNCH_CHECK(h, "class_finish_kernel");
+    if (!dump && h->tc2_prep_state >= 1) {
+      h->tc2_prep_state = 2;
+      h->tc2_prep_v = sa.vf; h->tc2_prep_scratch = sc; h->tc2_prep_scratch_bytes = h->scratch_bytes;
+      h->tc2_prep_items = n_items; h->tc2_prep_kp = kp;
+    }
   }
-  classify_kernel<<<nblk, PP_ROWS, 0, h->stream>>>(wnorm, n_items, tab, cls, bc);
-  RL_LAUNCH_CHECK(h, "classify_kernel");
-  // exact top-n of a few evenly spaced users: where the winners come from decides the scan order of the classes
-  const int n_sample = static_cast<int>(sa.n_users < T2_SAMPLE ? sa.n_users : T2_SAMPLE);
-  int32_t* slist = reinterpret_cast<int32_t*>(scb + o_slist);
-  int32_t* sidx = reinterpret_cast<int32_t*>(scb + o_sidx);
-  {
-    sample_users_kernel<<<1, T2_SAMPLE, 0, h->stream>>>(sa.n_users, n_sample, slist);
-    RL_LAUNCH_CHECK(h, "sample_users_kernel");
-    ScoreArgs ea = sa;
-    ea.user_list = slist;
-    ea.n_list = n_sample;
-    ea.scatter = false;
-    ea.idx_out = sidx;
-    ea.score_out = nullptr;
-    if ((rc = launch_score_exact(h, kp, ea)) != RL_OK) return rc;
-  }
-  class_scan_kernel<<<1, 32, 0, h->stream>>>(bc, nblk, tab, sidx, n_sample * sa.n, wnorm, n_items);
-  RL_LAUNCH_CHECK(h, "class_scan_kernel");
-  place_kernel<64><<<nblk, PP_ROWS, 0, h->stream>>>(sa.vf, n_items, kp, vbar, wnorm, cls, bc, tab, perm, inv, whi);
-  RL_LAUNCH_CHECK(h, "place_kernel");
-  class_finish_kernel<<<1, 32, 0, h->stream>>>(tab);
-  RL_LAUNCH_CHECK(h, "class_finish_kernel");
   if (sa.seen_indptr && !dump && seen_cap > 0) {
     int64_t g = (sa.n_users + 7) / 8;
     if (g > 16 * h->sm_count) g = 16 * h->sm_count;
