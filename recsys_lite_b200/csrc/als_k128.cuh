@@ -512,6 +512,9 @@ __global__ void __launch_bounds__(128, 4) als_k128_kernel(const AlsArgs a) {
       k64_backward(P11, invd, x1a, x1b, lane);
     };
     double xd[4] = {0.0, 0.0, 0.0, 0.0};          // warp 0: x entries lane, lane + 32, lane + 64, lane + 96
+    // Fewer observations than factors (64 < nnz < k: the dual kernel takes nnz <= 64): k - nnz eigenvalues of the matrix are
+    // exactly lambda, its condition number ~1e6 -- one refinement step leaves ~1e-4, so such rows get at least two.
+    const int ir_row = (nnz < a.k && a.ir_steps == 1) ? 2 : a.ir_steps;
     for (int it = 0;; ++it) {
       if (warp == 0) {
         float x1a, x1b, x2a, x2b;
@@ -519,7 +522,7 @@ __global__ void __launch_bounds__(128, 4) als_k128_kernel(const AlsArgs a) {
         xd[0] += static_cast<double>(x1a); xd[1] += static_cast<double>(x1b);
         xd[2] += static_cast<double>(x2a); xd[3] += static_cast<double>(x2b);
       }
-      if (it >= a.ir_steps) break;
+      if (it >= ir_row) break;
       if (warp == 0) {
         xs[lane] = xd[0]; xs[32 + lane] = xd[1]; xs[64 + lane] = xd[2]; xs[96 + lane] = xd[3];
       }

@@ -928,6 +928,64 @@ def test_full_size_config4_sampled_properties(h):
     assert bad == 0
 
 
+def test_config5_shard_sampled_properties(h):
+    """One rank's share of C5 (BASELINE configs[4]: 10M x 1M, 500M nnz, k = 128, 8 GPUs) at its size: the user half-step of a
+    1.25M-user shard against all 1M items (every row has fewer observations than factors: the dual-form kernel), then the item
+    half-step over the transposed shard (rows around the 64-observation boundary: dual and primal kernels side by side).  The
+    oracle cannot run at this size: sampled rows are checked against their own float64 normal equations (algo.py:318-322 /
+    :328-332), rows without observations keep their value, and a shuffled row order gives the same bits."""
+    from devbuf import Dev, padded, unpadded
+    from recsys_lite_b200 import synth
+    w = synth.CONFIGS["C5"]
+    world, k, lam = 8, 128, 0.01
+    nu, ni = w["n_users"] // world, w["n_items"]
+    indptr, indices = synth.synth_pattern(nu, ni, w["mean_deg"], w["seed"], row_offset=0)     # rank 0's user rows
+    nnz = int(indptr[-1])
+    rng = np.random.default_rng(55)
+    u0 = rng.random((nu, k), dtype=np.float32)
+    v0 = rng.random((ni, k), dtype=np.float32)
+    d_u, d_v = padded(h, u0, k), padded(h, v0, k)
+    d_ip, d_ix = Dev(h, indptr), Dev(h, indices)
+    d_tp, d_tx = Dev(h, shape=(ni + 1,), dtype=np.int64), Dev(h, shape=(nnz,), dtype=np.int32)
+    h.call("rl_csr_transpose_dev", nu, ni, nnz, d_ip.ptr, d_ix.ptr, d_tp.ptr, d_tx.ptr)
+
+    def solve_rows(rows, ptr, idx, other):
+        out = np.empty((len(rows), k))
+        for j, r in enumerate(rows):
+            ys = other[idx[ptr[r]:ptr[r + 1]]].astype(np.float64)
+            out[j] = np.linalg.solve(ys.T @ ys + lam * np.eye(k), ys.sum(axis=0))
+        return out
+
+    h.call("rl_als_half_step_dev", nu, ni, k, d_ip.ptr, d_ix.ptr, None, None, d_v.ptr, d_u.ptr, lam, 0.0, None, 0, 1, None)
+    U = unpadded(h, d_u, k, np.float32)
+    deg = np.diff(indptr)
+    assert deg.max() <= 128                                   # fewer observations than factors on the user side
+    rows = np.unique(np.concatenate([rng.integers(0, nu, 200), [int(deg.argmin()), int(deg.argmax()), 0, nu - 1]]))
+    ref = solve_rows(rows, indptr, indices, v0)
+    err = np.linalg.norm(U[rows] - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert err.max() <= compare.FACTOR_RTOL, (err.max(), int(deg[rows[err.argmax()]]))
+    order = rng.permutation(nu).astype(np.int32)              # rows are independent: any processing order, same bits
+    d_u2, d_order = padded(h, u0, k), Dev(h, order)
+    h.call("rl_als_half_step_dev", nu, ni, k, d_ip.ptr, d_ix.ptr, None, None, d_v.ptr, d_u2.ptr, lam, 0.0, None, 0, 1, d_order.ptr)
+    assert np.array_equal(unpadded(h, d_u2, k, np.float32), U)
+    del d_u2, d_order
+    # item half-step over the transposed shard: ~62 observations per row, both kernels at work
+    tp, tx = d_tp.get(), d_tx.get()
+    tdeg = np.diff(tp)
+    assert (tdeg <= 64).any() and (tdeg > 64).any()
+    h.call("rl_als_half_step_dev", ni, nu, k, d_tp.ptr, d_tx.ptr, None, None, d_u.ptr, d_v.ptr, lam, 0.0, None, 0, 1, None)
+    V = unpadded(h, d_v, k, np.float32)
+    short = np.nonzero((tdeg > 0) & (tdeg <= 64))[0]
+    long_ = np.nonzero(tdeg > 64)[0]
+    irows = np.unique(np.concatenate([rng.choice(short, 80), rng.choice(long_, 80), [int(tdeg.argmax())]]))
+    iref = solve_rows(irows, tp, tx, U)
+    ierr = np.linalg.norm(V[irows] - iref, axis=1) / np.linalg.norm(iref, axis=1)
+    assert ierr.max() <= compare.FACTOR_RTOL, ierr.max()
+    empty = np.nonzero(tdeg == 0)[0]
+    if len(empty):
+        assert np.array_equal(V[empty[:50]], v0[empty[:50]])
+
+
 def test_csr_transpose_dev_and_fit_without_host_transpose(h):
     """rl_csr_transpose_dev (stable device sort of the (item, user) pairs) equals the host transposition (scipy csr -> csc,
     sorted), incl. empty rows / columns; rl_als_fit_host with NULL transposed arrays equals the call that gets them."""
