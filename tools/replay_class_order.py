@@ -9,7 +9,9 @@ Printed per order: records per row (mean, p99) with a lag-free threshold (`ideal
 block old, and with a private bootstrap on the first 32 columns.  Result on the 25-iteration factors: rising-norm order
 (r1 / early r2) 165 ideal, falling sampled density (what class_scan_kernel does) 76 ideal / 130 with lag.
 """
-d=np.load('gpurun_out/conv_c4.npz')
+import numpy as np
+
+d = np.load('gpurun_out/conv_c4.npz')
 import sys
 tag=sys.argv[1]
 V=d['v_'+tag].astype(np.float64); U=d['u_'+tag][:300].astype(np.float64)
