@@ -638,7 +638,10 @@ def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
         p_ip, p_ix = pin(indptr), pin(indices)      # the item-side pattern is built on the device (as RecommenderSystem.fit does)
         p_u, p_v = pin(u_now), pin(v_now)
         idx = _ffi.pinned_empty((nu, n), np.int32)
-        h2d = p_ip.nbytes + p_ix.nbytes + 2 * (p_u.nbytes + p_v.nbytes) + p_ip.nbytes + p_ix.nbytes
+        # rl_als_fit_host sends the initial U only when some user row has no observation (every other row is overwritten by
+        # the first user half-step before anything reads it); rl_recommend_host uploads the fitted U, V and the seen lists
+        u_needed = bool((np.diff(indptr) == 0).any())
+        h2d = (p_ip.nbytes + p_ix.nbytes + p_v.nbytes + (p_u.nbytes if u_needed else 0)) + (p_u.nbytes + p_v.nbytes + p_ip.nbytes + p_ix.nbytes)
         d2h = p_u.nbytes + p_v.nbytes + idx.nbytes
         times = []
         for i in range(1 + steps):
@@ -670,7 +673,9 @@ def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
     # Each rank uploads the initial factors it needs: all of V (the first user half-step gathers from it) but only ITS
     # range of U -- every user row with observations is overwritten by its owner's half-step (and arrives through the
     # exchange) before anyone reads it, and rows without observations are read by nobody but their owner's scoring pass.
-    h2d = sum(t.numel() * t.element_size() for t in hp.values()) + (uhi - ulo) * k * 4 + hv.numel() * 4
+    # (the rank's rows of the initial U only travel when one of them has no observation: see rl_als_fit_host)
+    u_needed = bool((np.diff(prob.host["up"]) == 0).any())
+    h2d = sum(t.numel() * t.element_size() for t in hp.values()) + ((uhi - ulo) * k * 4 if u_needed else 0) + hv.numel() * 4
     d2h = out_u.numel() * 4 + out_v.numel() * 4 + out_idx.numel() * 4
     # Uploads and downloads run on a second stream: the user half-step starts on the first eighth of this rank's rows
     # while the rest of its pattern and factor rows travel (row ranges holding 1/8, 1/8, 1/4, 1/2 of its observations),
@@ -692,7 +697,8 @@ def run_e2e(args, w, h, prob, plan, inputs, prec, rank, world, device, barrier):
             for r0, r1 in parts:
                 o0, o1 = int(up_host[r0]), int(up_host[r1])
                 prob.ux[o0:o1].copy_(hp["ux"][o0:o1], non_blocking=True)
-                prob.U[ulo + r0:ulo + r1, :k].copy_(hu[ulo + r0:ulo + r1], non_blocking=True)
+                if u_needed:
+                    prob.U[ulo + r0:ulo + r1, :k].copy_(hu[ulo + r0:ulo + r1], non_blocking=True)
                 ev_parts.append(cs.record_event())
             prob.ip.copy_(hp["ip"], non_blocking=True)
             prob.ix.copy_(hp["ix"], non_blocking=True)
