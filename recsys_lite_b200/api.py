@@ -683,15 +683,83 @@ def _dense_errors(predictions, actual):
     return out3
 
 
+def _model_errors(model, actual):
+    """(sum of squared errors, sum |err|, #cells) of an ALS model's predictions ``U V^T`` over the cells with ``actual > 0``,
+    straight from the factors (SDDMM on the device, rl_observed_error_dev): the n_users x n_items prediction matrix the
+    reference's ``compute_rmse(model.predict(R), R)`` needs (algo.py:143-147, :662-701) is never formed.  `actual`: dense or
+    scipy.sparse."""
+    if not isinstance(model, RecommenderSystem) or model.algorithm != "als" or not model.is_fitted():
+        raise ValueError("the model form of compute_rmse / compute_mae needs a fitted RecommenderSystem('als')")
+    if model._resident is None:
+        m = model._need_model()
+        n_users, n_items, k = m["user_factors"].shape[0], m["item_factors"].shape[0], m["user_factors"].shape[1]
+    else:
+        n_users, n_items, k = model._resident.n_users, model._resident.n_items, model._resident.k
+    if tuple(actual.shape) != (n_users, n_items):
+        raise ValueError(f"Shape mismatch: predictions {(n_users, n_items)} vs actual {tuple(actual.shape)}")
+    if sparse.issparse(actual):
+        a = sparse.csr_matrix(actual)
+        if not a.has_canonical_format:
+            a = a.copy()
+            a.sum_duplicates()
+        keep = a.data > 0
+        if not keep.all():
+            a = sparse.csr_matrix((a.data * keep, a.indices.copy(), a.indptr.copy()), shape=a.shape)
+            a.eliminate_zeros()
+        indptr = np.ascontiguousarray(a.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(a.indices, dtype=np.int32)
+        values = np.ascontiguousarray(a.data, dtype=np.float32)
+    else:
+        d = np.asarray(actual)
+        if not np.isfinite(d).all():
+            raise ValueError("Input matrices must not contain NaN values." if np.isnan(d).any()
+                             else "Input matrices must not contain infinite values.")
+        mask = d > 0
+        indptr = np.zeros(n_users + 1, dtype=np.int64)
+        np.cumsum(mask.sum(axis=1), out=indptr[1:])
+        indices = np.ascontiguousarray(np.nonzero(mask)[1], dtype=np.int32)
+        values = np.ascontiguousarray(d[mask], dtype=np.float32)
+    cnt = int(indptr[-1])
+    if cnt == 0:
+        return 0.0, 0.0, 0
+    h = _ffi.default_handle()
+    res, own = model._resident, None
+    if res is None:                        # host model (edited or loaded): factors go up for this call
+        m = model._need_model()
+        own = res = _ResidentALS(h, n_users, n_items, k)
+        res.upload_factors(np.ascontiguousarray(m["user_factors"]), np.ascontiguousarray(m["item_factors"]))
+    bufs = [_DevBuf(h, indptr.nbytes), _DevBuf(h, indices.nbytes), _DevBuf(h, values.nbytes), _DevBuf(h, 16)]
+    out2 = np.zeros(2, dtype=np.float64)
+    try:
+        for b, arr in zip(bufs[:3], (indptr, indices, values)):
+            h.call("rl_memcpy_h2d", b.ptr, _ffi.ptr(arr), arr.nbytes)
+        h.call("rl_observed_error_dev", res.u.ptr, res.v.ptr, k, n_users, bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr)
+        h.call("rl_memcpy_d2h", _ffi.ptr(out2), bufs[3].ptr, 16)
+    finally:
+        for b in bufs:
+            b.free()
+        if own is not None:
+            own.free()
+    return float(out2[0]), float(out2[1]), cnt
+
+
 def compute_rmse(predictions, actual) -> float:
-    """RMSE over cells with ``actual > 0`` (algo.py:662-701); 0.0 when there is none."""
-    sse, _, cnt = _dense_errors(predictions, actual)
+    """RMSE over cells with ``actual > 0`` (algo.py:662-701); 0.0 when there is none.  `predictions` may also be a fitted
+    ``RecommenderSystem('als')``: the error of ``U V^T`` over the observed cells then comes straight from the factors
+    (no dense prediction matrix; `actual` dense or scipy.sparse)."""
+    if isinstance(predictions, RecommenderSystem):
+        sse, _, cnt = _model_errors(predictions, actual)
+    else:
+        sse, _, cnt = _dense_errors(predictions, actual)
     return float(np.sqrt(sse / cnt)) if cnt > 0 else 0.0
 
 
 def compute_mae(predictions, actual) -> float:
-    """MAE over cells with ``actual > 0`` (algo.py:704-743)."""
-    _, sae, cnt = _dense_errors(predictions, actual)
+    """MAE over cells with ``actual > 0`` (algo.py:704-743); `predictions` as in compute_rmse."""
+    if isinstance(predictions, RecommenderSystem):
+        _, sae, cnt = _model_errors(predictions, actual)
+    else:
+        _, sae, cnt = _dense_errors(predictions, actual)
     return float(sae / cnt) if cnt > 0 else 0.0
 
 

@@ -986,6 +986,37 @@ def test_config5_shard_sampled_properties(h):
         assert np.array_equal(V[empty[:50]], v0[empty[:50]])
 
 
+def test_compute_rmse_mae_from_a_resident_model():
+    """compute_rmse / compute_mae with a fitted ALS model in place of the prediction matrix (SDDMM over the
+    observed cells, rl_observed_error_dev) == the reference's compute_rmse(model.predict(R), R) (algo.py:143-147, :662-743),
+    for dense and scipy.sparse `actual` with real-valued ratings, before and after the model has moved to the host."""
+    from scipy import sparse
+    from recsys_lite_b200 import RecommenderSystem, compute_mae, compute_rmse
+    rng = np.random.default_rng(31)
+    n_users, n_items, k = 900, 300, 24
+    r = (rng.random((n_users, n_items)) < 0.06) * rng.integers(1, 6, (n_users, n_items)).astype(np.float32)
+    r[5] = 0.0                                                        # a user without ratings
+    r[7, 3] = -2.0                                                    # negatives are unobserved (algo.py:311, :690)
+    u0, v0 = rng.random((n_users, k)), rng.random((n_items, k))
+    model = RecommenderSystem("als").fit(r, k=k, iterations=3, lambda_=0.05, init=(u0, v0))
+    got = [(compute_rmse(model, a), compute_mae(model, a)) for a in (r, sparse.csr_matrix(r), sparse.coo_matrix(r))]
+    assert model._resident is not None                                # nothing was downloaded for it
+    pred = np.asarray(model.predict(r))
+    want = (compute_rmse(pred, r), compute_mae(pred, r))
+    uf, vf = model._model["user_factors"], model._model["item_factors"]            # (the model moves to the host here)
+    mask = r > 0
+    err = (uf @ vf.T - r)[mask]
+    ref = (float(np.sqrt(np.mean(err ** 2))), float(np.mean(np.abs(err))))
+    for g in got + [(compute_rmse(model, r), compute_mae(model, r))]:              # last: host-model path
+        assert abs(g[0] - ref[0]) <= 1e-5 and abs(g[1] - ref[1]) <= 1e-5, (g, ref)
+    assert abs(want[0] - ref[0]) <= 1e-5 and abs(want[1] - ref[1]) <= 1e-5
+    assert compute_rmse(model, np.zeros_like(r)) == 0.0
+    with pytest.raises(ValueError):
+        compute_rmse(model, r[:, :10])
+    with pytest.raises(ValueError):
+        compute_rmse(RecommenderSystem("als"), r)
+
+
 def test_csr_transpose_dev_and_fit_without_host_transpose(h):
     """rl_csr_transpose_dev (stable device sort of the (item, user) pairs) equals the host transposition (scipy csr -> csc,
     sorted), incl. empty rows / columns; rl_als_fit_host with NULL transposed arrays equals the call that gets them."""
