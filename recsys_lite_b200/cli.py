@@ -46,12 +46,10 @@ def predict(path: str, k: int = 50, n: int = 10, output=None, show_metrics: bool
     from . import RecommenderSystem, compute_mae, compute_rmse, svd_reconstruct, top_n
     ratings = load_matrix(path)
     print(f"Loaded {ratings.shape[0]} users, {ratings.shape[1]} items")
-    recon = None
+    recon = model = None
     if algorithm == "als":
         model = RecommenderSystem("als").fit(ratings, k=k, iterations=iterations)
         recs = model.recommend(ratings, n=n)
-        if show_metrics:
-            recon = model.predict(ratings)
     else:
         dense = ratings.toarray() if sparse.issparse(ratings) else ratings
         recon = svd_reconstruct(dense, k=k, use_sparse=False)
@@ -59,7 +57,9 @@ def predict(path: str, k: int = 50, n: int = 10, output=None, show_metrics: bool
     print(f"\nGenerated recommendations for {len(recs)} users")
     for i, row in enumerate(recs[:max_users]):
         print(f"User {i}: " + ", ".join(str(int(x)) for x in row if x >= 0))
-    if show_metrics:
+    if show_metrics and model is not None:       # from the resident factors over the observed cells: nothing is densified
+        print(f"RMSE: {compute_rmse(model, ratings):.4f}\nMAE: {compute_mae(model, ratings):.4f}")
+    elif show_metrics:
         dense = ratings.toarray() if sparse.issparse(ratings) else ratings
         print(f"RMSE: {compute_rmse(recon, dense):.4f}\nMAE: {compute_mae(recon, dense):.4f}")
     if output:

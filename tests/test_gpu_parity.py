@@ -1182,6 +1182,14 @@ def test_cli_predict_and_pipeline_route_to_the_fused_path(golden_dir, tmp_path, 
     np.random.seed(7)
     want = RecommenderSystem("als").fit(r, k=16, iterations=2).recommend(r, n=5)
     assert np.array_equal(np.loadtxt(out, delimiter=",").astype(np.int32), want)
+    # --metrics with --algorithm als: RMSE / MAE over the stored cells straight from the resident factors (no dense matrix)
+    np.random.seed(7)
+    assert cli.main(["predict", path, "--algorithm", "als", "--rank", "16", "--top-n", "5", "--iterations", "2", "--metrics"]) == 0
+    text = capsys.readouterr().out
+    np.random.seed(7)
+    mdl = RecommenderSystem("als").fit(r, k=16, iterations=2)
+    err = (mdl._model["user_factors"] @ mdl._model["item_factors"].T - 1.0)[r.toarray() > 0]
+    assert f"RMSE: {np.sqrt(np.mean(err ** 2)):.4f}" in text and f"MAE: {np.mean(np.abs(err)):.4f}" in text
     assert cli.main(["predict", str(tmp_path / "missing.csv")]) == 1
 
 
