@@ -26,11 +26,16 @@ def benchmark_algorithm(algorithm: str, ratings, k: int = 10, n_runs: int = 3, n
     """
     if algorithm not in ("svd", "als", "topn"):
         raise ValueError(f"Unknown algorithm: {algorithm}")
-    dense = _dense(ratings)
+    # ALS never needs the dense matrix (a scipy .npz pattern at C3 / C4 size would not fit): fit takes the CSR pattern and the
+    # accuracy comes from the factors over the observed cells (compute_rmse(model, R))
+    keep_sparse = algorithm == "als" and sparse.issparse(ratings)
+    dense = None if keep_sparse else _dense(ratings)
+    size = int(ratings.shape[0]) * int(ratings.shape[1])
+    nonzero = int(ratings.count_nonzero()) if keep_sparse else int(np.count_nonzero(dense))
     results: Dict[str, Any] = {
         "algorithm": algorithm,
         "matrix_shape": tuple(ratings.shape),
-        "sparsity": 1 - (np.count_nonzero(dense) / dense.size) if dense.size else 0,
+        "sparsity": 1 - (nonzero / size) if size else 0,
         "runs": [],
     }
     h = _ffi.default_handle()
@@ -42,9 +47,8 @@ def benchmark_algorithm(algorithm: str, ratings, k: int = 10, n_runs: int = 3, n
             predictions = _dense(svd_reconstruct(ratings, k=k))
             actual = dense
         elif algorithm == "als":
-            model = RecommenderSystem(algorithm="als").fit(ratings, k=k, iterations=1)
-            predictions = model.predict(ratings)
-            actual = (dense > 0).astype(np.float32)
+            predictions = RecommenderSystem(algorithm="als").fit(ratings, k=k, iterations=1)     # the model stands in for U V^T
+            actual = (ratings > 0).astype(np.float32)                                             # binarised (algo.py:311)
         else:
             predictions = _dense(svd_reconstruct(ratings, k=k))
             recs = top_n(predictions, dense, n=n)

@@ -737,7 +737,13 @@ def test_benchmark_entry_points_and_cli(tmp_path, capsys):
     q = quick_benchmark(m, k=5, n_runs=1)
     assert set(q) >= {"time", "rmse", "mae", "configurations"} and q["time"] is not None
     assert quick_benchmark(m, k=500, n_runs=1)["time"] is None            # k out of range -> error swallowed
-    assert quick_benchmark(m, k=8, n_runs=1, algorithm="als")["rmse"] < 1.0
+    np.random.seed(3)
+    qa = quick_benchmark(m, k=8, n_runs=1, algorithm="als")
+    assert qa["rmse"] < 1.0
+    np.random.seed(3)
+    qs = quick_benchmark(sparse.csr_matrix(m), k=8, n_runs=1, algorithm="als")      # a sparse input is never densified for ALS
+    assert abs(qs["rmse"] - qa["rmse"]) < 1e-6 and abs(qs["mae"] - qa["mae"]) < 1e-6
+    assert qs["configurations"][0]["sparsity"] == qa["configurations"][0]["sparsity"]
     path = tmp_path / "ratings.csv"
     np.savetxt(path, m, delimiter=",")
     assert main(["benchmark", str(path), "--rank", "5", "--iterations", "2", "--algorithm", "topn"]) == 0
