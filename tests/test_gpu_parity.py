@@ -1102,6 +1102,10 @@ def test_als_model_stays_on_the_device_until_read(tmp_path):
     assert isinstance(m._model, _LazyALSModel) and m._resident is not None
     rec_dev = m.recommend(r, n=10)                       # resident factors + the training pattern already in HBM
     rec_other = m.recommend(sparse.csr_matrix(r.toarray()), n=10)      # another object with the same content: pattern uploaded
+    r2 = r.copy()
+    r2.data[::3] = 0
+    r2.eliminate_zeros()                                  # other ratings than the model was fitted on: THEIR items are excluded
+    rec_r2 = m.recommend(r2, n=10)
     pred_dev = m.predict(r)
     assert m._resident is not None
     uf, vf = m._model["user_factors"], m._model["item_factors"]          # first read: download, device copy dropped
@@ -1109,6 +1113,11 @@ def test_als_model_stays_on_the_device_until_read(tmp_path):
         "user_factors", "item_factors", "factors"}
     rec_host = m.recommend(r, n=10)                       # host path (rl_recommend_host) on the downloaded arrays
     assert np.array_equal(rec_dev, rec_host) and np.array_equal(rec_dev, rec_other)
+    assert np.array_equal(rec_r2, m.recommend(r2, n=10)) and not np.array_equal(rec_r2, rec_dev)
+    uf32, vf32 = uf.astype(np.float32).astype(np.float64), vf.astype(np.float32).astype(np.float64)
+    ref_r2, _ = o_topn.recommend_blocked(uf32, vf32, r2.indptr.astype(np.int64), r2.indices, n=10)
+    chk = compare.topn_matches(rec_r2, ref_r2, lambda row: uf32[row] @ vf32.T, lambda row: r2.indices[r2.indptr[row]:r2.indptr[row + 1]])
+    assert not chk["bad"], chk
     assert np.allclose(pred_dev, uf @ vf.T, rtol=0, atol=1e-12)
     ti, tx = o_als.transpose_pattern(indptr, indices, 1300)
     ref = o_als.fit_csr(indptr, indices, ti, tx, 24, iterations=3, lam=0.01, init=(u0, v0))
