@@ -216,6 +216,225 @@ __global__ void __launch_bounds__(128, 4) als_k128_dual_kernel(const AlsArgs a) 
   }
 }
 
+// ---- the dual form, one WARP per row -----------------------------------------------------------------------------------------
+// The CTA-per-row version above keeps the gathered rows in shared memory (35 KB): four rows in flight per SM, and three of
+// the four warps wait at a barrier while warp 0 factors (40 % of the stall samples).  Here a warp owns a row, as in the
+// k = 64 kernel: G = Y Y^T is accumulated from 16-COLUMN chunks of the gathered rows (64 observations x 64 bytes, double
+// buffered: 12 KB), so only the 64 x 64 system and its factor live in shared memory (23 KB per warp, nine rows in flight per
+// SM), and the three matrix-vector passes of the refinement / the output (x = Y^T z, t = Y x, x = Y^T z) read the rows again
+// from L2, where the gather of a moment ago has left them.
+constexpr int KD_CW = 16;                 // factor columns per chunk
+constexpr int KD_LD = 24;                 // row stride of a chunk (floats): float2 fragment reads of rows g, columns 2 tq are conflict-free
+constexpr int KD_WARPS = 3, KD_CTAS = 3;
+struct K128WarpDualSmem {
+  static constexpr size_t bytes = sizeof(float) * (K64_LSZ + 64 + 64) + sizeof(double) * 64 + sizeof(int) * 64 + sizeof(float) * 2 * 64 * KD_LD;
+  static_assert(bytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
+};
+
+__global__ void __launch_bounds__(KD_WARPS * 32, KD_CTAS) als_k128_wdual_kernel(const AlsArgs a) {
+  constexpr int KP = K128;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  unsigned char* wb = smem_raw + static_cast<size_t>(warp) * K128WarpDualSmem::bytes;
+  float* Lt = reinterpret_cast<float*>(wb);
+  float* invd = Lt + K64_LSZ;
+  float* bs = invd + 64;
+  double* zs = reinterpret_cast<double*>(bs + 64);
+  int* ids = reinterpret_cast<int*>(zs + 64);
+  float* ybuf = reinterpret_cast<float*>(ids + 64);
+  const float lam = static_cast<float>(a.lambda);
+  const float ysc = pow2_scale(*a.other_absmax);
+  const float yunsc = (1.0f / ysc) * (1.0f / ysc);
+  for (;;) {
+    unsigned int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(a.counter + 1, 1u);
+    ticket = __shfl_sync(FULL_MASK, ticket, 0);
+    if (static_cast<int64_t>(ticket) >= a.n_rows) break;
+    const int64_t row = a.row_order ? a.row_order[ticket] : static_cast<int64_t>(ticket);
+    const int64_t s = a.indptr[row];
+    const int64_t nnz64 = a.indptr[row + 1] - s;
+    if (nnz64 <= 0 || nnz64 > K128_DUAL_MAX) continue;     // no observation: the row keeps its value (algo.py:316-317)
+    const int nnz = static_cast<int>(nnz64);
+    const int nblk = (nnz + 7) >> 3, mtiles = (nnz + 15) >> 4;
+    const int id0 = lane < nnz ? a.indices[s + lane] : -1;
+    const int id1 = 32 + lane < nnz ? a.indices[s + 32 + lane] : -1;
+    ids[lane] = id0;
+    ids[32 + lane] = id1;
+    bs[lane] = lane < nnz ? 1.0f : 0.0f;
+    bs[32 + lane] = 32 + lane < nnz ? 1.0f : 0.0f;
+    // chunk c: columns 16 c .. 16 c + 15 of the 64 (zero-filled beyond nnz) gathered rows; 256 pieces of 16 bytes
+    auto gather = [&](int c, float* yb) {
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int r = (lane >> 2) + 8 * p, q4 = lane & 3;
+        const int idx = __shfl_sync(FULL_MASK, p < 4 ? id0 : id1, (lane >> 2) + 8 * (p & 3));
+        const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(yb + r * KD_LD + 4 * q4));
+        if (idx >= 0) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(a.other + static_cast<int64_t>(idx) * KP + KD_CW * c + 4 * q4));
+        } else {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 0;\n" ::"r"(dst), "l"(a.other));
+        }
+      }
+      cp_async_commit();
+    };
+    // ---- G = Y Y^T on the tensor cores: A(m = observation, k = factor), the B fragment of n-tile nj is an A register ----
+    float acc[20][4];
+#pragma unroll
+    for (int t = 0; t < 20; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+    for (int c = -1; c < KP / KD_CW; ++c) {
+      const int buf = c & 1;
+      if (c + 1 < KP / KD_CW) {
+        gather(c + 1, ybuf + (buf ^ 1) * 64 * KD_LD);
+        if (c < 0) continue;
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncwarp();
+      const float* yb = ybuf + buf * 64 * KD_LD;
+#pragma unroll
+      for (int ks = 0; ks < KD_CW / 8; ++ks) {
+        const float* yk = yb + 8 * ks + 2 * tq;
+        uint32_t hi[4][2], lo[4][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+          if (mi >= mtiles) { hi[mi][0] = hi[mi][1] = lo[mi][0] = lo[mi][1] = 0u; continue; }
+          const float2 y0 = *reinterpret_cast<const float2*>(yk + (16 * mi + g) * KD_LD);
+          const float2 y1 = *reinterpret_cast<const float2*>(yk + (16 * mi + 8 + g) * KD_LD);
+          k64_split_h2(y0.x * ysc, y0.y * ysc, hi[mi][0], lo[mi][0]);
+          k64_split_h2(y1.x * ysc, y1.y * ysc, hi[mi][1], lo[mi][1]);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+          if (mi < mtiles) {
+#pragma unroll
+            for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], hi[mi][0], hi[mi][1], hi[nj >> 1][nj & 1]);
+          }
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+          if (mi < mtiles) {
+#pragma unroll
+            for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], hi[mi][0], hi[mi][1], lo[nj >> 1][nj & 1]);
+          }
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+          if (mi < mtiles) {
+#pragma unroll
+            for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], lo[mi][0], lo[mi][1], hi[nj >> 1][nj & 1]);
+          }
+      }
+      __syncwarp();
+    }
+    // ---- + lambda I (unit diagonal on the padding), accumulator tiles -> panel storage ----
+    {
+      const int oc = (2 * tq) ^ (((g >> 2) & 1) << 2);
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int nj = 0; nj <= 2 * mi + 1; ++nj) {
+          float (&d)[4] = acc[k64_tile(mi, nj)];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int gi = 16 * mi + g + ((e & 2) ? 8 : 0), gj = 8 * nj + 2 * tq + (e & 1);
+            d[e] *= yunsc;
+            if (nj >= 2 * mi && gi == gj) d[e] += (gi < nnz) ? lam : 1.0f;
+          }
+          if (nj <= 2 * mi) *reinterpret_cast<float2*>(Lt + k64_pb0(nj) + 8 * (16 * mi + g) + oc) = make_float2(d[0], d[1]);
+          *reinterpret_cast<float2*>(Lt + k64_pb0(nj) + 8 * (16 * mi + 8 + g) + oc) = make_float2(d[2], d[3]);
+        }
+    }
+    __syncwarp();
+    k64_chol(Lt, invd, bs, lane, nblk);
+    // x = Y^T z for the z in zs: lane owns entries lane + 32 q; the rows come from L2
+    auto yt_z = [&](double (&x)[4]) {
+      x[0] = x[1] = x[2] = x[3] = 0.0;
+      // eight rows (32 loads) in flight per lane: the pass is a chain of L2 latencies, not of work
+      for (int i0 = 0; i0 < nnz; i0 += 8) {
+        float y[8][4];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int i = min(i0 + e, nnz - 1);
+          const float* yr = a.other + static_cast<int64_t>(ids[i]) * KP + lane;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) y[e][q] = __ldg(yr + 32 * q);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const double z = i0 + e < nnz ? zs[i0 + e] : 0.0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) x[q] = fma(static_cast<double>(y[e][q]), z, x[q]);
+        }
+      }
+    };
+    double zd0 = 0.0, zd1 = 0.0;
+    double x[4];
+    for (int it = 0;; ++it) {
+      float v0 = bs[lane], v1 = bs[32 + lane];
+      __syncwarp();
+      k64_backward(Lt, invd, v0, v1, lane, nblk);
+      zd0 += static_cast<double>(v0);
+      zd1 += static_cast<double>(v1);
+      zs[lane] = zd0;
+      zs[32 + lane] = zd1;
+      __syncwarp();
+      yt_z(x);
+      if (it >= a.ir_steps) break;
+      // r_i = 1 - <y_i, x> - lambda z_i for the observed rows, 0 on the padding
+      bs[lane] = 0.0f;
+      bs[32 + lane] = 0.0f;
+      __syncwarp();
+      for (int i0 = 0; i0 < nnz; i0 += 8) {          // eight rows per batch: 32 loads in flight, one transposed reduction
+        float y[8][4];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int i = min(i0 + e, nnz - 1);
+          const float* yr = a.other + static_cast<int64_t>(ids[i]) * KP + lane;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) y[e][q] = __ldg(yr + 32 * q);
+        }
+        double t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          t[e] = 0.0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) t[e] = fma(static_cast<double>(y[e][q]), x[q], t[e]);
+        }
+        // lanes with bit 4 set keep rows 4 .. 7, then bit 3 picks the pair, bit 2 the row: row e = 4 b4 + 2 b3 + b2
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const bool up = lane & 16;
+          const double send = up ? t[e] : t[e + 4], keep = up ? t[e + 4] : t[e];
+          t[e] = keep + __shfl_xor_sync(FULL_MASK, send, 16);
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const bool up = lane & 8;
+          const double send = up ? t[e] : t[e + 2], keep = up ? t[e + 2] : t[e];
+          t[e] = keep + __shfl_xor_sync(FULL_MASK, send, 8);
+        }
+        {
+          const bool up = lane & 4;
+          const double send = up ? t[0] : t[1], keep = up ? t[1] : t[0];
+          t[0] = keep + __shfl_xor_sync(FULL_MASK, send, 4);
+        }
+        t[0] += __shfl_xor_sync(FULL_MASK, t[0], 2);
+        t[0] += __shfl_xor_sync(FULL_MASK, t[0], 1);
+        const int i = i0 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        if ((lane & 3) == 0 && i < nnz) bs[i] = static_cast<float>(1.0 - t[0] - a.lambda * zs[i]);
+      }
+      __syncwarp();
+      k64_forward(Lt, invd, bs, lane, nblk);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float xo = (lane + 32 * q < a.k) ? static_cast<float>(x[q]) : 0.0f;
+      a.mine[row * KP + lane + 32 * q] = xo;
+      for (int pr = 0; pr < a.n_peers; ++pr) a.peers[pr][row * KP + lane + 32 * q] = xo;
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(128, 4) als_k128_kernel(const AlsArgs a) {
   constexpr int KP = K128, CH = K128_CH, LDY = K128_LDY;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -595,7 +814,20 @@ __global__ void __launch_bounds__(128, 4) als_k128_kernel(const AlsArgs a) {
 
 int launch_k128(rl_context* h, const AlsArgs& args) {
   RL_CUDA(h, cudaMemsetAsync(args.counter, 0, 2 * sizeof(unsigned int), h->stream));
-  {   // rows with at most 64 observations: the dual form
+  if (!getenv("RL_ALS_DUAL_CTA")) {   // rows with at most 64 observations: the dual form, one warp per row
+    auto kern = als_k128_wdual_kernel;
+    const size_t smem = K128WarpDualSmem::bytes * KD_WARPS;
+    RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    RL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KD_WARPS * 32, smem));
+    if (per_sm < 1) return fail(h, RL_ERR_CUDA, "als_k128 (warp dual): kernel does not fit on an SM (smem %zu)", smem);
+    int64_t grid = static_cast<int64_t>(h->sm_count) * per_sm;
+    const int64_t want = (args.n_rows + KD_WARPS - 1) / KD_WARPS;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    kern<<<static_cast<unsigned>(grid), KD_WARPS * 32, smem, h->stream>>>(args);
+    RL_LAUNCH_CHECK(h, "als_k128_wdual_kernel");
+  } else {                            // (the CTA-per-row version, kept for comparison)
     auto kern = als_k128_dual_kernel;
     const size_t smem = K128DualSmem::bytes;
     RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
