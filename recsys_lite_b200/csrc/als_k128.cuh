@@ -223,9 +223,12 @@ __global__ void __launch_bounds__(128, 4) als_k128_dual_kernel(const AlsArgs a) 
 // buffered: 12 KB), so only the 64 x 64 system and its factor live in shared memory (23 KB per warp, nine rows in flight per
 // SM), and the three matrix-vector passes of the refinement / the output (x = Y^T z, t = Y x, x = Y^T z) read the rows again
 // from L2, where the gather of a moment ago has left them.
-constexpr int KD_CW = 16;                 // factor columns per chunk
-constexpr int KD_LD = 24;                 // row stride of a chunk (floats): float2 fragment reads of rows g, columns 2 tq are conflict-free
-constexpr int KD_WARPS = 3, KD_CTAS = 3;
+#ifndef KD_CW_
+#define KD_CW_ 8
+#endif
+constexpr int KD_CW = KD_CW_;             // factor columns per chunk (8: 32-byte pieces, 12 rows in flight per SM; 16: 64-byte pieces, 9 rows)
+constexpr int KD_LD = KD_CW == 8 ? 8 : 24;   // row stride of a chunk (floats): the float2 fragment reads of rows g, columns 2 tq are conflict-free
+constexpr int KD_WARPS = 3, KD_CTAS = KD_CW == 8 ? 4 : 3;
 struct K128WarpDualSmem {
   static constexpr size_t bytes = sizeof(float) * (K64_LSZ + 64 + 64) + sizeof(double) * 64 + sizeof(int) * 64 + sizeof(float) * 2 * 64 * KD_LD;
   static_assert(bytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
@@ -262,12 +265,13 @@ __global__ void __launch_bounds__(KD_WARPS * 32, KD_CTAS) als_k128_wdual_kernel(
     ids[32 + lane] = id1;
     bs[lane] = lane < nnz ? 1.0f : 0.0f;
     bs[32 + lane] = 32 + lane < nnz ? 1.0f : 0.0f;
-    // chunk c: columns 16 c .. 16 c + 15 of the 64 (zero-filled beyond nnz) gathered rows; 256 pieces of 16 bytes
+    // chunk c: columns KD_CW c .. KD_CW (c + 1) - 1 of the 64 (zero-filled beyond nnz) gathered rows, in 16-byte pieces
     auto gather = [&](int c, float* yb) {
+      constexpr int PPR = KD_CW / 4, RP = 32 / PPR;        // 16-byte pieces per row, rows covered by one pass of the warp
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int r = (lane >> 2) + 8 * p, q4 = lane & 3;
-        const int idx = __shfl_sync(FULL_MASK, p < 4 ? id0 : id1, (lane >> 2) + 8 * (p & 3));
+      for (int p = 0; p < 2 * PPR; ++p) {
+        const int r = lane / PPR + RP * p, q4 = lane % PPR;
+        const int idx = __shfl_sync(FULL_MASK, p < PPR ? id0 : id1, lane / PPR + RP * (p % PPR));
         const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(yb + r * KD_LD + 4 * q4));
         if (idx >= 0) {
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(a.other + static_cast<int64_t>(idx) * KP + KD_CW * c + 4 * q4));
