@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(128, 4) als_k128_dual_kernel(const AlsArgs a) 
 #endif
 constexpr int KD_CW = KD_CW_;             // factor columns per chunk (8: 32-byte pieces, 12 rows in flight per SM; 16: 64-byte pieces, 9 rows)
 constexpr int KD_LD = KD_CW == 8 ? 8 : 24;   // row stride of a chunk (floats): the float2 fragment reads of rows g, columns 2 tq are conflict-free
-constexpr int KD_WARPS = 3, KD_CTAS = KD_CW == 8 ? 4 : 3;
+constexpr int KD_WARPS = 3, KD_CTAS = KD_CW == 8 ? 5 : 3;
 struct K128WarpDualSmem {
   static constexpr size_t bytes = sizeof(float) * (K64_LSZ + 64 + 64) + sizeof(double) * 64 + sizeof(int) * 64 + sizeof(float) * 2 * 64 * KD_LD;
   static_assert(bytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
