@@ -17,7 +17,7 @@
 //   * back substitution and the float64 matrix-free refinement as in the k = 64 kernel (residual: one thread per
 //     factor dimension, no atomics).
 // Rows with at most 64 observations (fewer observations than factors: the user side of C5) are solved in the DUAL form,
-// k128_dual_row below.
+// als_k128_wdual_kernel below.
 // Unweighted (reference) mode only; weights / w0 run the general kernel.
 
 constexpr int K128 = 128;
@@ -42,184 +42,14 @@ struct K128Smem {
 // ---- rows with at most 64 observations: the DUAL form ---------------------------------------------------------------------
 // x = (Y^T Y + lambda I)^-1 Y^T 1 = Y^T (Y Y^T + lambda I)^-1 1  (Y: the nnz gathered rows, nnz x k).  With fewer observations
 // than factors -- every user row of the C5 configuration: ~50 observations, k = 128 -- the nnz x nnz system is an eighth of
-// the Cholesky work of the 128 x 128 one, fits ONE 64 x 64 factorisation of als_k64.cuh, and the gathered rows (64 x 512
-// bytes) stay in shared memory for the whole row: the refinement re-reads nothing from L2 / HBM.
-//   all warps   gather the rows; G = Y Y^T on the tensor cores (fp16 split operands; warp w contracts factor columns
-//               32 w .. 32 w + 31, partial tiles meet in the panel storage in a fixed order); padded rows get a unit diagonal
-//   warp 0      L = chol(G + lambda I), z = L^-T L^-1 1   (k64_chol / k64_backward)
-//   all warps   refinement in float64, matrix-free from the resident rows: x = Y^T z, r = 1 - Y x - lambda z, z += L^-T L^-1 r
-//   all threads x = Y^T z (float64), thread t owns factor t
+// the Cholesky work of the 128 x 128 one and fits ONE 64 x 64 factorisation of als_k64.cuh; it is also far better
+// conditioned (no eigenvalue sits at lambda), so one refinement step reaches ~1e-7.  Padded rows / columns of the 64 x 64
+// system form an identity block that is neither accumulated (16-row tile groups) nor factored (nblk panels).
 constexpr int K128_DUAL_MAX = 64;
-constexpr int K128_LDD = 136;     // row stride of the resident rows: the float2 fragment reads (rows g, columns 2 tq) are conflict-free
-struct K128DualSmem {
-  static constexpr size_t bytes = sizeof(float) * (K64_LSZ + 64 * K128_LDD + 64 + 64) + sizeof(double) * (64 + K128);
-  static_assert(bytes % 16 == 0, "shared memory layout must keep 16-byte alignment");
-};
 
-__device__ __forceinline__ void k128_dual_row(const AlsArgs& a, int64_t row, int64_t s, int nnz, unsigned char* smem, int tid,
-                                              float ysc, float yunsc, float lam) {
-  constexpr int KP = K128, LDD = K128_LDD;
-  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
-  float* Lt = reinterpret_cast<float*>(smem);
-  float* Y = Lt + K64_LSZ;
-  float* invd = Y + 64 * LDD;
-  float* bs = invd + 64;
-  double* zs = reinterpret_cast<double*>(bs + 64);
-  double* xs = zs + 64;
-  // ---- the rows of the observed items, resident for the whole solve (rows >= nnz: zero) ----
-#pragma unroll 4
-  for (int q = 0; q < 16; ++q) {
-    const int p = tid + 128 * q;
-    const int r = p >> 5, c4 = p & 31;
-    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(Y + r * LDD + 4 * c4));
-    if (r < nnz) {
-      const int idx = a.indices[s + r];
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(a.other + static_cast<int64_t>(idx) * KP + 4 * c4));
-    } else {
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 0;\n" ::"r"(dst), "l"(a.other));
-    }
-  }
-  cp_async_commit();
-  for (int p = tid; p < K64_LSZ; p += 128) Lt[p] = 0.f;
-  if (tid < 64) bs[tid] = tid < nnz ? 1.0f : 0.0f;
-  cp_async_wait<0>();
-  __syncthreads();
-  // ---- G = Y Y^T: A(m = observation, k = factor) and B = A^T, so the B fragment of n-tile nj is an A register ----
-  // only the leading 8 nblk rows / columns carry observations: the rest of G is an identity block that is neither
-  // accumulated (16-row tile groups) nor factored (8-column panels)
-  const int nblk = (nnz + 7) >> 3, mtiles = (nnz + 15) >> 4;
-  float acc[20][4];
-#pragma unroll
-  for (int t = 0; t < 20; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
-#pragma unroll 1
-  for (int ks = 0; ks < 4; ++ks) {
-    const float* yk = Y + 32 * warp + 8 * ks + 2 * tq;
-    uint32_t hi[4][2], lo[4][2];
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {
-      if (mi >= mtiles) { hi[mi][0] = hi[mi][1] = lo[mi][0] = lo[mi][1] = 0u; continue; }
-      const float2 y0 = *reinterpret_cast<const float2*>(yk + (16 * mi + g) * LDD);
-      const float2 y1 = *reinterpret_cast<const float2*>(yk + (16 * mi + 8 + g) * LDD);
-      k64_split_h2(y0.x * ysc, y0.y * ysc, hi[mi][0], lo[mi][0]);
-      k64_split_h2(y1.x * ysc, y1.y * ysc, hi[mi][1], lo[mi][1]);
-    }
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-      if (mi < mtiles) {
-#pragma unroll
-        for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], hi[mi][0], hi[mi][1], hi[nj >> 1][nj & 1]);
-      }
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-      if (mi < mtiles) {
-#pragma unroll
-        for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], hi[mi][0], hi[mi][1], lo[nj >> 1][nj & 1]);
-      }
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-      if (mi < mtiles) {
-#pragma unroll
-        for (int nj = 0; nj <= 2 * mi + 1; ++nj) mma_f16(acc[k64_tile(mi, nj)], lo[mi][0], lo[mi][1], hi[nj >> 1][nj & 1]);
-      }
-  }
-  // ---- partial tiles -> panel storage, warp after warp (fixed order); warp 0 brings the diagonal ----
-  {
-    const int oc = (2 * tq) ^ (((g >> 2) & 1) << 2);
-#pragma unroll 1
-    for (int w = 0; w < 4; ++w) {
-      if (warp == w) {
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-          for (int nj = 0; nj <= 2 * mi + 1; ++nj) {
-            float (&d)[4] = acc[k64_tile(mi, nj)];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int gi = 16 * mi + g + ((e & 2) ? 8 : 0), gj = 8 * nj + 2 * tq + (e & 1);
-              d[e] *= yunsc;
-              if (w == 0 && nj >= 2 * mi && gi == gj) d[e] += (gi < nnz) ? lam : 1.0f;
-            }
-            float2* p0 = reinterpret_cast<float2*>(Lt + k64_pb0(nj) + 8 * (16 * mi + g) + oc);
-            float2* p1 = reinterpret_cast<float2*>(Lt + k64_pb0(nj) + 8 * (16 * mi + 8 + g) + oc);
-            if (nj <= 2 * mi) { const float2 o = *p0; *p0 = make_float2(o.x + d[0], o.y + d[1]); }
-            const float2 o = *p1;
-            *p1 = make_float2(o.x + d[2], o.y + d[3]);
-          }
-      }
-      __syncthreads();
-    }
-  }
-  if (warp == 0) k64_chol(Lt, invd, bs, lane, nblk);
-  // ---- z = L^-T L^-1 rhs, refinement, x = Y^T z ----
-  double zd0 = 0.0, zd1 = 0.0;
-  for (int it = 0;; ++it) {
-    if (warp == 0) {
-      float v0 = bs[lane], v1 = bs[32 + lane];
-      __syncwarp();
-      k64_backward(Lt, invd, v0, v1, lane, nblk);
-      zd0 += static_cast<double>(v0);
-      zd1 += static_cast<double>(v1);
-      zs[lane] = zd0;
-      zs[32 + lane] = zd1;
-    }
-    __syncthreads();
-    double x = 0.0;                              // entry tid of Y^T z
-    for (int i = 0; i < nnz; ++i) x = fma(static_cast<double>(Y[i * LDD + tid]), zs[i], x);
-    if (it >= a.ir_steps) {
-      const float xo = (tid < a.k) ? static_cast<float>(x) : 0.0f;
-      a.mine[row * KP + tid] = xo;
-      for (int pr = 0; pr < a.n_peers; ++pr) a.peers[pr][row * KP + tid] = xo;
-      break;
-    }
-    xs[tid] = x;
-    __syncthreads();
-    // r_i = 1 - <y_i, x> - lambda z_i for the observed rows (padded rows: 0); warp w takes rows w, w + 4, ...
-    {
-      double xq[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) xq[q] = xs[lane + 32 * q];
-      for (int i = warp; i < 64; i += 4) {
-        if (i >= nnz) { if (lane == 0) bs[i] = 0.0f; continue; }
-        const float* yr = Y + i * LDD;
-        double t = 0.0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) t = fma(static_cast<double>(yr[lane + 32 * q]), xq[q], t);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL_MASK, t, o);
-        if (lane == 0) bs[i] = static_cast<float>(1.0 - t - a.lambda * zs[i]);
-      }
-    }
-    __syncthreads();
-    if (warp == 0) k64_forward(Lt, invd, bs, lane, nblk);
-  }
-}
-
-// the rows with 1 .. 64 observations, by ticket (its own counter: a.counter[1]); the other rows belong to als_k128_kernel
-__global__ void __launch_bounds__(128, 4) als_k128_dual_kernel(const AlsArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ unsigned int s_ticket;
-  const int tid = threadIdx.x;
-  const float lam = static_cast<float>(a.lambda);
-  const float ysc = pow2_scale(*a.other_absmax);
-  const float yunsc = (1.0f / ysc) * (1.0f / ysc);
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(a.counter + 1, 1u);
-    __syncthreads();
-    const unsigned int ticket = s_ticket;
-    if (static_cast<int64_t>(ticket) >= a.n_rows) break;
-    const int64_t row = a.row_order ? a.row_order[ticket] : static_cast<int64_t>(ticket);
-    const int64_t s = a.indptr[row];
-    const int64_t nnz64 = a.indptr[row + 1] - s;
-    if (nnz64 <= 0 || nnz64 > K128_DUAL_MAX) continue;   // no observation: the row keeps its value (algo.py:316-317)
-    k128_dual_row(a, row, s, static_cast<int>(nnz64), smem_raw, tid, ysc, yunsc, lam);
-  }
-}
-
-// ---- the dual form, one WARP per row -----------------------------------------------------------------------------------------
-// The CTA-per-row version above keeps the gathered rows in shared memory (35 KB): four rows in flight per SM, and three of
-// the four warps wait at a barrier while warp 0 factors (40 % of the stall samples).  Here a warp owns a row, as in the
-// k = 64 kernel: G = Y Y^T is accumulated from 16-COLUMN chunks of the gathered rows (64 observations x 64 bytes, double
+// One WARP per row, as in the k = 64 kernel.  (A first version gave a row to a CTA of four warps and kept the gathered rows
+// in shared memory, 35 KB: four rows in flight per SM, and three of the four warps waited at a barrier while warp 0 factored --
+// 40 % of the stall samples, 58 ms per C5 shard against 32 ms for this one.)  Here G = Y Y^T is accumulated from 16-COLUMN chunks of the gathered rows (64 observations x 64 bytes, double
 // buffered: 12 KB), so only the 64 x 64 system and its factor live in shared memory (23 KB per warp, nine rows in flight per
 // SM), and the three matrix-vector passes of the refinement / the output (x = Y^T z, t = Y x, x = Y^T z) read the rows again
 // from L2, where the gather of a moment ago has left them.
@@ -472,7 +302,7 @@ __global__ void __launch_bounds__(128, 4) als_k128_kernel(const AlsArgs a) {
     const int64_t nnz64 = a.indptr[row + 1] - s;
     if (nnz64 <= 0) continue;   // reference: rows with no observation keep their previous value (algo.py:316-317)
     const int nnz = static_cast<int>(nnz64);
-    if (nnz <= K128_DUAL_MAX) continue;          // fewer observations than factors: als_k128_dual_kernel has the row
+    if (nnz <= K128_DUAL_MAX) continue;          // fewer observations than factors: als_k128_wdual_kernel has the row
     const int nchunk = (nnz + CH - 1) / CH;
 
     // all threads: cp.async gather of chunk c into buffer `yb` (8 rows x 32 pieces of 16 bytes; short chunks zero-filled)
@@ -818,31 +648,19 @@ __global__ void __launch_bounds__(128, 4) als_k128_kernel(const AlsArgs a) {
 
 int launch_k128(rl_context* h, const AlsArgs& args) {
   RL_CUDA(h, cudaMemsetAsync(args.counter, 0, 2 * sizeof(unsigned int), h->stream));
-  if (!getenv("RL_ALS_DUAL_CTA")) {   // rows with at most 64 observations: the dual form, one warp per row
+  {   // rows with at most 64 observations: the dual form, one warp per row
     auto kern = als_k128_wdual_kernel;
     const size_t smem = K128WarpDualSmem::bytes * KD_WARPS;
     RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
     RL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KD_WARPS * 32, smem));
-    if (per_sm < 1) return fail(h, RL_ERR_CUDA, "als_k128 (warp dual): kernel does not fit on an SM (smem %zu)", smem);
+    if (per_sm < 1) return fail(h, RL_ERR_CUDA, "als_k128 (dual): kernel does not fit on an SM (smem %zu)", smem);
     int64_t grid = static_cast<int64_t>(h->sm_count) * per_sm;
     const int64_t want = (args.n_rows + KD_WARPS - 1) / KD_WARPS;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     kern<<<static_cast<unsigned>(grid), KD_WARPS * 32, smem, h->stream>>>(args);
     RL_LAUNCH_CHECK(h, "als_k128_wdual_kernel");
-  } else {                            // (the CTA-per-row version, kept for comparison)
-    auto kern = als_k128_dual_kernel;
-    const size_t smem = K128DualSmem::bytes;
-    RL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    int per_sm = 0;
-    RL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
-    if (per_sm < 1) return fail(h, RL_ERR_CUDA, "als_k128 (dual): kernel does not fit on an SM (smem %zu)", smem);
-    int64_t grid = static_cast<int64_t>(h->sm_count) * per_sm;
-    if (grid > args.n_rows) grid = args.n_rows;
-    if (grid < 1) grid = 1;
-    kern<<<static_cast<unsigned>(grid), 128, smem, h->stream>>>(args);
-    RL_LAUNCH_CHECK(h, "als_k128_dual_kernel");
   }
   auto kern = als_k128_kernel;
   const size_t smem = K128Smem::bytes;

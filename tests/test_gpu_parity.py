@@ -91,7 +91,7 @@ def test_half_step_dev_vs_oracle(h, k, precision):
 @pytest.mark.parametrize("k", [72, 128])
 def test_half_step_k128_dual_and_primal_rows(h, k):
     """64 < k <= 128: rows with at most 64 observations are solved in the dual form x = Y^T (Y Y^T + lambda I)^-1 1
-    (als_k128_dual_kernel), longer rows by the 128 x 128 normal equations (als_k128_kernel); both against the oracle
+    (als_k128_wdual_kernel), longer rows by the 128 x 128 normal equations (als_k128_kernel); both against the oracle
     (algo.py:314-322) on one pattern that mixes 1 .. 300 observations per row, rows of exactly 64 / 65 and empty rows."""
     from devbuf import Dev, padded, unpadded
     n_rows, n_other = 900, 400
