@@ -22,7 +22,10 @@
 
 constexpr int K128 = 128;
 constexpr int K128_LDY = 132;     // row stride of a gathered row (2 LDY = 8 mod 32: conflict-free fragment reads)
-constexpr int K128_CH = 8;
+#ifndef K128_CH_
+#define K128_CH_ 16
+#endif
+constexpr int K128_CH = K128_CH_;   // gathered rows per chunk (a multiple of 8: one mma k-step per 8 rows); two CTA barriers per chunk
 constexpr int K128_FSZ = 8 * 520; // the full 64 x 64 block A21 / L21: 8 panels of 64 rows x 8 floats, 8 floats of skew each
 
 // element (i, j) of the full block: B21[k128_f0(j >> 3) + 8 i + ((j & 7) ^ k64_swz(i))]
@@ -33,7 +36,7 @@ struct K128Smem {
   static constexpr size_t f_bytes = sizeof(float) * K128_FSZ;         // B21
   static constexpr size_t invd_bytes = sizeof(float) * K128;
   static constexpr size_t xs_bytes = sizeof(double) * K128;           // x in float64; aliased by the float right-hand side
-  static constexpr size_t ts_bytes = sizeof(double) * 8;
+  static constexpr size_t ts_bytes = sizeof(double) * K128_CH;
   static constexpr size_t y_bytes = sizeof(float) * 2 * K128_CH * K128_LDY;
   static constexpr size_t bytes = 2 * p_bytes + f_bytes + invd_bytes + xs_bytes + ts_bytes + y_bytes;
   static_assert(bytes % 16 == 0, "shared memory layout must keep 16-byte alignment");
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(128, 4) als_k128_kernel(const AlsArgs a) {
   double* xs = reinterpret_cast<double*>(invd + K128);
   float* bs = reinterpret_cast<float*>(xs);
   double* ts = xs + K128;
-  float* ybuf = reinterpret_cast<float*>(ts + 8);
+  float* ybuf = reinterpret_cast<float*>(ts + K128_CH);
   __shared__ unsigned int s_ticket;
 
   const float lam = static_cast<float>(a.lambda);
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(128, 4) als_k128_kernel(const AlsArgs a) {
     auto gather = [&](int c, float* yb) {
       const int cnt = min(CH, nnz - c * CH);
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < CH / 4; ++q) {
         const int p = tid + 128 * q;
         const int r = p >> 5, c4 = p & 31;
         const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(yb + r * LDY + 4 * c4));
@@ -343,7 +346,9 @@ __global__ void __launch_bounds__(128, 4) als_k128_kernel(const AlsArgs a) {
       const float* yb = ybuf + buf * CH * LDY;
 #pragma unroll
       for (int r = 0; r < CH; ++r) bsum += yb[r * LDY + tid];
-      const float* y0 = yb + (2 * tq) * LDY + g;
+#pragma unroll 1
+      for (int ks = 0; ks < CH / 8; ++ks) {      // one mma k-step per 8 gathered rows
+      const float* y0 = yb + (8 * ks + 2 * tq) * LDY + g;
       const float* y1 = y0 + LDY;
       if (warp < 2) {
         uint32_t hi[4][2], lo[4][2];
@@ -388,6 +393,7 @@ __global__ void __launch_bounds__(128, 4) als_k128_kernel(const AlsArgs a) {
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
           for (int nj = 0; nj < 8; ++nj) mma_f16(acc[8 * mi + nj], alo[mi][0], alo[mi][1], bhi[nj >> 1][nj & 1]);
+      }
       }
       __syncthreads();                           // the buffer may be overwritten by the gather after next
     }
@@ -596,8 +602,8 @@ __global__ void __launch_bounds__(128, 4) als_k128_kernel(const AlsArgs a) {
         const float* yb = ybuf + buf * CH * LDY;
         const int cnt = min(CH, nnz - c * CH);
 #pragma unroll
-        for (int rr2 = 0; rr2 < 2; ++rr2) {       // warp w: rows 2 w, 2 w + 1 of the chunk
-          const int i = 2 * warp + rr2;
+        for (int rr2 = 0; rr2 < CH / 4; ++rr2) {  // warp w: rows (CH / 4) w .. of the chunk
+          const int i = (CH / 4) * warp + rr2;
           const float* yr = yb + i * LDY;
           double t = 0.0;
 #pragma unroll
